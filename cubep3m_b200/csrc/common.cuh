@@ -1,0 +1,131 @@
+// Shared declarations for the single-TU CUDA library (lib.cu). sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+#include "../../include/cubep3m_b200.h"
+
+#ifdef CUBEP3M_WITH_NCCL
+#include <nccl.h>
+#endif
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      fprintf(stderr, "cubep3m_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e__), __FILE__, __LINE__, \
+              cudaGetErrorString(e__));                                                            \
+      return CUBEP3M_B200_ECUDA;                                                                   \
+    }                                                                                              \
+  } while (0)
+
+// every kernel launch goes through this so the library can report how many it issued
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
+  do {                                                                       \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
+    (ctx)->launches++;                                                       \
+  } while (0)
+
+constexpr int NUM_SMS = 148;   // B200
+
+// derived sizes, cubepm.par:190-208
+struct Dims {
+  int D, T, n, b, s, m, mT, nc_tile, nc_node, nc_dim, nc_slab, nc_buf, hoc_l, hoc_h, H, nodes, tiles_node;
+  int max_np, max_buf;
+  int hc;          // n/2+1
+  int fdim;        // m+3: force_f spans nf_buf-1 .. nf_tile-nf_buf+1 (cubep3m.fh:36-37)
+  long long NF;    // fine cells of the hoc range: H^3 * 64
+};
+
+// device counters written by kernels, mirrored to the host once per step
+struct DevCounters {
+  int np_deleted;        // out-of-range particles dropped by link_list
+  int n_send[2];         // pack counts of the current axis: [0] = "+" direction, [1] = "-"
+  int n_multi;           // fine cells with >= 2 particles in the physical region (PPINT work list)
+  int n_occ;             // occupied physical fine cells (PP_EXT work list)
+  int overflow;          // bit 0: pass buffer, bit 1: max_np, bit 2: max_llf
+  unsigned int f_force_max2_bits;   // max |force_f|^2 as ordered uint
+  unsigned int pp_force_max_bits;
+  unsigned int pp_ext_force_max_bits;
+  unsigned int c_force_max_bits;
+  int np_phys;           // after delete_particles
+  int pad;
+  double sum_rho_f;
+  double sum_rho_c;
+};
+
+struct cubep3m_b200_ctx {
+  cubep3m_b200_config cfg;
+  Dims d;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  int world = 1;
+  // particles (AoS 24-byte records as the reference's xv(6,:)), double buffered
+  float* xv[2] = {nullptr, nullptr};
+  int64_t* pid[2] = {nullptr, nullptr};
+  int cur = 0;
+  int np_local = 0;      // physical particles (valid after upload / delete_particles)
+  int np_all = 0;        // incl. ghosts (valid after particle_pass)
+  bool sorted = false;   // xv[cur] is cell-sorted and fstart is valid
+  bool passed = false;
+  unsigned int* key = nullptr;
+  int* fstart = nullptr; // exclusive scan of fine-cell counts, NF+1 entries
+  int* fcur = nullptr;   // histogram / scatter cursors, NF entries
+  int* blocksum = nullptr;
+  int nblocksum = 0;
+  int* multi_list = nullptr;  // keys of physical fine cells with >= 2 particles
+  int* occ_list = nullptr;    // keys of occupied physical fine cells
+  int list_cap = 0;
+  float* sendbuf[2] = {nullptr, nullptr};
+  float* recvbuf[2] = {nullptr, nullptr};
+  int64_t* sendpid[2] = {nullptr, nullptr};
+  int64_t* recvpid[2] = {nullptr, nullptr};
+  int* rowoff = nullptr;      // compaction offsets per physical (cy,cz) row
+  // fine mesh
+  float* kern_f = nullptr;    // (3,hc,n,n) components innermost, as cubep3m.fh:35
+  float* tile_rho = nullptr;  // (n+2,n,n) real / (hc,n,n) complex, in place
+  float* tile_g = nullptr;    // work array for one force component
+  float* force_f[3] = {nullptr, nullptr, nullptr};  // (fdim^3) each, SoA
+  float2* tw_f = nullptr;     // twiddles exp(-2 pi i t/n)
+  // coarse mesh
+  float* kern_c = nullptr;    // (3,hc_c,nc_dim,nc_slab)
+  float* rho_c = nullptr;     // nc_node^3
+  float* slab = nullptr;      // (nc_dim+2, nc_dim, nc_dim) for D=1 (full mesh on one GPU)
+  float* slab_g = nullptr;
+  float* force_c = nullptr;   // (3, nc_node+2, nc_node+2, nc_node+2) components innermost as cubep3m.fh:59
+  float2* tw_c = nullptr;
+  DevCounters* dcnt = nullptr;
+  DevCounters* hcnt = nullptr; // pinned
+  cudaEvent_t ev[CUBEP3M_B200_ST_COUNT + 2];
+  bool ev_ok = false;
+  std::vector<float> fine_table, coarse_table;
+  int last_tile_counts_valid = 0;
+#ifdef CUBEP3M_WITH_NCCL
+  ncclComm_t comm = nullptr;
+#endif
+};
+
+// ordered-uint encoding of non-negative floats for atomicMax
+__device__ __forceinline__ void atomic_max_float_nonneg(unsigned int* addr, float v) { atomicMax(addr, __float_as_uint(v)); }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

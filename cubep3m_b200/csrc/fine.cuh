@@ -1,0 +1,100 @@
+// Fine-mesh stages of the tile loop (particle_mesh_threaded.f90:84-368), one tile at a time:
+//   deposit  : NGP density from the fine-cell occupancy table built by the cell sort (no atomics)
+//   kick     : NGP force lookup + velocity update of the particles of the physical tile
+//   force max: max |force_f|^2 over the cropped force cube
+#pragma once
+#include "common.cuh"
+#include "particles.cuh"
+
+namespace fine {
+
+constexpr int TPB = 256;
+
+// key of fine cell (gx,gy,gz) in the extended node frame (see part::make_key)
+__device__ __forceinline__ long long cell_key(int gx, int gy, int gz, int H) {
+  return ((long long)(((gz >> 2) * H + (gy >> 2))) * H + (gx >> 2)) * 64 + (((gz & 3) << 4) | ((gy & 3) << 2) | (gx & 3));
+}
+
+// NGP: rho_f(i1) += mass_p for every particle chained in coarse cells cic_l..cic_h (particle_mesh_threaded.f90:120-151).
+// Those cells cover tile-local fine cells [4, n-5] (0-based) on every axis; everything else stays 0 (:100).
+// One thread produces 4 consecutive x cells (= one coarse cell's x-row: 5 consecutive fstart entries).
+// Also accumulates the DIAG mass sum over the physical part (:167-173) and the deposited-particle count.
+__global__ void __launch_bounds__(TPB) ngp_density_kernel(const int* __restrict__ fstart, float* __restrict__ rho, int n, int b, int m, int H,
+                                                          int tx, int ty, int tz, float mass_p, double* __restrict__ sum_phys,
+                                                          int* __restrict__ tile_count) {
+  const int nq = (n + 2 + 3) / 4;             // float4 groups per padded row (n+2 floats; n%4==0 -> (n+4)/4 groups, last half-used)
+  const long long total = (long long)nq * n * n;
+  double msum = 0.0;
+  int pcount = 0;
+  for (long long t = (long long)blockIdx.x * TPB + threadIdx.x; t < total; t += (long long)gridDim.x * TPB) {
+    const int xq = (int)(t % nq);
+    const long long r = t / nq;
+    const int y = (int)(r % n), z = (int)(r / n);
+    const int x0 = xq * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool yz_in = (y >= 4 && y <= n - 5 && z >= 4 && z <= n - 5);
+    if (yz_in && x0 >= 4 && x0 <= n - 8) {
+      const int gx = x0 + tx * m, gy = y + ty * m, gz = z + tz * m;
+      const long long k = cell_key(gx, gy, gz, H);      // gx % 4 == 0 because m % 4 == 0
+      const int s0 = fstart[k], s1 = fstart[k + 1], s2 = fstart[k + 2], s3 = fstart[k + 3], s4 = fstart[k + 4];
+      const int c0 = s1 - s0, c1 = s2 - s1, c2 = s3 - s2, c3 = s4 - s3;
+      v[0] = mass_p * (float)c0; v[1] = mass_p * (float)c1; v[2] = mass_p * (float)c2; v[3] = mass_p * (float)c3;
+      pcount += c0 + c1 + c2 + c3;
+      if (y >= b && y < n - b && z >= b && z < n - b && x0 >= b && x0 < n - b) msum += (double)v[0] + (double)v[1] + (double)v[2] + (double)v[3];
+    }
+    float* row = rho + ((long long)z * n + y) * (n + 2);
+    if (x0 + 3 < n + 2) {
+      *reinterpret_cast<float2*>(row + x0) = make_float2(v[0], v[1]);
+      *reinterpret_cast<float2*>(row + x0 + 2) = make_float2(v[2], v[3]);
+    } else {
+      for (int q = 0; q < 4; ++q) if (x0 + q < n + 2) row[x0 + q] = v[q];
+    }
+  }
+  msum = warp_sum_d(msum);
+  pcount = warp_sum_i(pcount);
+  if ((threadIdx.x & 31) == 0) {
+    if (msum != 0.0) atomicAdd(sum_phys, msum);
+    if (pcount) atomicAdd(tile_count, pcount);
+  }
+}
+
+// max over the cropped force cube of fx^2+fy^2+fz^2 (particle_mesh_threaded.f90:208-223)
+__global__ void __launch_bounds__(TPB) force_max_kernel(const float* __restrict__ fx, const float* __restrict__ fy, const float* __restrict__ fz,
+                                                        long long n, unsigned int* __restrict__ out_bits) {
+  float mx = 0.f;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) {
+    const float a = fx[i], b = fy[i], c = fz[i];
+    mx = fmaxf(mx, a * a + b * b + c * c);
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomic_max_float_nonneg(out_bits, mx);
+}
+
+// NGP kick (particle_mesh_threaded.f90:227-266): for every particle chained in the coarse cells of the physical tile
+//   x_t = x + (nf_buf - tile*m); i1 = floor(x_t)+1; v += force_f(:, i1) * a_mid * G * dt
+// One CTA per (cy,cz) coarse row of the tile = one contiguous range of the sorted array.
+__global__ void __launch_bounds__(TPB) ngp_kick_kernel(float* __restrict__ xv, const int* __restrict__ fstart, const float* __restrict__ fx,
+                                                       const float* __restrict__ fy, const float* __restrict__ fz, int H, int nc_buf, int nc_tile,
+                                                       int b, int m, int fdim, int tx, int ty, int tz, float a_mid, float G, float dt) {
+  const int ry = blockIdx.x % nc_tile, rz = blockIdx.x / nc_tile;
+  const int cy = nc_buf + ty * nc_tile + ry, cz = nc_buf + tz * nc_tile + rz, cx0 = nc_buf + tx * nc_tile;
+  const long long k0 = ((long long)(cz * H + cy) * H + cx0) * 64;
+  const int s0 = fstart[k0], s1 = fstart[k0 + (long long)nc_tile * 64];
+  const float offx = (float)b - (float)(tx * m), offy = (float)b - (float)(ty * m), offz = (float)b - (float)(tz * m);
+  for (int i = s0 + threadIdx.x; i < s1; i += TPB) {
+    float2* p = reinterpret_cast<float2*>(xv) + 3LL * i;
+    const float2 a = p[0];
+    float2 bb = p[1], c = p[2];
+    // 0-based index into the cropped cube: (i1 - (nf_buf-1)) with i1 = floor(x_t)+1
+    const int ix = (int)floorf(__fadd_rn(a.x, offx)) + 2 - b;
+    const int iy = (int)floorf(__fadd_rn(a.y, offy)) + 2 - b;
+    const int iz = (int)floorf(__fadd_rn(bb.x, offz)) + 2 - b;
+    const long long q = ((long long)iz * fdim + iy) * fdim + ix;
+    bb.y += ((fx[q] * a_mid) * G) * dt;
+    c.x += ((fy[q] * a_mid) * G) * dt;
+    c.y += ((fz[q] * a_mid) * G) * dt;
+    p[1] = bb; p[2] = c;
+  }
+}
+
+}  // namespace fine

@@ -1,0 +1,850 @@
+// libcubep3m_b200.so — the C ABI of include/cubep3m_b200.h on top of the hand-written sm_100a kernels.
+// Single translation unit: all kernels are in the .cuh parts included below.
+// There is NO CPU fallback: every entry point that computes needs a CUDA device and fails with ECUDA otherwise.
+#include "common.cuh"
+#include "fft_smem.cuh"
+#include "fft3d.cuh"
+#include "particles.cuh"
+#include "fine.cuh"
+#include "pp.cuh"
+#include "coarse.cuh"
+
+namespace {
+
+int derive(const cubep3m_b200_config& c, Dims& d) {
+  d.D = c.nodes_dim; d.T = c.tiles_node_dim; d.n = c.nf_tile; d.b = c.nf_buf; d.s = c.mesh_scale;
+  if (d.D < 1 || d.T < 1 || d.s != 4 || d.b <= 0 || d.b % d.s != 0) return CUBEP3M_B200_EINVAL;
+  d.m = d.n - 2 * d.b;                    // nf_physical_tile_dim  cubepm.par:197
+  if (d.m <= 0 || d.m % d.s != 0) return CUBEP3M_B200_EINVAL;
+  d.mT = d.m * d.T;                       // nf_physical_node_dim  cubepm.par:201
+  d.nc_buf = d.b / d.s;                   // cubepm.par:190
+  d.nc_tile = d.m / d.s;                  // cubepm.par:191
+  d.nc_node = d.nc_tile * d.T;            // cubepm.par:192
+  d.nc_dim = d.nc_node * d.D;             // cubepm.par:193
+  d.nodes = d.D * d.D * d.D;
+  if (d.nc_dim % d.nodes != 0) return CUBEP3M_B200_EINVAL;   // mpi_initialization.f90:25-29
+  d.nc_slab = d.nc_dim / d.nodes;         // cubepm.par:195
+  d.hoc_l = 1 - d.nc_buf; d.hoc_h = d.nc_node + d.nc_buf; d.H = d.hoc_h - d.hoc_l + 1;   // cubepm.par:204-205
+  d.tiles_node = d.T * d.T * d.T;
+  if (c.max_np > 0) d.max_np = c.max_np;
+  else {                                  // cubepm.par:170-172
+    const double half = (double)(d.mT / 2);
+    const double buf = (8.0 * d.b * d.b * d.b + 6.0 * d.b * (double)d.mT * d.mT + 12.0 * (double)d.b * d.b * d.mT) / 8.0;
+    d.max_np = (int)(c.density_buffer * (half * half * half + buf));
+  }
+  d.max_buf = c.max_buf > 0 ? c.max_buf : (int)(2.2 * (double)d.max_np);   // cubepm.par:175
+  d.hc = d.n / 2 + 1;
+  d.fdim = d.m + 3;
+  d.NF = (long long)d.H * d.H * d.H * 64;
+  if (d.NF >= (1LL << 31)) return CUBEP3M_B200_EINVAL;
+  if (!fftk::supported(d.n) || !fftk::supported(d.nc_dim)) return CUBEP3M_B200_EINVAL;
+  if (c.pp_range < 0 || c.pp_range > 2) return CUBEP3M_B200_EINVAL;
+  // LRCKCORR divides by Im(kernel) for |k| <= 8 (kernel_initialization.f90:573-581): Nyquist must lie beyond
+  if (c.lrckcorr && d.nc_dim / 2 <= 8) return CUBEP3M_B200_EINVAL;
+  return 0;
+}
+
+template <typename T> int dmalloc(T** p, size_t count) {
+  CK(cudaMalloc((void**)p, count * sizeof(T)));
+  return 0;
+}
+
+__global__ void extract_imag_kernel(const float2* __restrict__ spec, long long n, float* __restrict__ kern, int comp) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) kern[i * 3 + comp] = spec[i].y;
+}
+
+int grid_for(long long n, int tpb, int cap = NUM_SMS * 16) {
+  long long g = (n + tpb - 1) / tpb;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+// ---- kernel_initialization.f90:2-267 fine_kernel, with the library's own FFT
+int build_kern_f(cubep3m_b200_ctx* ctx) {
+  const Dims& d = ctx->d;
+  const cubep3m_b200_config& c = ctx->cfg;
+  const int n = d.n, n2 = n + 2, nfc = c.nf_cutoff;
+  if (nfc != 16 || n < 2 * nfc) return CUBEP3M_B200_EINVAL;
+  std::vector<float> rho((size_t)n2 * n * n);
+  auto R = [&](int i, int j, int k) -> float& { return rho[(size_t)(i - 1) + (size_t)n2 * ((j - 1) + (size_t)n * (k - 1))]; };
+  for (int comp = 0; comp < 3; ++comp) {
+    std::fill(rho.begin(), rho.end(), 0.f);
+    for (int k = 1; k <= nfc; ++k)
+      for (int j = 1; j <= nfc; ++j)
+        for (int i = 1; i <= nfc; ++i) R(i, j, k) = ctx->fine_table[(((size_t)(k - 1) * 16 + (j - 1)) * 16 + (i - 1)) * 3 + comp];   // :25-36
+    if (c.pp_ext && c.pp_ext_force_flag)                                                                                           // :38-54
+      for (int k = 1; k <= c.pp_range + 1; ++k)
+        for (int j = 1; j <= c.pp_range + 1; ++j)
+          for (int i = 1; i <= c.pp_range + 1; ++i) R(i, j, k) = 0.f;
+    const float sy = comp == 1 ? -1.f : 1.f, sx = comp == 0 ? -1.f : 1.f, sz = comp == 2 ? -1.f : 1.f;
+    for (int j = 2; j <= nfc; ++j)                     // :71-73
+      for (int k = 1; k <= nfc; ++k)
+        for (int i = 1; i <= nfc; ++i) R(i, n - j + 2, k) = sy * R(i, j, k);
+    for (int i = 2; i <= nfc; ++i)                     // :76-79
+      for (int k = 1; k <= nfc; ++k)
+        for (int j = 1; j <= n; ++j) R(n - i + 2, j, k) = sx * R(i, j, k);
+    for (int k = 2; k <= nfc; ++k)                     // :82-85
+      for (int j = 1; j <= n; ++j)
+        for (int i = 1; i <= n; ++i) R(i, j, n - k + 2) = sz * R(i, j, k);
+    CK(cudaMemcpyAsync(ctx->tile_rho, rho.data(), rho.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (int st = fftk::forward3d(ctx, n, ctx->tile_rho, ctx->tw_f)) return st;   // :89
+    const long long ns = (long long)d.hc * n * n;
+    LAUNCH(ctx, extract_imag_kernel, grid_for(ns, 256), 256, 0, reinterpret_cast<const float2*>(ctx->tile_rho), ns, ctx->kern_f, comp);   // :93-99
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+// ---- kernel_initialization.f90:272-732 coarse_kernel (global mesh; every rank builds the same table and uses its z-slab)
+int build_kern_c(cubep3m_b200_ctx* ctx) {
+  const Dims& d = ctx->d;
+  const cubep3m_b200_config& c = ctx->cfg;
+  const int N = d.nc_dim, N2 = N + 2, hc = N / 2 + 1;
+  const float pi = 3.141592654f;
+  std::vector<float> ck((size_t)3 * N * N * N), ckc;
+  auto CKA = [&](std::vector<float>& a, int comp, int i, int j, int k) -> float& {
+    return a[(size_t)comp + 3 * ((size_t)(i - 1) + (size_t)N * ((j - 1) + (size_t)N * (k - 1)))];
+  };
+  auto fill_plain = [&](std::vector<float>& a) {       // :302-336
+    for (int k = 1; k <= N; ++k) {
+      float z = (k < N / 2 + 2) ? (float)(k - 1) : (float)(k - 1 - N); z = d.s * z;
+      for (int j = 1; j <= N; ++j) {
+        float y = (j < N / 2 + 2) ? (float)(j - 1) : (float)(j - 1 - N); y = d.s * y;
+        for (int i = 1; i <= N; ++i) {
+          float x = (i < N / 2 + 2) ? (float)(i - 1) : (float)(i - 1 - N); x = d.s * x;
+          const float r = sqrtf(x * x + y * y + z * z);
+          if (r == 0.0f) { CKA(a, 0, i, j, k) = 0.f; CKA(a, 1, i, j, k) = 0.f; CKA(a, 2, i, j, k) = 0.f; }
+          else { const float r3 = r * r * r; CKA(a, 0, i, j, k) = -x / r3; CKA(a, 1, i, j, k) = -y / r3; CKA(a, 2, i, j, k) = -z / r3; }
+        }
+      }
+    }
+  };
+  fill_plain(ck);
+  for (int oz = -3; oz <= 3; ++oz)                     // :344-457 near-field table in all octants
+    for (int oy = -3; oy <= 3; ++oy)
+      for (int ox = -3; ox <= 3; ++ox) {
+        const int i = ox >= 0 ? ox + 1 : N + ox + 1, j = oy >= 0 ? oy + 1 : N + oy + 1, k = oz >= 0 ? oz + 1 : N + oz + 1;
+        if (i < 1 || j < 1 || k < 1 || i > N || j > N || k > N) continue;
+        const int o[3] = {ox, oy, oz};
+        for (int comp = 0; comp < 3; ++comp) {
+          const float v = ctx->coarse_table[(((size_t)abs(oz) * 4 + abs(oy)) * 4 + abs(ox)) * 3 + comp];
+          CKA(ck, comp, i, j, k) = (o[comp] < 0) ? -v : v;
+        }
+      }
+  std::vector<float> slab((size_t)N2 * N * N), tmp;
+  std::vector<float> kc((size_t)3 * hc * N * N);
+  auto transform = [&](std::vector<float>& a, int comp) -> int {
+    for (int k = 1; k <= N; ++k)
+      for (int j = 1; j <= N; ++j) {
+        float* row = &slab[(size_t)N2 * ((j - 1) + (size_t)N * (k - 1))];
+        for (int i = 1; i <= N; ++i) row[i - 1] = CKA(a, comp, i, j, k);
+        row[N] = row[N + 1] = 0.f;
+      }
+    CK(cudaMemcpyAsync(ctx->slab, slab.data(), slab.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (int st = fftk::forward3d(ctx, N, ctx->slab, ctx->tw_c)) return st;
+    CK(cudaMemcpyAsync(slab.data(), ctx->slab, slab.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  };
+  if (c.lrckcorr) {
+    ckc = ck;                                          // :469-475
+    fill_plain(ck);                                    // :479-513
+  }
+  for (int comp = 0; comp < 3; ++comp) {
+    if (c.lrckcorr) {
+      if (int st = transform(ck, comp)) return st;     // :519-551
+      tmp = slab;
+      if (int st = transform(ckc, comp)) return st;
+      for (int k = 1; k <= N; ++k) {                   // :558-591 / :602-635 / :646-679
+        const int kz = (k < N / 2 + 2) ? k - 1 : k - 1 - N;
+        for (int j = 1; j <= N; ++j) {
+          const int ky = (j < N / 2 + 2) ? j - 1 : j - 1 - N;
+          for (int i = 1; i <= N + 2; i += 2) {
+            const int kx = (i - 1) / 2;
+            const float kr = sqrtf((float)(kx * kx + ky * ky + kz * kz));
+            if (kr <= 8.f) {
+              const float ka = 2 * sinf(pi * kx / (float)N), kb = 2 * sinf(pi * ky / (float)N), kcc = 2 * sinf(pi * kz / (float)N);
+              const int kd = comp == 0 ? kx : (comp == 1 ? ky : kz);
+              const float kk = comp == 0 ? ka : (comp == 1 ? kb : kcc);
+              if (kd != 0) {
+                const size_t o = (size_t)i + (size_t)N2 * ((j - 1) + (size_t)N * (k - 1));
+                const float wa = slab[o], wb = tmp[o];
+                const float wc = 4.f * pi * kk / (ka * ka + kb * kb + kcc * kcc) / 16.f;
+                slab[o] = wa * (wc / wb);
+              }
+            }
+          }
+        }
+      }
+    } else {
+      if (int st = transform(ck, comp)) return st;     // :695-723
+    }
+    for (int k = 1; k <= N; ++k)                       // :593-599
+      for (int j = 1; j <= N; ++j)
+        for (int i = 1; i <= hc; ++i)
+          kc[(size_t)comp + 3 * ((size_t)(i - 1) + (size_t)hc * ((j - 1) + (size_t)N * (k - 1)))] =
+              slab[(size_t)(2 * i - 1) + (size_t)N2 * ((j - 1) + (size_t)N * (k - 1))];
+  }
+  CK(cudaMemcpy(ctx->kern_c, kc.data(), kc.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int fetch_counters(cubep3m_b200_ctx* ctx) {
+  CK(cudaMemcpyAsync(ctx->hcnt, ctx->dcnt, sizeof(DevCounters), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int overflow_status(const DevCounters* h) {
+  if (h->overflow & 1) return CUBEP3M_B200_EPASSBUF;
+  if (h->overflow & 2) return CUBEP3M_B200_EMAXNP;
+  if (h->overflow & 4) return CUBEP3M_B200_EMAXLLF;
+  return 0;
+}
+
+// ---------------------------------------------------------------- stages
+int do_drift(cubep3m_b200_ctx* ctx, float dt, float dt_old, const float off[3]) {
+  if (ctx->np_local > 0)
+    LAUNCH(ctx, part::drift_kernel, (ctx->np_local + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->np_local, dt + dt_old, off[0], off[1], off[2]);
+  CK(cudaGetLastError());
+  ctx->sorted = false; ctx->passed = false;
+  ctx->np_all = ctx->np_local;
+  return 0;
+}
+
+// particle_pass.f90:69-722 for nodes_dim = 1 (every neighbour is this rank) or over NCCL
+int exchange_axis(cubep3m_b200_ctx* ctx, int axis, int n_plus_out, int n_minus_out, int* n_from_minus, int* n_from_plus);
+
+int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max) {
+  const Dims& d = ctx->d;
+  const float lo = -(float)d.b, hi = (float)d.mT + (float)d.b;
+  const float fmT = (float)d.mT, rnf = (float)d.b;
+  const float cut_hi = fmT - rnf, cut_lo = rnf;
+  const float hi_clamp = (fmT + rnf) - ctx->cfg.eps;
+  const int cap = d.max_buf / 6;
+  int np = ctx->np_all;
+  *np_buf_max = 0;
+  for (int axis = 0; axis < 3; ++axis) {
+    CK(cudaMemsetAsync(&ctx->dcnt->n_send[0], 0, 2 * sizeof(int), ctx->stream));
+    if (np > 0)
+      LAUNCH(ctx, part::pass_pack_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], np, axis, lo, hi,
+             cut_hi, cut_lo, ctx->sendbuf[0], ctx->sendbuf[1], ctx->sendpid[0], ctx->sendpid[1], cap, ctx->dcnt);
+    CK(cudaGetLastError());
+    if (int st = fetch_counters(ctx)) return st;
+    if (int st = overflow_status(ctx->hcnt)) return st;
+    const int n_plus = ctx->hcnt->n_send[0], n_minus = ctx->hcnt->n_send[1];
+    if (n_plus * 6 > d.max_buf || n_minus * 6 > d.max_buf) return CUBEP3M_B200_EPASSBUF;      // particle_pass.f90:96-99
+    *np_buf_max = std::max(*np_buf_max, std::max(n_plus, n_minus));
+    int r_plus = 0, r_minus = 0;   // r_plus: particles that travelled in + direction (arrive from the - neighbour)
+    if (int st = exchange_axis(ctx, axis, n_plus, n_minus, &r_plus, &r_minus)) return st;
+    if ((long long)np + r_plus + r_minus > d.max_np) return CUBEP3M_B200_EMAXNP;              // particle_pass.f90:136-139
+    const int nr = r_plus + r_minus;
+    if (nr > 0)
+      LAUNCH(ctx, part::pass_unpack_kernel, (nr + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], np, axis,
+             ctx->recvbuf[0], r_plus, ctx->recvbuf[1], r_minus, ctx->recvpid[0], ctx->recvpid[1], fmT, rnf, ctx->cfg.eps, hi_clamp);
+    CK(cudaGetLastError());
+    np += nr;
+  }
+  ctx->np_all = np;
+  ctx->passed = true;
+  ctx->sorted = false;
+  return 0;
+}
+
+int exchange_axis(cubep3m_b200_ctx* ctx, int axis, int n_plus_out, int n_minus_out, int* r_plus, int* r_minus) {
+  if (ctx->d.D == 1) {
+    // the + and - neighbours are this rank: what was sent in + direction is received "from the - neighbour"
+    ctx->recvbuf[0] = ctx->sendbuf[0]; ctx->recvbuf[1] = ctx->sendbuf[1];
+    ctx->recvpid[0] = ctx->sendpid[0]; ctx->recvpid[1] = ctx->sendpid[1];
+    *r_plus = n_plus_out; *r_minus = n_minus_out;
+    return 0;
+  }
+  (void)axis;
+  return CUBEP3M_B200_EINVAL;   // multi-rank exchange: see nccl section (not built in this configuration)
+}
+
+// cell sort of xv[cur][0:np_all) -> xv[cur^1], builds fstart and the PP work lists
+int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
+  const Dims& d = ctx->d;
+  const int np = ctx->np_all;
+  const float lo = -(float)d.b, hi = (float)d.mT + (float)d.b;
+  CK(cudaMemsetAsync(ctx->fcur, 0, sizeof(int) * d.NF, ctx->stream));
+  CK(cudaMemsetAsync(&ctx->dcnt->np_deleted, 0, sizeof(int), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->dcnt->n_multi, 0, 2 * sizeof(int), ctx->stream));
+  if (np > 0)
+    LAUNCH(ctx, part::key_hist_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], np, lo, hi, d.b, d.H, ctx->key, ctx->fcur, ctx->dcnt);
+  const int nb = (int)((d.NF + part::SCAN_BLOCK - 1) / part::SCAN_BLOCK);
+  LAUNCH(ctx, part::scan_reduce_kernel, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum);
+  LAUNCH(ctx, part::scan_blocksums_kernel, 1, 1024, 0, ctx->blocksum, nb);
+  LAUNCH(ctx, part::scan_apply_kernel, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->multi_list,
+         ctx->occ_list, ctx->list_cap, ctx->cfg.ppint ? 1 : 0, ctx->cfg.pp_ext ? 1 : 0, ctx->dcnt);
+  if (np > 0)
+    LAUNCH(ctx, part::scatter_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->fcur,
+           ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1]);
+  CK(cudaGetLastError());
+  if (int st = fetch_counters(ctx)) return st;
+  ctx->cur ^= 1;
+  ctx->np_all = np - ctx->hcnt->np_deleted;
+  if (!ctx->passed) ctx->np_local = ctx->np_all;
+  if (np_deleted) *np_deleted = ctx->hcnt->np_deleted;
+  ctx->sorted = true;
+  return 0;
+}
+
+// delete_particles.f90:14-50 on the sorted array
+int do_delete(cubep3m_b200_ctx* ctx) {
+  const Dims& d = ctx->d;
+  const int rows = d.nc_node * d.nc_node;
+  CK(cudaMemsetAsync(ctx->rowoff + rows, 0, sizeof(int), ctx->stream));
+  LAUNCH(ctx, part::row_count_kernel, (rows + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->rowoff);
+  LAUNCH(ctx, part::scan_blocksums_kernel, 1, 1024, 0, ctx->rowoff, rows + 1);   // entry [rows] (initialised to 0) becomes the total
+  LAUNCH(ctx, part::compact_rows_kernel, rows, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->fstart, ctx->rowoff, d.H, d.nc_buf, d.nc_node,
+         ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1]);
+  CK(cudaGetLastError());
+  int total = 0;
+  CK(cudaMemcpyAsync(&ctx->hcnt->np_phys, ctx->rowoff + rows, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  total = ctx->hcnt->np_phys;
+  ctx->cur ^= 1;
+  ctx->np_local = total; ctx->np_all = total;
+  ctx->sorted = false; ctx->passed = false;
+  return 0;
+}
+
+// fine-mesh solve of one tile: deposit -> forward FFT -> 3 x (kernel multiply + backward FFT + crop) -> max force
+int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, int* tile_count_dev) {
+  const Dims& d = ctx->d;
+  const int T = d.T, n = d.n;
+  const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;   // particle_mesh_threaded.f90:86-90 (cur_tile-1, x fastest)
+  LAUNCH(ctx, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
+         &ctx->dcnt->sum_rho_f, tile_count_dev);
+  if (int st = fftk::forward3d(ctx, n, ctx->tile_rho, ctx->tw_f)) return st;
+  const float scale = 1.0f / (((float)n * (float)n) * (float)n);       // fft_fine.f90:51
+  for (int comp = 0; comp < 3; ++comp)
+    if (int st = fftk::backward3d(ctx, n, ctx->tile_rho, ctx->tile_g, ctx->kern_f, comp, ctx->force_f[comp], d.b - 2, d.fdim, d.fdim, d.fdim, scale, ctx->tw_f))
+      return st;
+  return 0;
+}
+
+int do_fine(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p, float* ms_dep_fft, float* ms_kick) {
+  const Dims& d = ctx->d;
+  const long long nf = (long long)d.fdim * d.fdim * d.fdim;
+  (void)ms_dep_fft; (void)ms_kick;
+  for (int tile = 0; tile < d.tiles_node; ++tile) {
+    if (ctx->cfg.tile_split > 1 && (tile % ctx->cfg.tile_split) != ctx->cfg.tile_split_rank) continue;
+    if (int st = fine_tile_solve(ctx, tile, mass_p, ctx->rowoff + d.nc_node * d.nc_node + 8 + tile)) return st;
+    LAUNCH(ctx, fine::force_max_kernel, NUM_SMS * 4, fine::TPB, 0, ctx->force_f[0], ctx->force_f[1], ctx->force_f[2], nf, &ctx->dcnt->f_force_max2_bits);
+    if (ctx->cfg.ngp_fmesh_force) {
+      const int T = d.T;
+      const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;
+      LAUNCH(ctx, fine::ngp_kick_kernel, d.nc_tile * d.nc_tile, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->force_f[0], ctx->force_f[1],
+             ctx->force_f[2], d.H, d.nc_buf, d.nc_tile, d.b, d.m, d.fdim, tx, ty, tz, a_mid, ctx->cfg.G, dt);
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int do_pp(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
+  pp::PPParams P;
+  P.mass_p = mass_p; P.rsoft = ctx->cfg.rsoft; P.pp_bias = ctx->cfg.pp_bias; P.a_mid = a_mid; P.G = ctx->cfg.G; P.dt = dt;
+  P.cutoff = (float)ctx->cfg.nf_cutoff;
+  if (ctx->cfg.ppint) {
+    P.apply = ctx->cfg.pp_force_flag;
+    const int n_multi = std::min(ctx->hcnt->n_multi, ctx->list_cap);
+    if (n_multi > 0)
+      LAUNCH(ctx, pp::ppint_kernel, std::min((n_multi + 3) / 4, NUM_SMS * 16), pp::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->multi_list,
+             &ctx->dcnt->n_multi, ctx->list_cap, P, ctx->cfg.max_llf, ctx->dcnt);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+int do_pp_ext(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
+  pp::PPParams P;
+  P.mass_p = mass_p; P.rsoft = ctx->cfg.rsoft; P.pp_bias = ctx->cfg.pp_bias; P.a_mid = a_mid; P.G = ctx->cfg.G; P.dt = dt;
+  P.cutoff = (float)ctx->cfg.nf_cutoff;
+  if (ctx->cfg.pp_ext && ctx->cfg.pp_range > 0) {
+    P.apply = ctx->cfg.pp_ext_force_flag;
+    const int n_occ = std::min(ctx->hcnt->n_occ, ctx->list_cap);
+    if (n_occ > 0)
+      LAUNCH(ctx, pp::ppext_kernel, std::min((n_occ + 3) / 4, NUM_SMS * 16), pp::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->occ_list,
+             &ctx->dcnt->n_occ, ctx->list_cap, ctx->d.H, ctx->cfg.pp_range, P, ctx->dcnt);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// coarse_mesh.f90 for nodes_dim = 1 (whole coarse mesh on this GPU)
+int do_coarse_mass(cubep3m_b200_ctx* ctx, float mass_p) {
+  const Dims& d = ctx->d;
+  const size_t nrc = (size_t)d.nc_node * d.nc_node * d.nc_node;
+  CK(cudaMemsetAsync(ctx->rho_c, 0, nrc * sizeof(float), ctx->stream));
+  LAUNCH(ctx, coarse::cic_mass_kernel, (d.nc_node + 2) * (d.nc_node + 2), coarse::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->rho_c, d.H, d.nc_buf,
+         d.nc_node, mass_p, ctx->cfg.coarse_ngp);
+  CK(cudaGetLastError());
+  return 0;
+}
+int do_coarse_force(cubep3m_b200_ctx* ctx) {
+  const Dims& d = ctx->d;
+  if (d.D != 1) return CUBEP3M_B200_EINVAL;
+  const int N = d.nc_dim;
+  const long long nrc = (long long)d.nc_node * d.nc_node * d.nc_node;
+  LAUNCH(ctx, coarse::cube_to_slab_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->rho_c, ctx->slab, d.nc_node, N, 0, 0, 0, &ctx->dcnt->sum_rho_c);
+  if (int st = fftk::forward3d(ctx, N, ctx->slab, ctx->tw_c)) return st;          // coarse_force.f90:18
+  const float scale = 1.0f / (((float)N * (float)N) * (float)N);                    // fft_coarse.f90:186
+  const size_t nfc = (size_t)3 * (d.nc_node + 2) * (d.nc_node + 2) * (d.nc_node + 2);
+  CK(cudaMemsetAsync(ctx->force_c, 0, nfc * sizeof(float), ctx->stream));
+  for (int comp = 0; comp < 3; ++comp) {                                            // coarse_force.f90:37-90
+    // real-space result goes to rho_c (as in the reference: force_c(comp,...) = rho_c)
+    if (int st = fftk::backward3d(ctx, N, ctx->slab, ctx->slab_g, ctx->kern_c, comp, ctx->rho_c, 0, N, N, N, scale, ctx->tw_c)) return st;
+    LAUNCH(ctx, coarse::slab_to_force_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->rho_c, (long long)N, (long long)N, d.nc_node, 0, 0, 0, ctx->force_c, comp);
+  }
+  for (int axis = 0; axis < 3; ++axis)                                              // coarse_force_buffer.f90:23-63
+    LAUNCH(ctx, coarse::halo_self_kernel, grid_for((long long)3 * (d.nc_node + 2) * (d.nc_node + 2), coarse::TPB), coarse::TPB, 0, ctx->force_c, d.nc_node, axis);
+  LAUNCH(ctx, coarse::force_max_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->force_c, d.nc_node, &ctx->dcnt->c_force_max_bits);
+  CK(cudaGetLastError());
+  return 0;
+}
+int do_coarse_vel(cubep3m_b200_ctx* ctx, float a_mid, float dt) {
+  const Dims& d = ctx->d;
+  LAUNCH(ctx, coarse::cic_kick_kernel, d.nc_node * d.nc_node, coarse::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->force_c, d.H, d.nc_buf, d.nc_node,
+         a_mid, ctx->cfg.G, dt, ctx->cfg.coarse_ngp);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* cubep3m_b200_version(void) { return "cubep3m_b200 0.1 (sm_100a, hand-written CUDA, no CPU fallback)"; }
+
+const char* cubep3m_b200_strerror(int st) {
+  switch (st) {
+    case 0: return "ok";
+    case CUBEP3M_B200_EINVAL: return "bad configuration";
+    case CUBEP3M_B200_ECUDA: return "CUDA failure";
+    case CUBEP3M_B200_EPASSBUF: return "not enough buffer space in pass";
+    case CUBEP3M_B200_EMAXNP: return "exceeded max_np in pass";
+    case CUBEP3M_B200_EMAXLLF: return "exceeded max_llf";
+    case CUBEP3M_B200_ENCCL: return "NCCL failure";
+    case CUBEP3M_B200_ENOTREADY: return "call order violated";
+  }
+  return "unknown";
+}
+
+void cubep3m_b200_default_config(cubep3m_b200_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->nodes_dim = 1; c->tiles_node_dim = 2; c->nf_tile = 176; c->nf_buf = 24; c->nf_cutoff = 16; c->mesh_scale = 4;
+  c->pp_range = 2; c->max_np = 0; c->max_buf = 0; c->max_llf = 100000;
+  c->density_buffer = 2.0f; c->rsoft = 0.1f; c->pp_bias = 1.0f; c->dt_pp_scale = 0.05f;
+  const float pi = 3.141592654f;
+  c->G = 1.0f / 6.0f / pi;
+  c->eps = 1.0e-3f;
+  c->ngp = 1; c->ppint = 1; c->pp_ext = 0; c->coarse_ngp = 0; c->pid = 0; c->lrckcorr = 1; c->move_grid_back = 0;
+  c->ngp_fmesh_force = c->pp_force_flag = c->pp_ext_force_flag = c->coarse_vel_update = 1;
+  c->rank = 0; c->local_gpu = 0; c->tile_split = 1; c->tile_split_rank = 0;
+}
+
+int cubep3m_b200_get_unique_id(void* id128) {
+#ifdef CUBEP3M_WITH_NCCL
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return CUBEP3M_B200_ENCCL;
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+#else
+  (void)id128;
+  return CUBEP3M_B200_ENCCL;
+#endif
+}
+
+int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  auto F = [](void* p) { if (p) cudaFree(p); };
+  for (int i = 0; i < 2; ++i) { F(ctx->xv[i]); F(ctx->pid[i]); F(ctx->sendbuf[i]); F(ctx->sendpid[i]); }
+  F(ctx->key); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
+  F(ctx->kern_f); F(ctx->tile_rho); F(ctx->tile_g); for (int i = 0; i < 3; ++i) F(ctx->force_f[i]);
+  F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->force_c); F(ctx->tw_c); F(ctx->dcnt);
+  if (ctx->hcnt) cudaFreeHost(ctx->hcnt);
+  if (ctx->ev_ok) for (auto& e : ctx->ev) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, const float* coarse_table, const float* kern_f,
+                      const float* kern_c, const void* nccl_unique_id, int world_size, cubep3m_b200_ctx** out) {
+  if (!cfg || !out) return CUBEP3M_B200_EINVAL;
+  Dims d;
+  if (int st = derive(*cfg, d)) return st;
+  if (!cfg->ngp) return CUBEP3M_B200_EINVAL;          // fine CIC (non -DNGP builds) is not built yet
+  if (d.D != 1) return CUBEP3M_B200_EINVAL;           // multi-rank exchange not built in this configuration
+  (void)nccl_unique_id;
+  if ((!kern_f || !kern_c) && (!fine_table || !coarse_table)) return CUBEP3M_B200_EINVAL;
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev < 1 || cfg->local_gpu >= ndev) return CUBEP3M_B200_ECUDA;
+  CK(cudaSetDevice(cfg->local_gpu));
+  cubep3m_b200_ctx* ctx = new cubep3m_b200_ctx();
+  ctx->cfg = *cfg; ctx->d = d; ctx->device = cfg->local_gpu; ctx->world = world_size > 0 ? world_size : 1;
+  if (fine_table) ctx->fine_table.assign(fine_table, fine_table + 16 * 16 * 16 * 3);
+  if (coarse_table) ctx->coarse_table.assign(coarse_table, coarse_table + 4 * 4 * 4 * 3);
+#define TRY(x) do { int st__ = (x); if (st__) { cubep3m_b200_finalize(ctx); return st__; } } while (0)
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CUBEP3M_B200_ECUDA; }
+  for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
+  ctx->ev_ok = true;
+  TRY(fftk::init_constants());
+  for (int i = 0; i < 2; ++i) {
+    TRY(dmalloc(&ctx->xv[i], (size_t)6 * d.max_np));
+    if (cfg->pid) TRY(dmalloc(&ctx->pid[i], (size_t)d.max_np));
+    TRY(dmalloc(&ctx->sendbuf[i], (size_t)d.max_buf));
+    if (cfg->pid) TRY(dmalloc(&ctx->sendpid[i], (size_t)d.max_buf / 6 + 1));
+  }
+  TRY(dmalloc(&ctx->key, (size_t)d.max_np));
+  TRY(dmalloc(&ctx->fstart, (size_t)d.NF + 64));
+  TRY(dmalloc(&ctx->fcur, (size_t)d.NF + 64));
+  ctx->nblocksum = (int)((d.NF + part::SCAN_BLOCK - 1) / part::SCAN_BLOCK);
+  TRY(dmalloc(&ctx->blocksum, (size_t)ctx->nblocksum + 1));
+  ctx->list_cap = cfg->pp_ext ? d.max_np : d.max_np / 2 + 1024;
+  if (cfg->ppint) TRY(dmalloc(&ctx->multi_list, (size_t)ctx->list_cap));
+  if (cfg->pp_ext) TRY(dmalloc(&ctx->occ_list, (size_t)ctx->list_cap));
+  const size_t rowoff_n = (size_t)d.nc_node * d.nc_node + 16 + d.tiles_node;
+  TRY(dmalloc(&ctx->rowoff, rowoff_n));
+  if (cudaMemset(ctx->rowoff, 0, rowoff_n * sizeof(int)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
+  const size_t tile_elems = (size_t)(d.n + 2) * d.n * d.n;
+  TRY(dmalloc(&ctx->tile_rho, tile_elems));
+  TRY(dmalloc(&ctx->tile_g, tile_elems));
+  for (int i = 0; i < 3; ++i) TRY(dmalloc(&ctx->force_f[i], (size_t)d.fdim * d.fdim * d.fdim));
+  TRY(dmalloc(&ctx->kern_f, (size_t)3 * d.hc * d.n * d.n));
+  TRY(fftk::make_twiddles(d.n, &ctx->tw_f));
+  const int N = d.nc_dim;
+  TRY(dmalloc(&ctx->kern_c, (size_t)3 * (N / 2 + 1) * N * N));
+  TRY(dmalloc(&ctx->rho_c, std::max((size_t)d.nc_node * d.nc_node * d.nc_node, (size_t)N * N * N)));
+  TRY(dmalloc(&ctx->slab, (size_t)(N + 2) * N * N));
+  TRY(dmalloc(&ctx->slab_g, (size_t)(N + 2) * N * N));
+  TRY(dmalloc(&ctx->force_c, (size_t)3 * (d.nc_node + 2) * (d.nc_node + 2) * (d.nc_node + 2)));
+  TRY(fftk::make_twiddles(N, &ctx->tw_c));
+  TRY(dmalloc(&ctx->dcnt, 1));
+  if (cudaMemset(ctx->dcnt, 0, sizeof(DevCounters)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
+  if (cudaMallocHost((void**)&ctx->hcnt, sizeof(DevCounters)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
+  memset(ctx->hcnt, 0, sizeof(DevCounters));
+  if (kern_f) { if (cudaMemcpy(ctx->kern_f, kern_f, sizeof(float) * 3 * d.hc * d.n * d.n, cudaMemcpyHostToDevice) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; } }
+  else TRY(build_kern_f(ctx));
+  if (kern_c) { if (cudaMemcpy(ctx->kern_c, kern_c, sizeof(float) * 3 * (N / 2 + 1) * N * N, cudaMemcpyHostToDevice) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; } }
+  else TRY(build_kern_c(ctx));
+#undef TRY
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
+  *out = ctx;
+  return 0;
+}
+
+int cubep3m_b200_upload_particles(cubep3m_b200_ctx* ctx, const float* xv, const int64_t* pid, int32_t np_local) {
+  if (!ctx || np_local < 0 || np_local > ctx->d.max_np) return CUBEP3M_B200_EMAXNP;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->xv[ctx->cur], xv, sizeof(float) * 6 * (size_t)np_local, cudaMemcpyHostToDevice, ctx->stream));
+  if (pid && ctx->cfg.pid) CK(cudaMemcpyAsync(ctx->pid[ctx->cur], pid, sizeof(int64_t) * (size_t)np_local, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->np_local = np_local; ctx->np_all = np_local; ctx->sorted = false; ctx->passed = false;
+  return 0;
+}
+
+int cubep3m_b200_download_particles(cubep3m_b200_ctx* ctx, float* xv, int64_t* pid, int32_t* np_local) {
+  if (!ctx) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  const int np = ctx->passed ? ctx->np_all : ctx->np_local;
+  if (xv) CK(cudaMemcpyAsync(xv, ctx->xv[ctx->cur], sizeof(float) * 6 * (size_t)np, cudaMemcpyDeviceToHost, ctx->stream));
+  if (pid && ctx->cfg.pid) CK(cudaMemcpyAsync(pid, ctx->pid[ctx->cur], sizeof(int64_t) * (size_t)np, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (np_local) *np_local = np;
+  return 0;
+}
+
+int cubep3m_b200_update_position(cubep3m_b200_ctx* ctx, float dt, float dt_old, const float offset[3]) {
+  if (!ctx) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  const float zero[3] = {0.f, 0.f, 0.f};
+  if (int st = do_drift(ctx, dt, dt_old, offset ? offset : zero)) return st;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int cubep3m_b200_move_grid_back(cubep3m_b200_ctx* ctx, const float s[3]) {
+  if (!ctx) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->np_local > 0)
+    LAUNCH(ctx, part::shift_kernel, (ctx->np_local + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->np_local, s[0], s[1], s[2]);
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->sorted = false;
+  return 0;
+}
+
+int cubep3m_b200_link_list(cubep3m_b200_ctx* ctx, int32_t* np_deleted) {
+  if (!ctx) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  ctx->np_all = ctx->np_local; ctx->passed = false;
+  return do_sort(ctx, np_deleted);
+}
+
+int cubep3m_b200_particle_pass(cubep3m_b200_ctx* ctx, int32_t* np_with_ghosts) {
+  if (!ctx) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->passed) return CUBEP3M_B200_ENOTREADY;
+  int bufmax = 0;
+  ctx->np_all = ctx->np_local;
+  if (int st = do_pass(ctx, &bufmax)) return st;
+  if (int st = do_sort(ctx, nullptr)) return st;
+  if (np_with_ghosts) *np_with_ghosts = ctx->np_all;
+  return 0;
+}
+
+int cubep3m_b200_delete_particles(cubep3m_b200_ctx* ctx, int32_t* np_local) {
+  if (!ctx) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->sorted) { if (int st = do_sort(ctx, nullptr)) return st; }
+  if (int st = do_delete(ctx)) return st;
+  if (np_local) *np_local = ctx->np_local;
+  return 0;
+}
+
+int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, float a_mid, float mass_p, const float offset[3],
+                               cubep3m_b200_step_out* out) {
+  if (!ctx || !out) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  const Dims& d = ctx->d;
+  const cubep3m_b200_config& c = ctx->cfg;
+  memset(out, 0, sizeof(*out));
+  const float zero[3] = {0.f, 0.f, 0.f};
+  cudaEvent_t* ev = ctx->ev;
+  // reset per-step device accumulators
+  CK(cudaMemsetAsync(ctx->dcnt, 0, sizeof(DevCounters), ctx->stream));
+  CK(cudaMemsetAsync(ctx->rowoff + d.nc_node * d.nc_node, 0, sizeof(int) * (16 + d.tiles_node), ctx->stream));
+  CK(cudaEventRecord(ev[0], ctx->stream));
+  if (int st = do_drift(ctx, dt, dt_old, offset ? offset : zero)) return st;             // particle_mesh_threaded.f90:56
+  CK(cudaEventRecord(ev[1], ctx->stream));
+  int bufmax = 0, ndel = 0;
+  if (int st = do_pass(ctx, &bufmax)) return st;                                          // :63 (range check of :61 folded in)
+  CK(cudaEventRecord(ev[2], ctx->stream));
+  if (int st = do_sort(ctx, &ndel)) return st;                                            // :61 link_list as a cell sort
+  const int np_ghost = ctx->np_all;
+  CK(cudaEventRecord(ev[3], ctx->stream));
+  if (int st = do_fine(ctx, a_mid, dt, mass_p, nullptr, nullptr)) return st;              // :84-368 (mesh part)
+  CK(cudaEventRecord(ev[4], ctx->stream));
+  if (int st = do_pp(ctx, a_mid, dt, mass_p)) return st;                                  // :274-361
+  CK(cudaEventRecord(ev[5], ctx->stream));
+  if (int st = do_pp_ext(ctx, a_mid, dt, mass_p)) return st;                              // :378-624
+  CK(cudaEventRecord(ev[6], ctx->stream));
+  if (int st = do_coarse_mass(ctx, mass_p)) return st;                                    // coarse_mesh.f90:28
+  CK(cudaEventRecord(ev[7], ctx->stream));
+  if (int st = do_coarse_force(ctx)) return st;                                           // coarse_mesh.f90:84-100
+  CK(cudaEventRecord(ev[8], ctx->stream));
+  if (c.coarse_vel_update) { if (int st = do_coarse_vel(ctx, a_mid, dt)) return st; }     // coarse_mesh.f90:106
+  CK(cudaEventRecord(ev[9], ctx->stream));
+  if (int st = fetch_counters(ctx)) return st;
+  const DevCounters hc = *ctx->hcnt;
+  if (int st = overflow_status(&hc)) return st;
+  if (int st = do_delete(ctx)) return st;                                                 // particle_mesh_threaded.f90:720
+  CK(cudaEventRecord(ev[10], ctx->stream));
+  CK(cudaEventSynchronize(ev[10]));
+  // limiters (particle_mesh_threaded.f90:643-696, coarse_max_dt.f90:36)
+  const float G = c.G;
+  auto asf = [](unsigned int u) { float f; memcpy(&f, &u, 4); return f; };
+  const float f2 = asf(hc.f_force_max2_bits), ppm = asf(hc.pp_force_max_bits), ppe = asf(hc.pp_ext_force_max_bits), cm = asf(hc.c_force_max_bits);
+  out->f_force_max = sqrtf(f2);
+  out->dt_f_acc = 1.0f / sqrtf(std::max(0.0001f, out->f_force_max) * a_mid * G);
+  out->pp_force_max = ppm;
+  out->dt_pp_acc = c.ppint ? sqrtf(c.dt_pp_scale * c.rsoft) / std::max(sqrtf(ppm * a_mid * G), 1e-3f) : 1000.f;
+  out->pp_ext_force_max = ppe;
+  out->dt_pp_ext_acc = c.pp_ext ? sqrtf(c.dt_pp_scale * c.rsoft) / std::max(sqrtf(ppe * a_mid * G), 1e-3f) : 1000.f;
+  out->c_force_max = cm;
+  out->dt_c_acc = sqrtf((float)d.s / (cm * a_mid * G));
+  out->sum_rho_f = hc.sum_rho_f; out->sum_rho_c = hc.sum_rho_c;
+  out->np_local = ctx->np_local; out->np_total = ctx->np_local; out->np_with_ghosts = np_ghost; out->np_deleted_ll = ndel; out->np_buf_max = bufmax;
+  out->stage_ms[CUBEP3M_B200_ST_DRIFT] = ev_ms(ev[0], ev[1]);
+  out->stage_ms[CUBEP3M_B200_ST_PASS] = ev_ms(ev[1], ev[2]);
+  out->stage_ms[CUBEP3M_B200_ST_LINK] = ev_ms(ev[2], ev[3]);
+  out->stage_ms[CUBEP3M_B200_ST_FINE_FFT] = ev_ms(ev[3], ev[4]);
+  out->stage_ms[CUBEP3M_B200_ST_PP] = ev_ms(ev[4], ev[5]);
+  out->stage_ms[CUBEP3M_B200_ST_PP_EXT] = ev_ms(ev[5], ev[6]);
+  out->stage_ms[CUBEP3M_B200_ST_COARSE_MASS] = ev_ms(ev[6], ev[7]);
+  out->stage_ms[CUBEP3M_B200_ST_COARSE_FORCE] = ev_ms(ev[7], ev[8]);
+  out->stage_ms[CUBEP3M_B200_ST_COARSE_VEL] = ev_ms(ev[8], ev[9]);
+  out->stage_ms[CUBEP3M_B200_ST_DELETE] = ev_ms(ev[9], ev[10]);
+  out->stage_ms[CUBEP3M_B200_ST_TOTAL] = ev_ms(ev[0], ev[10]);
+  ctx->last_tile_counts_valid = 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------- debug / parity getters
+int cubep3m_b200_debug_cell_counts(cubep3m_b200_ctx* ctx, int32_t* counts) {
+  if (!ctx || !ctx->sorted) return CUBEP3M_B200_ENOTREADY;
+  CK(cudaSetDevice(ctx->device));
+  const long long nco = ctx->d.NF / 64;
+  int* dtmp = nullptr;
+  CK(cudaMalloc(&dtmp, sizeof(int) * nco));
+  LAUNCH(ctx, part::coarse_counts_kernel, (int)((nco + part::TPB - 1) / part::TPB), part::TPB, 0, ctx->fstart, nco, dtmp);
+  CK(cudaMemcpyAsync(counts, dtmp, sizeof(int) * nco, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dtmp);
+  return 0;
+}
+int cubep3m_b200_debug_tile_counts(cubep3m_b200_ctx* ctx, int32_t* counts) {
+  if (!ctx || !ctx->last_tile_counts_valid) return CUBEP3M_B200_ENOTREADY;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(counts, ctx->rowoff + ctx->d.nc_node * ctx->d.nc_node + 8, sizeof(int) * ctx->d.tiles_node, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int cubep3m_b200_debug_sorted_particles(cubep3m_b200_ctx* ctx, float* xv, int32_t* np) {
+  if (!ctx || !ctx->sorted) return CUBEP3M_B200_ENOTREADY;
+  CK(cudaSetDevice(ctx->device));
+  if (xv) CK(cudaMemcpy(xv, ctx->xv[ctx->cur], sizeof(float) * 6 * (size_t)ctx->np_all, cudaMemcpyDeviceToHost));
+  if (np) *np = ctx->np_all;
+  return 0;
+}
+int cubep3m_b200_debug_kern_f(cubep3m_b200_ctx* ctx, float* kern_f) {
+  if (!ctx) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(kern_f, ctx->kern_f, sizeof(float) * 3 * ctx->d.hc * ctx->d.n * ctx->d.n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int cubep3m_b200_debug_kern_c(cubep3m_b200_ctx* ctx, float* kern_c) {
+  if (!ctx) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  const int N = ctx->d.nc_dim;
+  const size_t per = (size_t)3 * (N / 2 + 1) * N * ctx->d.nc_slab;
+  CK(cudaMemcpy(kern_c, ctx->kern_c + per * ctx->cfg.rank, sizeof(float) * per, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int cubep3m_b200_debug_rho_c(cubep3m_b200_ctx* ctx, float* rho_c) {
+  // note: after a full step rho_c holds the last force component (as in the reference, coarse_force.f90:88);
+  // call after cubep3m_b200_debug_coarse_mass-like use only. Here: recompute the deposit from the sorted array.
+  if (!ctx || !ctx->sorted) return CUBEP3M_B200_ENOTREADY;
+  (void)rho_c;
+  return CUBEP3M_B200_ENOTREADY;
+}
+int cubep3m_b200_debug_force_c(cubep3m_b200_ctx* ctx, float* force_c) {
+  if (!ctx) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  const size_t nfc = (size_t)3 * (ctx->d.nc_node + 2) * (ctx->d.nc_node + 2) * (ctx->d.nc_node + 2);
+  CK(cudaMemcpy(force_c, ctx->force_c, sizeof(float) * nfc, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int cubep3m_b200_debug_fine_tile(cubep3m_b200_ctx* ctx, int32_t tile, float mass_p, float* rho_f, float* force_f) {
+  if (!ctx || !ctx->sorted || !ctx->passed) return CUBEP3M_B200_ENOTREADY;
+  if (tile < 0 || tile >= ctx->d.tiles_node) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  const Dims& d = ctx->d;
+  const int T = d.T, n = d.n;
+  const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;
+  int* scratch = ctx->rowoff + d.nc_node * d.nc_node + 4;
+  double* dsum = nullptr;
+  CK(cudaMalloc(&dsum, sizeof(double)));
+  LAUNCH(ctx, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p, dsum, scratch);
+  if (rho_f) CK(cudaMemcpyAsync(rho_f, ctx->tile_rho, sizeof(float) * (size_t)(n + 2) * n * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dsum);
+  if (force_f) {
+    if (int st = fine_tile_solve(ctx, tile, mass_p, scratch)) return st;
+    const size_t nf = (size_t)d.fdim * d.fdim * d.fdim;
+    std::vector<float> tmp(nf);
+    for (int comp = 0; comp < 3; ++comp) {   // interleave to the reference's force_f(3,...) layout
+      CK(cudaMemcpyAsync(tmp.data(), ctx->force_f[comp], sizeof(float) * nf, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      for (size_t i = 0; i < nf; ++i) force_f[3 * i + comp] = tmp[i];
+    }
+  }
+  return 0;
+}
+int cubep3m_b200_debug_fft3d(cubep3m_b200_ctx* ctx, int32_t n, float* data, int32_t inverse) {
+  if (!ctx) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  float* buf; const float2* tw;
+  if (n == ctx->d.n) { buf = ctx->tile_rho; tw = ctx->tw_f; }
+  else if (n == ctx->d.nc_dim) { buf = ctx->slab; tw = ctx->tw_c; }
+  else return CUBEP3M_B200_EINVAL;
+  const size_t bytes = sizeof(float) * (size_t)(n + 2) * n * n;
+  CK(cudaMemcpyAsync(buf, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (!inverse) { if (int st = fftk::forward3d(ctx, n, buf, tw)) return st; }
+  else {
+    // unnormalised c2r back into the padded layout (pitch n+2)
+    if (int st = fftk::backward3d(ctx, n, buf, buf, nullptr, 0, (n == ctx->d.n) ? ctx->tile_g : ctx->slab_g, 0, n, n + 2, n, 1.0f, tw)) return st;
+    CK(cudaMemcpyAsync(buf, (n == ctx->d.n) ? ctx->tile_g : ctx->slab_g, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  CK(cudaMemcpyAsync(data, buf, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int64_t cubep3m_b200_launch_count(cubep3m_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------- driver twin (host): timestep.f90
+void cubep3m_b200_expansion(float a0, float dt0, float omega_m, float omega_l, float wde, float* da1, float* da2) {
+  // timestep.f90:241-293: two half steps of a 3rd-order Taylor expansion, real(8) arithmetic from real(4) arguments
+  const float dt_x = dt0 / 2;
+  double a_x = a0;
+  for (int half = 0; half < 2; ++half) {
+    const double omHsq = 4.0 / 9.0;
+    const double a3rlm = pow(a_x, (double)(-3 * wde)) * omega_l / omega_m;
+    const double arkm = a_x * (1.0 - omega_m - omega_l) / omega_m;
+    const double adot = sqrt(omHsq * a_x * a_x * a_x * (1.0 + arkm + a3rlm));
+    const double addot = a_x * a_x * omHsq * (1.5 + 2.0 * arkm + 1.5 * (1.0 - wde) * a3rlm);
+    const double atdot = a_x * adot * omHsq * (3.0 + 6.0 * arkm + 1.5 * (2.0 - 3.0 * wde) * (1.0 - wde) * a3rlm);
+    const float da = (float)(adot * dt_x + (addot * (double)dt_x * dt_x) / 2.0 + (atdot * (double)dt_x * dt_x * dt_x) / 6.0);
+    if (half == 0) { *da1 = da; a_x = (double)(a0 + da); } else *da2 = da;
+  }
+}
+void cubep3m_b200_clock_init(cubep3m_b200_clock* c, float z_i, float omega_m, float omega_l) {
+  memset(c, 0, sizeof(*c));
+  c->a = 1.0f / (z_i + 1.0f);                        // cubepm.par:30, variable_initialization.f90:15-34
+  c->tau = -3.0f / sqrtf(c->a);
+  c->dt_f_acc = c->dt_pp_acc = c->dt_pp_ext_acc = c->dt_c_acc = 1000.f;
+  c->omega_m = omega_m; c->omega_l = omega_l; c->wde = -1.0f;
+  c->a_target = 1.0f; c->cosmo = 1; c->ppint = 1;
+}
+void cubep3m_b200_timestep(cubep3m_b200_clock* c) {
+  // timestep.f90:20-196 (cosmo branch, dark matter only); dt_max = 1, ra_max = 0.01, dt_scale = 1 (cubepm.par:26-29)
+  const float dt_max = 1.0f, ra_max = 0.01f, dt_scale = 1.0f;
+  c->nts += 1;
+  if (c->nts != 1) c->dt_old = c->dt;
+  float da_1 = 0, da_2 = 0;
+  if (c->cosmo) {
+    float dt_e = dt_max;
+    int n = 0;
+    for (;;) {
+      n++;
+      cubep3m_b200_expansion(c->a, dt_e, c->omega_m, c->omega_l, c->wde, &da_1, &da_2);
+      c->da = da_1 + da_2;
+      const float ra = c->da / (c->a + c->da);
+      if (ra > ra_max) dt_e = dt_e * (ra_max / ra); else break;
+      if (n > 10) break;
+    }
+    float dt = std::min(dt_e, std::min(c->dt_f_acc, c->dt_c_acc));
+    if (c->ppint) dt = std::min(dt, c->dt_pp_acc);
+    if (c->ppint && c->pp_ext) dt = std::min(dt, c->dt_pp_ext_acc);
+    dt = dt * dt_scale;
+    cubep3m_b200_expansion(c->a, dt, c->omega_m, c->omega_l, c->wde, &da_1, &da_2);
+    c->da = da_1 + da_2;
+    c->checkpoint_step = 0;
+    if (c->a + c->da > c->a_target) {                 // timestep.f90:128-137
+      c->checkpoint_step = 1;
+      dt = dt * (c->a_target - c->a) / c->da;
+      cubep3m_b200_expansion(c->a, dt, c->omega_m, c->omega_l, c->wde, &da_1, &da_2);
+    }
+    c->da = da_1 + da_2;
+    c->a_mid = c->a + (c->da / 2);
+    c->dt = dt;
+    c->tau += dt; c->t += dt; c->a += c->da;
+  } else {                                            // timestep.f90:198-221
+    c->a = 1.0f; c->a_mid = 1.0f; c->da = 0.f;
+    float dt = std::min(1.0f, std::min(c->dt_f_acc, c->dt_c_acc));
+    if (c->ppint) dt = std::min(dt, c->dt_pp_acc);
+    if (c->ppint && c->pp_ext) dt = std::min(dt, c->dt_pp_ext_acc);
+    c->dt = dt; c->t += dt;
+  }
+}
+
+}  // extern "C"

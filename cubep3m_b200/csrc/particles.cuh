@@ -1,0 +1,311 @@
+// Particle-side stages: drift, ghost exchange (particle_pass), cell sort (the sorted-array replacement of
+// link_list's ll/hoc chains), ghost deletion.
+//
+// Particle records stay in the reference's layout: xv(6,i) = 24-byte AoS (cubep3m.fh:75), accessed as 3 x float2.
+// Positions are moved with explicit __fadd_rn/__fmul_rn so nvcc cannot contract them into FMAs: cell
+// membership must be bit-identical to the reference's unfused evaluation.
+#pragma once
+#include "common.cuh"
+
+namespace part {
+
+constexpr int TPB = 256;
+constexpr unsigned int KEY_DEAD = 0xffffffffu;
+
+__device__ __forceinline__ void load_xv(const float* __restrict__ xv, long long i, float2& a, float2& b, float2& c) {
+  const float2* p = reinterpret_cast<const float2*>(xv) + 3 * i;
+  a = p[0]; b = p[1]; c = p[2];
+}
+__device__ __forceinline__ void store_xv(float* __restrict__ xv, long long i, float2 a, float2 b, float2 c) {
+  float2* p = reinterpret_cast<float2*>(xv) + 3 * i;
+  p[0] = a; p[1] = b; p[2] = c;
+}
+
+// update_position.f90:71  x = ((x + ((v*0.5)*(dt+dt_old))) + offset), evaluated unfused
+__global__ void __launch_bounds__(TPB) drift_kernel(float* __restrict__ xv, int np, float hdt, float ox, float oy, float oz) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i >= np) return;
+  float2 a, b, c;
+  load_xv(xv, i, a, b, c);   // a=(x,y) b=(z,vx) c=(vy,vz)
+  a.x = __fadd_rn(__fadd_rn(a.x, __fmul_rn(__fmul_rn(b.y, 0.5f), hdt)), ox);
+  a.y = __fadd_rn(__fadd_rn(a.y, __fmul_rn(__fmul_rn(c.x, 0.5f), hdt)), oy);
+  b.x = __fadd_rn(__fadd_rn(b.x, __fmul_rn(__fmul_rn(c.y, 0.5f), hdt)), oz);
+  float2* p = reinterpret_cast<float2*>(xv) + 3 * i;
+  p[0] = a; p[1] = b;
+}
+
+// move_grid_back.f90:20-23
+__global__ void __launch_bounds__(TPB) shift_kernel(float* __restrict__ xv, int np, float sx, float sy, float sz) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i >= np) return;
+  float2* p = reinterpret_cast<float2*>(xv) + 3 * i;
+  float2 a = p[0], b = p[1];
+  a.x = __fsub_rn(a.x, sx); a.y = __fsub_rn(a.y, sy); b.x = __fsub_rn(b.x, sz);
+  p[0] = a; p[1] = b;
+}
+
+// link_list.f90:26-31: a particle is chained iff floor(x/4)+1 lies in [hoc_nc_l, hoc_nc_h] on all axes,
+// i.e. -nf_buf <= x < mT + nf_buf.
+__device__ __forceinline__ bool in_hoc_range(float x, float y, float z, float lo, float hi) {
+  return x >= lo && x < hi && y >= lo && y < hi && z >= lo && z < hi;
+}
+
+// particle_pass.f90:73-94 (+ pass) and :173-192 (- pass) for one axis: every chained particle with
+// x >= mT - nf_buf goes to the + neighbour, every one with x < nf_buf to the - neighbour.
+// Both directions read the same pre-axis particle list (the reference relinks only after both).
+__global__ void __launch_bounds__(TPB) pass_pack_kernel(const float* __restrict__ xv, const int64_t* __restrict__ pid, int np, int axis,
+                                                        float lo, float hi, float cut_hi, float cut_lo,
+                                                        float* __restrict__ send_plus, float* __restrict__ send_minus,
+                                                        int64_t* __restrict__ pid_plus, int64_t* __restrict__ pid_minus,
+                                                        int cap, DevCounters* __restrict__ cnt) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  bool gp = false, gm = false;
+  float2 a, b, c;
+  if (i < np) {
+    load_xv(xv, i, a, b, c);
+    if (in_hoc_range(a.x, a.y, b.x, lo, hi)) {
+      const float q = axis == 0 ? a.x : (axis == 1 ? a.y : b.x);
+      gp = q >= cut_hi;
+      gm = q < cut_lo;
+    }
+  }
+  // warp-aggregated slot allocation
+  const unsigned mp = __ballot_sync(0xffffffffu, gp), mm = __ballot_sync(0xffffffffu, gm);
+  const int lane = threadIdx.x & 31;
+  int basep = 0, basem = 0;
+  if (lane == 0) {
+    if (mp) basep = atomicAdd(&cnt->n_send[0], __popc(mp));
+    if (mm) basem = atomicAdd(&cnt->n_send[1], __popc(mm));
+  }
+  basep = __shfl_sync(0xffffffffu, basep, 0);
+  basem = __shfl_sync(0xffffffffu, basem, 0);
+  if (gp) {
+    const int slot = basep + __popc(mp & ((1u << lane) - 1));
+    if (slot < cap) { store_xv(send_plus, slot, a, b, c); if (pid) pid_plus[slot] = pid[i]; }
+    else atomicOr(&cnt->overflow, 1);
+  }
+  if (gm) {
+    const int slot = basem + __popc(mm & ((1u << lane) - 1));
+    if (slot < cap) { store_xv(send_minus, slot, a, b, c); if (pid) pid_minus[slot] = pid[i]; }
+    else atomicOr(&cnt->overflow, 1);
+  }
+}
+
+// receive side: shift + clamp, append at xv[np0 ...]
+//   from the - neighbour's "+" buffer:  x = max(x - mT, -nf_buf)                          particle_pass.f90:162
+//   from the + neighbour's "-" buffer:  |x|<eps -> +-eps ; x = min(x + mT, mT+nf_buf-eps)   particle_pass.f90:257-265
+__global__ void __launch_bounds__(TPB) pass_unpack_kernel(float* __restrict__ xv, int64_t* __restrict__ pid, int np0, int axis,
+                                                          const float* __restrict__ recv_plus, int n_plus,
+                                                          const float* __restrict__ recv_minus, int n_minus,
+                                                          const int64_t* __restrict__ rpid_plus, const int64_t* __restrict__ rpid_minus,
+                                                          float fmT, float rnf_buf, float eps, float hi_clamp) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n_plus + n_minus) return;
+  float2 a, b, c;
+  const bool plus = i < n_plus;
+  if (plus) load_xv(recv_plus, i, a, b, c); else load_xv(recv_minus, i - n_plus, a, b, c);
+  float q = axis == 0 ? a.x : (axis == 1 ? a.y : b.x);
+  if (plus) {
+    q = fmaxf(__fsub_rn(q, fmT), -rnf_buf);
+  } else {
+    if (fabsf(q) < eps) q = (q < 0.0f) ? -eps : eps;
+    q = fminf(__fadd_rn(q, fmT), hi_clamp);
+  }
+  if (axis == 0) a.x = q; else if (axis == 1) a.y = q; else b.x = q;
+  store_xv(xv, (long long)np0 + i, a, b, c);
+  if (pid) pid[np0 + i] = plus ? rpid_plus[i] : rpid_minus[i - n_plus];
+}
+
+// ---- cell keys.  Fine cell of a particle in the extended node frame: g = floor(x) + nf_buf in [0, mT + 2 nf_buf);
+// coarse cell (0-based inside the hoc range) = g >> 2 == floor(x/4)+1 - hoc_nc_l  (link_list.f90:26-28);
+// key = ((cz*H + cy)*H + cx)*64 + (fz*16 + fy*4 + fx): x-rows of coarse cells are contiguous, and so are the
+// 64 fine cells of one coarse cell (the llf(.,4,4,4) binning of particle_mesh_threaded.f90:276-284).
+__device__ __forceinline__ unsigned int make_key(float x, float y, float z, int b, int H) {
+  const int gx = (int)floorf(x) + b, gy = (int)floorf(y) + b, gz = (int)floorf(z) + b;
+  const unsigned int cx = gx >> 2, cy = gy >> 2, cz = gz >> 2;
+  return ((cz * H + cy) * H + cx) * 64u + (unsigned)(((gz & 3) << 4) | ((gy & 3) << 2) | (gx & 3));
+}
+
+__global__ void __launch_bounds__(TPB) key_hist_kernel(const float* __restrict__ xv, int np, float lo, float hi, int b, int H,
+                                                       unsigned int* __restrict__ key, int* __restrict__ hist, DevCounters* __restrict__ cnt) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i >= np) return;
+  const float2* p = reinterpret_cast<const float2*>(xv) + 3 * i;
+  const float2 a = p[0];
+  const float z = p[1].x;
+  unsigned int k = KEY_DEAD;
+  if (in_hoc_range(a.x, a.y, z, lo, hi)) {
+    k = make_key(a.x, a.y, z, b, H);
+    atomicAdd(&hist[k], 1);
+  } else {
+    atomicAdd(&cnt->np_deleted, 1);   // 'PARTICLE DELETED' link_list.f90:32
+  }
+  key[i] = k;
+}
+
+// ---- exclusive scan over NF fine-cell counts: block reduce -> scan of block sums -> block scan.
+constexpr int SCAN_ITEMS = 16;                       // ints per thread
+constexpr int SCAN_BLOCK = TPB * SCAN_ITEMS;         // 4096 ints per block
+
+__global__ void __launch_bounds__(TPB) scan_reduce_kernel(const int* __restrict__ hist, long long n, int* __restrict__ blocksum) {
+  const long long base = (long long)blockIdx.x * SCAN_BLOCK;
+  int s = 0;
+  const int4* h4 = reinterpret_cast<const int4*>(hist + base);
+#pragma unroll
+  for (int it = 0; it < SCAN_ITEMS / 4; ++it) {
+    const long long e = base + ((long long)it * TPB + threadIdx.x) * 4;
+    if (e + 3 < n) { const int4 v = h4[it * TPB + threadIdx.x]; s += v.x + v.y + v.z + v.w; }
+    else for (int q = 0; q < 4; ++q) if (e + q < n) s += hist[e + q];
+  }
+  __shared__ int ws[TPB / 32];
+  s = warp_sum_i(s);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < TPB / 32; ++w) t += ws[w]; blocksum[blockIdx.x] = t; }
+}
+
+// single block: exclusive scan of the block sums in place
+__global__ void __launch_bounds__(1024) scan_blocksums_kernel(int* __restrict__ blocksum, int nb) {
+  __shared__ int ws[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nb ? blocksum[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = ws[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += y; }
+      ws[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int warp_off = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0;
+    const int incl = x + warp_off;
+    const int c = carry;
+    if (i < nb) blocksum[i] = c + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c + incl;
+    __syncthreads();
+  }
+}
+
+// block scan + offset; writes fstart (exclusive) and re-initialises the cursors; also emits the PP work lists:
+// physical fine cells (coarse cell in 1..nc_node on all axes) with >= 2 particles (PPINT) / >= 1 (PP_EXT).
+__global__ void __launch_bounds__(TPB) scan_apply_kernel(int* __restrict__ hist_cur, long long n, const int* __restrict__ blocksum,
+                                                         int* __restrict__ fstart, int H, int nc_buf, int nc_node,
+                                                         int* __restrict__ multi_list, int* __restrict__ occ_list, int list_cap,
+                                                         int want_multi, int want_occ, DevCounters* __restrict__ cnt) {
+  const long long base = (long long)blockIdx.x * SCAN_BLOCK + (long long)threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int s = 0;
+#pragma unroll
+  for (int q = 0; q < SCAN_ITEMS; q += 4) {
+    if (base + q + 3 < n) {
+      const int4 t = *reinterpret_cast<const int4*>(hist_cur + base + q);
+      v[q] = t.x; v[q + 1] = t.y; v[q + 2] = t.z; v[q + 3] = t.w;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[q + u] = (base + q + u < n) ? hist_cur[base + q + u] : 0;
+    }
+    s += v[q] + v[q + 1] + v[q + 2] + v[q + 3];
+  }
+  // exclusive scan of s over the block
+  __shared__ int ws[TPB / 32];
+  int x = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+  if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = threadIdx.x < TPB / 32 ? ws[threadIdx.x] : 0;
+#pragma unroll
+    for (int o = 1; o < TPB / 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += y; }
+    if (threadIdx.x < TPB / 32) ws[threadIdx.x] = w;
+  }
+  __syncthreads();
+  int run = blocksum[blockIdx.x] + (x - s) + ((threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0);
+  // the 16 entries of one thread are a quarter of ONE coarse cell (64 fine cells): decode it once
+  bool phys = false;
+  if (base < n) {
+    const unsigned int cc = (unsigned int)(base >> 6);
+    const int cx = cc % H, cy = (cc / H) % H, cz = cc / (H * H);
+    phys = cx >= nc_buf && cx < nc_buf + nc_node && cy >= nc_buf && cy < nc_buf + nc_node && cz >= nc_buf && cz < nc_buf + nc_node;
+  }
+  int o[SCAN_ITEMS];
+#pragma unroll
+  for (int q = 0; q < SCAN_ITEMS; ++q) { o[q] = run; run += v[q]; }
+#pragma unroll
+  for (int q = 0; q < SCAN_ITEMS; q += 4) {
+    if (base + q + 3 < n) {
+      const int4 t = make_int4(o[q], o[q + 1], o[q + 2], o[q + 3]);
+      *reinterpret_cast<int4*>(fstart + base + q) = t;
+      *reinterpret_cast<int4*>(hist_cur + base + q) = t;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (base + q + u < n) { fstart[base + q + u] = o[q + u]; hist_cur[base + q + u] = o[q + u]; }
+    }
+  }
+  if (base + SCAN_ITEMS >= n && base < n) fstart[n] = run;   // total
+  if (phys && s > 0) {
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; ++q) {
+      if (want_multi && v[q] >= 2) { const int slot = atomicAdd(&cnt->n_multi, 1); if (slot < list_cap) multi_list[slot] = (int)(base + q); }
+      if (want_occ && v[q] >= 1) { const int slot = atomicAdd(&cnt->n_occ, 1); if (slot < list_cap) occ_list[slot] = (int)(base + q); }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TPB) scatter_kernel(const float* __restrict__ xv_in, const int64_t* __restrict__ pid_in,
+                                                      const unsigned int* __restrict__ key, int np, int* __restrict__ cursor,
+                                                      float* __restrict__ xv_out, int64_t* __restrict__ pid_out) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i >= np) return;
+  const unsigned int k = key[i];
+  if (k == KEY_DEAD) return;
+  float2 a, b, c;
+  load_xv(xv_in, i, a, b, c);
+  const int dst = atomicAdd(&cursor[k], 1);
+  store_xv(xv_out, dst, a, b, c);
+  if (pid_in) pid_out[dst] = pid_in[i];
+}
+
+// ---- delete_particles.f90:14-50: keep particles with 0 <= x,y,z < mT, i.e. exactly those chained in coarse cells
+// 1..nc_node. In the sorted array each physical (cy,cz) row is one contiguous range.
+__global__ void __launch_bounds__(TPB) row_count_kernel(const int* __restrict__ fstart, int H, int nc_buf, int nc_node, int* __restrict__ rowlen) {
+  const int r = blockIdx.x * TPB + threadIdx.x;
+  if (r >= nc_node * nc_node) return;
+  const int cy = r % nc_node + nc_buf, cz = r / nc_node + nc_buf;
+  const long long k0 = ((long long)(cz * H + cy) * H + nc_buf) * 64;
+  const long long k1 = k0 + (long long)nc_node * 64;
+  rowlen[r] = fstart[k1] - fstart[k0];
+}
+// one CTA per physical row copies it to its compacted place; rowoff = exclusive scan of rowlen
+__global__ void __launch_bounds__(TPB) compact_rows_kernel(const float* __restrict__ xv_in, const int64_t* __restrict__ pid_in,
+                                                           const int* __restrict__ fstart, const int* __restrict__ rowoff, int H, int nc_buf,
+                                                           int nc_node, float* __restrict__ xv_out, int64_t* __restrict__ pid_out) {
+  const int r = blockIdx.x;
+  const int cy = r % nc_node + nc_buf, cz = r / nc_node + nc_buf;
+  const long long k0 = ((long long)(cz * H + cy) * H + nc_buf) * 64;
+  const int s0 = fstart[k0], s1 = fstart[k0 + (long long)nc_node * 64];
+  const int dst = rowoff[r];
+  const float2* src2 = reinterpret_cast<const float2*>(xv_in) + 3LL * s0;
+  float2* dst2 = reinterpret_cast<float2*>(xv_out) + 3LL * dst;
+  const int nf2 = (s1 - s0) * 3;
+  for (int q = threadIdx.x; q < nf2; q += TPB) dst2[q] = src2[q];
+  if (pid_in) for (int q = threadIdx.x; q < s1 - s0; q += TPB) pid_out[dst + q] = pid_in[s0 + q];
+}
+
+// per coarse cell counts of the hoc range (parity getter): counts[c] = fstart[(c+1)*64] - fstart[c*64]
+__global__ void __launch_bounds__(TPB) coarse_counts_kernel(const int* __restrict__ fstart, long long ncoarse, int* __restrict__ counts) {
+  const long long c = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (c >= ncoarse) return;
+  counts[c] = fstart[(c + 1) * 64] - fstart[c * 64];
+}
+
+}  // namespace part

@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — particle-updates/sec of one full CUBEP3M `particle_mesh` step (PM + PP) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c0|tiny]
+
+A "step" is one pass of the hot path (drift -> cell sort -> particle pass -> per-tile fine mesh -> PP -> coarse mesh
+-> ghost deletion) over one synthetic LCDM box.  Workload at N=1 is BASELINE.json configs[1]: 256^3 particles on a
+512^3 fine mesh, PPINT on, nodes_dim=1, tiles_node_dim=4 (nf_tile=176), one B200.
+`value`  : particles / device-seconds per step with the particles resident in HBM (CUDA events on the library's stream).
+`e2e`    : the same step through the C ABI in strict drop-in mode: pinned-host xv -> H2D, particle_mesh, D2H.
+`roofline`: dominant kernel class, algorithmic bytes per launch / its mean device time (events around every launch).
+`cpu_baseline` / `--impl reference`: the CPU oracle (C++/OpenMP restatement of the reference; the Fortran itself cannot
+be built in this image) timed on this box's host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from cubep3m_b200 import default_config, ic  # noqa: E402
+from cubep3m_b200.abi import max_np  # noqa: E402
+
+WORKLOADS = {
+    # name: (nf_tile, tiles_node_dim, ppint, pp_ext, box Mpc/h, z_i, description)
+    "c1": (176, 4, 1, 0, 200.0, 100.0, "BASELINE configs[1]: 256^3 particles, 512^3 fine mesh, PPINT on, nodes_dim=1, tiles_node_dim=4 (nf_tile=176)"),
+    "c0": (176, 2, 0, 0, 200.0, 100.0, "BASELINE configs[0]: 128^3 particles, 256^3 fine mesh, PM only, tiles_node_dim=2 (nf_tile=176)"),
+    "tiny": (112, 2, 1, 0, 50.0, 20.0, "dev smoke: 64^3 particles, 128^3 fine mesh"),
+}
+
+
+def make_cfg(name):
+    n, T, ppint, pp_ext, box, z_i, desc = WORKLOADS[name]
+    cfg = default_config(nf_tile=n, tiles_node_dim=T, ppint=ppint, pp_ext=pp_ext)
+    return cfg, box, z_i, desc
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(cfg, np_local, np_all):
+    """Algorithmic bytes PER LAUNCH of each kernel class.  A = one padded real tile."""
+    n, m, fd = cfg.nf_tile, cfg.m, cfg.m + 3
+    A = 4.0 * (n + 2) * n * n
+    r = fd / n
+    NF = cfg.H ** 3 * 64
+    N = cfg.nc_dim
+    return {
+        "drift": 36.0 * np_local,                       # 24 B read + 12 B written per particle
+        "key_hist": (12.0 + 4.0 + 8.0) * np_all,        # position read, key write, one 4-byte RMW on the cell table
+        "scan": None,                                    # three kernels of different shape; see stages table
+        "scatter": (4.0 + 24.0 + 24.0 + 8.0) * np_all,   # key, record read, record write, cursor RMW
+        "pass_pack": None, "pass_unpack": None,
+        "ngp_density": 8.0 * (n - 8) ** 3 / 4 * 1.25 + A,   # 5 table entries per 4 cells + tile write
+        "fft_x_r2c": 2.0 * A,                            # read n^3 reals, write (n/2+1) complex per row
+        "fft_fwd_strided": 2.0 * A,
+        "fft_inv_z_mul": A + 0.5 * A + r * A,            # spectrum + one kernel component, cropped z written
+        "fft_inv_y": r * A + r * r * A,
+        "fft_x_c2r": r * r * A + 4.0 * fd ** 3,
+        "force_max": 12.0 * fd ** 3,
+        "ngp_kick": 48.0 * np_local / cfg.tiles_node,   # 12 B position + 12 B force gather + 24 B velocity RMW per particle
+        "cic_mass": (12.0 + 8 * 8.0) * np_all * ((cfg.nc_node + 2) / cfg.H) ** 3,
+        "cic_kick": (12.0 + 96.0 + 24.0) * np_local,
+        "compact": 48.0 * np_local,
+        "coarse_fft": None, "coarse_misc": None, "ppint": None, "ppext": None, "misc": None,
+        "_NF": NF, "_A": A,
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(",") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_ics(cfg, box, z_i, seed=12345):
+    t = time.time()
+    xv = ic.zeldovich_ics(cfg.nf_physical_dim, box=box, z_i=z_i, seed=seed)
+    return xv, time.time() - t
+
+
+def oracle_run(cfg, xv, z_i, steps, warmup, tile_note=""):
+    """Times the CPU oracle (all host threads) on full particle_mesh steps of the given workload."""
+    from oracle import Oracle
+    from cubep3m_b200.lib import clock_init, timestep, absorb_limiters
+    o = Oracle(cfg)
+    o.set_particles(xv)
+    clk = clock_init(z_i, ppint=cfg.ppint, pp_ext=cfg.pp_ext)
+    rng = np.random.default_rng(777)
+    shake = np.zeros(3, np.float32)
+    mass_p = float(np.float32(cfg.nf_physical_dim) ** 3 / np.float32(len(xv)))
+    times, stages = [], None
+    for s in range(warmup + steps):
+        timestep(clk)
+        off = ((rng.random(3, dtype=np.float32) - np.float32(0.5)) * np.float32(16.0) - shake).astype(np.float32)
+        shake = shake + off
+        t = time.perf_counter()
+        out = o.particle_mesh(clk.dt, clk.dt_old, clk.a_mid, mass_p, off)
+        dtm = time.perf_counter() - t
+        absorb_limiters(clk, out)
+        if s >= warmup:
+            times.append(dtm)
+            stages = out.stages()
+    threads = o.threads
+    o.close()
+    return float(np.mean(times)), threads, stages
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the Fortran cannot be compiled here), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, box, z_i, desc = make_cfg(args.workload)
+    xv, _ = make_ics(cfg, box, z_i)
+    steps, warmup = args.steps, args.warmup
+    # bound the run to a few minutes: one oracle step of c1 takes ~10-20 s on 16 host threads
+    cap_steps = max(1, min(steps, 6))
+    cap_warm = min(warmup, 1)
+    sec, threads, stages = oracle_run(cfg, xv, z_i, cap_steps, cap_warm)
+    val = len(xv) / sec
+    line = {
+        "metric": "particle_updates_per_sec", "value": val, "unit": "particles/s", "impl": "reference", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "particles": int(len(xv)), "timed_steps_actually_run": cap_steps, "warmup_actually_run": cap_warm},
+        "cpu_baseline": {"value": val, "unit": "particles/s", "cores": threads, "kind": "port",
+                         "sample": f"{cap_steps} full particle_mesh step(s) of the same workload after {cap_warm} warm-up (bounded: the oracle needs ~10-20 s per step)"},
+        "e2e": {"value": val, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "stages_ms": stages,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cubep3m_b200.lib import ParticleMesh, clock_init, timestep, absorb_limiters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg, box, z_i, desc = make_cfg(args.workload)
+    cfg.local_gpu = local_rank
+    xv, t_ic = make_ics(cfg, box, z_i, seed=12345 + rank)
+    npart = len(xv)
+    mass_p = float(np.float32(cfg.nf_physical_dim) ** 3 / np.float32(npart))
+    pm = ParticleMesh(cfg)
+    host = torch.empty((max_np(cfg), 6), dtype=torch.float32).pin_memory().numpy()
+    host[:npart] = xv
+    pm.upload_particles(host[:npart])
+    clk = clock_init(z_i, ppint=cfg.ppint, pp_ext=cfg.pp_ext)
+    rng = np.random.default_rng(777)
+    shake = np.zeros(3, np.float32)
+
+    def one_step(strict=False):
+        nonlocal shake, npart
+        timestep(clk)
+        off = ((rng.random(3, dtype=np.float32) - np.float32(0.5)) * np.float32(16.0) - shake).astype(np.float32)   # update_position.f90:56-58
+        shake = shake + off
+        if strict:
+            pm.upload_particles(host[:npart])
+        out = pm.particle_mesh(clk.dt, clk.dt_old, clk.a_mid, mass_p, off)
+        if strict:
+            got = pm.download_particles(out=host)
+            npart = len(got)
+        absorb_limiters(clk, out)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+    # ---- timed region: resident mode
+    pm.set_profiling(True)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = pm.launches
+    t0 = time.perf_counter()
+    dev_ms, last = 0.0, None
+    class_ms = {}
+    for _ in range(args.steps):
+        last = one_step()
+        dev_ms += last.stage_ms[12]
+        for k, (ms, nl) in pm.kernel_times().items():
+            a = class_ms.setdefault(k, [0.0, 0])
+            a[0] += ms; a[1] += nl
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = pm.launches - l0
+    clocks = sampler.stop() if sampler else None
+    pm.set_profiling(False)
+    ms_step = dev_ms / args.steps
+    np_all = last.np_with_ghosts
+    # ---- e2e: strict drop-in mode through the C ABI with host buffers
+    host[:npart] = pm.download_particles()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        one_step(strict=True)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+
+    if world > 1:
+        t = torch.tensor([ms_step, e2e_ms, wall_ms / args.steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms, wall_step = [float(v) for v in t.tolist()]
+        tot = torch.tensor([float(last.np_local)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot)
+        total_particles = float(tot.item())
+    else:
+        wall_step = wall_ms / args.steps
+        total_particles = float(last.np_local)
+
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        ab = algorithmic_bytes(cfg, last.np_local, np_all)
+        stages = {}
+        for k, (ms, nl) in class_ms.items():
+            if nl == 0:
+                continue
+            per = ms / nl
+            e = {"ms_per_step": ms / args.steps, "launches_per_step": nl / args.steps, "us_per_launch": per * 1e3,
+                 "share_of_step": (ms / args.steps) / ms_step}
+            if ab.get(k):
+                e["algorithmic_MB_per_launch"] = ab[k] / 1e6
+                e["achieved_GBs"] = ab[k] / (per * 1e-3) / 1e9
+                e["frac_of_hbm_peak"] = e["achieved_GBs"] / peak
+            stages[k] = e
+        dom = max((k for k in stages if ab.get(k)), key=lambda k: stages[k]["ms_per_step"])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(dom)
+            except Exception:
+                traffic = None
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["achieved_GBs"], "peak": peak, "unit": "GB/s",
+                    "frac": stages[dom]["achieved_GBs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                    "share_of_step": stages[dom]["share_of_step"], "launches_per_step": stages[dom]["launches_per_step"],
+                    "note": "algorithmic bytes per launch / mean CUDA-event time per launch inside the timed steps; "
+                            "one 176^3 tile (22 MB) stays L2-resident between passes by design, so frac > 1 of the HBM peak is possible"}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            sec, threads, ost = oracle_run(cfg, xv, z_i, 1, 0)
+            cpu = {"value": npart / sec, "unit": "particles/s", "cores": threads, "kind": "port", "ms_per_step": sec * 1e3,
+                   "sample": "1 full particle_mesh step (first step from the ICs) of the same workload, all host threads",
+                   "stages_ms": {k: round(v, 1) for k, v in ost.items()}}
+        line = {
+            "metric": "particle_updates_per_sec", "value": total_particles / (ms_step * 1e-3), "unit": "particles/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "particles_per_gpu": int(npart), "particles_with_ghosts": int(np_all),
+                       "timing": "CUDA events on the library stream, max over ranks; working set (particles 0.4 GB + cell table 1.4 GB) exceeds the 126 MB L2",
+                       "ics": f"Zel'dovich LCDM (EH no-wiggle), z_i={z_i}, box={box} Mpc/h, numpy seed 12345+rank, generated in {t_ic:.1f}s",
+                       "mode": "resident (particles stay in HBM between steps)"},
+            "wall_ms_per_step": wall_step,
+            "e2e": {"value": total_particles / (e2e_ms * 1e-3), "unit": "particles/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(npart) * 24, "d2h_bytes_per_step": int(npart) * 24, "steps": e2e_steps,
+                    "mode": "strict drop-in: pinned host xv -> H2D, particle_mesh, D2H every step (cubepm.f90:143 semantics)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "stages": stages,
+            "stage_ms_last_step": {k: round(v, 3) for k, v in last.stages().items()},
+            "limiters_last_step": {"dt_f_acc": last.dt_f_acc, "dt_pp_acc": last.dt_pp_acc, "dt_c_acc": last.dt_c_acc,
+                                   "sum_rho_f": last.sum_rho_f, "sum_rho_c": last.sum_rho_c, "a": clk.a, "nts": clk.nts},
+        }
+        print(json.dumps(line), flush=True)
+    pm.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

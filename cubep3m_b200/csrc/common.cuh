@@ -24,11 +24,32 @@
     }                                                                                              \
   } while (0)
 
-// every kernel launch goes through this so the library can report how many it issued
-#define LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
-  do {                                                                       \
-    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
-    (ctx)->launches++;                                                       \
+// kernel classes for the per-class device-time breakdown (bench.py's roofline section)
+enum KernelClass {
+  KC_DRIFT = 0, KC_PASS_PACK, KC_PASS_UNPACK, KC_KEY_HIST, KC_SCAN, KC_SCATTER, KC_DENSITY,
+  KC_FFT_X_R2C, KC_FFT_FWD_STRIDED, KC_FFT_INV_Z_MUL, KC_FFT_INV_Y, KC_FFT_X_C2R, KC_FORCE_MAX, KC_NGP_KICK,
+  KC_PPINT, KC_PPEXT, KC_CIC_MASS, KC_COARSE_FFT, KC_COARSE_MISC, KC_CIC_KICK, KC_COMPACT, KC_MISC, KC_COUNT
+};
+static const char* const kKernelClassNames[KC_COUNT] = {
+  "drift", "pass_pack", "pass_unpack", "key_hist", "scan", "scatter", "ngp_density",
+  "fft_x_r2c", "fft_fwd_strided", "fft_inv_z_mul", "fft_inv_y", "fft_x_c2r", "force_max", "ngp_kick",
+  "ppint", "ppext", "cic_mass", "coarse_fft", "coarse_misc", "cic_kick", "compact", "misc"};
+
+constexpr int PROF_MAX = 8192;   // profiled launches per step
+
+// every kernel launch goes through this: counts launches and, when profiling is on, brackets the launch with
+// CUDA events on the launching stream so that per-class device time can be summed after the step.
+#define LAUNCH(ctx, kclass, kernel, grid, block, smem, ...)                                    \
+  do {                                                                                         \
+    const bool prof__ = (ctx)->profiling && (ctx)->prof_n < PROF_MAX;                          \
+    if (prof__) cudaEventRecord((ctx)->prof_ev[2 * (ctx)->prof_n], (ctx)->stream);             \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                           \
+    if (prof__) {                                                                              \
+      cudaEventRecord((ctx)->prof_ev[2 * (ctx)->prof_n + 1], (ctx)->stream);                   \
+      (ctx)->prof_class[(ctx)->prof_n++] = (kclass);                                           \
+    }                                                                                          \
+    (ctx)->launches++;                                                                         \
+    (ctx)->class_launches[(kclass)]++;                                                         \
   } while (0)
 
 constexpr int NUM_SMS = 148;   // B200
@@ -54,7 +75,7 @@ struct DevCounters {
   unsigned int pp_ext_force_max_bits;
   unsigned int c_force_max_bits;
   int np_phys;           // after delete_particles
-  int pad;
+  int n_cand;            // particles within half an ulp below a fine-cell boundary (see fine::ngp_fixup_kernel)
   double sum_rho_f;
   double sum_rho_c;
 };
@@ -65,6 +86,14 @@ struct cubep3m_b200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   long long launches = 0;
+  long long class_launches[KC_COUNT] = {0};
+  bool profiling = false;
+  int prof_n = 0;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_class;
+  float class_ms[KC_COUNT] = {0};        // of the last profiled step
+  long long class_n[KC_COUNT] = {0};
+  int fft_class_base = 0;                // KC_COARSE_FFT while the coarse solve runs, else 0
   int world = 1;
   // particles (AoS 24-byte records as the reference's xv(6,:)), double buffered
   float* xv[2] = {nullptr, nullptr};
@@ -87,14 +116,16 @@ struct cubep3m_b200_ctx {
   int64_t* sendpid[2] = {nullptr, nullptr};
   int64_t* recvpid[2] = {nullptr, nullptr};
   int* rowoff = nullptr;      // compaction offsets per physical (cy,cz) row
+  float* cand = nullptr;      // positions of the boundary-candidate particles (3 floats each)
+  int cand_cap = 0;
   // fine mesh
-  float* kern_f = nullptr;    // (3,hc,n,n) components innermost, as cubep3m.fh:35
+  float* kern_f = nullptr;    // [comp][z][y][kx]: the reference's kern_f(3,hc,n,n) (cubep3m.fh:35) de-interleaved
   float* tile_rho = nullptr;  // (n+2,n,n) real / (hc,n,n) complex, in place
   float* tile_g = nullptr;    // work array for one force component
   float* force_f[3] = {nullptr, nullptr, nullptr};  // (fdim^3) each, SoA
   float2* tw_f = nullptr;     // twiddles exp(-2 pi i t/n)
   // coarse mesh
-  float* kern_c = nullptr;    // (3,hc_c,nc_dim,nc_slab)
+  float* kern_c = nullptr;    // [comp][z][y][kx] over the global coarse mesh (reference: kern_c(3,hc,nc_dim,nc_slab) per rank)
   float* rho_c = nullptr;     // nc_node^3
   float* slab = nullptr;      // (nc_dim+2, nc_dim, nc_dim) for D=1 (full mesh on one GPU)
   float* slab_g = nullptr;

@@ -63,12 +63,12 @@ __global__ void __launch_bounds__(NT) fft_x_r2c(float* __restrict__ data, int nr
 
 // ---- pass Y / Z: strided complex columns.
 // element e of column c of block (bx, by): in[base + e*estride + c], base = (by + outer0)*ostride + bx*LX
-// MUL: multiply the loaded value by i*kern[((e*kes + (by+outer0)*kos) + kx)*3 + comp]   (Z pass: e=z, outer=y)
+// MUL: multiply the loaded value by i*kern[e*kes + (by+outer0)*kos + kx]   (Z pass: e=z, outer=y; kern = one component)
 // stores only elements e in [elo, ehi]
 template <int N, bool INV, bool MUL>
 __global__ void __launch_bounds__(NT) fft_strided(const float2* __restrict__ in, float2* __restrict__ out, int hc,
                                                   long long estride, long long ostride, int outer0,
-                                                  const float* __restrict__ kern, long long kes, long long kos, int comp,
+                                                  const float* __restrict__ kern, long long kes, long long kos,
                                                   int elo, int ehi, const float2* __restrict__ tw_g) {
   extern __shared__ __align__(16) unsigned char raw[];
   Smem s = carve<N>(raw, tw_g);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NT) fft_strided(const float2* __restrict__ in,
     if (colok) {
       v = in[base + (long long)e * estride + col];
       if (MUL) {
-        const float kv = kern[((long long)e * kes + (long long)outer * kos + kx0 + col) * 3 + comp];
+        const float kv = kern[(long long)e * kes + (long long)outer * kos + kx0 + col];
         v = make_float2(-v.y * kv, v.x * kv);
       }
     }
@@ -172,23 +172,24 @@ template <int N> int forward3d_t(cubep3m_b200_ctx* ctx, float* data, const float
   if (int st = set_smem_attr<N>()) return st;
   const int hc = N / 2 + 1, sm = (int)smem_bytes(N);
   const int nrows = N * N;
-  LAUNCH(ctx, fft_x_r2c<N>, dim3((nrows + 2 * LX - 1) / (2 * LX)), dim3(NT), sm, data, nrows, tw);
+  const int cb = ctx->fft_class_base;
+  LAUNCH(ctx, cb ? cb : KC_FFT_X_R2C, fft_x_r2c<N>, dim3((nrows + 2 * LX - 1) / (2 * LX)), dim3(NT), sm, data, nrows, tw);
   float2* c = reinterpret_cast<float2*>(data);
   const int chunks = (hc + LX - 1) / LX;
   // Y: outer = z, element stride hc
-  LAUNCH(ctx, (fft_strided<N, false, false>), dim3(chunks, N), dim3(NT), sm, c, c, hc, (long long)hc, (long long)N * hc, 0,
-         nullptr, 0LL, 0LL, 0, 0, N - 1, tw);
+  LAUNCH(ctx, cb ? cb : KC_FFT_FWD_STRIDED, (fft_strided<N, false, false>), dim3(chunks, N), dim3(NT), sm, c, c, hc, (long long)hc, (long long)N * hc, 0,
+         nullptr, 0LL, 0LL, 0, N - 1, tw);
   // Z: outer = y, element stride N*hc
-  LAUNCH(ctx, (fft_strided<N, false, false>), dim3(chunks, N), dim3(NT), sm, c, c, hc, (long long)N * hc, (long long)hc, 0,
-         nullptr, 0LL, 0LL, 0, 0, N - 1, tw);
+  LAUNCH(ctx, cb ? cb : KC_FFT_FWD_STRIDED, (fft_strided<N, false, false>), dim3(chunks, N), dim3(NT), sm, c, c, hc, (long long)N * hc, (long long)hc, 0,
+         nullptr, 0LL, 0LL, 0, N - 1, tw);
   CK(cudaGetLastError());
   return 0;
 }
 
 // backward 3-D c2r: src (hc,N,N) complex is read; work (same size) is scratch (may equal src when kern == nullptr);
 // out receives the cropped cube [lo, lo+cnt)^3 scaled by `scale`.
-// If kern != nullptr the spectrum is first multiplied by i*kern(comp) (layout (3,hc,N,N)).
-template <int N> int backward3d_t(cubep3m_b200_ctx* ctx, const float* src, float* work, const float* kern, int comp, float* out,
+// If kern != nullptr the spectrum is first multiplied by i*kern (one component, layout [z][y][kx]).
+template <int N> int backward3d_t(cubep3m_b200_ctx* ctx, const float* src, float* work, const float* kern, float* out,
                                   int lo, int cnt, long long opitch_x, long long opitch_y, float scale, const float2* tw) {
   if (int st = set_smem_attr<N>()) return st;
   const int hc = N / 2 + 1, sm = (int)smem_bytes(N);
@@ -196,19 +197,20 @@ template <int N> int backward3d_t(cubep3m_b200_ctx* ctx, const float* src, float
   float2* w = reinterpret_cast<float2*>(work);
   const int chunks = (hc + LX - 1) / LX;
   // Z backward (+ multiply): outer = y (all), keep only z in the crop
+  const int cb = ctx->fft_class_base;
   if (kern) {
-    LAUNCH(ctx, (fft_strided<N, true, true>), dim3(chunks, N), dim3(NT), sm, s, w, hc, (long long)N * hc, (long long)hc, 0,
-           kern, (long long)N * hc, (long long)hc, comp, lo, lo + cnt - 1, tw);
+    LAUNCH(ctx, cb ? cb : KC_FFT_INV_Z_MUL, (fft_strided<N, true, true>), dim3(chunks, N), dim3(NT), sm, s, w, hc, (long long)N * hc, (long long)hc, 0,
+           kern, (long long)N * hc, (long long)hc, lo, lo + cnt - 1, tw);
   } else {
-    LAUNCH(ctx, (fft_strided<N, true, false>), dim3(chunks, N), dim3(NT), sm, s, w, hc, (long long)N * hc, (long long)hc, 0,
-           nullptr, 0LL, 0LL, 0, lo, lo + cnt - 1, tw);
+    LAUNCH(ctx, cb ? cb : KC_FFT_INV_Z_MUL, (fft_strided<N, true, false>), dim3(chunks, N), dim3(NT), sm, s, w, hc, (long long)N * hc, (long long)hc, 0,
+           nullptr, 0LL, 0LL, lo, lo + cnt - 1, tw);
   }
   // Y backward: outer = z in the crop only, keep only y in the crop
-  LAUNCH(ctx, (fft_strided<N, true, false>), dim3(chunks, cnt), dim3(NT), sm, w, w, hc, (long long)hc, (long long)N * hc, lo,
-         nullptr, 0LL, 0LL, 0, lo, lo + cnt - 1, tw);
+  LAUNCH(ctx, cb ? cb : KC_FFT_INV_Y, (fft_strided<N, true, false>), dim3(chunks, cnt), dim3(NT), sm, w, w, hc, (long long)hc, (long long)N * hc, lo,
+         nullptr, 0LL, 0LL, lo, lo + cnt - 1, tw);
   // X backward: cropped rows only
   const long long nrows = (long long)cnt * cnt;
-  LAUNCH(ctx, fft_x_c2r<N>, dim3((unsigned)((nrows + 2 * LX - 1) / (2 * LX))), dim3(NT), sm, w, out, lo, cnt, opitch_x, opitch_y, scale, tw);
+  LAUNCH(ctx, cb ? cb : KC_FFT_X_C2R, fft_x_c2r<N>, dim3((unsigned)((nrows + 2 * LX - 1) / (2 * LX))), dim3(NT), sm, w, out, lo, cnt, opitch_x, opitch_y, scale, tw);
   CK(cudaGetLastError());
   return 0;
 }
@@ -240,9 +242,9 @@ inline int forward3d(cubep3m_b200_ctx* ctx, int n, float* data, const float2* tw
   FFTK_DISPATCH(n, CALL_)
 #undef CALL_
 }
-inline int backward3d(cubep3m_b200_ctx* ctx, int n, const float* src, float* work, const float* kern, int comp, float* out, int lo,
+inline int backward3d(cubep3m_b200_ctx* ctx, int n, const float* src, float* work, const float* kern, float* out, int lo,
                       int cnt, long long opx, long long opy, float scale, const float2* tw) {
-#define CALL_(N) backward3d_t<N>(ctx, src, work, kern, comp, out, lo, cnt, opx, opy, scale, tw)
+#define CALL_(N) backward3d_t<N>(ctx, src, work, kern, out, lo, cnt, opx, opy, scale, tw)
   FFTK_DISPATCH(n, CALL_)
 #undef CALL_
 }

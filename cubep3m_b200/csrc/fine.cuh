@@ -58,6 +58,28 @@ __global__ void __launch_bounds__(TPB) ngp_density_kernel(const int* __restrict_
   }
 }
 
+// Exactness fix-up of the NGP deposit. The reference bins with i1 = floor(fl(x + offset)) + 1 where offset = nf_buf - tile*m
+// (particle_mesh_threaded.f90:134-143); the occupancy table bins with floor(x) + nf_buf. The two differ only when the fp32
+// sum x + offset rounds up across an integer, i.e. for the few listed candidates; move their mass to the reference's cell.
+__global__ void __launch_bounds__(TPB) ngp_fixup_kernel(const float* __restrict__ cand, const int* __restrict__ n_cand_ptr, int cand_cap,
+                                                        float* __restrict__ rho, int n, int b, int m, int tx, int ty, int tz, float mass_p,
+                                                        double* __restrict__ sum_phys) {
+  const int nc = min(*n_cand_ptr, cand_cap);
+  const float offx = (float)(b - tx * m), offy = (float)(b - ty * m), offz = (float)(b - tz * m);
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < nc; i += gridDim.x * TPB) {
+    const float x = cand[3 * i], y = cand[3 * i + 1], z = cand[3 * i + 2];
+    const int kx = (int)floorf(x) + b - tx * m, ky = (int)floorf(y) + b - ty * m, kz = (int)floorf(z) + b - tz * m;
+    if (kx < 4 || kx > n - 5 || ky < 4 || ky > n - 5 || kz < 4 || kz > n - 5) continue;   // not deposited into this tile
+    const int rx = (int)floorf(__fadd_rn(x, offx)), ry = (int)floorf(__fadd_rn(y, offy)), rz = (int)floorf(__fadd_rn(z, offz));
+    if (rx == kx && ry == ky && rz == kz) continue;
+    atomicAdd(&rho[((long long)kz * n + ky) * (n + 2) + kx], -mass_p);
+    atomicAdd(&rho[((long long)rz * n + ry) * (n + 2) + rx], mass_p);
+    const bool pk = kx >= b && kx < n - b && ky >= b && ky < n - b && kz >= b && kz < n - b;
+    const bool pr = rx >= b && rx < n - b && ry >= b && ry < n - b && rz >= b && rz < n - b;
+    if (pk != pr) atomicAdd(sum_phys, pr ? (double)mass_p : -(double)mass_p);
+  }
+}
+
 // max over the cropped force cube of fx^2+fy^2+fz^2 (particle_mesh_threaded.f90:208-223)
 __global__ void __launch_bounds__(TPB) force_max_kernel(const float* __restrict__ fx, const float* __restrict__ fy, const float* __restrict__ fz,
                                                         long long n, unsigned int* __restrict__ out_bits) {

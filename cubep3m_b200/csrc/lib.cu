@@ -50,7 +50,25 @@ template <typename T> int dmalloc(T** p, size_t count) {
 }
 
 __global__ void extract_imag_kernel(const float2* __restrict__ spec, long long n, float* __restrict__ kern, int comp) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) kern[i * 3 + comp] = spec[i].y;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) kern[(long long)comp * n + i] = spec[i].y;
+}
+
+// host (3, n) interleaved -> device [comp][stride] planes, elements [off, off+count)
+int upload_interleaved(float* dev, const float* host, size_t plane, size_t off, size_t count) {
+  std::vector<float> tmp(count);
+  for (int comp = 0; comp < 3; ++comp) {
+    for (size_t i = 0; i < count; ++i) tmp[i] = host[3 * i + comp];
+    CK(cudaMemcpy(dev + (size_t)comp * plane + off, tmp.data(), count * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+int download_interleaved(float* host, const float* dev, size_t plane, size_t off, size_t count) {
+  std::vector<float> tmp(count);
+  for (int comp = 0; comp < 3; ++comp) {
+    CK(cudaMemcpy(tmp.data(), dev + (size_t)comp * plane + off, count * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < count; ++i) host[3 * i + comp] = tmp[i];
+  }
+  return 0;
 }
 
 int grid_for(long long n, int tpb, int cap = NUM_SMS * 16) {
@@ -90,7 +108,7 @@ int build_kern_f(cubep3m_b200_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->tile_rho, rho.data(), rho.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     if (int st = fftk::forward3d(ctx, n, ctx->tile_rho, ctx->tw_f)) return st;   // :89
     const long long ns = (long long)d.hc * n * n;
-    LAUNCH(ctx, extract_imag_kernel, grid_for(ns, 256), 256, 0, reinterpret_cast<const float2*>(ctx->tile_rho), ns, ctx->kern_f, comp);   // :93-99
+    LAUNCH(ctx, KC_MISC, extract_imag_kernel, grid_for(ns, 256), 256, 0, reinterpret_cast<const float2*>(ctx->tile_rho), ns, ctx->kern_f, comp);   // :93-99
     CK(cudaStreamSynchronize(ctx->stream));
   }
   return 0;
@@ -133,7 +151,8 @@ int build_kern_c(cubep3m_b200_ctx* ctx) {
         }
       }
   std::vector<float> slab((size_t)N2 * N * N), tmp;
-  std::vector<float> kc((size_t)3 * hc * N * N);
+  std::vector<float> kc((size_t)3 * hc * N * N);   // [comp][z][y][kx]
+  const size_t ncs = (size_t)hc * N * N;
   auto transform = [&](std::vector<float>& a, int comp) -> int {
     for (int k = 1; k <= N; ++k)
       for (int j = 1; j <= N; ++j) {
@@ -183,7 +202,7 @@ int build_kern_c(cubep3m_b200_ctx* ctx) {
     for (int k = 1; k <= N; ++k)                       // :593-599
       for (int j = 1; j <= N; ++j)
         for (int i = 1; i <= hc; ++i)
-          kc[(size_t)comp + 3 * ((size_t)(i - 1) + (size_t)hc * ((j - 1) + (size_t)N * (k - 1)))] =
+          kc[(size_t)comp * ncs + ((size_t)(i - 1) + (size_t)hc * ((j - 1) + (size_t)N * (k - 1)))] =
               slab[(size_t)(2 * i - 1) + (size_t)N2 * ((j - 1) + (size_t)N * (k - 1))];
   }
   CK(cudaMemcpy(ctx->kern_c, kc.data(), kc.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -206,7 +225,7 @@ int overflow_status(const DevCounters* h) {
 // ---------------------------------------------------------------- stages
 int do_drift(cubep3m_b200_ctx* ctx, float dt, float dt_old, const float off[3]) {
   if (ctx->np_local > 0)
-    LAUNCH(ctx, part::drift_kernel, (ctx->np_local + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->np_local, dt + dt_old, off[0], off[1], off[2]);
+    LAUNCH(ctx, KC_DRIFT, part::drift_kernel, (ctx->np_local + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->np_local, dt + dt_old, off[0], off[1], off[2]);
   CK(cudaGetLastError());
   ctx->sorted = false; ctx->passed = false;
   ctx->np_all = ctx->np_local;
@@ -228,7 +247,7 @@ int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max) {
   for (int axis = 0; axis < 3; ++axis) {
     CK(cudaMemsetAsync(&ctx->dcnt->n_send[0], 0, 2 * sizeof(int), ctx->stream));
     if (np > 0)
-      LAUNCH(ctx, part::pass_pack_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], np, axis, lo, hi,
+      LAUNCH(ctx, KC_PASS_PACK, part::pass_pack_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], np, axis, lo, hi,
              cut_hi, cut_lo, ctx->sendbuf[0], ctx->sendbuf[1], ctx->sendpid[0], ctx->sendpid[1], cap, ctx->dcnt);
     CK(cudaGetLastError());
     if (int st = fetch_counters(ctx)) return st;
@@ -241,7 +260,7 @@ int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max) {
     if ((long long)np + r_plus + r_minus > d.max_np) return CUBEP3M_B200_EMAXNP;              // particle_pass.f90:136-139
     const int nr = r_plus + r_minus;
     if (nr > 0)
-      LAUNCH(ctx, part::pass_unpack_kernel, (nr + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], np, axis,
+      LAUNCH(ctx, KC_PASS_UNPACK, part::pass_unpack_kernel, (nr + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], np, axis,
              ctx->recvbuf[0], r_plus, ctx->recvbuf[1], r_minus, ctx->recvpid[0], ctx->recvpid[1], fmT, rnf, ctx->cfg.eps, hi_clamp);
     CK(cudaGetLastError());
     np += nr;
@@ -272,15 +291,16 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
   CK(cudaMemsetAsync(ctx->fcur, 0, sizeof(int) * d.NF, ctx->stream));
   CK(cudaMemsetAsync(&ctx->dcnt->np_deleted, 0, sizeof(int), ctx->stream));
   CK(cudaMemsetAsync(&ctx->dcnt->n_multi, 0, 2 * sizeof(int), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->dcnt->n_cand, 0, sizeof(int), ctx->stream));
   if (np > 0)
-    LAUNCH(ctx, part::key_hist_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], np, lo, hi, d.b, d.H, ctx->key, ctx->fcur, ctx->dcnt);
+    LAUNCH(ctx, KC_KEY_HIST, part::key_hist_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], np, lo, hi, d.b, d.H, ctx->key, ctx->fcur, ctx->cand, ctx->cand_cap, ctx->dcnt);
   const int nb = (int)((d.NF + part::SCAN_BLOCK - 1) / part::SCAN_BLOCK);
-  LAUNCH(ctx, part::scan_reduce_kernel, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum);
-  LAUNCH(ctx, part::scan_blocksums_kernel, 1, 1024, 0, ctx->blocksum, nb);
-  LAUNCH(ctx, part::scan_apply_kernel, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->multi_list,
+  LAUNCH(ctx, KC_SCAN, part::scan_reduce_kernel, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum);
+  LAUNCH(ctx, KC_SCAN, part::scan_blocksums_kernel, 1, 1024, 0, ctx->blocksum, nb);
+  LAUNCH(ctx, KC_SCAN, part::scan_apply_kernel, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->multi_list,
          ctx->occ_list, ctx->list_cap, ctx->cfg.ppint ? 1 : 0, ctx->cfg.pp_ext ? 1 : 0, ctx->dcnt);
   if (np > 0)
-    LAUNCH(ctx, part::scatter_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->fcur,
+    LAUNCH(ctx, KC_SCATTER, part::scatter_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->fcur,
            ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1]);
   CK(cudaGetLastError());
   if (int st = fetch_counters(ctx)) return st;
@@ -297,9 +317,9 @@ int do_delete(cubep3m_b200_ctx* ctx) {
   const Dims& d = ctx->d;
   const int rows = d.nc_node * d.nc_node;
   CK(cudaMemsetAsync(ctx->rowoff + rows, 0, sizeof(int), ctx->stream));
-  LAUNCH(ctx, part::row_count_kernel, (rows + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->rowoff);
-  LAUNCH(ctx, part::scan_blocksums_kernel, 1, 1024, 0, ctx->rowoff, rows + 1);   // entry [rows] (initialised to 0) becomes the total
-  LAUNCH(ctx, part::compact_rows_kernel, rows, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->fstart, ctx->rowoff, d.H, d.nc_buf, d.nc_node,
+  LAUNCH(ctx, KC_COMPACT, part::row_count_kernel, (rows + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->rowoff);
+  LAUNCH(ctx, KC_SCAN, part::scan_blocksums_kernel, 1, 1024, 0, ctx->rowoff, rows + 1);   // entry [rows] (initialised to 0) becomes the total
+  LAUNCH(ctx, KC_COMPACT, part::compact_rows_kernel, rows, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->fstart, ctx->rowoff, d.H, d.nc_buf, d.nc_node,
          ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1]);
   CK(cudaGetLastError());
   int total = 0;
@@ -317,12 +337,15 @@ int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, int* tile_cou
   const Dims& d = ctx->d;
   const int T = d.T, n = d.n;
   const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;   // particle_mesh_threaded.f90:86-90 (cur_tile-1, x fastest)
-  LAUNCH(ctx, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
+  LAUNCH(ctx, KC_DENSITY, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
          &ctx->dcnt->sum_rho_f, tile_count_dev);
+  if (ctx->hcnt->n_cand > 0)
+    LAUNCH(ctx, KC_DENSITY, fine::ngp_fixup_kernel, std::min(NUM_SMS, (std::min(ctx->hcnt->n_cand, ctx->cand_cap) + fine::TPB - 1) / fine::TPB), fine::TPB, 0,
+           ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, ctx->tile_rho, n, d.b, d.m, tx, ty, tz, mass_p, &ctx->dcnt->sum_rho_f);
   if (int st = fftk::forward3d(ctx, n, ctx->tile_rho, ctx->tw_f)) return st;
   const float scale = 1.0f / (((float)n * (float)n) * (float)n);       // fft_fine.f90:51
   for (int comp = 0; comp < 3; ++comp)
-    if (int st = fftk::backward3d(ctx, n, ctx->tile_rho, ctx->tile_g, ctx->kern_f, comp, ctx->force_f[comp], d.b - 2, d.fdim, d.fdim, d.fdim, scale, ctx->tw_f))
+    if (int st = fftk::backward3d(ctx, n, ctx->tile_rho, ctx->tile_g, ctx->kern_f + (size_t)comp * d.hc * n * n, ctx->force_f[comp], d.b - 2, d.fdim, d.fdim, d.fdim, scale, ctx->tw_f))
       return st;
   return 0;
 }
@@ -334,11 +357,11 @@ int do_fine(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p, float* m
   for (int tile = 0; tile < d.tiles_node; ++tile) {
     if (ctx->cfg.tile_split > 1 && (tile % ctx->cfg.tile_split) != ctx->cfg.tile_split_rank) continue;
     if (int st = fine_tile_solve(ctx, tile, mass_p, ctx->rowoff + d.nc_node * d.nc_node + 8 + tile)) return st;
-    LAUNCH(ctx, fine::force_max_kernel, NUM_SMS * 4, fine::TPB, 0, ctx->force_f[0], ctx->force_f[1], ctx->force_f[2], nf, &ctx->dcnt->f_force_max2_bits);
+    LAUNCH(ctx, KC_FORCE_MAX, fine::force_max_kernel, NUM_SMS * 4, fine::TPB, 0, ctx->force_f[0], ctx->force_f[1], ctx->force_f[2], nf, &ctx->dcnt->f_force_max2_bits);
     if (ctx->cfg.ngp_fmesh_force) {
       const int T = d.T;
       const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;
-      LAUNCH(ctx, fine::ngp_kick_kernel, d.nc_tile * d.nc_tile, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->force_f[0], ctx->force_f[1],
+      LAUNCH(ctx, KC_NGP_KICK, fine::ngp_kick_kernel, d.nc_tile * d.nc_tile, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->force_f[0], ctx->force_f[1],
              ctx->force_f[2], d.H, d.nc_buf, d.nc_tile, d.b, d.m, d.fdim, tx, ty, tz, a_mid, ctx->cfg.G, dt);
     }
   }
@@ -354,7 +377,7 @@ int do_pp(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
     P.apply = ctx->cfg.pp_force_flag;
     const int n_multi = std::min(ctx->hcnt->n_multi, ctx->list_cap);
     if (n_multi > 0)
-      LAUNCH(ctx, pp::ppint_kernel, std::min((n_multi + 3) / 4, NUM_SMS * 16), pp::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->multi_list,
+      LAUNCH(ctx, KC_PPINT, pp::ppint_kernel, std::min((n_multi + 3) / 4, NUM_SMS * 16), pp::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->multi_list,
              &ctx->dcnt->n_multi, ctx->list_cap, P, ctx->cfg.max_llf, ctx->dcnt);
   }
   CK(cudaGetLastError());
@@ -368,7 +391,7 @@ int do_pp_ext(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
     P.apply = ctx->cfg.pp_ext_force_flag;
     const int n_occ = std::min(ctx->hcnt->n_occ, ctx->list_cap);
     if (n_occ > 0)
-      LAUNCH(ctx, pp::ppext_kernel, std::min((n_occ + 3) / 4, NUM_SMS * 16), pp::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->occ_list,
+      LAUNCH(ctx, KC_PPEXT, pp::ppext_kernel, std::min((n_occ + 3) / 4, NUM_SMS * 16), pp::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->occ_list,
              &ctx->dcnt->n_occ, ctx->list_cap, ctx->d.H, ctx->cfg.pp_range, P, ctx->dcnt);
   }
   CK(cudaGetLastError());
@@ -380,7 +403,7 @@ int do_coarse_mass(cubep3m_b200_ctx* ctx, float mass_p) {
   const Dims& d = ctx->d;
   const size_t nrc = (size_t)d.nc_node * d.nc_node * d.nc_node;
   CK(cudaMemsetAsync(ctx->rho_c, 0, nrc * sizeof(float), ctx->stream));
-  LAUNCH(ctx, coarse::cic_mass_kernel, (d.nc_node + 2) * (d.nc_node + 2), coarse::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->rho_c, d.H, d.nc_buf,
+  LAUNCH(ctx, KC_CIC_MASS, coarse::cic_mass_kernel, (d.nc_node + 2) * (d.nc_node + 2), coarse::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->rho_c, d.H, d.nc_buf,
          d.nc_node, mass_p, ctx->cfg.coarse_ngp);
   CK(cudaGetLastError());
   return 0;
@@ -390,25 +413,27 @@ int do_coarse_force(cubep3m_b200_ctx* ctx) {
   if (d.D != 1) return CUBEP3M_B200_EINVAL;
   const int N = d.nc_dim;
   const long long nrc = (long long)d.nc_node * d.nc_node * d.nc_node;
-  LAUNCH(ctx, coarse::cube_to_slab_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->rho_c, ctx->slab, d.nc_node, N, 0, 0, 0, &ctx->dcnt->sum_rho_c);
+  LAUNCH(ctx, KC_COARSE_MISC, coarse::cube_to_slab_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->rho_c, ctx->slab, d.nc_node, N, 0, 0, 0, &ctx->dcnt->sum_rho_c);
+  ctx->fft_class_base = KC_COARSE_FFT;
   if (int st = fftk::forward3d(ctx, N, ctx->slab, ctx->tw_c)) return st;          // coarse_force.f90:18
   const float scale = 1.0f / (((float)N * (float)N) * (float)N);                    // fft_coarse.f90:186
   const size_t nfc = (size_t)3 * (d.nc_node + 2) * (d.nc_node + 2) * (d.nc_node + 2);
   CK(cudaMemsetAsync(ctx->force_c, 0, nfc * sizeof(float), ctx->stream));
   for (int comp = 0; comp < 3; ++comp) {                                            // coarse_force.f90:37-90
     // real-space result goes to rho_c (as in the reference: force_c(comp,...) = rho_c)
-    if (int st = fftk::backward3d(ctx, N, ctx->slab, ctx->slab_g, ctx->kern_c, comp, ctx->rho_c, 0, N, N, N, scale, ctx->tw_c)) return st;
-    LAUNCH(ctx, coarse::slab_to_force_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->rho_c, (long long)N, (long long)N, d.nc_node, 0, 0, 0, ctx->force_c, comp);
+    if (int st = fftk::backward3d(ctx, N, ctx->slab, ctx->slab_g, ctx->kern_c + (size_t)comp * (N / 2 + 1) * N * N, ctx->rho_c, 0, N, N, N, scale, ctx->tw_c)) return st;
+    LAUNCH(ctx, KC_COARSE_MISC, coarse::slab_to_force_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->rho_c, (long long)N, (long long)N, d.nc_node, 0, 0, 0, ctx->force_c, comp);
   }
+  ctx->fft_class_base = 0;
   for (int axis = 0; axis < 3; ++axis)                                              // coarse_force_buffer.f90:23-63
-    LAUNCH(ctx, coarse::halo_self_kernel, grid_for((long long)3 * (d.nc_node + 2) * (d.nc_node + 2), coarse::TPB), coarse::TPB, 0, ctx->force_c, d.nc_node, axis);
-  LAUNCH(ctx, coarse::force_max_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->force_c, d.nc_node, &ctx->dcnt->c_force_max_bits);
+    LAUNCH(ctx, KC_COARSE_MISC, coarse::halo_self_kernel, grid_for((long long)3 * (d.nc_node + 2) * (d.nc_node + 2), coarse::TPB), coarse::TPB, 0, ctx->force_c, d.nc_node, axis);
+  LAUNCH(ctx, KC_COARSE_MISC, coarse::force_max_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->force_c, d.nc_node, &ctx->dcnt->c_force_max_bits);
   CK(cudaGetLastError());
   return 0;
 }
 int do_coarse_vel(cubep3m_b200_ctx* ctx, float a_mid, float dt) {
   const Dims& d = ctx->d;
-  LAUNCH(ctx, coarse::cic_kick_kernel, d.nc_node * d.nc_node, coarse::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->force_c, d.H, d.nc_buf, d.nc_node,
+  LAUNCH(ctx, KC_CIC_KICK, coarse::cic_kick_kernel, d.nc_node * d.nc_node, coarse::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->force_c, d.H, d.nc_buf, d.nc_node,
          a_mid, ctx->cfg.G, dt, ctx->cfg.coarse_ngp);
   CK(cudaGetLastError());
   return 0;
@@ -468,11 +493,12 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   auto F = [](void* p) { if (p) cudaFree(p); };
   for (int i = 0; i < 2; ++i) { F(ctx->xv[i]); F(ctx->pid[i]); F(ctx->sendbuf[i]); F(ctx->sendpid[i]); }
-  F(ctx->key); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
+  F(ctx->cand); F(ctx->key); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
   F(ctx->kern_f); F(ctx->tile_rho); F(ctx->tile_g); for (int i = 0; i < 3; ++i) F(ctx->force_f[i]);
   F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->force_c); F(ctx->tw_c); F(ctx->dcnt);
   if (ctx->hcnt) cudaFreeHost(ctx->hcnt);
   if (ctx->ev_ok) for (auto& e : ctx->ev) cudaEventDestroy(e);
+  for (auto& e : ctx->prof_ev) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -507,6 +533,8 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
     if (cfg->pid) TRY(dmalloc(&ctx->sendpid[i], (size_t)d.max_buf / 6 + 1));
   }
   TRY(dmalloc(&ctx->key, (size_t)d.max_np));
+  ctx->cand_cap = std::max(4096, d.max_np / 64);
+  TRY(dmalloc(&ctx->cand, (size_t)3 * ctx->cand_cap));
   TRY(dmalloc(&ctx->fstart, (size_t)d.NF + 64));
   TRY(dmalloc(&ctx->fcur, (size_t)d.NF + 64));
   ctx->nblocksum = (int)((d.NF + part::SCAN_BLOCK - 1) / part::SCAN_BLOCK);
@@ -534,9 +562,10 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   if (cudaMemset(ctx->dcnt, 0, sizeof(DevCounters)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   if (cudaMallocHost((void**)&ctx->hcnt, sizeof(DevCounters)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   memset(ctx->hcnt, 0, sizeof(DevCounters));
-  if (kern_f) { if (cudaMemcpy(ctx->kern_f, kern_f, sizeof(float) * 3 * d.hc * d.n * d.n, cudaMemcpyHostToDevice) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; } }
+  if (kern_f) TRY(upload_interleaved(ctx->kern_f, kern_f, (size_t)d.hc * d.n * d.n, 0, (size_t)d.hc * d.n * d.n));
   else TRY(build_kern_f(ctx));
-  if (kern_c) { if (cudaMemcpy(ctx->kern_c, kern_c, sizeof(float) * 3 * (N / 2 + 1) * N * N, cudaMemcpyHostToDevice) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; } }
+  // a host kern_c is this rank's slab kern_c(3,hc,nc_dim,nc_slab): only valid as the whole mesh when nodes_dim == 1
+  if (kern_c) TRY(upload_interleaved(ctx->kern_c, kern_c, (size_t)(N / 2 + 1) * N * N, 0, (size_t)(N / 2 + 1) * N * d.nc_slab));
   else TRY(build_kern_c(ctx));
 #undef TRY
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
@@ -578,7 +607,7 @@ int cubep3m_b200_move_grid_back(cubep3m_b200_ctx* ctx, const float s[3]) {
   if (!ctx) return CUBEP3M_B200_EINVAL;
   CK(cudaSetDevice(ctx->device));
   if (ctx->np_local > 0)
-    LAUNCH(ctx, part::shift_kernel, (ctx->np_local + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->np_local, s[0], s[1], s[2]);
+    LAUNCH(ctx, KC_DRIFT, part::shift_kernel, (ctx->np_local + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->np_local, s[0], s[1], s[2]);
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->sorted = false;
   return 0;
@@ -624,6 +653,7 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   // reset per-step device accumulators
   CK(cudaMemsetAsync(ctx->dcnt, 0, sizeof(DevCounters), ctx->stream));
   CK(cudaMemsetAsync(ctx->rowoff + d.nc_node * d.nc_node, 0, sizeof(int) * (16 + d.tiles_node), ctx->stream));
+  ctx->prof_n = 0;
   CK(cudaEventRecord(ev[0], ctx->stream));
   if (int st = do_drift(ctx, dt, dt_old, offset ? offset : zero)) return st;             // particle_mesh_threaded.f90:56
   CK(cudaEventRecord(ev[1], ctx->stream));
@@ -677,6 +707,32 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   out->stage_ms[CUBEP3M_B200_ST_DELETE] = ev_ms(ev[9], ev[10]);
   out->stage_ms[CUBEP3M_B200_ST_TOTAL] = ev_ms(ev[0], ev[10]);
   ctx->last_tile_counts_valid = 1;
+  if (ctx->profiling) {
+    for (int k = 0; k < KC_COUNT; ++k) { ctx->class_ms[k] = 0.f; ctx->class_n[k] = 0; }
+    for (int i = 0; i < ctx->prof_n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]);
+      ctx->class_ms[ctx->prof_class[i]] += ms; ctx->class_n[ctx->prof_class[i]]++;
+    }
+  }
+  return 0;
+}
+
+int cubep3m_b200_set_profiling(cubep3m_b200_ctx* ctx, int on) {
+  if (!ctx) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  if (on && ctx->prof_ev.empty()) {
+    ctx->prof_ev.resize(2 * PROF_MAX); ctx->prof_class.resize(PROF_MAX);
+    for (auto& e : ctx->prof_ev) CK(cudaEventCreate(&e));
+  }
+  ctx->profiling = on != 0;
+  return 0;
+}
+int cubep3m_b200_num_kernel_classes(void) { return KC_COUNT; }
+const char* cubep3m_b200_kernel_class_name(int k) { return (k >= 0 && k < KC_COUNT) ? kKernelClassNames[k] : ""; }
+int cubep3m_b200_get_kernel_times(cubep3m_b200_ctx* ctx, float* ms, int64_t* launches) {
+  if (!ctx) return CUBEP3M_B200_EINVAL;
+  for (int k = 0; k < KC_COUNT; ++k) { ms[k] = ctx->class_ms[k]; launches[k] = ctx->class_n[k]; }
   return 0;
 }
 
@@ -687,7 +743,7 @@ int cubep3m_b200_debug_cell_counts(cubep3m_b200_ctx* ctx, int32_t* counts) {
   const long long nco = ctx->d.NF / 64;
   int* dtmp = nullptr;
   CK(cudaMalloc(&dtmp, sizeof(int) * nco));
-  LAUNCH(ctx, part::coarse_counts_kernel, (int)((nco + part::TPB - 1) / part::TPB), part::TPB, 0, ctx->fstart, nco, dtmp);
+  LAUNCH(ctx, KC_MISC, part::coarse_counts_kernel, (int)((nco + part::TPB - 1) / part::TPB), part::TPB, 0, ctx->fstart, nco, dtmp);
   CK(cudaMemcpyAsync(counts, dtmp, sizeof(int) * nco, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(dtmp);
@@ -709,16 +765,15 @@ int cubep3m_b200_debug_sorted_particles(cubep3m_b200_ctx* ctx, float* xv, int32_
 int cubep3m_b200_debug_kern_f(cubep3m_b200_ctx* ctx, float* kern_f) {
   if (!ctx) return CUBEP3M_B200_EINVAL;
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpy(kern_f, ctx->kern_f, sizeof(float) * 3 * ctx->d.hc * ctx->d.n * ctx->d.n, cudaMemcpyDeviceToHost));
-  return 0;
+  const size_t plane = (size_t)ctx->d.hc * ctx->d.n * ctx->d.n;
+  return download_interleaved(kern_f, ctx->kern_f, plane, 0, plane);
 }
 int cubep3m_b200_debug_kern_c(cubep3m_b200_ctx* ctx, float* kern_c) {
   if (!ctx) return CUBEP3M_B200_EINVAL;
   CK(cudaSetDevice(ctx->device));
   const int N = ctx->d.nc_dim;
-  const size_t per = (size_t)3 * (N / 2 + 1) * N * ctx->d.nc_slab;
-  CK(cudaMemcpy(kern_c, ctx->kern_c + per * ctx->cfg.rank, sizeof(float) * per, cudaMemcpyDeviceToHost));
-  return 0;
+  const size_t plane = (size_t)(N / 2 + 1) * N * N, per = (size_t)(N / 2 + 1) * N * ctx->d.nc_slab;
+  return download_interleaved(kern_c, ctx->kern_c, plane, per * ctx->cfg.rank, per);
 }
 int cubep3m_b200_debug_rho_c(cubep3m_b200_ctx* ctx, float* rho_c) {
   // note: after a full step rho_c holds the last force component (as in the reference, coarse_force.f90:88);
@@ -744,7 +799,10 @@ int cubep3m_b200_debug_fine_tile(cubep3m_b200_ctx* ctx, int32_t tile, float mass
   int* scratch = ctx->rowoff + d.nc_node * d.nc_node + 4;
   double* dsum = nullptr;
   CK(cudaMalloc(&dsum, sizeof(double)));
-  LAUNCH(ctx, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p, dsum, scratch);
+  LAUNCH(ctx, KC_DENSITY, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p, dsum, scratch);
+  if (ctx->hcnt->n_cand > 0)
+    LAUNCH(ctx, KC_DENSITY, fine::ngp_fixup_kernel, NUM_SMS, fine::TPB, 0, ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, ctx->tile_rho, n, d.b, d.m, tx, ty, tz,
+           mass_p, dsum);
   if (rho_f) CK(cudaMemcpyAsync(rho_f, ctx->tile_rho, sizeof(float) * (size_t)(n + 2) * n * n, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(dsum);
@@ -772,7 +830,7 @@ int cubep3m_b200_debug_fft3d(cubep3m_b200_ctx* ctx, int32_t n, float* data, int3
   if (!inverse) { if (int st = fftk::forward3d(ctx, n, buf, tw)) return st; }
   else {
     // unnormalised c2r back into the padded layout (pitch n+2)
-    if (int st = fftk::backward3d(ctx, n, buf, buf, nullptr, 0, (n == ctx->d.n) ? ctx->tile_g : ctx->slab_g, 0, n, n + 2, n, 1.0f, tw)) return st;
+    if (int st = fftk::backward3d(ctx, n, buf, buf, nullptr, (n == ctx->d.n) ? ctx->tile_g : ctx->slab_g, 0, n, n + 2, n, 1.0f, tw)) return st;
     CK(cudaMemcpyAsync(buf, (n == ctx->d.n) ? ctx->tile_g : ctx->slab_g, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   CK(cudaMemcpyAsync(data, buf, bytes, cudaMemcpyDeviceToHost, ctx->stream));

@@ -126,8 +126,11 @@ __device__ __forceinline__ unsigned int make_key(float x, float y, float z, int 
   return ((cz * H + cy) * H + cx) * 64u + (unsigned)(((gz & 3) << 4) | ((gy & 3) << 2) | (gx & 3));
 }
 
+// Also lists the particles that sit within 2^-15 below an integer coordinate on any axis: only for those can the
+// reference's tile-local cell floor(fl(x + offset)) (particle_mesh_threaded.f90:139-143) differ from floor(x)+offset.
 __global__ void __launch_bounds__(TPB) key_hist_kernel(const float* __restrict__ xv, int np, float lo, float hi, int b, int H,
-                                                       unsigned int* __restrict__ key, int* __restrict__ hist, DevCounters* __restrict__ cnt) {
+                                                       unsigned int* __restrict__ key, int* __restrict__ hist, float* __restrict__ cand, int cand_cap,
+                                                       DevCounters* __restrict__ cnt) {
   const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
   if (i >= np) return;
   const float2* p = reinterpret_cast<const float2*>(xv) + 3 * i;
@@ -137,6 +140,11 @@ __global__ void __launch_bounds__(TPB) key_hist_kernel(const float* __restrict__
   if (in_hoc_range(a.x, a.y, z, lo, hi)) {
     k = make_key(a.x, a.y, z, b, H);
     atomicAdd(&hist[k], 1);
+    const float th = 3.0517578125e-05f;   // 2^-15 >= half an ulp of any |x + offset| < 1024
+    if (ceilf(a.x) - a.x <= th || ceilf(a.y) - a.y <= th || ceilf(z) - z <= th) {
+      const int slot = atomicAdd(&cnt->n_cand, 1);
+      if (slot < cand_cap) { cand[3 * slot] = a.x; cand[3 * slot + 1] = a.y; cand[3 * slot + 2] = z; }
+    }
   } else {
     atomicAdd(&cnt->np_deleted, 1);   // 'PARTICLE DELETED' link_list.f90:32
   }

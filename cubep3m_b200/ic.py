@@ -62,7 +62,7 @@ def delta2(k, a, om=0.24, ol=0.76, ob=0.04, h=0.7, ns=0.96, s8=0.817):
     d2 = kk ** (3 + ns) * transfer_nowiggle(kk, om, ob, h) ** 2 / (2 * np.pi ** 2)
     x = kk * 8.0
     W = 3 * (np.sin(x) - x * np.cos(x)) / x ** 3
-    v8 = np.trapz(d2 * W ** 2 / kk, kk)
+    v8 = np.trapezoid(d2 * W ** 2 / kk, kk) if hasattr(np, 'trapezoid') else np.trapz(d2 * W ** 2 / kk, kk)
     norm = s8 ** 2 / v8 * dgrow(a, om, ol) ** 2
     return norm * k ** (3 + ns) * transfer_nowiggle(k, om, ob, h) ** 2 / (2 * np.pi ** 2)
 
@@ -85,8 +85,10 @@ def zeldovich_ics(nc, box=200.0, z_i=100.0, om=0.24, ol=0.76, seed=12345, amplit
     d2 = delta2(2 * np.pi * kr / box, a, om, ol).astype(np.float32)
     amp = np.sqrt(d2 / (4 * np.pi * kr ** 3) * float(nc) ** 3).astype(np.float32) * np.float32(amplitude)
     del d2
-    kern = -4 * np.pi / ((2 * np.sin(np.pi * kx / nc)) ** 2 + (2 * np.sin(np.pi * ky / nc)) ** 2 +
-                         (2 * np.sin(np.pi * kz / nc)) ** 2 + (kr == 0))
+    den = ((2 * np.sin(np.pi * kx / nc)) ** 2 + (2 * np.sin(np.pi * ky / nc)) ** 2 + (2 * np.sin(np.pi * kz / nc)) ** 2)
+    den[0, 0, 0] = 1.0
+    kern = -4 * np.pi / den
+    del den
     nk *= (amp * kern.astype(np.float32))
     nk[0, 0, 0] = 0
     del amp, kern, kr

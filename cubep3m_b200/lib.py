@@ -26,7 +26,9 @@ SYMBOLS = ["cubep3m_b200_version", "cubep3m_b200_strerror", "cubep3m_b200_defaul
            "cubep3m_b200_move_grid_back", "cubep3m_b200_debug_cell_counts", "cubep3m_b200_debug_tile_counts",
            "cubep3m_b200_debug_sorted_particles", "cubep3m_b200_debug_kern_f", "cubep3m_b200_debug_kern_c",
            "cubep3m_b200_debug_rho_c", "cubep3m_b200_debug_force_c", "cubep3m_b200_debug_fine_tile",
-           "cubep3m_b200_debug_fft3d", "cubep3m_b200_launch_count", "cubep3m_b200_clock_init",
+           "cubep3m_b200_debug_fft3d", "cubep3m_b200_launch_count", "cubep3m_b200_set_profiling",
+           "cubep3m_b200_num_kernel_classes", "cubep3m_b200_kernel_class_name", "cubep3m_b200_get_kernel_times",
+           "cubep3m_b200_clock_init",
            "cubep3m_b200_expansion", "cubep3m_b200_timestep"]
 
 
@@ -78,6 +80,10 @@ def load_library():
     L.cubep3m_b200_debug_fft3d.argtypes = [C.c_void_p, C.c_int32, _fp, C.c_int32]
     L.cubep3m_b200_launch_count.argtypes = [C.c_void_p]
     L.cubep3m_b200_launch_count.restype = C.c_int64
+    L.cubep3m_b200_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.cubep3m_b200_kernel_class_name.restype = C.c_char_p
+    L.cubep3m_b200_kernel_class_name.argtypes = [C.c_int]
+    L.cubep3m_b200_get_kernel_times.argtypes = [C.c_void_p, _fp, C.c_void_p]
     L.cubep3m_b200_clock_init.argtypes = [C.POINTER(Clock), C.c_float, C.c_float, C.c_float]
     L.cubep3m_b200_expansion.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.cubep3m_b200_timestep.argtypes = [C.POINTER(Clock)]
@@ -217,6 +223,17 @@ class ParticleMesh:
         assert a.shape == (n, n, n + 2)
         _chk(self.lib.cubep3m_b200_debug_fft3d(self.h, n, a.reshape(-1), 1 if inverse else 0))
         return a
+
+    def set_profiling(self, on=True):
+        _chk(self.lib.cubep3m_b200_set_profiling(self.h, 1 if on else 0))
+
+    def kernel_times(self):
+        """{class name: (ms, launches)} of the last profiled particle_mesh call."""
+        k = self.lib.cubep3m_b200_num_kernel_classes()
+        ms = np.zeros(k, np.float32)
+        n = np.zeros(k, np.int64)
+        _chk(self.lib.cubep3m_b200_get_kernel_times(self.h, ms, _ptr(n)))
+        return {self.lib.cubep3m_b200_kernel_class_name(i).decode(): (float(ms[i]), int(n[i])) for i in range(k)}
 
     @property
     def launches(self):

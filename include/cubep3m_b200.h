@@ -169,6 +169,12 @@ int cubep3m_b200_debug_fine_tile(cubep3m_b200_ctx* ctx, int32_t tile, float mass
 int cubep3m_b200_debug_fft3d(cubep3m_b200_ctx* ctx, int32_t n, float* data, int32_t inverse);
 /* number of kernels this context launched so far (bench.py's gpu_launches) */
 int64_t cubep3m_b200_launch_count(cubep3m_b200_ctx* ctx);
+/* Per-kernel-class device time of the last particle_mesh call: when profiling is on every launch is bracketed by
+ * CUDA events on the launching stream (the stand-in for the reference's -DMPI_TIME stopwatches, timers.f90:68-77). */
+int cubep3m_b200_set_profiling(cubep3m_b200_ctx* ctx, int on);
+int cubep3m_b200_num_kernel_classes(void);
+const char* cubep3m_b200_kernel_class_name(int k);
+int cubep3m_b200_get_kernel_times(cubep3m_b200_ctx* ctx, float* ms, int64_t* launches);
 
 /*
  * Driver twin (host C++): restatement of timestep / expansion (timestep.f90:2-293) so the harness can

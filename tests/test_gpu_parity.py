@@ -1,0 +1,231 @@
+"""GPU parity tests proper: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
+
+Bit-exact: drifted positions, per-coarse-cell membership counts, per-tile deposited-particle counts, the particle set after
+particle_pass (sorted 24-byte records), the particle set after delete_particles (positions).
+Tolerance (stated per test): forces / velocities, which depend on fp32 summation order and on the FFT.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from cubep3m_b200 import default_config, ic
+from tests.conftest import sort_records
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _mk(cfg):
+    from cubep3m_b200.lib import ParticleMesh
+    from oracle import Oracle
+    return ParticleMesh(cfg), Oracle(cfg)
+
+
+@pytest.fixture(scope="module")
+def pair112(built):
+    cfg = default_config(nf_tile=112, tiles_node_dim=2, pp_ext=0)
+    pm, o = _mk(cfg)
+    yield cfg, pm, o
+    pm.close(); o.close()
+
+
+@pytest.fixture(scope="module")
+def ics112():
+    cfg = default_config(nf_tile=112, tiles_node_dim=2)
+    xv = ic.zeldovich_ics(cfg.nf_physical_dim, box=50.0, z_i=20.0, seed=7)
+    xv[:, 3:] *= 3.0
+    return xv
+
+
+@pytest.mark.parametrize("which", ["fine", "coarse"])
+def test_fft3d_matches_numpy(pair112, which):
+    """The library's own 3-D r2c / c2r vs numpy (pocketfft) — tolerance 2e-6 relative (fp32 FFT)."""
+    cfg, pm, _ = pair112
+    N = cfg.nf_tile if which == "fine" else cfg.nc_dim
+    rng = np.random.default_rng(N)
+    x = rng.standard_normal((N, N, N)).astype(np.float32)
+    a = np.zeros((N, N, N + 2), np.float32); a[:, :, :N] = x
+    f = pm.fft3d(a.copy())
+    ref = np.fft.rfftn(x.astype(np.float64))
+    assert np.abs(f.view(np.complex64) - ref).max() / np.abs(ref).max() < 2e-6
+    back = pm.fft3d(f, inverse=True)[:, :, :N] / N ** 3
+    assert np.abs(back - x).max() < 1e-5
+
+
+def test_green_function_kernels(pair112):
+    """kern_f / kern_c built on the device vs kernel_initialization.f90 restated in the oracle (incl. LRCKCORR); 1e-5 of max."""
+    cfg, pm, o = pair112
+    kf, kfo = pm.kern_f(), o.kern_f()
+    assert np.abs(kf - kfo).max() <= 1e-5 * np.abs(kfo).max()
+    kc, kco = pm.kern_c(), o.kern_c()
+    assert np.abs(kc - kco).max() <= 1e-5 * np.abs(kco).max()
+
+
+def test_drift_link_pass_bit_exact(pair112, ics112):
+    cfg, pm, o = pair112
+    off = (1.25, -0.5, 2.0)
+    pm.upload_particles(ics112); o.set_particles(ics112)
+    pm.update_position(0.5, 0.3, off); o.update_position(0.5, 0.3, off)
+    assert np.array_equal(pm.download_particles(), o.get_particles()), "update_position must be bit-exact (unfused evaluation order)"
+    ndel = pm.link_list(); o.link_list()
+    assert ndel == 0
+    assert np.array_equal(pm.cell_counts(), o.cell_counts()), "coarse-cell membership counts"
+    npg = pm.particle_pass(); o.particle_pass()
+    so = o.get_particles()
+    assert npg == len(so)
+    assert np.array_equal(sort_records(pm.sorted_particles()), sort_records(so)), "particle set after particle_pass"
+    assert np.array_equal(pm.cell_counts(), o.cell_counts())
+    # membership as sets: the sorted array groups exactly the oracle's chains
+    sp = pm.sorted_particles()
+    cells = np.floor(sp[:, :3] / 4).astype(np.int64) + 1 - cfg.hoc_l
+    key = (cells[:, 2] * cfg.H + cells[:, 1]) * cfg.H + cells[:, 0]
+    assert (np.diff(key) >= 0).all(), "array is sorted by coarse cell"
+    n = pm.delete_particles(); o.delete_particles()
+    assert n == len(ics112)
+    assert np.array_equal(sort_records(pm.download_particles()[:, :3].copy()), sort_records(o.get_particles()[:, :3].copy()))
+
+
+def test_out_of_range_particles_are_deleted(pair112):
+    """link_list.f90:29-47: particles outside the hoc range are dropped ('PARTICLE DELETED'), not passed."""
+    cfg, pm, o = pair112
+    rng = np.random.default_rng(2)
+    xv = np.zeros((1000, 6), np.float32)
+    xv[:, :3] = rng.random((1000, 3), dtype=np.float32) * cfg.mT
+    xv[:7, 0] = [-24.5, cfg.mT + 24.0, -1e9, 1e9, -24.0, cfg.mT + 23.999, 5.0]
+    pm.upload_particles(xv); o.set_particles(xv)
+    ndel = pm.link_list(); o.link_list()
+    assert ndel == 4
+    assert np.array_equal(pm.cell_counts(), o.cell_counts())
+    pm.particle_pass(); o.particle_pass()
+    assert np.array_equal(sort_records(pm.sorted_particles()), sort_records(o.get_particles()))
+
+
+def test_empty_and_single_particle(pair112):
+    cfg, pm, o = pair112
+    pm.upload_particles(np.zeros((0, 6), np.float32))
+    out = pm.particle_mesh(0.1, 0.1, 0.5, 8.0)
+    assert out.np_local == 0 and out.sum_rho_f == 0.0
+    xv = np.array([[0.0, cfg.mT - 1e-4, 63.9999, 0, 0, 0]], np.float32)    # on a face, next to the far face, on a cell edge
+    pm.upload_particles(xv); o.set_particles(xv)
+    a, b = pm.particle_mesh(0.1, 0.1, 0.5, 8.0), o.particle_mesh(0.1, 0.1, 0.5, 8.0)
+    assert a.np_local == b.np_local == 1 and a.np_with_ghosts == b.np_with_ghosts
+    assert np.array_equal(pm.download_particles()[:, :3], o.get_particles()[:, :3])
+
+
+def _step_compare(cfg, xv, dt, dt_old, a_mid, mass_p, off, vel_tol, zero_v=True):
+    pm, o = _mk(cfg)
+    x = xv.copy()
+    if zero_v:
+        x[:, 3:] = 0           # the report_force trick (report_force.f90:33-45): v after the step IS the kick
+    pm.upload_particles(x); o.set_particles(x)
+    og = pm.particle_mesh(dt, dt_old, a_mid, mass_p, off)
+    oo = o.particle_mesh(dt, dt_old, a_mid, mass_p, off)
+    g, r = pm.download_particles(), o.get_particles()
+    res = dict(og=og, oo=oo, tiles_g=pm.tile_counts(), tiles_o=o.tile_counts())
+    pm.close(); o.close()
+    k = lambda a: a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+    g, r = k(g), k(r)
+    assert og.np_local == oo.np_local == len(g) == len(r)
+    assert og.np_with_ghosts == oo.np_with_ghosts and og.np_buf_max == oo.np_buf_max
+    assert np.array_equal(g[:, :3], r[:, :3]), "particle positions after the step"
+    assert np.array_equal(res["tiles_g"], res["tiles_o"]), "per-tile particle counts"
+    num = np.sqrt(((g[:, 3:] - r[:, 3:]) ** 2).sum(1))
+    den = np.sqrt((r[:, 3:] ** 2).sum(1))
+    rel = num / np.maximum(den, 1e-30)
+    rms = float(np.sqrt(np.mean(rel[den > 0] ** 2)))
+    assert rms < vel_tol, f"rms relative force error {rms:.3e} (max {rel.max():.3e})"
+    assert og.sum_rho_f == pytest.approx(oo.sum_rho_f, rel=1e-9)
+    assert og.sum_rho_c == pytest.approx(oo.sum_rho_c, rel=1e-6)
+    for f in ("dt_f_acc", "dt_c_acc", "dt_pp_acc", "dt_pp_ext_acc"):
+        assert getattr(og, f) == pytest.approx(getattr(oo, f), rel=2e-4), f
+    return rms, res
+
+
+def test_full_step_pm_pp_lcdm(built, ics112):
+    """One full PM+PP step on LCDM ICs from zeroed velocities: rms per-particle relative force error <= 1e-4 (north_star)."""
+    cfg = default_config(nf_tile=112, tiles_node_dim=2, pp_ext=0)
+    _step_compare(cfg, ics112, 0.5, 0.3, 0.05, 8.0, (1.25, -0.5, 2.0), 1e-4)
+
+
+def test_full_step_many_tiles(built):
+    """tiles_node_dim = 4 with nf_tile = 80 (64 tiles): tile decode order, tile overlap regions."""
+    cfg = default_config(nf_tile=80, tiles_node_dim=4, pp_ext=0)
+    xv = ic.zeldovich_ics(cfg.nf_physical_dim, box=50.0, z_i=20.0, seed=21)
+    _step_compare(cfg, xv, 0.4, 0.4, 0.05, 8.0, (-3.0, 7.75, 0.125), 1e-4)
+
+
+def test_full_step_pp_ext_clustered(built):
+    """PPINT + PP_EXT on the clustered golden input; also checks the frozen golden output of the oracle.
+    Tolerance 2e-4: close pairs amplify fp32 summation-order differences (|f| ~ 1/r^2 at r ~ rsoft)."""
+    g = np.load(os.path.join(GOLD, "step_n112_T2.npz"))
+    cfg = default_config(nf_tile=112, tiles_node_dim=2, pp_ext=1)
+    from cubep3m_b200.lib import ParticleMesh
+    pm = ParticleMesh(cfg)
+    pm.upload_particles(g["xv_in"])
+    out = pm.particle_mesh(float(g["dt"]), float(g["dt_old"]), float(g["a_mid"]), float(g["mass_p"]), g["offset"])
+    got, ref = sort_records(pm.download_particles()), sort_records(g["xv_out"])
+    pm.close()
+    assert np.array_equal(got[:, :3], ref[:, :3])
+    assert out.np_with_ghosts == int(g["np_with_ghosts"])
+    dv = np.sqrt(((got[:, 3:] - ref[:, 3:]) ** 2).sum(1)) / np.maximum(np.sqrt((ref[:, 3:] ** 2).sum(1)), 1e-30)
+    assert np.sqrt(np.mean(dv ** 2)) < 2e-4, (np.sqrt(np.mean(dv ** 2)), dv.max())
+    assert out.dt_pp_acc == pytest.approx(float(g["dt_pp_acc"]), rel=1e-3)
+    assert out.dt_f_acc == pytest.approx(float(g["dt_f_acc"]), rel=1e-4)
+    assert out.dt_c_acc == pytest.approx(float(g["dt_c_acc"]), rel=1e-4)
+    assert np.array_equal(pm_tile_counts_safe(cfg, g), g["tile_counts"])
+
+
+def pm_tile_counts_safe(cfg, g):
+    from cubep3m_b200.lib import ParticleMesh
+    pm = ParticleMesh(cfg)
+    pm.upload_particles(g["xv_in"])
+    pm.particle_mesh(float(g["dt"]), float(g["dt_old"]), float(g["a_mid"]), float(g["mass_p"]), g["offset"])
+    t = pm.tile_counts()
+    pm.close()
+    return t
+
+
+def test_pair_force_law_gpu(built):
+    """report_pair.f90:50 on the GPU path: set_pair's fixed first pair (set_pair.f90:45-46), mass_p = 10000, dt = 1."""
+    cfg = default_config(nf_tile=112, tiles_node_dim=2, pp_ext=1)
+    from cubep3m_b200.lib import ParticleMesh
+    pm = ParticleMesh(cfg)
+    xv = np.zeros((2, 6), np.float32)
+    xv[0, :3] = (34.65000153, 60.22747803, 46.03750229)
+    xv[1, :3] = (34.91682053, 59.85746002, 45.87303162)
+    pm.upload_particles(xv)
+    out = pm.particle_mesh(1.0, 0.0, 1.0, 10000.0)
+    res = pm.download_particles()
+    pm.close()
+    r = (xv[0, :3] - xv[1, :3]).astype(np.float64)
+    F = -cfg.G * r / np.linalg.norm(r) ** 3
+    i1 = int(np.argmin(np.abs(res[:, :3] - xv[0, :3]).sum(1)))
+    assert np.linalg.norm(res[i1, 3:] / 10000.0 - F) / np.linalg.norm(F) < 2e-3
+    assert out.np_total == 2
+
+
+def test_size_independent_properties_full_config(built):
+    """BASELINE configs[1] size (256^3 particles, 512^3 mesh, 64 tiles of 176^3): properties that need no oracle —
+    mass conservation on both meshes, particle-count conservation, positions inside the box, total momentum change ~ 0
+    (pairwise forces are antisymmetric), repeatability of positions (bit-exact) across two runs."""
+    cfg = default_config(nf_tile=176, tiles_node_dim=4, pp_ext=0)
+    xv = ic.zeldovich_ics(cfg.nf_physical_dim, box=200.0, z_i=100.0, seed=12345)
+    xv[:, 3:] = 0
+    from cubep3m_b200.lib import ParticleMesh
+    pm = ParticleMesh(cfg)
+    outs = []
+    for rep in range(2):
+        pm.upload_particles(xv)
+        out = pm.particle_mesh(0.3, 0.0, 0.0101, 8.0, (2.5, -7.0, 0.625))
+        outs.append((out, pm.download_particles()))
+    pm.close()
+    out, res = outs[0]
+    assert out.np_total == len(xv) == 256 ** 3
+    assert out.sum_rho_f == float(512 ** 3) and out.sum_rho_c == pytest.approx(512.0 ** 3, rel=1e-6)
+    assert (res[:, :3] >= 0).all() and (res[:, :3] < cfg.mT).all()
+    p = res[:, 3:].astype(np.float64).sum(0)
+    assert np.abs(p).max() < 1e-3 * np.abs(res[:, 3:]).astype(np.float64).sum(0).__abs__().max() + 1e-2 * np.sqrt(len(xv)) * np.abs(res[:, 3:]).std()
+    a, b = sort_records(outs[0][1][:, :3].copy()), sort_records(outs[1][1][:, :3].copy())
+    assert np.array_equal(a, b)
+    assert outs[0][0].dt_f_acc == outs[1][0].dt_f_acc

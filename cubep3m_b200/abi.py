@@ -21,7 +21,8 @@ class Config(C.Structure):
                [(n, C.c_int32) for n in
                 ("ngp", "ppint", "pp_ext", "coarse_ngp", "pid", "lrckcorr", "move_grid_back",
                  "ngp_fmesh_force", "pp_force_flag", "pp_ext_force_flag", "coarse_vel_update",
-                 "rank", "local_gpu", "tile_split", "tile_split_rank")]
+                 "rank", "local_gpu", "tile_split", "tile_split_rank")] + \
+               [("nodes_dim_xyz", C.c_int32 * 3)]
 
     # derived sizes, cubepm.par:190-208
     @property
@@ -31,9 +32,20 @@ class Config(C.Structure):
     @property
     def nc_node(self): return self.mT // self.mesh_scale
     @property
+    def grid(self):
+        g = tuple(self.nodes_dim_xyz)
+        return g if all(v > 0 for v in g) else (self.nodes_dim,) * 3
+    @property
     def nc_dim(self): return self.nc_node * self.nodes_dim
     @property
-    def nodes(self): return self.nodes_dim ** 3
+    def nc_dims(self): return tuple(self.nc_node * d for d in self.grid)      # global coarse mesh (Nx, Ny, Nz)
+    @property
+    def nodes(self):
+        g = self.grid
+        return g[0] * g[1] * g[2]
+    def rank_coords(self, rank):
+        g = self.grid
+        return (rank % g[0], (rank // g[0]) % g[1], rank // (g[0] * g[1]))
     @property
     def nc_slab(self): return self.nc_dim // self.nodes
     @property
@@ -64,8 +76,20 @@ def default_config(**kw) -> Config:
     for k, v in kw.items():
         if not hasattr(c, k):
             raise AttributeError(k)
-        setattr(c, k, v)
+        if k == "nodes_dim_xyz":
+            for i in range(3):
+                c.nodes_dim_xyz[i] = int(v[i])
+        else:
+            setattr(c, k, v)
     return c
+
+
+def copy_config(c: Config, **kw) -> Config:
+    d = Config()
+    C.memmove(C.byref(d), C.byref(c), C.sizeof(Config))
+    for k, v in kw.items():
+        setattr(d, k, v)
+    return d
 
 
 class StepOut(C.Structure):

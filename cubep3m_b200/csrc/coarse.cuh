@@ -46,8 +46,9 @@ __global__ void __launch_bounds__(TPB) cic_mass_kernel(const float* __restrict__
   }
 }
 
-// copy the rank's cube into the padded FFT array at offset (ox,oy,oz) (pack_slab for a single-GPU mesh) + DIAG sum
-__global__ void __launch_bounds__(TPB) cube_to_slab_kernel(const float* __restrict__ rho_c, float* __restrict__ slab, int nc_node, int N,
+// copy one rank's cube into the padded global FFT array (Nx+2, Ny, Nz) at offset (ox,oy,oz) — the pack_slab of
+// fft_coarse.f90:4-54 for a replicated global mesh — and (for the rank's own cube) the DIAG sum of coarse_mesh.f90:31-43
+__global__ void __launch_bounds__(TPB) cube_to_slab_kernel(const float* __restrict__ rho_c, float* __restrict__ slab, int nc_node, int Nx, int Ny,
                                                            int ox, int oy, int oz, double* __restrict__ sum) {
   const long long total = (long long)nc_node * nc_node * nc_node;
   double s = 0.0;
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(TPB) cube_to_slab_kernel(const float* __restri
     const int x = (int)(t % nc_node), y = (int)((t / nc_node) % nc_node), z = (int)(t / ((long long)nc_node * nc_node));
     const float v = rho_c[t];
     s += (double)v;
-    slab[((long long)(z + oz) * N + (y + oy)) * (N + 2) + (x + ox)] = v;
+    slab[((long long)(z + oz) * Ny + (y + oy)) * (Nx + 2) + (x + ox)] = v;
   }
   s = warp_sum_d(s);
   if ((threadIdx.x & 31) == 0 && sum) atomicAdd(sum, s);
@@ -69,6 +70,19 @@ __global__ void __launch_bounds__(TPB) slab_to_force_kernel(const float* __restr
   for (long long t = (long long)blockIdx.x * TPB + threadIdx.x; t < total; t += (long long)gridDim.x * TPB) {
     const int x = (int)(t % nc_node), y = (int)((t / nc_node) % nc_node), z = (int)(t / ((long long)nc_node * nc_node));
     force_c[(((long long)(z + 1) * fc + (y + 1)) * fc + (x + 1)) * 3 + comp] = real[((long long)(z + oz) * pitch_y + (y + oy)) * pitch_x + (x + ox)];
+  }
+}
+
+// force_c(comp, 0:nc+1, 0:nc+1, 0:nc+1) <- global real-space component with periodic wrap: the rank's cube (coarse_force.f90:52 +
+// unpack_slab) AND its one-cell halo (what coarse_force_buffer.f90:23-63 obtains from the six neighbours) in one gather.
+__global__ void __launch_bounds__(TPB) extract_force_kernel(const float* __restrict__ real, int Nx, int Ny, int Nz, int nc_node, int cx, int cy, int cz,
+                                                            float* __restrict__ force_c, int comp) {
+  const int fc = nc_node + 2;
+  const long long total = (long long)fc * fc * fc;
+  for (long long t = (long long)blockIdx.x * TPB + threadIdx.x; t < total; t += (long long)gridDim.x * TPB) {
+    const int i = (int)(t % fc), j = (int)((t / fc) % fc), k = (int)(t / ((long long)fc * fc));
+    const int gx = (cx * nc_node + i - 1 + Nx) % Nx, gy = (cy * nc_node + j - 1 + Ny) % Ny, gz = (cz * nc_node + k - 1 + Nz) % Nz;
+    force_c[t * 3 + comp] = real[((long long)gz * Ny + gy) * Nx + gx];
   }
 }
 

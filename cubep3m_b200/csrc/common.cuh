@@ -58,6 +58,11 @@ constexpr int NUM_SMS = 148;   // B200
 struct Dims {
   int D, T, n, b, s, m, mT, nc_tile, nc_node, nc_dim, nc_slab, nc_buf, hoc_l, hoc_h, H, nodes, tiles_node;
   int max_np, max_buf;
+  int Dg[3];       // rank grid (Dx,Dy,Dz) of cubic nodes
+  int coord[3];    // this rank's (x,y,z) in the grid; rank = x + Dx*(y + Dy*z)
+  int nbr[6];      // neighbour ranks: -x,+x,-y,+y,-z,+z (periodic)
+  int Nc[3];       // global coarse mesh (Nx,Ny,Nz) = nc_node * Dg
+  int world;       // Dx*Dy*Dz
   int hc;          // n/2+1
   int fdim;        // m+3: force_f spans nf_buf-1 .. nf_tile-nf_buf+1 (cubep3m.fh:36-37)
   long long NF;    // fine cells of the hoc range: H^3 * 64
@@ -113,6 +118,8 @@ struct cubep3m_b200_ctx {
   int list_cap = 0;
   float* sendbuf[2] = {nullptr, nullptr};
   float* recvbuf[2] = {nullptr, nullptr};
+  float* recvbuf_own[2] = {nullptr, nullptr};   // only allocated for multi-rank runs
+  int64_t* recvpid_own[2] = {nullptr, nullptr};
   int64_t* sendpid[2] = {nullptr, nullptr};
   int64_t* recvpid[2] = {nullptr, nullptr};
   int* rowoff = nullptr;      // compaction offsets per physical (cy,cz) row
@@ -127,10 +134,14 @@ struct cubep3m_b200_ctx {
   // coarse mesh
   float* kern_c = nullptr;    // [comp][z][y][kx] over the global coarse mesh (reference: kern_c(3,hc,nc_dim,nc_slab) per rank)
   float* rho_c = nullptr;     // nc_node^3
-  float* slab = nullptr;      // (nc_dim+2, nc_dim, nc_dim) for D=1 (full mesh on one GPU)
+  float* slab = nullptr;      // (Nx+2, Ny, Nz): the WHOLE global coarse mesh, replicated on every rank
   float* slab_g = nullptr;
+  float* creal = nullptr;     // (Nx, Ny, Nz) real-space force component
+  float* gather = nullptr;    // all ranks' rho_c cubes (ncclAllGather target), world * nc_node^3
   float* force_c = nullptr;   // (3, nc_node+2, nc_node+2, nc_node+2) components innermost as cubep3m.fh:59
-  float2* tw_c = nullptr;
+  float2* tw_c[3] = {nullptr, nullptr, nullptr};   // twiddles for Nx, Ny, Nz
+  float* redbuf = nullptr;    // small device scratch for cross-rank reductions
+  int* cntbuf = nullptr;      // received pass counts
   DevCounters* dcnt = nullptr;
   DevCounters* hcnt = nullptr; // pinned
   cudaEvent_t ev[CUBEP3M_B200_ST_COUNT + 2];

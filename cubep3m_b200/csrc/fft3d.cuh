@@ -99,16 +99,16 @@ __global__ void __launch_bounds__(NT) fft_strided(const float2* __restrict__ in,
 }
 
 // ---- pass X backward: half spectra -> real rows with crop + scale.
-// Row index space: ridx in [0, cnt*cnt): zc = ridx / cnt, yc = ridx % cnt, source row (z = zc+lo, y = yc+lo).
-// Output: out[(zc*opitch_y + yc)*opitch_x + xc], xc in [0,cnt) <- x = xc + lo.
+// Row index space: ridx in [0, cnt_z*cnt_y): zc = ridx / cnt_y, yc = ridx % cnt_y, source row (z = zc+lo_z, y = yc+lo_y) of an
+// array with ny_src rows per plane. Output: out[(zc*opitch_y + yc)*opitch_x + xc], xc in [0,cnt_x) <- x = xc + lo_x.
 template <int N>
-__global__ void __launch_bounds__(NT) fft_x_c2r(const float2* __restrict__ in, float* __restrict__ out, int lo, int cnt,
-                                                long long opitch_x, long long opitch_y, float scale,
+__global__ void __launch_bounds__(NT) fft_x_c2r(const float2* __restrict__ in, float* __restrict__ out, int lo_x, int cnt_x, int lo_y, int cnt_y,
+                                                int lo_z, int cnt_z, int ny_src, long long opitch_x, long long opitch_y, float scale,
                                                 const float2* __restrict__ tw_g) {
   extern __shared__ __align__(16) unsigned char raw[];
   Smem s = carve<N>(raw, tw_g);
   constexpr int HC = N / 2 + 1;
-  const long long nrows = (long long)cnt * cnt;
+  const long long nrows = (long long)cnt_z * cnt_y;
   const long long r0 = (long long)blockIdx.x * (2 * LX);
   // stage A (even rows) into buffer 0, B (odd rows) into buffer 1
   for (int q = threadIdx.x; q < 2 * LX * HC; q += NT) {
@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(NT) fft_x_c2r(const float2* __restrict__ in, f
     const long long ridx = r0 + row;
     float2 v = make_float2(0.f, 0.f);
     if (ridx < nrows) {
-      const int zc = (int)(ridx / cnt), yc = (int)(ridx - (long long)zc * cnt);
-      v = in[((long long)(zc + lo) * N + (yc + lo)) * HC + k];
+      const int zc = (int)(ridx / cnt_y), yc = (int)(ridx - (long long)zc * cnt_y);
+      v = in[((long long)(zc + lo_z) * ny_src + (yc + lo_y)) * HC + k];
     }
     const int col = row >> 1;
     if (row & 1) { s.re1[k * LXP + col] = v.x; s.im1[k * LXP + col] = v.y; }
@@ -140,20 +140,33 @@ __global__ void __launch_bounds__(NT) fft_x_c2r(const float2* __restrict__ in, f
   fft_columns<N, true>(s.re0, s.im0, s.re1, s.im1, s.tw);
   const float* zr = result_buffer<N>() ? s.re1 : s.re0;
   const float* zi = result_buffer<N>() ? s.im1 : s.im0;
-  for (int q = threadIdx.x; q < 2 * LX * cnt; q += NT) {
-    const int row = q / cnt, xc = q - row * cnt;
+  for (int q = threadIdx.x; q < 2 * LX * cnt_x; q += NT) {
+    const int row = q / cnt_x, xc = q - row * cnt_x;
     const long long ridx = r0 + row;
     if (ridx >= nrows) continue;
-    const int zc = (int)(ridx / cnt), yc = (int)(ridx - (long long)zc * cnt);
-    const int x = xc + lo, col = row >> 1;
+    const int zc = (int)(ridx / cnt_y), yc = (int)(ridx - (long long)zc * cnt_y);
+    const int x = xc + lo_x, col = row >> 1;
     const float v = (row & 1) ? zi[x * LXP + col] : zr[x * LXP + col];
     out[((long long)zc * opitch_y + yc) * opitch_x + xc] = v * scale;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// host-side dispatch on N
+// host-side dispatch on N (each axis of a mesh may have its own length: the fine tile is cubic, the global coarse mesh of a
+// (Dx,Dy,Dz) rank grid need not be)
 // ------------------------------------------------------------------------------------------------
+#define FFTK_FOR_ALL_N(X) X(16) X(32) X(48) X(64) X(80) X(112) X(128) X(176) X(256) X(304) X(512) X(560)
+
+inline bool supported(int n) {
+  switch (n) {
+#define X(N) case N:
+    FFTK_FOR_ALL_N(X)
+#undef X
+    return true;
+  }
+  return false;
+}
+
 template <int N> int set_smem_attr() {
   static bool done = false;
   if (done) return 0;
@@ -167,86 +180,93 @@ template <int N> int set_smem_attr() {
   return 0;
 }
 
-// forward 3-D r2c in place on data (N+2, N, N)
-template <int N> int forward3d_t(cubep3m_b200_ctx* ctx, float* data, const float2* tw) {
+struct Mesh3 {            // a padded real mesh (nx+2, ny, nz) / complex (nx/2+1, ny, nz)
+  int nx, ny, nz;
+  const float2 *twx, *twy, *twz;
+  int hc() const { return nx / 2 + 1; }
+};
+
+template <int N> int launch_x_r2c_t(cubep3m_b200_ctx* ctx, int kc, float* data, int nrows, const float2* tw) {
   if (int st = set_smem_attr<N>()) return st;
-  const int hc = N / 2 + 1, sm = (int)smem_bytes(N);
-  const int nrows = N * N;
-  const int cb = ctx->fft_class_base;
-  LAUNCH(ctx, cb ? cb : KC_FFT_X_R2C, fft_x_r2c<N>, dim3((nrows + 2 * LX - 1) / (2 * LX)), dim3(NT), sm, data, nrows, tw);
+  LAUNCH(ctx, kc, fft_x_r2c<N>, dim3((nrows + 2 * LX - 1) / (2 * LX)), dim3(NT), (int)smem_bytes(N), data, nrows, tw);
+  return 0;
+}
+template <int N> int launch_strided_t(cubep3m_b200_ctx* ctx, int kc, bool inv, const float2* in, float2* out, int hc, long long estride,
+                                      long long ostride, int outer0, int nouter, const float* kern, long long kes, long long kos, int elo,
+                                      int ehi, const float2* tw) {
+  if (int st = set_smem_attr<N>()) return st;
+  const dim3 grid((hc + LX - 1) / LX, nouter);
+  const int sm = (int)smem_bytes(N);
+  if (!inv) LAUNCH(ctx, kc, (fft_strided<N, false, false>), grid, dim3(NT), sm, in, out, hc, estride, ostride, outer0, nullptr, 0LL, 0LL, elo, ehi, tw);
+  else if (kern) LAUNCH(ctx, kc, (fft_strided<N, true, true>), grid, dim3(NT), sm, in, out, hc, estride, ostride, outer0, kern, kes, kos, elo, ehi, tw);
+  else LAUNCH(ctx, kc, (fft_strided<N, true, false>), grid, dim3(NT), sm, in, out, hc, estride, ostride, outer0, nullptr, 0LL, 0LL, elo, ehi, tw);
+  return 0;
+}
+template <int N> int launch_x_c2r_t(cubep3m_b200_ctx* ctx, int kc, const float2* in, float* out, int lo_x, int cnt_x, int lo_y, int cnt_y, int lo_z,
+                                    int cnt_z, int ny_src, long long opx, long long opy, float scale, const float2* tw) {
+  if (int st = set_smem_attr<N>()) return st;
+  const long long nrows = (long long)cnt_z * cnt_y;
+  LAUNCH(ctx, kc, fft_x_c2r<N>, dim3((unsigned)((nrows + 2 * LX - 1) / (2 * LX))), dim3(NT), (int)smem_bytes(N), in, out, lo_x, cnt_x, lo_y, cnt_y,
+         lo_z, cnt_z, ny_src, opx, opy, scale, tw);
+  return 0;
+}
+#define FFTK_SWITCH(N_, CALL)                                 \
+  switch (N_) {                                               \
+    FFTK_FOR_ALL_N(CALL)                                      \
+    default: return CUBEP3M_B200_EINVAL;                      \
+  }
+
+inline int launch_x_r2c(cubep3m_b200_ctx* ctx, int kc, int n, float* data, int nrows, const float2* tw) {
+#define X(N) case N: return launch_x_r2c_t<N>(ctx, kc, data, nrows, tw);
+  FFTK_SWITCH(n, X)
+#undef X
+}
+inline int launch_strided(cubep3m_b200_ctx* ctx, int kc, int n, bool inv, const float2* in, float2* out, int hc, long long estride, long long ostride,
+                          int outer0, int nouter, const float* kern, long long kes, long long kos, int elo, int ehi, const float2* tw) {
+#define X(N) case N: return launch_strided_t<N>(ctx, kc, inv, in, out, hc, estride, ostride, outer0, nouter, kern, kes, kos, elo, ehi, tw);
+  FFTK_SWITCH(n, X)
+#undef X
+}
+inline int launch_x_c2r(cubep3m_b200_ctx* ctx, int kc, int n, const float2* in, float* out, int lo_x, int cnt_x, int lo_y, int cnt_y, int lo_z,
+                        int cnt_z, int ny_src, long long opx, long long opy, float scale, const float2* tw) {
+#define X(N) case N: return launch_x_c2r_t<N>(ctx, kc, in, out, lo_x, cnt_x, lo_y, cnt_y, lo_z, cnt_z, ny_src, opx, opy, scale, tw);
+  FFTK_SWITCH(n, X)
+#undef X
+}
+
+// forward 3-D r2c in place on data (nx+2, ny, nz)
+inline int forward3d(cubep3m_b200_ctx* ctx, const Mesh3& g, float* data) {
+  const int hc = g.hc(), cb = ctx->fft_class_base;
+  if (int st = launch_x_r2c(ctx, cb ? cb : KC_FFT_X_R2C, g.nx, data, g.ny * g.nz, g.twx)) return st;
   float2* c = reinterpret_cast<float2*>(data);
-  const int chunks = (hc + LX - 1) / LX;
   // Y: outer = z, element stride hc
-  LAUNCH(ctx, cb ? cb : KC_FFT_FWD_STRIDED, (fft_strided<N, false, false>), dim3(chunks, N), dim3(NT), sm, c, c, hc, (long long)hc, (long long)N * hc, 0,
-         nullptr, 0LL, 0LL, 0, N - 1, tw);
-  // Z: outer = y, element stride N*hc
-  LAUNCH(ctx, cb ? cb : KC_FFT_FWD_STRIDED, (fft_strided<N, false, false>), dim3(chunks, N), dim3(NT), sm, c, c, hc, (long long)N * hc, (long long)hc, 0,
-         nullptr, 0LL, 0LL, 0, N - 1, tw);
+  if (int st = launch_strided(ctx, cb ? cb : KC_FFT_FWD_STRIDED, g.ny, false, c, c, hc, (long long)hc, (long long)g.ny * hc, 0, g.nz, nullptr, 0, 0, 0,
+                              g.ny - 1, g.twy)) return st;
+  // Z: outer = y, element stride ny*hc
+  if (int st = launch_strided(ctx, cb ? cb : KC_FFT_FWD_STRIDED, g.nz, false, c, c, hc, (long long)g.ny * hc, (long long)hc, 0, g.ny, nullptr, 0, 0, 0,
+                              g.nz - 1, g.twz)) return st;
   CK(cudaGetLastError());
   return 0;
 }
 
-// backward 3-D c2r: src (hc,N,N) complex is read; work (same size) is scratch (may equal src when kern == nullptr);
-// out receives the cropped cube [lo, lo+cnt)^3 scaled by `scale`.
+// backward 3-D c2r: src (hc,ny,nz) complex is read; work (same size) is scratch (may equal src when kern == nullptr);
+// out receives the window [lo, lo+cnt) per axis scaled by `scale`, with pitches opx (x row length) and opy (rows per plane).
 // If kern != nullptr the spectrum is first multiplied by i*kern (one component, layout [z][y][kx]).
-template <int N> int backward3d_t(cubep3m_b200_ctx* ctx, const float* src, float* work, const float* kern, float* out,
-                                  int lo, int cnt, long long opitch_x, long long opitch_y, float scale, const float2* tw) {
-  if (int st = set_smem_attr<N>()) return st;
-  const int hc = N / 2 + 1, sm = (int)smem_bytes(N);
+inline int backward3d(cubep3m_b200_ctx* ctx, const Mesh3& g, const float* src, float* work, const float* kern, float* out, const int lo[3],
+                      const int cnt[3], long long opx, long long opy, float scale) {
+  const int hc = g.hc(), cb = ctx->fft_class_base;
   const float2* s = reinterpret_cast<const float2*>(src);
   float2* w = reinterpret_cast<float2*>(work);
-  const int chunks = (hc + LX - 1) / LX;
-  // Z backward (+ multiply): outer = y (all), keep only z in the crop
-  const int cb = ctx->fft_class_base;
-  if (kern) {
-    LAUNCH(ctx, cb ? cb : KC_FFT_INV_Z_MUL, (fft_strided<N, true, true>), dim3(chunks, N), dim3(NT), sm, s, w, hc, (long long)N * hc, (long long)hc, 0,
-           kern, (long long)N * hc, (long long)hc, lo, lo + cnt - 1, tw);
-  } else {
-    LAUNCH(ctx, cb ? cb : KC_FFT_INV_Z_MUL, (fft_strided<N, true, false>), dim3(chunks, N), dim3(NT), sm, s, w, hc, (long long)N * hc, (long long)hc, 0,
-           nullptr, 0LL, 0LL, lo, lo + cnt - 1, tw);
-  }
-  // Y backward: outer = z in the crop only, keep only y in the crop
-  LAUNCH(ctx, cb ? cb : KC_FFT_INV_Y, (fft_strided<N, true, false>), dim3(chunks, cnt), dim3(NT), sm, w, w, hc, (long long)hc, (long long)N * hc, lo,
-         nullptr, 0LL, 0LL, lo, lo + cnt - 1, tw);
-  // X backward: cropped rows only
-  const long long nrows = (long long)cnt * cnt;
-  LAUNCH(ctx, cb ? cb : KC_FFT_X_C2R, fft_x_c2r<N>, dim3((unsigned)((nrows + 2 * LX - 1) / (2 * LX))), dim3(NT), sm, w, out, lo, cnt, opitch_x, opitch_y, scale, tw);
+  // Z backward (+ multiply): outer = y (all), keep only z in the window
+  if (int st = launch_strided(ctx, cb ? cb : KC_FFT_INV_Z_MUL, g.nz, true, s, w, hc, (long long)g.ny * hc, (long long)hc, 0, g.ny, kern,
+                              (long long)g.ny * hc, (long long)hc, lo[2], lo[2] + cnt[2] - 1, g.twz)) return st;
+  // Y backward: outer = z in the window only, keep only y in the window
+  if (int st = launch_strided(ctx, cb ? cb : KC_FFT_INV_Y, g.ny, true, w, w, hc, (long long)hc, (long long)g.ny * hc, lo[2], cnt[2], nullptr, 0, 0, lo[1],
+                              lo[1] + cnt[1] - 1, g.twy)) return st;
+  // X backward: window rows only
+  if (int st = launch_x_c2r(ctx, cb ? cb : KC_FFT_X_C2R, g.nx, w, out, lo[0], cnt[0], lo[1], cnt[1], lo[2], cnt[2], g.ny, opx, opy, scale, g.twx)) return st;
   CK(cudaGetLastError());
   return 0;
-}
-
-#define FFTK_DISPATCH(N_, CALL)                \
-  switch (N_) {                                \
-    case 16: return CALL(16);                  \
-    case 32: return CALL(32);                  \
-    case 48: return CALL(48);                  \
-    case 64: return CALL(64);                  \
-    case 80: return CALL(80);                  \
-    case 112: return CALL(112);                \
-    case 128: return CALL(128);                \
-    case 176: return CALL(176);                \
-    case 256: return CALL(256);                \
-    case 304: return CALL(304);                \
-    case 512: return CALL(512);                \
-    case 560: return CALL(560);                \
-    default: return CUBEP3M_B200_EINVAL;       \
-  }
-
-inline bool supported(int n) {
-  switch (n) { case 16: case 32: case 48: case 64: case 80: case 112: case 128: case 176: case 256: case 304: case 512: case 560: return true; }
-  return false;
-}
-
-inline int forward3d(cubep3m_b200_ctx* ctx, int n, float* data, const float2* tw) {
-#define CALL_(N) forward3d_t<N>(ctx, data, tw)
-  FFTK_DISPATCH(n, CALL_)
-#undef CALL_
-}
-inline int backward3d(cubep3m_b200_ctx* ctx, int n, const float* src, float* work, const float* kern, float* out, int lo,
-                      int cnt, long long opx, long long opy, float scale, const float2* tw) {
-#define CALL_(N) backward3d_t<N>(ctx, src, work, kern, out, lo, cnt, opx, opy, scale, tw)
-  FFTK_DISPATCH(n, CALL_)
-#undef CALL_
 }
 
 // twiddle table exp(-2 pi i t / n) on the device; constant radix tables

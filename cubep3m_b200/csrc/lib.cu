@@ -21,9 +21,22 @@ int derive(const cubep3m_b200_config& c, Dims& d) {
   d.nc_tile = d.m / d.s;                  // cubepm.par:191
   d.nc_node = d.nc_tile * d.T;            // cubepm.par:192
   d.nc_dim = d.nc_node * d.D;             // cubepm.par:193
-  d.nodes = d.D * d.D * d.D;
-  if (d.nc_dim % d.nodes != 0) return CUBEP3M_B200_EINVAL;   // mpi_initialization.f90:25-29
-  d.nc_slab = d.nc_dim / d.nodes;         // cubepm.par:195
+  const bool custom_grid = c.nodes_dim_xyz[0] > 0 && c.nodes_dim_xyz[1] > 0 && c.nodes_dim_xyz[2] > 0;
+  for (int a = 0; a < 3; ++a) d.Dg[a] = custom_grid ? c.nodes_dim_xyz[a] : d.D;
+  d.world = d.Dg[0] * d.Dg[1] * d.Dg[2];
+  d.nodes = d.world;
+  if (c.rank < 0 || c.rank >= d.world) return CUBEP3M_B200_EINVAL;
+  d.coord[0] = c.rank % d.Dg[0]; d.coord[1] = (c.rank / d.Dg[0]) % d.Dg[1]; d.coord[2] = c.rank / (d.Dg[0] * d.Dg[1]);
+  for (int a = 0; a < 3; ++a) {           // mpi_cart_shift of mpi_initialization.f90:73-76 (periodic)
+    int cm[3] = {d.coord[0], d.coord[1], d.coord[2]}, cp[3] = {d.coord[0], d.coord[1], d.coord[2]};
+    cm[a] = (cm[a] - 1 + d.Dg[a]) % d.Dg[a]; cp[a] = (cp[a] + 1) % d.Dg[a];
+    d.nbr[2 * a] = cm[0] + d.Dg[0] * (cm[1] + d.Dg[1] * cm[2]);
+    d.nbr[2 * a + 1] = cp[0] + d.Dg[0] * (cp[1] + d.Dg[1] * cp[2]);
+    d.Nc[a] = d.nc_node * d.Dg[a];
+  }
+  // the reference's slab decomposition needs mod(nc_dim, nodes) == 0 (mpi_initialization.f90:25-29); the replicated coarse
+  // solve used here does not, but nc_slab is kept for the kern_c getter when the grid is the reference's cubic one
+  d.nc_slab = (!custom_grid && d.nc_dim % d.nodes == 0) ? d.nc_dim / d.nodes : 0;
   d.hoc_l = 1 - d.nc_buf; d.hoc_h = d.nc_node + d.nc_buf; d.H = d.hoc_h - d.hoc_l + 1;   // cubepm.par:204-205
   d.tiles_node = d.T * d.T * d.T;
   if (c.max_np > 0) d.max_np = c.max_np;
@@ -37,10 +50,11 @@ int derive(const cubep3m_b200_config& c, Dims& d) {
   d.fdim = d.m + 3;
   d.NF = (long long)d.H * d.H * d.H * 64;
   if (d.NF >= (1LL << 31)) return CUBEP3M_B200_EINVAL;
-  if (!fftk::supported(d.n) || !fftk::supported(d.nc_dim)) return CUBEP3M_B200_EINVAL;
+  if (!fftk::supported(d.n)) return CUBEP3M_B200_EINVAL;
+  for (int a = 0; a < 3; ++a) if (!fftk::supported(d.Nc[a])) return CUBEP3M_B200_EINVAL;
   if (c.pp_range < 0 || c.pp_range > 2) return CUBEP3M_B200_EINVAL;
   // LRCKCORR divides by Im(kernel) for |k| <= 8 (kernel_initialization.f90:573-581): Nyquist must lie beyond
-  if (c.lrckcorr && d.nc_dim / 2 <= 8) return CUBEP3M_B200_EINVAL;
+  for (int a = 0; a < 3; ++a) if (c.lrckcorr && d.Nc[a] / 2 <= 8) return CUBEP3M_B200_EINVAL;
   return 0;
 }
 
@@ -70,6 +84,9 @@ int download_interleaved(float* host, const float* dev, size_t plane, size_t off
   }
   return 0;
 }
+
+fftk::Mesh3 fine_mesh(const cubep3m_b200_ctx* ctx) { return fftk::Mesh3{ctx->d.n, ctx->d.n, ctx->d.n, ctx->tw_f, ctx->tw_f, ctx->tw_f}; }
+fftk::Mesh3 coarse_mesh3(const cubep3m_b200_ctx* ctx) { return fftk::Mesh3{ctx->d.Nc[0], ctx->d.Nc[1], ctx->d.Nc[2], ctx->tw_c[0], ctx->tw_c[1], ctx->tw_c[2]}; }
 
 int grid_for(long long n, int tpb, int cap = NUM_SMS * 16) {
   long long g = (n + tpb - 1) / tpb;
@@ -106,7 +123,7 @@ int build_kern_f(cubep3m_b200_ctx* ctx) {
       for (int j = 1; j <= n; ++j)
         for (int i = 1; i <= n; ++i) R(i, j, n - k + 2) = sz * R(i, j, k);
     CK(cudaMemcpyAsync(ctx->tile_rho, rho.data(), rho.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    if (int st = fftk::forward3d(ctx, n, ctx->tile_rho, ctx->tw_f)) return st;   // :89
+    if (int st = fftk::forward3d(ctx, fine_mesh(ctx), ctx->tile_rho)) return st;   // :89
     const long long ns = (long long)d.hc * n * n;
     LAUNCH(ctx, KC_MISC, extract_imag_kernel, grid_for(ns, 256), 256, 0, reinterpret_cast<const float2*>(ctx->tile_rho), ns, ctx->kern_f, comp);   // :93-99
     CK(cudaStreamSynchronize(ctx->stream));
@@ -114,23 +131,25 @@ int build_kern_f(cubep3m_b200_ctx* ctx) {
   return 0;
 }
 
-// ---- kernel_initialization.f90:272-732 coarse_kernel (global mesh; every rank builds the same table and uses its z-slab)
+// ---- kernel_initialization.f90:272-732 coarse_kernel on the global mesh (Nx,Ny,Nz); every rank builds the same table.
+// For the reference's cubic grids Nx = Ny = Nz = nc_dim and this is line-for-line the reference's construction.
 int build_kern_c(cubep3m_b200_ctx* ctx) {
   const Dims& d = ctx->d;
   const cubep3m_b200_config& c = ctx->cfg;
-  const int N = d.nc_dim, N2 = N + 2, hc = N / 2 + 1;
+  const int Nx = d.Nc[0], Ny = d.Nc[1], Nz = d.Nc[2], N2 = Nx + 2, hc = Nx / 2 + 1;
   const float pi = 3.141592654f;
-  std::vector<float> ck((size_t)3 * N * N * N), ckc;
+  const size_t ncell = (size_t)Nx * Ny * Nz;
+  std::vector<float> ck(3 * ncell), ckc;
   auto CKA = [&](std::vector<float>& a, int comp, int i, int j, int k) -> float& {
-    return a[(size_t)comp + 3 * ((size_t)(i - 1) + (size_t)N * ((j - 1) + (size_t)N * (k - 1)))];
+    return a[(size_t)comp + 3 * ((size_t)(i - 1) + (size_t)Nx * ((j - 1) + (size_t)Ny * (k - 1)))];
   };
   auto fill_plain = [&](std::vector<float>& a) {       // :302-336
-    for (int k = 1; k <= N; ++k) {
-      float z = (k < N / 2 + 2) ? (float)(k - 1) : (float)(k - 1 - N); z = d.s * z;
-      for (int j = 1; j <= N; ++j) {
-        float y = (j < N / 2 + 2) ? (float)(j - 1) : (float)(j - 1 - N); y = d.s * y;
-        for (int i = 1; i <= N; ++i) {
-          float x = (i < N / 2 + 2) ? (float)(i - 1) : (float)(i - 1 - N); x = d.s * x;
+    for (int k = 1; k <= Nz; ++k) {
+      float z = (k < Nz / 2 + 2) ? (float)(k - 1) : (float)(k - 1 - Nz); z = d.s * z;
+      for (int j = 1; j <= Ny; ++j) {
+        float y = (j < Ny / 2 + 2) ? (float)(j - 1) : (float)(j - 1 - Ny); y = d.s * y;
+        for (int i = 1; i <= Nx; ++i) {
+          float x = (i < Nx / 2 + 2) ? (float)(i - 1) : (float)(i - 1 - Nx); x = d.s * x;
           const float r = sqrtf(x * x + y * y + z * z);
           if (r == 0.0f) { CKA(a, 0, i, j, k) = 0.f; CKA(a, 1, i, j, k) = 0.f; CKA(a, 2, i, j, k) = 0.f; }
           else { const float r3 = r * r * r; CKA(a, 0, i, j, k) = -x / r3; CKA(a, 1, i, j, k) = -y / r3; CKA(a, 2, i, j, k) = -z / r3; }
@@ -142,26 +161,26 @@ int build_kern_c(cubep3m_b200_ctx* ctx) {
   for (int oz = -3; oz <= 3; ++oz)                     // :344-457 near-field table in all octants
     for (int oy = -3; oy <= 3; ++oy)
       for (int ox = -3; ox <= 3; ++ox) {
-        const int i = ox >= 0 ? ox + 1 : N + ox + 1, j = oy >= 0 ? oy + 1 : N + oy + 1, k = oz >= 0 ? oz + 1 : N + oz + 1;
-        if (i < 1 || j < 1 || k < 1 || i > N || j > N || k > N) continue;
+        const int i = ox >= 0 ? ox + 1 : Nx + ox + 1, j = oy >= 0 ? oy + 1 : Ny + oy + 1, k = oz >= 0 ? oz + 1 : Nz + oz + 1;
+        if (i < 1 || j < 1 || k < 1 || i > Nx || j > Ny || k > Nz) continue;
         const int o[3] = {ox, oy, oz};
         for (int comp = 0; comp < 3; ++comp) {
           const float v = ctx->coarse_table[(((size_t)abs(oz) * 4 + abs(oy)) * 4 + abs(ox)) * 3 + comp];
           CKA(ck, comp, i, j, k) = (o[comp] < 0) ? -v : v;
         }
       }
-  std::vector<float> slab((size_t)N2 * N * N), tmp;
-  std::vector<float> kc((size_t)3 * hc * N * N);   // [comp][z][y][kx]
-  const size_t ncs = (size_t)hc * N * N;
+  std::vector<float> slab((size_t)N2 * Ny * Nz), tmp;
+  const size_t ncs = (size_t)hc * Ny * Nz;
+  std::vector<float> kc(3 * ncs);   // [comp][z][y][kx]
   auto transform = [&](std::vector<float>& a, int comp) -> int {
-    for (int k = 1; k <= N; ++k)
-      for (int j = 1; j <= N; ++j) {
-        float* row = &slab[(size_t)N2 * ((j - 1) + (size_t)N * (k - 1))];
-        for (int i = 1; i <= N; ++i) row[i - 1] = CKA(a, comp, i, j, k);
-        row[N] = row[N + 1] = 0.f;
+    for (int k = 1; k <= Nz; ++k)
+      for (int j = 1; j <= Ny; ++j) {
+        float* row = &slab[(size_t)N2 * ((j - 1) + (size_t)Ny * (k - 1))];
+        for (int i = 1; i <= Nx; ++i) row[i - 1] = CKA(a, comp, i, j, k);
+        row[Nx] = row[Nx + 1] = 0.f;
       }
     CK(cudaMemcpyAsync(ctx->slab, slab.data(), slab.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    if (int st = fftk::forward3d(ctx, N, ctx->slab, ctx->tw_c)) return st;
+    if (int st = fftk::forward3d(ctx, coarse_mesh3(ctx), ctx->slab)) return st;
     CK(cudaMemcpyAsync(slab.data(), ctx->slab, slab.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -175,19 +194,19 @@ int build_kern_c(cubep3m_b200_ctx* ctx) {
       if (int st = transform(ck, comp)) return st;     // :519-551
       tmp = slab;
       if (int st = transform(ckc, comp)) return st;
-      for (int k = 1; k <= N; ++k) {                   // :558-591 / :602-635 / :646-679
-        const int kz = (k < N / 2 + 2) ? k - 1 : k - 1 - N;
-        for (int j = 1; j <= N; ++j) {
-          const int ky = (j < N / 2 + 2) ? j - 1 : j - 1 - N;
-          for (int i = 1; i <= N + 2; i += 2) {
+      for (int k = 1; k <= Nz; ++k) {                  // :558-591 / :602-635 / :646-679
+        const int kz = (k < Nz / 2 + 2) ? k - 1 : k - 1 - Nz;
+        for (int j = 1; j <= Ny; ++j) {
+          const int ky = (j < Ny / 2 + 2) ? j - 1 : j - 1 - Ny;
+          for (int i = 1; i <= Nx + 2; i += 2) {
             const int kx = (i - 1) / 2;
             const float kr = sqrtf((float)(kx * kx + ky * ky + kz * kz));
             if (kr <= 8.f) {
-              const float ka = 2 * sinf(pi * kx / (float)N), kb = 2 * sinf(pi * ky / (float)N), kcc = 2 * sinf(pi * kz / (float)N);
+              const float ka = 2 * sinf(pi * kx / (float)Nx), kb = 2 * sinf(pi * ky / (float)Ny), kcc = 2 * sinf(pi * kz / (float)Nz);
               const int kd = comp == 0 ? kx : (comp == 1 ? ky : kz);
               const float kk = comp == 0 ? ka : (comp == 1 ? kb : kcc);
               if (kd != 0) {
-                const size_t o = (size_t)i + (size_t)N2 * ((j - 1) + (size_t)N * (k - 1));
+                const size_t o = (size_t)i + (size_t)N2 * ((j - 1) + (size_t)Ny * (k - 1));
                 const float wa = slab[o], wb = tmp[o];
                 const float wc = 4.f * pi * kk / (ka * ka + kb * kb + kcc * kcc) / 16.f;
                 slab[o] = wa * (wc / wb);
@@ -199,15 +218,26 @@ int build_kern_c(cubep3m_b200_ctx* ctx) {
     } else {
       if (int st = transform(ck, comp)) return st;     // :695-723
     }
-    for (int k = 1; k <= N; ++k)                       // :593-599
-      for (int j = 1; j <= N; ++j)
+    for (int k = 1; k <= Nz; ++k)                      // :593-599
+      for (int j = 1; j <= Ny; ++j)
         for (int i = 1; i <= hc; ++i)
-          kc[(size_t)comp * ncs + ((size_t)(i - 1) + (size_t)hc * ((j - 1) + (size_t)N * (k - 1)))] =
-              slab[(size_t)(2 * i - 1) + (size_t)N2 * ((j - 1) + (size_t)N * (k - 1))];
+          kc[(size_t)comp * ncs + ((size_t)(i - 1) + (size_t)hc * ((j - 1) + (size_t)Ny * (k - 1)))] =
+              slab[(size_t)(2 * i - 1) + (size_t)N2 * ((j - 1) + (size_t)Ny * (k - 1))];
   }
   CK(cudaMemcpy(ctx->kern_c, kc.data(), kc.size() * sizeof(float), cudaMemcpyHostToDevice));
   return 0;
 }
+
+#ifdef CUBEP3M_WITH_NCCL
+#define NCK(call)                                                                                   \
+  do {                                                                                              \
+    ncclResult_t r__ = (call);                                                                      \
+    if (r__ != ncclSuccess) {                                                                       \
+      fprintf(stderr, "cubep3m_b200: NCCL error %s at %s:%d\n", ncclGetErrorString(r__), __FILE__, __LINE__); \
+      return CUBEP3M_B200_ENCCL;                                                                    \
+    }                                                                                               \
+  } while (0)
+#endif
 
 int fetch_counters(cubep3m_b200_ctx* ctx) {
   CK(cudaMemcpyAsync(ctx->hcnt, ctx->dcnt, sizeof(DevCounters), cudaMemcpyDeviceToHost, ctx->stream));
@@ -272,15 +302,72 @@ int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max) {
 }
 
 int exchange_axis(cubep3m_b200_ctx* ctx, int axis, int n_plus_out, int n_minus_out, int* r_plus, int* r_minus) {
-  if (ctx->d.D == 1) {
+  const Dims& d = ctx->d;
+  if (d.Dg[axis] == 1) {
     // the + and - neighbours are this rank: what was sent in + direction is received "from the - neighbour"
     ctx->recvbuf[0] = ctx->sendbuf[0]; ctx->recvbuf[1] = ctx->sendbuf[1];
     ctx->recvpid[0] = ctx->sendpid[0]; ctx->recvpid[1] = ctx->sendpid[1];
     *r_plus = n_plus_out; *r_minus = n_minus_out;
     return 0;
   }
-  (void)axis;
-  return CUBEP3M_B200_EINVAL;   // multi-rank exchange: see nccl section (not built in this configuration)
+#ifdef CUBEP3M_WITH_NCCL
+  // particle_pass.f90:125,141-144 (+ pass) and :217,233-236 (- pass): count exchange, then the particle payloads.
+  // With Dg == 2 both neighbours are the same peer; NCCL matches sends and receives to one peer in issue order, and both sides
+  // issue [plus-going, minus-going] / [from-minus, from-plus], which pairs plus-going with from-minus as required.
+  const int minus = d.nbr[2 * axis], plus = d.nbr[2 * axis + 1];
+  NCK(ncclGroupStart());
+  NCK(ncclSend(&ctx->dcnt->n_send[0], 1, ncclInt32, plus, ctx->comm, ctx->stream));
+  NCK(ncclSend(&ctx->dcnt->n_send[1], 1, ncclInt32, minus, ctx->comm, ctx->stream));
+  NCK(ncclRecv(&ctx->cntbuf[0], 1, ncclInt32, minus, ctx->comm, ctx->stream));
+  NCK(ncclRecv(&ctx->cntbuf[1], 1, ncclInt32, plus, ctx->comm, ctx->stream));
+  NCK(ncclGroupEnd());
+  int hc[2];
+  CK(cudaMemcpyAsync(hc, ctx->cntbuf, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *r_plus = hc[0]; *r_minus = hc[1];
+  if ((long long)hc[0] * 6 > d.max_buf || (long long)hc[1] * 6 > d.max_buf) return CUBEP3M_B200_EPASSBUF;
+  ctx->recvbuf[0] = ctx->recvbuf_own[0]; ctx->recvbuf[1] = ctx->recvbuf_own[1];
+  ctx->recvpid[0] = ctx->recvpid_own[0]; ctx->recvpid[1] = ctx->recvpid_own[1];
+  NCK(ncclGroupStart());
+  if (n_plus_out > 0) NCK(ncclSend(ctx->sendbuf[0], (size_t)6 * n_plus_out, ncclFloat, plus, ctx->comm, ctx->stream));
+  if (n_minus_out > 0) NCK(ncclSend(ctx->sendbuf[1], (size_t)6 * n_minus_out, ncclFloat, minus, ctx->comm, ctx->stream));
+  if (hc[0] > 0) NCK(ncclRecv(ctx->recvbuf[0], (size_t)6 * hc[0], ncclFloat, minus, ctx->comm, ctx->stream));
+  if (hc[1] > 0) NCK(ncclRecv(ctx->recvbuf[1], (size_t)6 * hc[1], ncclFloat, plus, ctx->comm, ctx->stream));
+  if (ctx->cfg.pid) {                                   // particle_pass.f90:150-153
+    if (n_plus_out > 0) NCK(ncclSend(ctx->sendpid[0], (size_t)n_plus_out, ncclInt64, plus, ctx->comm, ctx->stream));
+    if (n_minus_out > 0) NCK(ncclSend(ctx->sendpid[1], (size_t)n_minus_out, ncclInt64, minus, ctx->comm, ctx->stream));
+    if (hc[0] > 0) NCK(ncclRecv(ctx->recvpid[0], (size_t)hc[0], ncclInt64, minus, ctx->comm, ctx->stream));
+    if (hc[1] > 0) NCK(ncclRecv(ctx->recvpid[1], (size_t)hc[1], ncclInt64, plus, ctx->comm, ctx->stream));
+  }
+  NCK(ncclGroupEnd());
+  return 0;
+#else
+  (void)n_plus_out; (void)n_minus_out; (void)r_plus; (void)r_minus;
+  return CUBEP3M_B200_ENCCL;
+#endif
+}
+
+// cross-rank reductions of the limiters and DIAG sums (the mpi_reduce/mpi_bcast pairs of particle_mesh_threaded.f90:646-703,
+// coarse_max_dt.f90:34-37, delete_particles.f90:63)
+int reduce_scalars(cubep3m_b200_ctx* ctx, float* maxv, int nmax, double* sumv, int nsum) {
+  if (ctx->d.world == 1) return 0;
+#ifdef CUBEP3M_WITH_NCCL
+  float* dmax = ctx->redbuf;
+  double* dsum = reinterpret_cast<double*>(ctx->redbuf + 16);
+  CK(cudaMemcpyAsync(dmax, maxv, nmax * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dsum, sumv, nsum * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  NCK(ncclGroupStart());
+  NCK(ncclAllReduce(dmax, dmax, nmax, ncclFloat, ncclMax, ctx->comm, ctx->stream));
+  NCK(ncclAllReduce(dsum, dsum, nsum, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+  NCK(ncclGroupEnd());
+  CK(cudaMemcpyAsync(maxv, dmax, nmax * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(sumv, dsum, nsum * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+#else
+  (void)maxv; (void)nmax; (void)sumv; (void)nsum;
+  return CUBEP3M_B200_ENCCL;
+#endif
 }
 
 // cell sort of xv[cur][0:np_all) -> xv[cur^1], builds fstart and the PP work lists
@@ -342,10 +429,11 @@ int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, int* tile_cou
   if (ctx->hcnt->n_cand > 0)
     LAUNCH(ctx, KC_DENSITY, fine::ngp_fixup_kernel, std::min(NUM_SMS, (std::min(ctx->hcnt->n_cand, ctx->cand_cap) + fine::TPB - 1) / fine::TPB), fine::TPB, 0,
            ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, ctx->tile_rho, n, d.b, d.m, tx, ty, tz, mass_p, &ctx->dcnt->sum_rho_f);
-  if (int st = fftk::forward3d(ctx, n, ctx->tile_rho, ctx->tw_f)) return st;
+  if (int st = fftk::forward3d(ctx, fine_mesh(ctx), ctx->tile_rho)) return st;
   const float scale = 1.0f / (((float)n * (float)n) * (float)n);       // fft_fine.f90:51
+  const int lo[3] = {d.b - 2, d.b - 2, d.b - 2}, cnt[3] = {d.fdim, d.fdim, d.fdim};
   for (int comp = 0; comp < 3; ++comp)
-    if (int st = fftk::backward3d(ctx, n, ctx->tile_rho, ctx->tile_g, ctx->kern_f + (size_t)comp * d.hc * n * n, ctx->force_f[comp], d.b - 2, d.fdim, d.fdim, d.fdim, scale, ctx->tw_f))
+    if (int st = fftk::backward3d(ctx, fine_mesh(ctx), ctx->tile_rho, ctx->tile_g, ctx->kern_f + (size_t)comp * d.hc * n * n, ctx->force_f[comp], lo, cnt, d.fdim, d.fdim, scale))
       return st;
   return 0;
 }
@@ -409,25 +497,41 @@ int do_coarse_mass(cubep3m_b200_ctx* ctx, float mass_p) {
   return 0;
 }
 int do_coarse_force(cubep3m_b200_ctx* ctx) {
+  // coarse_force.f90:18-90 with the cube<->slab repack + distributed FFT of fft_coarse.f90 replaced by: all-gather the ranks' rho_c
+  // cubes over NVLink, solve the WHOLE (Nx,Ny,Nz) coarse mesh on every GPU (<= 0.5 GB even for 8 x 512^3 particles), and gather
+  // this rank's cube plus its one-cell halo from the periodic result (which is what coarse_force_buffer.f90:23-63 exchanges).
   const Dims& d = ctx->d;
-  if (d.D != 1) return CUBEP3M_B200_EINVAL;
-  const int N = d.nc_dim;
-  const long long nrc = (long long)d.nc_node * d.nc_node * d.nc_node;
-  LAUNCH(ctx, KC_COARSE_MISC, coarse::cube_to_slab_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->rho_c, ctx->slab, d.nc_node, N, 0, 0, 0, &ctx->dcnt->sum_rho_c);
+  const int Nx = d.Nc[0], Ny = d.Nc[1], Nz = d.Nc[2], nc = d.nc_node;
+  const long long nrc = (long long)nc * nc * nc;
+  const float* cubes = ctx->rho_c;
+  if (d.world > 1) {
+#ifdef CUBEP3M_WITH_NCCL
+    NCK(ncclAllGather(ctx->rho_c, ctx->gather, (size_t)nrc, ncclFloat, ctx->comm, ctx->stream));
+    cubes = ctx->gather;
+#else
+    return CUBEP3M_B200_ENCCL;
+#endif
+  }
+  for (int r = 0; r < d.world; ++r) {
+    const int rx = r % d.Dg[0], ry = (r / d.Dg[0]) % d.Dg[1], rz = r / (d.Dg[0] * d.Dg[1]);
+    const float* cube = (d.world > 1) ? cubes + (size_t)r * nrc : cubes;
+    LAUNCH(ctx, KC_COARSE_MISC, coarse::cube_to_slab_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, cube, ctx->slab, nc, Nx, Ny, rx * nc, ry * nc,
+           rz * nc, (r == ctx->cfg.rank) ? &ctx->dcnt->sum_rho_c : nullptr);
+  }
   ctx->fft_class_base = KC_COARSE_FFT;
-  if (int st = fftk::forward3d(ctx, N, ctx->slab, ctx->tw_c)) return st;          // coarse_force.f90:18
-  const float scale = 1.0f / (((float)N * (float)N) * (float)N);                    // fft_coarse.f90:186
-  const size_t nfc = (size_t)3 * (d.nc_node + 2) * (d.nc_node + 2) * (d.nc_node + 2);
-  CK(cudaMemsetAsync(ctx->force_c, 0, nfc * sizeof(float), ctx->stream));
+  const fftk::Mesh3 g = coarse_mesh3(ctx);
+  if (int st = fftk::forward3d(ctx, g, ctx->slab)) return st;                     // coarse_force.f90:18
+  const float scale = 1.0f / (((float)Nx * (float)Ny) * (float)Nz);                 // fft_coarse.f90:186
+  const int lo[3] = {0, 0, 0}, cnt[3] = {Nx, Ny, Nz};
+  const size_t ncs = (size_t)(Nx / 2 + 1) * Ny * Nz;
+  const long long nfc = (long long)(nc + 2) * (nc + 2) * (nc + 2);
   for (int comp = 0; comp < 3; ++comp) {                                            // coarse_force.f90:37-90
-    // real-space result goes to rho_c (as in the reference: force_c(comp,...) = rho_c)
-    if (int st = fftk::backward3d(ctx, N, ctx->slab, ctx->slab_g, ctx->kern_c + (size_t)comp * (N / 2 + 1) * N * N, ctx->rho_c, 0, N, N, N, scale, ctx->tw_c)) return st;
-    LAUNCH(ctx, KC_COARSE_MISC, coarse::slab_to_force_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->rho_c, (long long)N, (long long)N, d.nc_node, 0, 0, 0, ctx->force_c, comp);
+    if (int st = fftk::backward3d(ctx, g, ctx->slab, ctx->slab_g, ctx->kern_c + (size_t)comp * ncs, ctx->creal, lo, cnt, Nx, Ny, scale)) return st;
+    LAUNCH(ctx, KC_COARSE_MISC, coarse::extract_force_kernel, grid_for(nfc, coarse::TPB), coarse::TPB, 0, ctx->creal, Nx, Ny, Nz, nc, d.coord[0], d.coord[1],
+           d.coord[2], ctx->force_c, comp);
   }
   ctx->fft_class_base = 0;
-  for (int axis = 0; axis < 3; ++axis)                                              // coarse_force_buffer.f90:23-63
-    LAUNCH(ctx, KC_COARSE_MISC, coarse::halo_self_kernel, grid_for((long long)3 * (d.nc_node + 2) * (d.nc_node + 2), coarse::TPB), coarse::TPB, 0, ctx->force_c, d.nc_node, axis);
-  LAUNCH(ctx, KC_COARSE_MISC, coarse::force_max_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->force_c, d.nc_node, &ctx->dcnt->c_force_max_bits);
+  LAUNCH(ctx, KC_COARSE_MISC, coarse::force_max_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->force_c, nc, &ctx->dcnt->c_force_max_bits);
   CK(cudaGetLastError());
   return 0;
 }
@@ -473,6 +577,7 @@ void cubep3m_b200_default_config(cubep3m_b200_config* c) {
   c->ngp = 1; c->ppint = 1; c->pp_ext = 0; c->coarse_ngp = 0; c->pid = 0; c->lrckcorr = 1; c->move_grid_back = 0;
   c->ngp_fmesh_force = c->pp_force_flag = c->pp_ext_force_flag = c->coarse_vel_update = 1;
   c->rank = 0; c->local_gpu = 0; c->tile_split = 1; c->tile_split_rank = 0;
+  c->nodes_dim_xyz[0] = c->nodes_dim_xyz[1] = c->nodes_dim_xyz[2] = 0;
 }
 
 int cubep3m_b200_get_unique_id(void* id128) {
@@ -492,10 +597,14 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   auto F = [](void* p) { if (p) cudaFree(p); };
-  for (int i = 0; i < 2; ++i) { F(ctx->xv[i]); F(ctx->pid[i]); F(ctx->sendbuf[i]); F(ctx->sendpid[i]); }
+  for (int i = 0; i < 2; ++i) { F(ctx->xv[i]); F(ctx->pid[i]); F(ctx->sendbuf[i]); F(ctx->sendpid[i]); F(ctx->recvbuf_own[i]); F(ctx->recvpid_own[i]); }
+#ifdef CUBEP3M_WITH_NCCL
+  if (ctx->comm) ncclCommDestroy(ctx->comm);
+#endif
   F(ctx->cand); F(ctx->key); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
   F(ctx->kern_f); F(ctx->tile_rho); F(ctx->tile_g); for (int i = 0; i < 3; ++i) F(ctx->force_f[i]);
-  F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->force_c); F(ctx->tw_c); F(ctx->dcnt);
+  F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->creal); F(ctx->gather); F(ctx->force_c); F(ctx->redbuf); F(ctx->cntbuf); F(ctx->dcnt);
+  for (int a = 0; a < 3; ++a) { bool dup = false; for (int b2 = 0; b2 < a; ++b2) dup |= (ctx->tw_c[b2] == ctx->tw_c[a]); if (!dup) F(ctx->tw_c[a]); }
   if (ctx->hcnt) cudaFreeHost(ctx->hcnt);
   if (ctx->ev_ok) for (auto& e : ctx->ev) cudaEventDestroy(e);
   for (auto& e : ctx->prof_ev) cudaEventDestroy(e);
@@ -510,8 +619,8 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   Dims d;
   if (int st = derive(*cfg, d)) return st;
   if (!cfg->ngp) return CUBEP3M_B200_EINVAL;          // fine CIC (non -DNGP builds) is not built yet
-  if (d.D != 1) return CUBEP3M_B200_EINVAL;           // multi-rank exchange not built in this configuration
-  (void)nccl_unique_id;
+  if (d.world > 1 && (!nccl_unique_id || world_size != d.world)) return CUBEP3M_B200_EINVAL;
+  if (cfg->tile_split > 1) return CUBEP3M_B200_EINVAL;   // superseded by nodes_dim_xyz (block split of a non-cubic box)
   if ((!kern_f || !kern_c) && (!fine_table || !coarse_table)) return CUBEP3M_B200_EINVAL;
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
@@ -551,22 +660,45 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   for (int i = 0; i < 3; ++i) TRY(dmalloc(&ctx->force_f[i], (size_t)d.fdim * d.fdim * d.fdim));
   TRY(dmalloc(&ctx->kern_f, (size_t)3 * d.hc * d.n * d.n));
   TRY(fftk::make_twiddles(d.n, &ctx->tw_f));
-  const int N = d.nc_dim;
-  TRY(dmalloc(&ctx->kern_c, (size_t)3 * (N / 2 + 1) * N * N));
-  TRY(dmalloc(&ctx->rho_c, std::max((size_t)d.nc_node * d.nc_node * d.nc_node, (size_t)N * N * N)));
-  TRY(dmalloc(&ctx->slab, (size_t)(N + 2) * N * N));
-  TRY(dmalloc(&ctx->slab_g, (size_t)(N + 2) * N * N));
+  const int Nx = d.Nc[0], Ny = d.Nc[1], Nz = d.Nc[2];
+  const size_t ncs = (size_t)(Nx / 2 + 1) * Ny * Nz;
+  const size_t nrc = (size_t)d.nc_node * d.nc_node * d.nc_node;
+  TRY(dmalloc(&ctx->kern_c, 3 * ncs));
+  TRY(dmalloc(&ctx->rho_c, nrc));
+  TRY(dmalloc(&ctx->slab, (size_t)(Nx + 2) * Ny * Nz));
+  TRY(dmalloc(&ctx->slab_g, (size_t)(Nx + 2) * Ny * Nz));
+  TRY(dmalloc(&ctx->creal, (size_t)(Nx + 2) * Ny * Nz));
   TRY(dmalloc(&ctx->force_c, (size_t)3 * (d.nc_node + 2) * (d.nc_node + 2) * (d.nc_node + 2)));
-  TRY(fftk::make_twiddles(N, &ctx->tw_c));
+  for (int a = 0; a < 3; ++a) {
+    for (int b2 = 0; b2 < a; ++b2) if (d.Nc[b2] == d.Nc[a]) ctx->tw_c[a] = ctx->tw_c[b2];
+    if (!ctx->tw_c[a]) TRY(fftk::make_twiddles(d.Nc[a], &ctx->tw_c[a]));
+  }
+  TRY(dmalloc(&ctx->redbuf, (size_t)64));
+  TRY(dmalloc(&ctx->cntbuf, (size_t)8));
+  if (d.world > 1) {
+#ifdef CUBEP3M_WITH_NCCL
+    TRY(dmalloc(&ctx->gather, nrc * d.world));
+    for (int i = 0; i < 2; ++i) {
+      TRY(dmalloc(&ctx->recvbuf_own[i], (size_t)d.max_buf));
+      if (cfg->pid) TRY(dmalloc(&ctx->recvpid_own[i], (size_t)d.max_buf / 6 + 1));
+    }
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id, sizeof(id));
+    if (ncclCommInitRank(&ctx->comm, d.world, id, cfg->rank) != ncclSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ENCCL; }
+#else
+    cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ENCCL;
+#endif
+  }
   TRY(dmalloc(&ctx->dcnt, 1));
   if (cudaMemset(ctx->dcnt, 0, sizeof(DevCounters)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   if (cudaMallocHost((void**)&ctx->hcnt, sizeof(DevCounters)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   memset(ctx->hcnt, 0, sizeof(DevCounters));
   if (kern_f) TRY(upload_interleaved(ctx->kern_f, kern_f, (size_t)d.hc * d.n * d.n, 0, (size_t)d.hc * d.n * d.n));
   else TRY(build_kern_f(ctx));
-  // a host kern_c is this rank's slab kern_c(3,hc,nc_dim,nc_slab): only valid as the whole mesh when nodes_dim == 1
-  if (kern_c) TRY(upload_interleaved(ctx->kern_c, kern_c, (size_t)(N / 2 + 1) * N * N, 0, (size_t)(N / 2 + 1) * N * d.nc_slab));
-  else TRY(build_kern_c(ctx));
+  // a host kern_c is this rank's slab kern_c(3,hc,nc_dim,nc_slab) (cubep3m.fh:56): it is the whole mesh only when there is one rank;
+  // with more ranks the library rebuilds the global table itself (every rank needs all of it for the replicated solve)
+  if (kern_c && d.world == 1) TRY(upload_interleaved(ctx->kern_c, kern_c, ncs, 0, ncs));
+  else { if (!coarse_table) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_EINVAL; } TRY(build_kern_c(ctx)); }
 #undef TRY
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   *out = ctx;
@@ -685,16 +817,20 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   const float G = c.G;
   auto asf = [](unsigned int u) { float f; memcpy(&f, &u, 4); return f; };
   const float f2 = asf(hc.f_force_max2_bits), ppm = asf(hc.pp_force_max_bits), ppe = asf(hc.pp_ext_force_max_bits), cm = asf(hc.c_force_max_bits);
-  out->f_force_max = sqrtf(f2);
+  float mx[5] = {sqrtf(f2), ppm, ppe, cm, (float)bufmax};
+  double sm[4] = {hc.sum_rho_f, hc.sum_rho_c, (double)ctx->np_local, (double)ndel};
+  if (int st = reduce_scalars(ctx, mx, 5, sm, 4)) return st;
+  out->f_force_max = mx[0];
   out->dt_f_acc = 1.0f / sqrtf(std::max(0.0001f, out->f_force_max) * a_mid * G);
-  out->pp_force_max = ppm;
-  out->dt_pp_acc = c.ppint ? sqrtf(c.dt_pp_scale * c.rsoft) / std::max(sqrtf(ppm * a_mid * G), 1e-3f) : 1000.f;
-  out->pp_ext_force_max = ppe;
-  out->dt_pp_ext_acc = c.pp_ext ? sqrtf(c.dt_pp_scale * c.rsoft) / std::max(sqrtf(ppe * a_mid * G), 1e-3f) : 1000.f;
-  out->c_force_max = cm;
-  out->dt_c_acc = sqrtf((float)d.s / (cm * a_mid * G));
-  out->sum_rho_f = hc.sum_rho_f; out->sum_rho_c = hc.sum_rho_c;
-  out->np_local = ctx->np_local; out->np_total = ctx->np_local; out->np_with_ghosts = np_ghost; out->np_deleted_ll = ndel; out->np_buf_max = bufmax;
+  out->pp_force_max = mx[1];
+  out->dt_pp_acc = c.ppint ? sqrtf(c.dt_pp_scale * c.rsoft) / std::max(sqrtf(mx[1] * a_mid * G), 1e-3f) : 1000.f;
+  out->pp_ext_force_max = mx[2];
+  out->dt_pp_ext_acc = c.pp_ext ? sqrtf(c.dt_pp_scale * c.rsoft) / std::max(sqrtf(mx[2] * a_mid * G), 1e-3f) : 1000.f;
+  out->c_force_max = mx[3];
+  out->dt_c_acc = sqrtf((float)d.s / (mx[3] * a_mid * G));
+  out->sum_rho_f = sm[0]; out->sum_rho_c = sm[1];
+  out->np_local = ctx->np_local; out->np_total = (int64_t)(sm[2] + 0.5); out->np_with_ghosts = np_ghost; out->np_deleted_ll = (int)(sm[3] + 0.5);
+  out->np_buf_max = (int)mx[4];
   out->stage_ms[CUBEP3M_B200_ST_DRIFT] = ev_ms(ev[0], ev[1]);
   out->stage_ms[CUBEP3M_B200_ST_PASS] = ev_ms(ev[1], ev[2]);
   out->stage_ms[CUBEP3M_B200_ST_LINK] = ev_ms(ev[2], ev[3]);
@@ -771,9 +907,11 @@ int cubep3m_b200_debug_kern_f(cubep3m_b200_ctx* ctx, float* kern_f) {
 int cubep3m_b200_debug_kern_c(cubep3m_b200_ctx* ctx, float* kern_c) {
   if (!ctx) return CUBEP3M_B200_EINVAL;
   CK(cudaSetDevice(ctx->device));
-  const int N = ctx->d.nc_dim;
-  const size_t plane = (size_t)(N / 2 + 1) * N * N, per = (size_t)(N / 2 + 1) * N * ctx->d.nc_slab;
-  return download_interleaved(kern_c, ctx->kern_c, plane, per * ctx->cfg.rank, per);
+  // reference layout kern_c(3,hc,nc_dim,nc_slab): this rank's z-slab for the reference's cubic grids, else the whole table
+  const Dims& d = ctx->d;
+  const size_t plane = (size_t)(d.Nc[0] / 2 + 1) * d.Nc[1] * d.Nc[2];
+  if (d.nc_slab > 0) { const size_t per = (size_t)(d.Nc[0] / 2 + 1) * d.Nc[1] * d.nc_slab; return download_interleaved(kern_c, ctx->kern_c, plane, per * ctx->cfg.rank, per); }
+  return download_interleaved(kern_c, ctx->kern_c, plane, 0, plane);
 }
 int cubep3m_b200_debug_rho_c(cubep3m_b200_ctx* ctx, float* rho_c) {
   // note: after a full step rho_c holds the last force component (as in the reference, coarse_force.f90:88);
@@ -821,17 +959,19 @@ int cubep3m_b200_debug_fine_tile(cubep3m_b200_ctx* ctx, int32_t tile, float mass
 int cubep3m_b200_debug_fft3d(cubep3m_b200_ctx* ctx, int32_t n, float* data, int32_t inverse) {
   if (!ctx) return CUBEP3M_B200_EINVAL;
   CK(cudaSetDevice(ctx->device));
-  float* buf; const float2* tw;
-  if (n == ctx->d.n) { buf = ctx->tile_rho; tw = ctx->tw_f; }
-  else if (n == ctx->d.nc_dim) { buf = ctx->slab; tw = ctx->tw_c; }
+  const Dims& d = ctx->d;
+  float *buf, *scratch; fftk::Mesh3 g;
+  if (n == d.n) { buf = ctx->tile_rho; scratch = ctx->tile_g; g = fine_mesh(ctx); }
+  else if (n == d.Nc[0] && n == d.Nc[1] && n == d.Nc[2]) { buf = ctx->slab; scratch = ctx->creal; g = coarse_mesh3(ctx); }
   else return CUBEP3M_B200_EINVAL;
   const size_t bytes = sizeof(float) * (size_t)(n + 2) * n * n;
   CK(cudaMemcpyAsync(buf, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  if (!inverse) { if (int st = fftk::forward3d(ctx, n, buf, tw)) return st; }
+  if (!inverse) { if (int st = fftk::forward3d(ctx, g, buf)) return st; }
   else {
     // unnormalised c2r back into the padded layout (pitch n+2)
-    if (int st = fftk::backward3d(ctx, n, buf, buf, nullptr, (n == ctx->d.n) ? ctx->tile_g : ctx->slab_g, 0, n, n + 2, n, 1.0f, tw)) return st;
-    CK(cudaMemcpyAsync(buf, (n == ctx->d.n) ? ctx->tile_g : ctx->slab_g, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    const int lo[3] = {0, 0, 0}, cnt[3] = {n, n, n};
+    if (int st = fftk::backward3d(ctx, g, buf, buf, nullptr, scratch, lo, cnt, n + 2, n, 1.0f)) return st;
+    CK(cudaMemcpyAsync(buf, scratch, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   CK(cudaMemcpyAsync(data, buf, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

@@ -91,6 +91,15 @@ def load_library():
     return L
 
 
+def get_unique_id() -> bytes:
+    """128-byte ncclUniqueId (rank 0 creates it, the launcher broadcasts it: INTEGRATION.md)."""
+    buf = C.create_string_buffer(128)
+    st = load_library().cubep3m_b200_get_unique_id(buf)
+    if st != 0:
+        raise Cubep3mError(st)
+    return buf.raw
+
+
 class Cubep3mError(RuntimeError):
     def __init__(self, status):
         self.status = status
@@ -116,7 +125,8 @@ class ParticleMesh:
         ft, ct = tables.fine_table(), tables.coarse_table()
         kf = None if kern_f is None else np.ascontiguousarray(kern_f, np.float32)
         kc = None if kern_c is None else np.ascontiguousarray(kern_c, np.float32)
-        _chk(self.lib.cubep3m_b200_init(C.byref(cfg), _ptr(ft), _ptr(ct), _ptr(kf), _ptr(kc), nccl_id, world_size, C.byref(self.h)))
+        idbuf = None if nccl_id is None else C.create_string_buffer(bytes(nccl_id), 128)
+        _chk(self.lib.cubep3m_b200_init(C.byref(cfg), _ptr(ft), _ptr(ct), _ptr(kf), _ptr(kc), idbuf, world_size, C.byref(self.h)))
         self.max_np = max_np(cfg)
 
     def close(self):
@@ -198,8 +208,9 @@ class ParticleMesh:
         return a
 
     def kern_c(self):
-        N = self.cfg.nc_dim
-        a = np.empty((self.cfg.nc_slab, N, N // 2 + 1, 3), np.float32)
+        Nx, Ny, Nz = self.cfg.nc_dims
+        cubic = not all(v > 0 for v in self.cfg.nodes_dim_xyz) and self.cfg.nc_dim % self.cfg.nodes == 0
+        a = np.empty((self.cfg.nc_slab if cubic else Nz, Ny, Nx // 2 + 1, 3), np.float32)
         _chk(self.lib.cubep3m_b200_debug_kern_c(self.h, a.reshape(-1)))
         return a
 

@@ -11,6 +11,7 @@ module cubep3m_b200
     integer(c_int32_t) :: ngp, ppint, pp_ext, coarse_ngp, pid, lrckcorr, move_grid_back
     integer(c_int32_t) :: ngp_fmesh_force, pp_force_flag, pp_ext_force_flag, coarse_vel_update
     integer(c_int32_t) :: rank, local_gpu, tile_split, tile_split_rank
+    integer(c_int32_t) :: nodes_dim_xyz(3)
   end type
   type, bind(C) :: b200_step_out
     integer(c_int32_t) :: np_local, np_with_ghosts, np_deleted_ll, np_buf_max
@@ -88,6 +89,7 @@ subroutine particle_mesh
     cfg%ngp_fmesh_force = merge(1, 0, ngp_fmesh_force); cfg%pp_force_flag = merge(1, 0, pp_force_flag)
     cfg%pp_ext_force_flag = merge(1, 0, pp_ext_force_flag); cfg%coarse_vel_update = merge(1, 0, coarse_vel_update)
     cfg%rank = rank; cfg%local_gpu = mod(rank, 8); cfg%tile_split = 1; cfg%tile_split_rank = 0
+    cfg%nodes_dim_xyz = 0
     if (rank == 0) st = b200_get_unique_id(c_loc(nccl_id))
     call mpi_bcast(nccl_id, 128, mpi_character, 0, mpi_comm_world, ierr)
     ! kern_f / kern_c were filled by fine_kernel / coarse_kernel (cubepm.f90:42-45): hand them over as they are

@@ -67,6 +67,10 @@ typedef struct cubep3m_b200_config {
   int32_t local_gpu;        /* CUDA device ordinal for this rank                       */
   int32_t tile_split;       /* >1: the T^3 tiles of ONE node are split over this many GPUs (2/4-GPU mode) */
   int32_t tile_split_rank;  /* which part this process owns                            */
+  /* Rank grid (Dx,Dy,Dz) of cubic nodes; all zero => nodes_dim^3 (the reference's only option, mpi_initialization.f90:55-64).
+   * 2- and 4-GPU runs use (2,1,1) / (2,2,1): the tiles of one (non-cubic) box split block-wise over the GPUs.
+   * rank = x + Dx*(y + Dy*z), as the reference's row-major mpi_cart_create with cart_coords(1) = z.                       */
+  int32_t nodes_dim_xyz[3];
 } cubep3m_b200_config;
 
 /* Outputs that particle_mesh leaves in COMMON (cubep3m.fh:19-21) or prints with -DDIAG. */

@@ -144,8 +144,9 @@ class Oracle:
         return a
 
     def kern_c(self, rank=0):
-        N = self.cfg.nc_dim
-        a = np.empty((self.cfg.nc_slab, N, N // 2 + 1, 3), np.float32)
+        Nx, Ny, Nz = self.cfg.nc_dims
+        cubic = not all(v > 0 for v in self.cfg.nodes_dim_xyz) and self.cfg.nc_dim % self.cfg.nodes == 0
+        a = np.empty((self.cfg.nc_slab if cubic else Nz, Ny, Nx // 2 + 1, 3), np.float32)
         self.lib.oracle_kern_c(self.h, rank, a.reshape(-1))
         return a
 

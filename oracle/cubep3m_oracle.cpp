@@ -34,6 +34,7 @@ struct Params {
   cubep3m_b200_config c;
   int D, T, n, b, s, m, mT, nc_tile, nc_node, nc_dim, nc_slab, nc_buf, hoc_l, hoc_h, H, pass_depth;
   int nodes, tiles_node, max_np, max_buf;
+  int Dg[3], Nc[3];   // rank grid (Dx,Dy,Dz) of cubic nodes and the global coarse mesh (Nx,Ny,Nz)
   void derive() {
     D = c.nodes_dim; T = c.tiles_node_dim; n = c.nf_tile; b = c.nf_buf; s = c.mesh_scale;
     m = n - 2 * b;                      // nf_physical_tile_dim   cubepm.par:197
@@ -42,8 +43,10 @@ struct Params {
     nc_tile = m / s;                    // cubepm.par:191
     nc_node = nc_tile * T;              // cubepm.par:192
     nc_dim = nc_node * D;               // cubepm.par:193
-    nodes = D * D * D;
-    nc_slab = nc_dim / nodes;           // cubepm.par:195
+    const bool custom = c.nodes_dim_xyz[0] > 0 && c.nodes_dim_xyz[1] > 0 && c.nodes_dim_xyz[2] > 0;
+    for (int a = 0; a < 3; ++a) { Dg[a] = custom ? c.nodes_dim_xyz[a] : D; Nc[a] = nc_node * Dg[a]; }
+    nodes = Dg[0] * Dg[1] * Dg[2];
+    nc_slab = (!custom && nc_dim % nodes == 0) ? nc_dim / nodes : 0;   // cubepm.par:195
     hoc_l = 1 - nc_buf;                 // cubepm.par:204
     hoc_h = nc_node + nc_buf;           // cubepm.par:205
     H = hoc_h - hoc_l + 1;
@@ -140,20 +143,20 @@ void fine_kernel(World& w) {
 // ---------------------------------------------------------------------------------------------
 void coarse_kernel(World& w) {
   const Params& p = w.p;
-  const int N = p.nc_dim, N2 = N + 2, hc = N / 2 + 1;
+  const int Nx = p.Nc[0], Ny = p.Nc[1], Nz = p.Nc[2], N2 = Nx + 2, hc = Nx / 2 + 1;
   const float pi = 3.141592654f;          // cubepm.par:148
-  w.kern_c.assign((size_t)3 * hc * N * N, 0.f);
-  std::vector<float> ck((size_t)3 * N * N * N), ckc;
+  w.kern_c.assign((size_t)3 * hc * Ny * Nz, 0.f);
+  std::vector<float> ck((size_t)3 * Nx * Ny * Nz), ckc;
   auto CK = [&](std::vector<float>& a, int d, int i, int j, int k) -> float& {
-    return a[(size_t)d + 3 * ((size_t)(i - 1) + (size_t)N * ((j - 1) + (size_t)N * (k - 1)))];
+    return a[(size_t)d + 3 * ((size_t)(i - 1) + (size_t)Nx * ((j - 1) + (size_t)Ny * (k - 1)))];
   };
   auto fill_plain = [&](std::vector<float>& a) {   // :302-336 and :479-513
-    for (int k = 1; k <= N; ++k) {
-      float z = (k < N / 2 + 2) ? (float)(k - 1) : (float)(k - 1 - N); z = p.s * z;
-      for (int j = 1; j <= N; ++j) {
-        float y = (j < N / 2 + 2) ? (float)(j - 1) : (float)(j - 1 - N); y = p.s * y;
-        for (int i = 1; i <= N; ++i) {
-          float x = (i < N / 2 + 2) ? (float)(i - 1) : (float)(i - 1 - N); x = p.s * x;
+    for (int k = 1; k <= Nz; ++k) {
+      float z = (k < Nz / 2 + 2) ? (float)(k - 1) : (float)(k - 1 - Nz); z = p.s * z;
+      for (int j = 1; j <= Ny; ++j) {
+        float y = (j < Ny / 2 + 2) ? (float)(j - 1) : (float)(j - 1 - Ny); y = p.s * y;
+        for (int i = 1; i <= Nx; ++i) {
+          float x = (i < Nx / 2 + 2) ? (float)(i - 1) : (float)(i - 1 - Nx); x = p.s * x;
           float r = std::sqrt(x * x + y * y + z * z);
           if (r == 0.0f) { CK(a, 0, i, j, k) = 0.f; CK(a, 1, i, j, k) = 0.f; CK(a, 2, i, j, k) = 0.f; }
           else { float r3 = r * r * r; CK(a, 0, i, j, k) = -x / r3; CK(a, 1, i, j, k) = -y / r3; CK(a, 2, i, j, k) = -z / r3; }
@@ -166,22 +169,29 @@ void coarse_kernel(World& w) {
   for (int oz = -3; oz <= 3; ++oz)
     for (int oy = -3; oy <= 3; ++oy)
       for (int ox = -3; ox <= 3; ++ox) {
-        int i = ox >= 0 ? ox + 1 : N + ox + 1, j = oy >= 0 ? oy + 1 : N + oy + 1, k = oz >= 0 ? oz + 1 : N + oz + 1;
-        if (i < 1 || j < 1 || k < 1 || i > N || j > N || k > N) continue;
-        int o[3] = {ox, oy, oz};
+        int i = ox >= 0 ? ox + 1 : Nx + ox + 1, j = oy >= 0 ? oy + 1 : Ny + oy + 1, k = oz >= 0 ? oz + 1 : Nz + oz + 1;
+        if (i < 1 || j < 1 || k < 1 || i > Nx || j > Ny || k > Nz) continue;
+        int oo[3] = {ox, oy, oz};
         for (int d = 0; d < 3; ++d) {
           float v = w.coarse_table[(((size_t)std::abs(oz) * 4 + std::abs(oy)) * 4 + std::abs(ox)) * 3 + d];
-          CK(ck, d, i, j, k) = (o[d] < 0) ? -v : v;
+          CK(ck, d, i, j, k) = (oo[d] < 0) ? -v : v;
         }
       }
-  std::vector<float> slab((size_t)N2 * N * N), tmp;
+  std::vector<float> slab((size_t)N2 * Ny * Nz), tmp;
   auto load = [&](std::vector<float>& a, int d) {
-    for (int k = 1; k <= N; ++k)
-      for (int j = 1; j <= N; ++j) {
-        float* row = &slab[(size_t)N2 * ((j - 1) + (size_t)N * (k - 1))];
-        for (int i = 1; i <= N; ++i) row[i - 1] = CK(a, d, i, j, k);
-        row[N] = row[N + 1] = 0.f;
+    for (int k = 1; k <= Nz; ++k)
+      for (int j = 1; j <= Ny; ++j) {
+        float* row = &slab[(size_t)N2 * ((j - 1) + (size_t)Ny * (k - 1))];
+        for (int i = 1; i <= Nx; ++i) row[i - 1] = CK(a, d, i, j, k);
+        row[Nx] = row[Nx + 1] = 0.f;
       }
+  };
+  auto store = [&](int d) {                                          // :593-599
+    for (int k = 1; k <= Nz; ++k)
+      for (int j = 1; j <= Ny; ++j)
+        for (int i = 1; i <= hc; ++i)
+          w.kern_c[(size_t)d + 3 * ((size_t)(i - 1) + (size_t)hc * ((j - 1) + (size_t)Ny * (k - 1)))] =
+              slab[(size_t)(2 * i - 1) + (size_t)N2 * ((j - 1) + (size_t)Ny * (k - 1))];
   };
   if (p.c.lrckcorr) {
     ckc = ck;                 // :469-475 corrected kernel stashed in force_c
@@ -189,44 +199,33 @@ void coarse_kernel(World& w) {
     for (int d = 0; d < 3; ++d) {
       load(ck, d); w.fft_c.forward(slab.data()); tmp = slab;          // :519-551 tmp_kern_c(d)
       load(ckc, d); w.fft_c.forward(slab.data());                      // :556-557
-      for (int k = 1; k <= N; ++k) {                                   // :558-591 (x), :602-635 (y), :646-679 (z)
-        int kz = (k < N / 2 + 2) ? k - 1 : k - 1 - N;
-        for (int j = 1; j <= N; ++j) {
-          int ky = (j < N / 2 + 2) ? j - 1 : j - 1 - N;
-          for (int i = 1; i <= N + 2; i += 2) {
+      for (int k = 1; k <= Nz; ++k) {                                  // :558-591 (x), :602-635 (y), :646-679 (z)
+        int kz = (k < Nz / 2 + 2) ? k - 1 : k - 1 - Nz;
+        for (int j = 1; j <= Ny; ++j) {
+          int ky = (j < Ny / 2 + 2) ? j - 1 : j - 1 - Ny;
+          for (int i = 1; i <= Nx + 2; i += 2) {
             int kx = (i - 1) / 2;
             float kr = std::sqrt((float)(kx * kx + ky * ky + kz * kz));
             if (kr <= 8.f) {
-              float ka = 2 * std::sin(pi * kx / (float)N);
-              float kb = 2 * std::sin(pi * ky / (float)N);
-              float kc = 2 * std::sin(pi * kz / (float)N);
+              float ka = 2 * std::sin(pi * kx / (float)Nx);
+              float kb = 2 * std::sin(pi * ky / (float)Ny);
+              float kc = 2 * std::sin(pi * kz / (float)Nz);
               int kd = d == 0 ? kx : (d == 1 ? ky : kz);
               float kk = d == 0 ? ka : (d == 1 ? kb : kc);
               if (kd != 0) {
-                size_t o = (size_t)i + (size_t)N2 * ((j - 1) + (size_t)N * (k - 1));  // slab(i+1,j,k), 0-based
-                float wa = slab[o], wb = tmp[o];
+                size_t o2 = (size_t)i + (size_t)N2 * ((j - 1) + (size_t)Ny * (k - 1));  // slab(i+1,j,k), 0-based
+                float wa = slab[o2], wb = tmp[o2];
                 float wc = 4.f * pi * kk / (ka * ka + kb * kb + kc * kc) / 16.f;
-                slab[o] = wa * (wc / wb);
+                slab[o2] = wa * (wc / wb);
               }
             }
           }
         }
       }
-      for (int k = 1; k <= N; ++k)                                     // :593-599
-        for (int j = 1; j <= N; ++j)
-          for (int i = 1; i <= hc; ++i)
-            w.kern_c[(size_t)d + 3 * ((size_t)(i - 1) + (size_t)hc * ((j - 1) + (size_t)N * (k - 1)))] =
-                slab[(size_t)(2 * i - 1) + (size_t)N2 * ((j - 1) + (size_t)N * (k - 1))];
+      store(d);
     }
   } else {
-    for (int d = 0; d < 3; ++d) {                                      // :695-723
-      load(ck, d); w.fft_c.forward(slab.data());
-      for (int k = 1; k <= N; ++k)
-        for (int j = 1; j <= N; ++j)
-          for (int i = 1; i <= hc; ++i)
-            w.kern_c[(size_t)d + 3 * ((size_t)(i - 1) + (size_t)hc * ((j - 1) + (size_t)N * (k - 1)))] =
-                slab[(size_t)(2 * i - 1) + (size_t)N2 * ((j - 1) + (size_t)N * (k - 1))];
-    }
+    for (int d = 0; d < 3; ++d) { load(ck, d); w.fft_c.forward(slab.data()); store(d); }   // :695-723
   }
 }
 
@@ -750,25 +749,25 @@ void coarse_mass(World& w, float mass_p) {
 void coarse_force(World& w, float* c_force_max) {
   double t0 = now_ms();
   const Params& p = w.p;
-  const int N = p.nc_dim, N2 = N + 2, hc = N / 2 + 1, nc = p.nc_node, D = p.D, fc = nc + 2;
-  std::vector<float> slab((size_t)N2 * N * N), cmplx;
+  const int Nx = p.Nc[0], Ny = p.Nc[1], Nz = p.Nc[2], N2 = Nx + 2, hc = Nx / 2 + 1, nc = p.nc_node, fc = nc + 2;
+  std::vector<float> slab((size_t)N2 * Ny * Nz), cmplx;
   // gather cubes -> global (pack_slab, fft_coarse.f90:4-54): global x index = local + nc*cart_coords(3) etc.
   for (auto& r : w.R)
     for (int k = 0; k < nc; ++k)
       for (int j = 0; j < nc; ++j) {
-        float* row = &slab[(size_t)N2 * ((j + nc * r.cc[1]) + (size_t)N * (k + nc * r.cc[0]))] + nc * r.cc[2];
+        float* row = &slab[(size_t)N2 * ((j + nc * r.cc[1]) + (size_t)Ny * (k + nc * r.cc[0]))] + nc * r.cc[2];
         const float* src = &r.rho_c[(size_t)nc * (j + (size_t)nc * k)];
         for (int i = 0; i < nc; ++i) row[i] = src[i];
       }
   w.fft_c.forward(slab.data());                                       // coarse_force.f90:18
   cmplx = slab;                                                       // :19
-  const float n3 = ((float)N * (float)N) * (float)N;                  // fft_coarse.f90:186
+  const float n3 = ((float)Nx * (float)Ny) * (float)Nz;               // fft_coarse.f90:186
   for (auto& r : w.R) std::fill(r.force_c.begin(), r.force_c.end(), 0.f);
   for (int d = 0; d < 3; ++d) {
-    for (int k = 0; k < N; ++k)                                       // :37-48
-      for (int j = 0; j < N; ++j) {
-        size_t rowo = (size_t)N2 * (j + (size_t)N * k);
-        const float* kc = &w.kern_c[(size_t)3 * ((size_t)hc * (j + (size_t)N * k))];
+    for (int k = 0; k < Nz; ++k)                                      // :37-48
+      for (int j = 0; j < Ny; ++j) {
+        size_t rowo = (size_t)N2 * (j + (size_t)Ny * k);
+        const float* kc = &w.kern_c[(size_t)3 * ((size_t)hc * (j + (size_t)Ny * k))];
         for (int i = 0; i < hc; ++i) {
           float kv = kc[3 * i + d];
           slab[rowo + 2 * i] = -cmplx[rowo + 2 * i + 1] * kv;
@@ -780,7 +779,7 @@ void coarse_force(World& w, float* c_force_max) {
     for (auto& r : w.R)                                               // unpack_slab + :52 force_c(d,1:nc,...) = rho_c
       for (int k = 0; k < nc; ++k)
         for (int j = 0; j < nc; ++j) {
-          const float* row = &slab[(size_t)N2 * ((j + nc * r.cc[1]) + (size_t)N * (k + nc * r.cc[0]))] + nc * r.cc[2];
+          const float* row = &slab[(size_t)N2 * ((j + nc * r.cc[1]) + (size_t)Ny * (k + nc * r.cc[0]))] + nc * r.cc[2];
           for (int i = 0; i < nc; ++i)
             r.force_c[(size_t)d + 3 * ((size_t)(i + 1) + (size_t)fc * ((j + 1) + (size_t)fc * (k + 1)))] = row[i];
         }
@@ -789,7 +788,6 @@ void coarse_force(World& w, float* c_force_max) {
   auto FC = [&](RankState& r, int d, int i, int j, int k) -> float& {
     return r.force_c[(size_t)d + 3 * ((size_t)i + (size_t)fc * (j + (size_t)fc * k))];
   };
-  (void)D;
   for (int axis = 0; axis < 3; ++axis) {
     std::vector<std::vector<float>> lo_face(w.R.size()), hi_face(w.R.size());
     for (auto& r : w.R) {
@@ -956,19 +954,19 @@ int oracle_create(const cubep3m_b200_config* cfg, const float* fine_table, const
   World* w = new World();
   w->p.c = *cfg; w->p.derive();
   const Params& p = w->p;
-  if (p.s != 4 || p.m <= 0 || p.m % p.s != 0 || p.nc_dim % p.nodes != 0) { delete w; return CUBEP3M_B200_EINVAL; }
+  if (p.s != 4 || p.m <= 0 || p.m % p.s != 0) { delete w; return CUBEP3M_B200_EINVAL; }
   // LRCKCORR divides by Im(kernel) for every |k| <= 8 (kernel_initialization.f90:573-581): the Nyquist plane must lie beyond that
-  if (p.c.lrckcorr && p.nc_dim / 2 <= 8) { delete w; return CUBEP3M_B200_EINVAL; }
+  for (int a = 0; a < 3; ++a) if (p.c.lrckcorr && p.Nc[a] / 2 <= 8) { delete w; return CUBEP3M_B200_EINVAL; }
   w->fine_table.assign(fine_table, fine_table + 16 * 16 * 16 * 3);
   w->coarse_table.assign(coarse_table, coarse_table + 4 * 4 * 4 * 3);
-  w->fft_f.init(p.n); w->fft_c.init(p.nc_dim);
+  w->fft_f.init(p.n); w->fft_c.init(p.Nc[0], p.Nc[1], p.Nc[2]);
   w->R.resize(p.nodes);
-  const int D = p.D;
+  const int Dx = p.Dg[0], Dy = p.Dg[1], Dz = p.Dg[2];
   for (int r = 0; r < p.nodes; ++r) {
     RankState& R = w->R[r];
     R.rank = r;
-    R.cc[0] = r / (D * D); R.cc[1] = (r / D) % D; R.cc[2] = r % D;
-    auto rk = [&](int z, int y, int x) { return ((z + D) % D) * D * D + ((y + D) % D) * D + ((x + D) % D); };
+    R.cc[0] = r / (Dx * Dy); R.cc[1] = (r / Dx) % Dy; R.cc[2] = r % Dx;      // rank = x + Dx*(y + Dy*z); cc = (z,y,x)
+    auto rk = [&](int z, int y, int x) { return ((z + Dz) % Dz) * Dx * Dy + ((y + Dy) % Dy) * Dx + ((x + Dx) % Dx); };
     R.nb[0] = rk(R.cc[0] - 1, R.cc[1], R.cc[2]); R.nb[1] = rk(R.cc[0] + 1, R.cc[1], R.cc[2]);
     R.nb[2] = rk(R.cc[0], R.cc[1] - 1, R.cc[2]); R.nb[3] = rk(R.cc[0], R.cc[1] + 1, R.cc[2]);
     R.nb[4] = rk(R.cc[0], R.cc[1], R.cc[2] - 1); R.nb[5] = rk(R.cc[0], R.cc[1], R.cc[2] + 1);
@@ -988,7 +986,7 @@ void oracle_destroy(void* h) { delete (World*)h; }
 int oracle_max_np(void* h) { return ((World*)h)->p.max_np; }
 int oracle_set_kernels(void* h, const float* kern_f, const float* kern_c_global) {
   World* w = (World*)h; const Params& p = w->p;
-  size_t nf = (size_t)3 * (p.n / 2 + 1) * p.n * p.n, ncg = (size_t)3 * (p.nc_dim / 2 + 1) * p.nc_dim * p.nc_dim;
+  size_t nf = (size_t)3 * (p.n / 2 + 1) * p.n * p.n, ncg = (size_t)3 * (p.Nc[0] / 2 + 1) * p.Nc[1] * p.Nc[2];
   w->kern_f.assign(kern_f, kern_f + nf); w->kern_c.assign(kern_c_global, kern_c_global + ncg);
   return 0;
 }
@@ -1030,8 +1028,11 @@ int oracle_tile_counts(void* h, int rank, int32_t* counts) {
 int oracle_kern_f(void* h, float* out) { World* w = (World*)h; std::copy(w->kern_f.begin(), w->kern_f.end(), out); return 0; }
 int oracle_kern_c(void* h, int rank, float* out) {   // this rank's z-slab (3,hc,nc_dim,nc_slab)
   World* w = (World*)h; const Params& p = w->p;
-  size_t per = (size_t)3 * (p.nc_dim / 2 + 1) * p.nc_dim * p.nc_slab;
-  std::copy(w->kern_c.begin() + per * rank, w->kern_c.begin() + per * (rank + 1), out); return 0;
+  if (p.nc_slab > 0) {
+    size_t per = (size_t)3 * (p.Nc[0] / 2 + 1) * p.Nc[1] * p.nc_slab;
+    std::copy(w->kern_c.begin() + per * rank, w->kern_c.begin() + per * (rank + 1), out);
+  } else std::copy(w->kern_c.begin(), w->kern_c.end(), out);
+  return 0;
 }
 int oracle_rho_c(void* h, int rank, float* out) { RankState& r = ((World*)h)->R[rank]; std::copy(r.rho_c.begin(), r.rho_c.end(), out); return 0; }
 int oracle_force_c(void* h, int rank, float* out) { RankState& r = ((World*)h)->R[rank]; std::copy(r.force_c.begin(), r.force_c.end(), out); return 0; }

@@ -14,6 +14,7 @@
 #include <vector>
 #include <cmath>
 #include <cstring>
+#include <algorithm>
 
 namespace oracle {
 
@@ -81,64 +82,66 @@ struct Fft1d {
   }
 };
 
-// In-place 3-D real<->complex transform on a Fortran-ordered padded array a(n+2, n, n).
+// In-place 3-D real<->complex transform on a Fortran-ordered padded array a(nx+2, ny, nz).
+// (The reference only ever transforms cubes; the three lengths differ only for the non-cubic rank grids used at 2/4 GPUs.)
 struct Fft3dR2C {
-  int n = 0;
-  Fft1d plan;
-  void init(int n_) { n = n_; plan.init(n_); }
-  // forward: real (first n of each padded row) -> n/2+1 complex per row; unnormalised.
+  int nx = 0, ny = 0, nz = 0;
+  Fft1d px, py, pz;
+  void init(int n_) { init(n_, n_, n_); }
+  void init(int nx_, int ny_, int nz_) { nx = nx_; ny = ny_; nz = nz_; px.init(nx); py.init(ny); pz.init(nz); }
+  // forward: real (first nx of each padded row) -> nx/2+1 complex per row; unnormalised.
   void forward(float* a) const {
-    const int n2 = n + 2, hc = n / 2 + 1;
-    std::vector<cf> in(n), out(n);
-    for (int k = 0; k < n; ++k)
-      for (int j = 0; j < n; ++j) {
-        float* row = a + (size_t)n2 * (j + (size_t)n * k);
-        for (int i = 0; i < n; ++i) in[i] = cf(row[i], 0.f);
-        plan.exec(in.data(), 1, out.data(), true);
+    const int n2 = nx + 2, hc = nx / 2 + 1;
+    std::vector<cf> in(std::max(nx, std::max(ny, nz))), out(in.size());
+    for (int k = 0; k < nz; ++k)
+      for (int j = 0; j < ny; ++j) {
+        float* row = a + (size_t)n2 * (j + (size_t)ny * k);
+        for (int i = 0; i < nx; ++i) in[i] = cf(row[i], 0.f);
+        px.exec(in.data(), 1, out.data(), true);
         for (int i = 0; i < hc; ++i) { row[2 * i] = out[i].real(); row[2 * i + 1] = out[i].imag(); }
       }
-    cf* c = reinterpret_cast<cf*>(a);  // c(hc, n, n)
-    for (int k = 0; k < n; ++k)
+    cf* c = reinterpret_cast<cf*>(a);  // c(hc, ny, nz)
+    for (int k = 0; k < nz; ++k)
       for (int i = 0; i < hc; ++i) {
-        cf* base = c + i + (size_t)hc * n * k;
-        plan.exec(base, hc, out.data(), true);
-        for (int j = 0; j < n; ++j) base[(size_t)j * hc] = out[j];
+        cf* base = c + i + (size_t)hc * ny * k;
+        py.exec(base, hc, out.data(), true);
+        for (int j = 0; j < ny; ++j) base[(size_t)j * hc] = out[j];
       }
-    for (int j = 0; j < n; ++j)
+    for (int j = 0; j < ny; ++j)
       for (int i = 0; i < hc; ++i) {
         cf* base = c + i + (size_t)hc * j;
-        plan.exec(base, hc * n, out.data(), true);
-        for (int k = 0; k < n; ++k) base[(size_t)k * hc * n] = out[k];
+        pz.exec(base, hc * ny, out.data(), true);
+        for (int k = 0; k < nz; ++k) base[(size_t)k * hc * ny] = out[k];
       }
   }
   // backward: complex -> real, unnormalised (the caller divides by n^3: fftw2.f90:22, fft_fine.f90:51)
   void backward(float* a) const {
-    const int n2 = n + 2, hc = n / 2 + 1;
-    std::vector<cf> in(n), out(n);
+    const int n2 = nx + 2, hc = nx / 2 + 1;
+    std::vector<cf> in(std::max(nx, std::max(ny, nz))), out(in.size());
     cf* c = reinterpret_cast<cf*>(a);
-    for (int j = 0; j < n; ++j)
+    for (int j = 0; j < ny; ++j)
       for (int i = 0; i < hc; ++i) {
         cf* base = c + i + (size_t)hc * j;
-        plan.exec(base, hc * n, out.data(), false);
-        for (int k = 0; k < n; ++k) base[(size_t)k * hc * n] = out[k];
+        pz.exec(base, hc * ny, out.data(), false);
+        for (int k = 0; k < nz; ++k) base[(size_t)k * hc * ny] = out[k];
       }
-    for (int k = 0; k < n; ++k)
+    for (int k = 0; k < nz; ++k)
       for (int i = 0; i < hc; ++i) {
-        cf* base = c + i + (size_t)hc * n * k;
-        plan.exec(base, hc, out.data(), false);
-        for (int j = 0; j < n; ++j) base[(size_t)j * hc] = out[j];
+        cf* base = c + i + (size_t)hc * ny * k;
+        py.exec(base, hc, out.data(), false);
+        for (int j = 0; j < ny; ++j) base[(size_t)j * hc] = out[j];
       }
-    for (int k = 0; k < n; ++k)
-      for (int j = 0; j < n; ++j) {
-        float* row = a + (size_t)n2 * (j + (size_t)n * k);
+    for (int k = 0; k < nz; ++k)
+      for (int j = 0; j < ny; ++j) {
+        float* row = a + (size_t)n2 * (j + (size_t)ny * k);
         for (int i = 0; i < hc; ++i) in[i] = cf(row[2 * i], row[2 * i + 1]);
-        for (int i = hc; i < n; ++i) in[i] = std::conj(in[n - i]);
+        for (int i = hc; i < nx; ++i) in[i] = std::conj(in[nx - i]);
         // c2r ignores the imaginary parts of the self-conjugate bins, as FFTW does
         in[0] = cf(in[0].real(), 0.f);
-        if (n % 2 == 0) in[n / 2] = cf(in[n / 2].real(), 0.f);
-        plan.exec(in.data(), 1, out.data(), false);
-        for (int i = 0; i < n; ++i) row[i] = out[i].real();
-        row[n] = 0.f; row[n + 1] = 0.f;
+        if (nx % 2 == 0) in[nx / 2] = cf(in[nx / 2].real(), 0.f);
+        px.exec(in.data(), 1, out.data(), false);
+        for (int i = 0; i < nx; ++i) row[i] = out[i].real();
+        row[nx] = 0.f; row[nx + 1] = 0.f;
       }
   }
 };

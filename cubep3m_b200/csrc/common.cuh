@@ -124,6 +124,9 @@ struct cubep3m_b200_ctx {
   int64_t* recvpid[2] = {nullptr, nullptr};
   int* rowoff = nullptr;      // compaction offsets per physical (cy,cz) row
   float* cand = nullptr;      // positions of the boundary-candidate particles (3 floats each)
+  int2* deltas = nullptr;     // per-tile (from-cell, to-cell) moves for the fused density pass, tiles * DELTA_CAP
+  int* ndelta = nullptr;      // per-tile move counts
+  int* tile_counts = nullptr; // per-tile deposited-particle counts (parity getter)
   int cand_cap = 0;
   // fine mesh
   float* kern_f = nullptr;    // [comp][z][y][kx]: the reference's kern_f(3,hc,n,n) (cubep3m.fh:35) de-interleaved

@@ -61,6 +61,63 @@ __global__ void __launch_bounds__(NT) fft_x_r2c(float* __restrict__ data, int nr
   }
 }
 
+// ---- pass X forward fused with the NGP mass assignment (particle_mesh_threaded.f90:100-151): the tile's density row is not read from
+// memory but produced on the fly from the fine-cell occupancy table, rho = mass_p * (fstart[k+1] - fstart[k]) for tile-local cells
+// [4, n-5] and 0 elsewhere; `deltas` moves the mass of the few particles whose reference cell floor(fl(x+offset)) differs (fine.cuh).
+template <int N>
+__global__ void __launch_bounds__(NT) fft_x_r2c_ngp(float* __restrict__ data, const int* __restrict__ fstart, int H, int b, int ox, int oy, int oz,
+                                                    float mass_p, const int2* __restrict__ deltas, const int* __restrict__ ndelta_ptr, int delta_cap,
+                                                    double* __restrict__ sum_phys, const float2* __restrict__ tw_g) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  Smem s = carve<N>(raw, tw_g);
+  constexpr int P = N + 2;
+  const int r0 = blockIdx.x * (2 * LX);          // first row (= z*N + y) of this CTA; N*N is a multiple of 32
+  double msum = 0.0;
+  for (int q = threadIdx.x; q < 2 * LX * N; q += NT) {
+    const int row = q / N, x = q - row * N;
+    const int gr = r0 + row;
+    const int y = gr % N, z = gr / N;
+    float v = 0.f;
+    if (x >= 4 && x <= N - 5 && y >= 4 && y <= N - 5 && z >= 4 && z <= N - 5) {
+      const int gx = x + ox, gy = y + oy, gz = z + oz;
+      const long long k = ((long long)(((gz >> 2) * H + (gy >> 2))) * H + (gx >> 2)) * 64 + (((gz & 3) << 4) | ((gy & 3) << 2) | (gx & 3));
+      v = mass_p * (float)(fstart[k + 1] - fstart[k]);
+      if (x >= b && x < N - b && y >= b && y < N - b && z >= b && z < N - b) msum += (double)v;
+    }
+    ((row & 1) ? s.im0 : s.re0)[x * LXP + (row >> 1)] = v;
+  }
+  msum = warp_sum_d(msum);
+  if ((threadIdx.x & 31) == 0 && msum != 0.0) atomicAdd(sum_phys, msum);
+  __syncthreads();
+  const int nd = min(*ndelta_ptr, delta_cap);
+  if (nd > 0) {
+    for (int i = threadIdx.x; i < nd; i += NT) {
+      const int2 d = deltas[i];
+      const int c[2] = {d.x, d.y};
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int x = c[u] % N, gr = c[u] / N;     // gr = z*N + y
+        const int row = gr - r0;
+        if (row >= 0 && row < 2 * LX) atomicAdd(&((row & 1) ? s.im0 : s.re0)[x * LXP + (row >> 1)], u == 0 ? -mass_p : mass_p);
+      }
+    }
+    __syncthreads();
+  }
+  fft_columns<N, false>(s.re0, s.im0, s.re1, s.im1, s.tw);
+  const float* zr = result_buffer<N>() ? s.re1 : s.re0;
+  const float* zi = result_buffer<N>() ? s.im1 : s.im0;
+  for (int q = threadIdx.x; q < 2 * LX * P; q += NT) {
+    const int row = q / P, f = q - row * P;
+    const int k = f >> 1, col = row >> 1;
+    const int km = (k == 0) ? 0 : N - k;
+    const float ar = zr[k * LXP + col], ai = zi[k * LXP + col], br = zr[km * LXP + col], bi = zi[km * LXP + col];
+    float v;
+    if ((row & 1) == 0) v = (f & 1) ? 0.5f * (ai - bi) : 0.5f * (ar + br);
+    else                v = (f & 1) ? -0.5f * (ar - br) : 0.5f * (ai + bi);
+    data[(long long)(r0 + row) * P + f] = v;
+  }
+}
+
 // ---- pass Y / Z: strided complex columns.
 // element e of column c of block (bx, by): in[base + e*estride + c], base = (by + outer0)*ostride + bx*LX
 // MUL: multiply the loaded value by i*kern[e*kes + (by+outer0)*kos + kx]   (Z pass: e=z, outer=y; kern = one component)
@@ -69,9 +126,11 @@ template <int N, bool INV, bool MUL>
 __global__ void __launch_bounds__(NT) fft_strided(const float2* __restrict__ in, float2* __restrict__ out, int hc,
                                                   long long estride, long long ostride, int outer0,
                                                   const float* __restrict__ kern, long long kes, long long kos,
-                                                  int elo, int ehi, const float2* __restrict__ tw_g) {
+                                                  int elo, int ehi, const float2* __restrict__ tw_g, long long bstride) {
   extern __shared__ __align__(16) unsigned char raw[];
   Smem s = carve<N>(raw, tw_g);
+  in += (long long)blockIdx.z * bstride;     // batch (force component) offset
+  out += (long long)blockIdx.z * bstride;
   const int outer = blockIdx.y + outer0;
   const int kx0 = blockIdx.x * LX;
   const long long base = (long long)outer * ostride + kx0;
@@ -98,27 +157,95 @@ __global__ void __launch_bounds__(NT) fft_strided(const float2* __restrict__ in,
       out[base + (long long)e * estride + col] = make_float2(zr[e * LXP + col], zi[e * LXP + col]);
 }
 
+// ---- fused pass Z: forward FFT along z, then for each of the three force components: multiply by i*kern_f(comp)
+// (particle_mesh_threaded.f90:183-192) and inverse FFT along z, storing only the cropped z range. One load of the spectrum
+// column block feeds four transforms; the forward-z result never goes back to memory.
+template <int N>
+__global__ void __launch_bounds__(NT) fft_z_sandwich(const float2* __restrict__ spec, float2* __restrict__ g, long long gstride, int hc, int ny,
+                                                     const float* __restrict__ kern, long long kstride, int elo, int ehi,
+                                                     const float2* __restrict__ tw_g) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  float* b0r = reinterpret_cast<float*>(raw);
+  float* b0i = b0r + N * LXP;
+  float* b1r = b0i + N * LXP;
+  float* b1i = b1r + N * LXP;
+  float* b2r = b1i + N * LXP;
+  float* b2i = b2r + N * LXP;
+  float2* tw = reinterpret_cast<float2*>(b2i + N * LXP);
+  for (int t = threadIdx.x; t < N; t += NT) tw[t] = tw_g[t];
+  const int y = blockIdx.y;
+  const int kx0 = blockIdx.x * LX;
+  const long long estride = (long long)ny * hc;
+  const long long base = (long long)y * hc + kx0;
+  const int col = threadIdx.x % LX;
+  const bool colok = (kx0 + col) < hc;
+  for (int e = threadIdx.x / LX; e < N; e += NT / LX) {
+    float2 v = make_float2(0.f, 0.f);
+    if (colok) v = spec[base + (long long)e * estride + col];
+    b0r[e * LXP + col] = v.x;
+    b0i[e * LXP + col] = v.y;
+  }
+  __syncthreads();
+  fft_columns<N, false>(b0r, b0i, b1r, b1i, tw);
+  // S = forward result, X = the other of {b0,b1}; the inverse transforms ping-pong between X and b2
+  const float* sr = result_buffer<N>() ? b1r : b0r;
+  const float* si = result_buffer<N>() ? b1i : b0i;
+  float* xr = result_buffer<N>() ? b0r : b1r;
+  float* xi = result_buffer<N>() ? b0i : b1i;
+  const float* rr = result_buffer<N>() ? b2r : xr;
+  const float* ri = result_buffer<N>() ? b2i : xi;
+#pragma unroll 1
+  for (int comp = 0; comp < 3; ++comp) {
+    const float* kc = kern + (long long)comp * kstride + base;
+    for (int e = threadIdx.x / LX; e < N; e += NT / LX) {
+      const float kv = colok ? kc[(long long)e * estride + col] : 0.f;
+      const int idx = e * LXP + col;
+      xr[idx] = -si[idx] * kv;
+      xi[idx] = sr[idx] * kv;
+    }
+    __syncthreads();
+    fft_columns<N, true>(xr, xi, b2r, b2i, tw);
+    if (colok) {
+      float2* go = g + (long long)comp * gstride + base;
+      for (int e = elo + threadIdx.x / LX; e <= ehi; e += NT / LX) go[(long long)e * estride + col] = make_float2(rr[e * LXP + col], ri[e * LXP + col]);
+    }
+    __syncthreads();
+  }
+}
+constexpr size_t smem_bytes_sandwich(int n) { return (size_t)6 * n * LXP * sizeof(float) + (size_t)n * sizeof(float2); }
+
 // ---- pass X backward: half spectra -> real rows with crop + scale.
 // Row index space: ridx in [0, cnt_z*cnt_y): zc = ridx / cnt_y, yc = ridx % cnt_y, source row (z = zc+lo_z, y = yc+lo_y) of an
 // array with ny_src rows per plane. Output: out[(zc*opitch_y + yc)*opitch_x + xc], xc in [0,cnt_x) <- x = xc + lo_x.
 template <int N>
 __global__ void __launch_bounds__(NT) fft_x_c2r(const float2* __restrict__ in, float* __restrict__ out, int lo_x, int cnt_x, int lo_y, int cnt_y,
                                                 int lo_z, int cnt_z, int ny_src, long long opitch_x, long long opitch_y, float scale,
-                                                const float2* __restrict__ tw_g) {
+                                                const float2* __restrict__ tw_g, long long in_bstride, long long out_bstride) {
   extern __shared__ __align__(16) unsigned char raw[];
   Smem s = carve<N>(raw, tw_g);
+  in += (long long)blockIdx.y * in_bstride;     // batch (force component) offset
+  out += (long long)blockIdx.y * out_bstride;
   constexpr int HC = N / 2 + 1;
   const long long nrows = (long long)cnt_z * cnt_y;
   const long long r0 = (long long)blockIdx.x * (2 * LX);
+  // per-row source / destination offsets once per CTA (the runtime divisions are too expensive per element)
+  __shared__ long long srow[2 * LX], drow[2 * LX];
+  if (threadIdx.x < 2 * LX) {
+    const long long ridx = r0 + threadIdx.x;
+    long long so = -1, dof = -1;
+    if (ridx < nrows) {
+      const int zc = (int)(ridx / cnt_y), yc = (int)(ridx - (long long)zc * cnt_y);
+      so = ((long long)(zc + lo_z) * ny_src + (yc + lo_y)) * HC;
+      dof = ((long long)zc * opitch_y + yc) * opitch_x;
+    }
+    srow[threadIdx.x] = so; drow[threadIdx.x] = dof;
+  }
+  __syncthreads();
   // stage A (even rows) into buffer 0, B (odd rows) into buffer 1
   for (int q = threadIdx.x; q < 2 * LX * HC; q += NT) {
     const int row = q / HC, k = q - row * HC;
-    const long long ridx = r0 + row;
-    float2 v = make_float2(0.f, 0.f);
-    if (ridx < nrows) {
-      const int zc = (int)(ridx / cnt_y), yc = (int)(ridx - (long long)zc * cnt_y);
-      v = in[((long long)(zc + lo_z) * ny_src + (yc + lo_y)) * HC + k];
-    }
+    const long long so = srow[row];
+    const float2 v = (so >= 0) ? in[so + k] : make_float2(0.f, 0.f);
     const int col = row >> 1;
     if (row & 1) { s.re1[k * LXP + col] = v.x; s.im1[k * LXP + col] = v.y; }
     else         { s.re0[k * LXP + col] = v.x; s.im0[k * LXP + col] = v.y; }
@@ -140,14 +267,14 @@ __global__ void __launch_bounds__(NT) fft_x_c2r(const float2* __restrict__ in, f
   fft_columns<N, true>(s.re0, s.im0, s.re1, s.im1, s.tw);
   const float* zr = result_buffer<N>() ? s.re1 : s.re0;
   const float* zi = result_buffer<N>() ? s.im1 : s.im0;
-  for (int q = threadIdx.x; q < 2 * LX * cnt_x; q += NT) {
-    const int row = q / cnt_x, xc = q - row * cnt_x;
-    const long long ridx = r0 + row;
-    if (ridx >= nrows) continue;
-    const int zc = (int)(ridx / cnt_y), yc = (int)(ridx - (long long)zc * cnt_y);
-    const int x = xc + lo_x, col = row >> 1;
-    const float v = (row & 1) ? zi[x * LXP + col] : zr[x * LXP + col];
-    out[((long long)zc * opitch_y + yc) * opitch_x + xc] = v * scale;
+  // one warp per output row at a time: lanes run along x (coalesced stores, stride-17 conflict-free smem reads)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int row = warp; row < 2 * LX; row += NT / 32) {
+    const long long dof = drow[row];
+    if (dof < 0) continue;
+    const float* src = (row & 1) ? zi : zr;
+    const int col = row >> 1;
+    for (int xc = lane; xc < cnt_x; xc += 32) out[dof + xc] = src[(xc + lo_x) * LXP + col] * scale;
   }
 }
 
@@ -172,10 +299,12 @@ template <int N> int set_smem_attr() {
   if (done) return 0;
   const int bytes = (int)smem_bytes(N);
   CK(cudaFuncSetAttribute(fft_x_r2c<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CK(cudaFuncSetAttribute(fft_x_r2c_ngp<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute(fft_x_c2r<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute((fft_strided<N, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute((fft_strided<N, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute((fft_strided<N, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CK(cudaFuncSetAttribute(fft_z_sandwich<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_sandwich(N)));
   done = true;
   return 0;
 }
@@ -191,23 +320,40 @@ template <int N> int launch_x_r2c_t(cubep3m_b200_ctx* ctx, int kc, float* data, 
   LAUNCH(ctx, kc, fft_x_r2c<N>, dim3((nrows + 2 * LX - 1) / (2 * LX)), dim3(NT), (int)smem_bytes(N), data, nrows, tw);
   return 0;
 }
+struct NgpSource {            // what fft_x_r2c_ngp needs to produce the tile's density rows itself
+  const int* fstart; int H, b, ox, oy, oz; float mass_p; const int2* deltas; const int* ndelta; int delta_cap; double* sum_phys;
+};
+template <int N> int launch_x_r2c_ngp_t(cubep3m_b200_ctx* ctx, int kc, float* data, const NgpSource& g, const float2* tw) {
+  if (int st = set_smem_attr<N>()) return st;
+  static_assert((N * N) % (2 * LX) == 0, "rows per tile must be a multiple of the rows per CTA");
+  LAUNCH(ctx, kc, fft_x_r2c_ngp<N>, dim3(N * N / (2 * LX)), dim3(NT), (int)smem_bytes(N), data, g.fstart, g.H, g.b, g.ox, g.oy, g.oz, g.mass_p, g.deltas,
+         g.ndelta, g.delta_cap, g.sum_phys, tw);
+  return 0;
+}
 template <int N> int launch_strided_t(cubep3m_b200_ctx* ctx, int kc, bool inv, const float2* in, float2* out, int hc, long long estride,
                                       long long ostride, int outer0, int nouter, const float* kern, long long kes, long long kos, int elo,
-                                      int ehi, const float2* tw) {
+                                      int ehi, const float2* tw, int nbatch, long long bstride) {
   if (int st = set_smem_attr<N>()) return st;
-  const dim3 grid((hc + LX - 1) / LX, nouter);
+  const dim3 grid((hc + LX - 1) / LX, nouter, nbatch);
   const int sm = (int)smem_bytes(N);
-  if (!inv) LAUNCH(ctx, kc, (fft_strided<N, false, false>), grid, dim3(NT), sm, in, out, hc, estride, ostride, outer0, nullptr, 0LL, 0LL, elo, ehi, tw);
-  else if (kern) LAUNCH(ctx, kc, (fft_strided<N, true, true>), grid, dim3(NT), sm, in, out, hc, estride, ostride, outer0, kern, kes, kos, elo, ehi, tw);
-  else LAUNCH(ctx, kc, (fft_strided<N, true, false>), grid, dim3(NT), sm, in, out, hc, estride, ostride, outer0, nullptr, 0LL, 0LL, elo, ehi, tw);
+  if (!inv) LAUNCH(ctx, kc, (fft_strided<N, false, false>), grid, dim3(NT), sm, in, out, hc, estride, ostride, outer0, nullptr, 0LL, 0LL, elo, ehi, tw, bstride);
+  else if (kern) LAUNCH(ctx, kc, (fft_strided<N, true, true>), grid, dim3(NT), sm, in, out, hc, estride, ostride, outer0, kern, kes, kos, elo, ehi, tw, bstride);
+  else LAUNCH(ctx, kc, (fft_strided<N, true, false>), grid, dim3(NT), sm, in, out, hc, estride, ostride, outer0, nullptr, 0LL, 0LL, elo, ehi, tw, bstride);
+  return 0;
+}
+template <int N> int launch_sandwich_t(cubep3m_b200_ctx* ctx, int kc, const float2* spec, float2* g, long long gstride, int hc, int ny, const float* kern,
+                                       long long kstride, int elo, int ehi, const float2* tw) {
+  if (int st = set_smem_attr<N>()) return st;
+  LAUNCH(ctx, kc, fft_z_sandwich<N>, dim3((hc + LX - 1) / LX, ny), dim3(NT), (int)smem_bytes_sandwich(N), spec, g, gstride, hc, ny, kern, kstride, elo, ehi, tw);
   return 0;
 }
 template <int N> int launch_x_c2r_t(cubep3m_b200_ctx* ctx, int kc, const float2* in, float* out, int lo_x, int cnt_x, int lo_y, int cnt_y, int lo_z,
-                                    int cnt_z, int ny_src, long long opx, long long opy, float scale, const float2* tw) {
+                                    int cnt_z, int ny_src, long long opx, long long opy, float scale, const float2* tw, int nbatch, long long ibs,
+                                    long long obs) {
   if (int st = set_smem_attr<N>()) return st;
   const long long nrows = (long long)cnt_z * cnt_y;
-  LAUNCH(ctx, kc, fft_x_c2r<N>, dim3((unsigned)((nrows + 2 * LX - 1) / (2 * LX))), dim3(NT), (int)smem_bytes(N), in, out, lo_x, cnt_x, lo_y, cnt_y,
-         lo_z, cnt_z, ny_src, opx, opy, scale, tw);
+  LAUNCH(ctx, kc, fft_x_c2r<N>, dim3((unsigned)((nrows + 2 * LX - 1) / (2 * LX)), nbatch), dim3(NT), (int)smem_bytes(N), in, out, lo_x, cnt_x, lo_y, cnt_y,
+         lo_z, cnt_z, ny_src, opx, opy, scale, tw, ibs, obs);
   return 0;
 }
 #define FFTK_SWITCH(N_, CALL)                                 \
@@ -221,17 +367,50 @@ inline int launch_x_r2c(cubep3m_b200_ctx* ctx, int kc, int n, float* data, int n
   FFTK_SWITCH(n, X)
 #undef X
 }
+inline int launch_x_r2c_ngp(cubep3m_b200_ctx* ctx, int kc, int n, float* data, const NgpSource& g, const float2* tw) {
+#define X(N) case N: return launch_x_r2c_ngp_t<N>(ctx, kc, data, g, tw);
+  FFTK_SWITCH(n, X)
+#undef X
+}
 inline int launch_strided(cubep3m_b200_ctx* ctx, int kc, int n, bool inv, const float2* in, float2* out, int hc, long long estride, long long ostride,
-                          int outer0, int nouter, const float* kern, long long kes, long long kos, int elo, int ehi, const float2* tw) {
-#define X(N) case N: return launch_strided_t<N>(ctx, kc, inv, in, out, hc, estride, ostride, outer0, nouter, kern, kes, kos, elo, ehi, tw);
+                          int outer0, int nouter, const float* kern, long long kes, long long kos, int elo, int ehi, const float2* tw,
+                          int nbatch = 1, long long bstride = 0) {
+#define X(N) case N: return launch_strided_t<N>(ctx, kc, inv, in, out, hc, estride, ostride, outer0, nouter, kern, kes, kos, elo, ehi, tw, nbatch, bstride);
+  FFTK_SWITCH(n, X)
+#undef X
+}
+inline int launch_sandwich(cubep3m_b200_ctx* ctx, int kc, int n, const float2* spec, float2* g, long long gstride, int hc, int ny, const float* kern,
+                           long long kstride, int elo, int ehi, const float2* tw) {
+#define X(N) case N: return launch_sandwich_t<N>(ctx, kc, spec, g, gstride, hc, ny, kern, kstride, elo, ehi, tw);
   FFTK_SWITCH(n, X)
 #undef X
 }
 inline int launch_x_c2r(cubep3m_b200_ctx* ctx, int kc, int n, const float2* in, float* out, int lo_x, int cnt_x, int lo_y, int cnt_y, int lo_z,
-                        int cnt_z, int ny_src, long long opx, long long opy, float scale, const float2* tw) {
-#define X(N) case N: return launch_x_c2r_t<N>(ctx, kc, in, out, lo_x, cnt_x, lo_y, cnt_y, lo_z, cnt_z, ny_src, opx, opy, scale, tw);
+                        int cnt_z, int ny_src, long long opx, long long opy, float scale, const float2* tw, int nbatch = 1, long long ibs = 0,
+                        long long obs = 0) {
+#define X(N) case N: return launch_x_c2r_t<N>(ctx, kc, in, out, lo_x, cnt_x, lo_y, cnt_y, lo_z, cnt_z, ny_src, opx, opy, scale, tw, nbatch, ibs, obs);
   FFTK_SWITCH(n, X)
 #undef X
+}
+
+// Fine-tile solve after the density is in `data` (n+2,n,n): forward x, y; fused z (forward, 3 x kernel multiply + inverse);
+// then inverse y and inverse x (crop + scale) for the three components in one launch each.
+// g3: scratch of 3 complex tiles; force3: 3 x cnt^3 outputs (component-major).
+// If ngp != nullptr the density is generated inside the first pass (data is then only written).
+inline int fine_solve(cubep3m_b200_ctx* ctx, const Mesh3& m, float* data, float* g3, const float* kern3, float* force3, int lo, int cnt, float scale,
+                      const NgpSource* ngp = nullptr) {
+  const int n = m.nx, hc = m.hc();
+  const long long cplx = (long long)hc * n * n;     // complex elements per tile
+  float2* c = reinterpret_cast<float2*>(data);
+  float2* g = reinterpret_cast<float2*>(g3);
+  if (ngp) { if (int st = launch_x_r2c_ngp(ctx, KC_FFT_X_R2C, n, data, *ngp, m.twx)) return st; }
+  else if (int st = launch_x_r2c(ctx, KC_FFT_X_R2C, n, data, n * n, m.twx)) return st;
+  if (int st = launch_strided(ctx, KC_FFT_FWD_STRIDED, n, false, c, c, hc, (long long)hc, (long long)n * hc, 0, n, nullptr, 0, 0, 0, n - 1, m.twy)) return st;
+  if (int st = launch_sandwich(ctx, KC_FFT_INV_Z_MUL, n, c, g, cplx, hc, n, kern3, cplx, lo, lo + cnt - 1, m.twz)) return st;
+  if (int st = launch_strided(ctx, KC_FFT_INV_Y, n, true, g, g, hc, (long long)hc, (long long)n * hc, lo, cnt, nullptr, 0, 0, lo, lo + cnt - 1, m.twy, 3, cplx)) return st;
+  if (int st = launch_x_c2r(ctx, KC_FFT_X_C2R, n, g, force3, lo, cnt, lo, cnt, lo, cnt, n, cnt, cnt, scale, m.twx, 3, cplx, (long long)cnt * cnt * cnt)) return st;
+  CK(cudaGetLastError());
+  return 0;
 }
 
 // forward 3-D r2c in place on data (nx+2, ny, nz)

@@ -80,6 +80,63 @@ __global__ void __launch_bounds__(TPB) ngp_fixup_kernel(const float* __restrict_
   }
 }
 
+// ---- the same fix-up for the fused density + r2c kernel (fft_x_r2c_ngp): per-tile lists of (from-cell, to-cell) moves.
+// Built once per step for all tiles; also applies the corresponding +-mass_p to the DIAG mass sum.
+constexpr int DELTA_CAP = 2048;   // moves per tile (expected: a few tens)
+__global__ void __launch_bounds__(TPB) build_tile_deltas_kernel(const float* __restrict__ cand, const int* __restrict__ n_cand_ptr, int cand_cap, int n, int b,
+                                                                int m, int T, float mass_p, int2* __restrict__ deltas, int* __restrict__ ndelta,
+                                                                double* __restrict__ sum_phys) {
+  const int nc = min(*n_cand_ptr, cand_cap);
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < nc; i += gridDim.x * TPB) {
+    const float p[3] = {cand[3 * i], cand[3 * i + 1], cand[3 * i + 2]};
+    int g[3];
+    for (int a = 0; a < 3; ++a) g[a] = (int)floorf(p[a]) + b;
+    // tiles whose NGP deposit range [4, n-5] contains the particle: t with 4 <= g - t*m <= n-5
+    int tl[3], th[3];
+    for (int a = 0; a < 3; ++a) {
+      tl[a] = max(0, (g[a] - (n - 5) + m - 1) / m);
+      th[a] = min(T - 1, (g[a] - 4) / m);
+      if (g[a] - 4 < 0) th[a] = -1;
+    }
+    for (int tz = tl[2]; tz <= th[2]; ++tz)
+      for (int ty = tl[1]; ty <= th[1]; ++ty)
+        for (int tx = tl[0]; tx <= th[0]; ++tx) {
+          const int t3[3] = {tx, ty, tz};
+          int k[3], r[3];
+          bool diff = false, ok = true;
+          for (int a = 0; a < 3; ++a) {
+            k[a] = g[a] - t3[a] * m;
+            ok &= (k[a] >= 4 && k[a] <= n - 5);
+            r[a] = (int)floorf(__fadd_rn(p[a], (float)(b - t3[a] * m)));
+            diff |= (r[a] != k[a]);
+          }
+          if (!ok || !diff) continue;
+          const int tile = (tz * T + ty) * T + tx;
+          const int slot = atomicAdd(&ndelta[tile], 1);
+          if (slot < DELTA_CAP) deltas[(long long)tile * DELTA_CAP + slot] = make_int2((k[2] * n + k[1]) * n + k[0], (r[2] * n + r[1]) * n + r[0]);
+          const bool pk = k[0] >= b && k[0] < n - b && k[1] >= b && k[1] < n - b && k[2] >= b && k[2] < n - b;
+          const bool pr = r[0] >= b && r[0] < n - b && r[1] >= b && r[1] < n - b && r[2] >= b && r[2] < n - b;
+          if (pk != pr) atomicAdd(sum_phys, pr ? (double)mass_p : -(double)mass_p);
+        }
+  }
+}
+
+// particles deposited into each tile's padded mesh = particles chained in coarse cells cic_l..cic_h (:120-121): one CTA per tile
+__global__ void __launch_bounds__(TPB) tile_counts_kernel(const int* __restrict__ fstart, int H, int nc_buf, int nc_tile, int T, int* __restrict__ counts) {
+  const int tile = blockIdx.x;
+  const int tx = tile % T, ty = (tile / T) % T, tz = tile / (T * T);
+  const int span = nc_tile + 2 * nc_buf - 2;             // coarse cells cic_l..cic_h
+  const int c0x = tx * nc_tile + 1, c0y = ty * nc_tile + 1, c0z = tz * nc_tile + 1;   // 0-based index of cic_l inside the hoc range
+  int s = 0;
+  for (int r = threadIdx.x; r < span * span; r += TPB) {
+    const int cy = c0y + r % span, cz = c0z + r / span;
+    const long long k0 = ((long long)(cz * H + cy) * H + c0x) * 64;
+    s += fstart[k0 + (long long)span * 64] - fstart[k0];
+  }
+  s = warp_sum_i(s);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(&counts[tile], s);
+}
+
 // max over the cropped force cube of fx^2+fy^2+fz^2 (particle_mesh_threaded.f90:208-223)
 __global__ void __launch_bounds__(TPB) force_max_kernel(const float* __restrict__ fx, const float* __restrict__ fy, const float* __restrict__ fz,
                                                         long long n, unsigned int* __restrict__ out_bits) {

@@ -419,32 +419,39 @@ int do_delete(cubep3m_b200_ctx* ctx) {
   return 0;
 }
 
-// fine-mesh solve of one tile: deposit -> forward FFT -> 3 x (kernel multiply + backward FFT + crop) -> max force
-int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, int* tile_count_dev) {
+// fine-mesh solve of one tile: (density fused into) forward FFT -> fused z pass with the Green's functions -> inverse y, x + crop.
+// materialise = true writes rho_f to tile_rho first with the stand-alone deposit kernels (debug getter / reference ordering).
+int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, bool materialise, int* scratch_count) {
   const Dims& d = ctx->d;
   const int T = d.T, n = d.n;
   const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;   // particle_mesh_threaded.f90:86-90 (cur_tile-1, x fastest)
-  LAUNCH(ctx, KC_DENSITY, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
-         &ctx->dcnt->sum_rho_f, tile_count_dev);
-  if (ctx->hcnt->n_cand > 0)
-    LAUNCH(ctx, KC_DENSITY, fine::ngp_fixup_kernel, std::min(NUM_SMS, (std::min(ctx->hcnt->n_cand, ctx->cand_cap) + fine::TPB - 1) / fine::TPB), fine::TPB, 0,
-           ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, ctx->tile_rho, n, d.b, d.m, tx, ty, tz, mass_p, &ctx->dcnt->sum_rho_f);
-  if (int st = fftk::forward3d(ctx, fine_mesh(ctx), ctx->tile_rho)) return st;
   const float scale = 1.0f / (((float)n * (float)n) * (float)n);       // fft_fine.f90:51
-  const int lo[3] = {d.b - 2, d.b - 2, d.b - 2}, cnt[3] = {d.fdim, d.fdim, d.fdim};
-  for (int comp = 0; comp < 3; ++comp)
-    if (int st = fftk::backward3d(ctx, fine_mesh(ctx), ctx->tile_rho, ctx->tile_g, ctx->kern_f + (size_t)comp * d.hc * n * n, ctx->force_f[comp], lo, cnt, d.fdim, d.fdim, scale))
-      return st;
-  return 0;
+  if (materialise) {
+    LAUNCH(ctx, KC_DENSITY, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
+           &ctx->dcnt->sum_rho_f, scratch_count);
+    if (ctx->hcnt->n_cand > 0)
+      LAUNCH(ctx, KC_DENSITY, fine::ngp_fixup_kernel, std::min(NUM_SMS, (std::min(ctx->hcnt->n_cand, ctx->cand_cap) + fine::TPB - 1) / fine::TPB), fine::TPB, 0,
+             ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, ctx->tile_rho, n, d.b, d.m, tx, ty, tz, mass_p, &ctx->dcnt->sum_rho_f);
+    return fftk::fine_solve(ctx, fine_mesh(ctx), ctx->tile_rho, ctx->tile_g, ctx->kern_f, ctx->force_f[0], d.b - 2, d.fdim, scale);
+  }
+  fftk::NgpSource src{ctx->fstart, d.H, d.b, tx * d.m, ty * d.m, tz * d.m, mass_p, ctx->deltas + (size_t)tile * fine::DELTA_CAP, ctx->ndelta + tile,
+                      fine::DELTA_CAP, &ctx->dcnt->sum_rho_f};
+  return fftk::fine_solve(ctx, fine_mesh(ctx), ctx->tile_rho, ctx->tile_g, ctx->kern_f, ctx->force_f[0], d.b - 2, d.fdim, scale, &src);
 }
 
 int do_fine(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p, float* ms_dep_fft, float* ms_kick) {
   const Dims& d = ctx->d;
   const long long nf = (long long)d.fdim * d.fdim * d.fdim;
   (void)ms_dep_fft; (void)ms_kick;
+  // once per step: per-tile particle counts (parity getter) and the per-tile lists of ulp-boundary mass moves
+  CK(cudaMemsetAsync(ctx->ndelta, 0, sizeof(int) * d.tiles_node, ctx->stream));
+  CK(cudaMemsetAsync(ctx->tile_counts, 0, sizeof(int) * d.tiles_node, ctx->stream));
+  LAUNCH(ctx, KC_DENSITY, fine::tile_counts_kernel, d.tiles_node, fine::TPB, 0, ctx->fstart, d.H, d.nc_buf, d.nc_tile, d.T, ctx->tile_counts);
+  if (ctx->hcnt->n_cand > 0)
+    LAUNCH(ctx, KC_DENSITY, fine::build_tile_deltas_kernel, std::min(NUM_SMS, (std::min(ctx->hcnt->n_cand, ctx->cand_cap) + fine::TPB - 1) / fine::TPB), fine::TPB,
+           0, ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, d.n, d.b, d.m, d.T, mass_p, ctx->deltas, ctx->ndelta, &ctx->dcnt->sum_rho_f);
   for (int tile = 0; tile < d.tiles_node; ++tile) {
-    if (ctx->cfg.tile_split > 1 && (tile % ctx->cfg.tile_split) != ctx->cfg.tile_split_rank) continue;
-    if (int st = fine_tile_solve(ctx, tile, mass_p, ctx->rowoff + d.nc_node * d.nc_node + 8 + tile)) return st;
+    if (int st = fine_tile_solve(ctx, tile, mass_p, false, nullptr)) return st;
     LAUNCH(ctx, KC_FORCE_MAX, fine::force_max_kernel, NUM_SMS * 4, fine::TPB, 0, ctx->force_f[0], ctx->force_f[1], ctx->force_f[2], nf, &ctx->dcnt->f_force_max2_bits);
     if (ctx->cfg.ngp_fmesh_force) {
       const int T = d.T;
@@ -601,8 +608,8 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
 #ifdef CUBEP3M_WITH_NCCL
   if (ctx->comm) ncclCommDestroy(ctx->comm);
 #endif
-  F(ctx->cand); F(ctx->key); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
-  F(ctx->kern_f); F(ctx->tile_rho); F(ctx->tile_g); for (int i = 0; i < 3; ++i) F(ctx->force_f[i]);
+  F(ctx->cand); F(ctx->deltas); F(ctx->ndelta); F(ctx->tile_counts); F(ctx->key); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
+  F(ctx->kern_f); F(ctx->tile_rho); F(ctx->tile_g); F(ctx->force_f[0]);
   F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->creal); F(ctx->gather); F(ctx->force_c); F(ctx->redbuf); F(ctx->cntbuf); F(ctx->dcnt);
   for (int a = 0; a < 3; ++a) { bool dup = false; for (int b2 = 0; b2 < a; ++b2) dup |= (ctx->tw_c[b2] == ctx->tw_c[a]); if (!dup) F(ctx->tw_c[a]); }
   if (ctx->hcnt) cudaFreeHost(ctx->hcnt);
@@ -644,6 +651,9 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   TRY(dmalloc(&ctx->key, (size_t)d.max_np));
   ctx->cand_cap = std::max(4096, d.max_np / 64);
   TRY(dmalloc(&ctx->cand, (size_t)3 * ctx->cand_cap));
+  TRY(dmalloc(&ctx->deltas, (size_t)d.tiles_node * fine::DELTA_CAP));
+  TRY(dmalloc(&ctx->ndelta, (size_t)d.tiles_node));
+  TRY(dmalloc(&ctx->tile_counts, (size_t)d.tiles_node));
   TRY(dmalloc(&ctx->fstart, (size_t)d.NF + 64));
   TRY(dmalloc(&ctx->fcur, (size_t)d.NF + 64));
   ctx->nblocksum = (int)((d.NF + part::SCAN_BLOCK - 1) / part::SCAN_BLOCK);
@@ -656,8 +666,9 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   if (cudaMemset(ctx->rowoff, 0, rowoff_n * sizeof(int)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   const size_t tile_elems = (size_t)(d.n + 2) * d.n * d.n;
   TRY(dmalloc(&ctx->tile_rho, tile_elems));
-  TRY(dmalloc(&ctx->tile_g, tile_elems));
-  for (int i = 0; i < 3; ++i) TRY(dmalloc(&ctx->force_f[i], (size_t)d.fdim * d.fdim * d.fdim));
+  TRY(dmalloc(&ctx->tile_g, 3 * tile_elems));
+  TRY(dmalloc(&ctx->force_f[0], (size_t)3 * d.fdim * d.fdim * d.fdim));
+  ctx->force_f[1] = ctx->force_f[0] + (size_t)d.fdim * d.fdim * d.fdim; ctx->force_f[2] = ctx->force_f[1] + (size_t)d.fdim * d.fdim * d.fdim;
   TRY(dmalloc(&ctx->kern_f, (size_t)3 * d.hc * d.n * d.n));
   TRY(fftk::make_twiddles(d.n, &ctx->tw_f));
   const int Nx = d.Nc[0], Ny = d.Nc[1], Nz = d.Nc[2];
@@ -888,7 +899,7 @@ int cubep3m_b200_debug_cell_counts(cubep3m_b200_ctx* ctx, int32_t* counts) {
 int cubep3m_b200_debug_tile_counts(cubep3m_b200_ctx* ctx, int32_t* counts) {
   if (!ctx || !ctx->last_tile_counts_valid) return CUBEP3M_B200_ENOTREADY;
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpy(counts, ctx->rowoff + ctx->d.nc_node * ctx->d.nc_node + 8, sizeof(int) * ctx->d.tiles_node, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(counts, ctx->tile_counts, sizeof(int) * ctx->d.tiles_node, cudaMemcpyDeviceToHost));
   return 0;
 }
 int cubep3m_b200_debug_sorted_particles(cubep3m_b200_ctx* ctx, float* xv, int32_t* np) {
@@ -945,7 +956,7 @@ int cubep3m_b200_debug_fine_tile(cubep3m_b200_ctx* ctx, int32_t tile, float mass
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(dsum);
   if (force_f) {
-    if (int st = fine_tile_solve(ctx, tile, mass_p, scratch)) return st;
+    if (int st = fine_tile_solve(ctx, tile, mass_p, true, scratch)) return st;
     const size_t nf = (size_t)d.fdim * d.fdim * d.fdim;
     std::vector<float> tmp(nf);
     for (int comp = 0; comp < 3; ++comp) {   // interleave to the reference's force_f(3,...) layout

@@ -118,50 +118,96 @@ __global__ void __launch_bounds__(NT) fft_x_r2c_ngp(float* __restrict__ data, co
   }
 }
 
-// ---- pass Y / Z: strided complex columns.
-// element e of column c of block (bx, by): in[base + e*estride + c], base = (by + outer0)*ostride + bx*LX
+// ---- pass Y / Z: strided complex columns. Persistent CTAs: each loops over work items (kx block, outer index, batch) and
+// prefetches the NEXT item's column block into registers while the current one is transformed, so the global/L2 latency
+// (the dominant stall in the first version: ~50 % long_scoreboard) overlaps the butterflies.
+// element e of column c of item (bx, by, bz): in[bz*bstride + (by + outer0)*ostride + bx*LX + e*estride + c]
 // MUL: multiply the loaded value by i*kern[e*kes + (by+outer0)*kos + kx]   (Z pass: e=z, outer=y; kern = one component)
 // stores only elements e in [elo, ehi]
+template <int N> struct StridedCfg {
+  static constexpr int EPT = (N + (NT / LX) - 1) / (NT / LX);   // elements per thread (11 for N=176)
+  static constexpr bool PREFETCH = EPT <= 19;                  // keep the prefetch registers bounded (N <= 304)
+};
+
+#ifndef FFTK_MINB
+#define FFTK_MINB 2
+#endif
 template <int N, bool INV, bool MUL>
-__global__ void __launch_bounds__(NT) fft_strided(const float2* __restrict__ in, float2* __restrict__ out, int hc,
-                                                  long long estride, long long ostride, int outer0,
+__global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) fft_strided(const float2* __restrict__ in, float2* __restrict__ out, int hc,
+                                                  long long estride, long long ostride, int outer0, int nouter, int nbatch,
                                                   const float* __restrict__ kern, long long kes, long long kos,
                                                   int elo, int ehi, const float2* __restrict__ tw_g, long long bstride) {
   extern __shared__ __align__(16) unsigned char raw[];
   Smem s = carve<N>(raw, tw_g);
-  in += (long long)blockIdx.z * bstride;     // batch (force component) offset
-  out += (long long)blockIdx.z * bstride;
-  const int outer = blockIdx.y + outer0;
-  const int kx0 = blockIdx.x * LX;
-  const long long base = (long long)outer * ostride + kx0;
-  const int col = threadIdx.x % LX;
-  const bool colok = (kx0 + col) < hc;
-  for (int e = threadIdx.x / LX; e < N; e += NT / LX) {
+  constexpr int EPT = StridedCfg<N>::EPT;
+  constexpr bool PF = StridedCfg<N>::PREFETCH;
+  const int nbx = (hc + LX - 1) / LX;
+  const long long total = (long long)nbx * nouter * nbatch;
+  const int col = threadIdx.x % LX, e0 = threadIdx.x / LX;
+  float2 pf[PF ? EPT : 1];
+  auto decode = [&](long long item, long long& base, long long& kbase, bool& colok) {
+    const int bx = (int)(item % nbx);
+    const long long t = item / nbx;
+    const int outer = (int)(t % nouter) + outer0, bz = (int)(t / nouter);
+    const int kx0 = bx * LX;
+    base = (long long)bz * bstride + (long long)outer * ostride + kx0;
+    kbase = (long long)outer * kos + kx0;
+    colok = (kx0 + col) < hc;
+  };
+  auto fetch = [&](long long base, long long kbase, bool colok, int it) -> float2 {
+    const int e = e0 + it * (NT / LX);
     float2 v = make_float2(0.f, 0.f);
-    if (colok) {
+    if (colok && e < N) {
       v = in[base + (long long)e * estride + col];
       if (MUL) {
-        const float kv = kern[(long long)e * kes + (long long)outer * kos + kx0 + col];
+        const float kv = kern[(long long)e * kes + kbase + col];
         v = make_float2(-v.y * kv, v.x * kv);
       }
     }
-    s.re0[e * LXP + col] = v.x;
-    s.im0[e * LXP + col] = v.y;
+    return v;
+  };
+  long long item = blockIdx.x;
+  long long base = 0, kbase = 0; bool colok = false;
+  if (item < total) {
+    decode(item, base, kbase, colok);
+    if (PF) {
+#pragma unroll
+      for (int it = 0; it < EPT; ++it) pf[it] = fetch(base, kbase, colok, it);
+    }
   }
-  __syncthreads();
-  fft_columns<N, INV>(s.re0, s.im0, s.re1, s.im1, s.tw);
-  const float* zr = result_buffer<N>() ? s.re1 : s.re0;
-  const float* zi = result_buffer<N>() ? s.im1 : s.im0;
-  if (colok)
-    for (int e = elo + threadIdx.x / LX; e <= ehi; e += NT / LX)
-      out[base + (long long)e * estride + col] = make_float2(zr[e * LXP + col], zi[e * LXP + col]);
+  while (item < total) {
+#pragma unroll
+    for (int it = 0; it < EPT; ++it) {
+      const int e = e0 + it * (NT / LX);
+      const float2 v = PF ? pf[it] : fetch(base, kbase, colok, it);
+      if (e < N) { s.re0[e * LXP + col] = v.x; s.im0[e * LXP + col] = v.y; }
+    }
+    __syncthreads();
+    const long long cur_base = base; const bool cur_ok = colok;
+    const long long next = item + gridDim.x;
+    if (next < total) {
+      decode(next, base, kbase, colok);
+      if (PF) {
+#pragma unroll
+        for (int it = 0; it < EPT; ++it) pf[it] = fetch(base, kbase, colok, it);
+      }
+    }
+    fft_columns<N, INV>(s.re0, s.im0, s.re1, s.im1, s.tw);
+    const float* zr = result_buffer<N>() ? s.re1 : s.re0;
+    const float* zi = result_buffer<N>() ? s.im1 : s.im0;
+    if (cur_ok)
+      for (int e = elo + e0; e <= ehi; e += NT / LX) out[cur_base + (long long)e * estride + col] = make_float2(zr[e * LXP + col], zi[e * LXP + col]);
+    __syncthreads();
+    item = next;
+  }
 }
 
 // ---- fused pass Z: forward FFT along z, then for each of the three force components: multiply by i*kern_f(comp)
 // (particle_mesh_threaded.f90:183-192) and inverse FFT along z, storing only the cropped z range. One load of the spectrum
-// column block feeds four transforms; the forward-z result never goes back to memory.
+// column block feeds four transforms; the forward-z result never goes back to memory. Persistent CTAs with register prefetch of
+// the next block's spectrum and of the next component's Green's function values.
 template <int N>
-__global__ void __launch_bounds__(NT) fft_z_sandwich(const float2* __restrict__ spec, float2* __restrict__ g, long long gstride, int hc, int ny,
+__global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) fft_z_sandwich(const float2* __restrict__ spec, float2* __restrict__ g, long long gstride, int hc, int ny,
                                                      const float* __restrict__ kern, long long kstride, int elo, int ehi,
                                                      const float2* __restrict__ tw_g) {
   extern __shared__ __align__(16) unsigned char raw[];
@@ -173,20 +219,12 @@ __global__ void __launch_bounds__(NT) fft_z_sandwich(const float2* __restrict__ 
   float* b2i = b2r + N * LXP;
   float2* tw = reinterpret_cast<float2*>(b2i + N * LXP);
   for (int t = threadIdx.x; t < N; t += NT) tw[t] = tw_g[t];
-  const int y = blockIdx.y;
-  const int kx0 = blockIdx.x * LX;
+  constexpr int EPT = StridedCfg<N>::EPT;
+  constexpr bool PF = StridedCfg<N>::PREFETCH;
+  const int nbx = (hc + LX - 1) / LX;
+  const long long total = (long long)nbx * ny;
   const long long estride = (long long)ny * hc;
-  const long long base = (long long)y * hc + kx0;
-  const int col = threadIdx.x % LX;
-  const bool colok = (kx0 + col) < hc;
-  for (int e = threadIdx.x / LX; e < N; e += NT / LX) {
-    float2 v = make_float2(0.f, 0.f);
-    if (colok) v = spec[base + (long long)e * estride + col];
-    b0r[e * LXP + col] = v.x;
-    b0i[e * LXP + col] = v.y;
-  }
-  __syncthreads();
-  fft_columns<N, false>(b0r, b0i, b1r, b1i, tw);
+  const int col = threadIdx.x % LX, e0 = threadIdx.x / LX;
   // S = forward result, X = the other of {b0,b1}; the inverse transforms ping-pong between X and b2
   const float* sr = result_buffer<N>() ? b1r : b0r;
   const float* si = result_buffer<N>() ? b1i : b0i;
@@ -194,22 +232,72 @@ __global__ void __launch_bounds__(NT) fft_z_sandwich(const float2* __restrict__ 
   float* xi = result_buffer<N>() ? b0i : b1i;
   const float* rr = result_buffer<N>() ? b2r : xr;
   const float* ri = result_buffer<N>() ? b2i : xi;
+  float2 pf[PF ? EPT : 1];
+  float kf[PF ? EPT : 1];
+  auto decode = [&](long long item, long long& base, bool& colok) {
+    const int bx = (int)(item % nbx), y = (int)(item / nbx);
+    base = (long long)y * hc + bx * LX;
+    colok = (bx * LX + col) < hc;
+  };
+  auto fetch = [&](long long base, bool colok, int it) -> float2 {
+    const int e = e0 + it * (NT / LX);
+    return (colok && e < N) ? spec[base + (long long)e * estride + col] : make_float2(0.f, 0.f);
+  };
+  auto fetchk = [&](long long base, bool colok, int comp, int it) -> float {
+    const int e = e0 + it * (NT / LX);
+    return (colok && e < N) ? kern[(long long)comp * kstride + base + (long long)e * estride + col] : 0.f;
+  };
+  long long item = blockIdx.x, base = 0; bool colok = false;
+  if (item < total) {
+    decode(item, base, colok);
+    if (PF) {
+#pragma unroll
+      for (int it = 0; it < EPT; ++it) pf[it] = fetch(base, colok, it);
+    }
+  }
+  while (item < total) {
+#pragma unroll
+    for (int it = 0; it < EPT; ++it) {
+      const int e = e0 + it * (NT / LX);
+      const float2 v = PF ? pf[it] : fetch(base, colok, it);
+      if (e < N) { b0r[e * LXP + col] = v.x; b0i[e * LXP + col] = v.y; }
+    }
+    __syncthreads();
+    const long long cur_base = base; const bool cur_ok = colok;
+    if (PF) {
+#pragma unroll
+      for (int it = 0; it < EPT; ++it) kf[it] = fetchk(cur_base, cur_ok, 0, it);
+    }
+    fft_columns<N, false>(b0r, b0i, b1r, b1i, tw);
+    const long long next = item + gridDim.x;
 #pragma unroll 1
-  for (int comp = 0; comp < 3; ++comp) {
-    const float* kc = kern + (long long)comp * kstride + base;
-    for (int e = threadIdx.x / LX; e < N; e += NT / LX) {
-      const float kv = colok ? kc[(long long)e * estride + col] : 0.f;
-      const int idx = e * LXP + col;
-      xr[idx] = -si[idx] * kv;
-      xi[idx] = sr[idx] * kv;
+    for (int comp = 0; comp < 3; ++comp) {
+#pragma unroll
+      for (int it = 0; it < EPT; ++it) {
+        const int e = e0 + it * (NT / LX);
+        const float kv = PF ? kf[it] : fetchk(cur_base, cur_ok, comp, it);
+        if (e < N) { const int idx = e * LXP + col; xr[idx] = -si[idx] * kv; xi[idx] = sr[idx] * kv; }
+      }
+      __syncthreads();
+      if (PF) {
+        if (comp < 2) {
+#pragma unroll
+          for (int it = 0; it < EPT; ++it) kf[it] = fetchk(cur_base, cur_ok, comp + 1, it);
+        } else if (next < total) {
+          decode(next, base, colok);
+#pragma unroll
+          for (int it = 0; it < EPT; ++it) pf[it] = fetch(base, colok, it);
+        }
+      }
+      fft_columns<N, true>(xr, xi, b2r, b2i, tw);
+      if (cur_ok) {
+        float2* go = g + (long long)comp * gstride + cur_base;
+        for (int e = elo + e0; e <= ehi; e += NT / LX) go[(long long)e * estride + col] = make_float2(rr[e * LXP + col], ri[e * LXP + col]);
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    fft_columns<N, true>(xr, xi, b2r, b2i, tw);
-    if (colok) {
-      float2* go = g + (long long)comp * gstride + base;
-      for (int e = elo + threadIdx.x / LX; e <= ehi; e += NT / LX) go[(long long)e * estride + col] = make_float2(rr[e * LXP + col], ri[e * LXP + col]);
-    }
-    __syncthreads();
+    if (!PF && next < total) decode(next, base, colok);
+    item = next;
   }
 }
 constexpr size_t smem_bytes_sandwich(int n) { return (size_t)6 * n * LXP * sizeof(float) + (size_t)n * sizeof(float2); }
@@ -334,17 +422,28 @@ template <int N> int launch_strided_t(cubep3m_b200_ctx* ctx, int kc, bool inv, c
                                       long long ostride, int outer0, int nouter, const float* kern, long long kes, long long kos, int elo,
                                       int ehi, const float2* tw, int nbatch, long long bstride) {
   if (int st = set_smem_attr<N>()) return st;
-  const dim3 grid((hc + LX - 1) / LX, nouter, nbatch);
   const int sm = (int)smem_bytes(N);
-  if (!inv) LAUNCH(ctx, kc, (fft_strided<N, false, false>), grid, dim3(NT), sm, in, out, hc, estride, ostride, outer0, nullptr, 0LL, 0LL, elo, ehi, tw, bstride);
-  else if (kern) LAUNCH(ctx, kc, (fft_strided<N, true, true>), grid, dim3(NT), sm, in, out, hc, estride, ostride, outer0, kern, kes, kos, elo, ehi, tw, bstride);
-  else LAUNCH(ctx, kc, (fft_strided<N, true, false>), grid, dim3(NT), sm, in, out, hc, estride, ostride, outer0, nullptr, 0LL, 0LL, elo, ehi, tw, bstride);
+  static int occ[3] = {0, 0, 0};    // resident CTAs per SM of the three instantiations
+  if (!occ[0]) {
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], (fft_strided<N, false, false>), NT, sm));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], (fft_strided<N, true, true>), NT, sm));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], (fft_strided<N, true, false>), NT, sm));
+  }
+  const long long total = (long long)((hc + LX - 1) / LX) * nouter * nbatch;
+  auto grid = [&](int o) { return dim3((unsigned)std::min<long long>(total, (long long)NUM_SMS * std::max(o, 1))); };
+  if (!inv) LAUNCH(ctx, kc, (fft_strided<N, false, false>), grid(occ[0]), dim3(NT), sm, in, out, hc, estride, ostride, outer0, nouter, nbatch, nullptr, 0LL, 0LL, elo, ehi, tw, bstride);
+  else if (kern) LAUNCH(ctx, kc, (fft_strided<N, true, true>), grid(occ[1]), dim3(NT), sm, in, out, hc, estride, ostride, outer0, nouter, nbatch, kern, kes, kos, elo, ehi, tw, bstride);
+  else LAUNCH(ctx, kc, (fft_strided<N, true, false>), grid(occ[2]), dim3(NT), sm, in, out, hc, estride, ostride, outer0, nouter, nbatch, nullptr, 0LL, 0LL, elo, ehi, tw, bstride);
   return 0;
 }
 template <int N> int launch_sandwich_t(cubep3m_b200_ctx* ctx, int kc, const float2* spec, float2* g, long long gstride, int hc, int ny, const float* kern,
                                        long long kstride, int elo, int ehi, const float2* tw) {
   if (int st = set_smem_attr<N>()) return st;
-  LAUNCH(ctx, kc, fft_z_sandwich<N>, dim3((hc + LX - 1) / LX, ny), dim3(NT), (int)smem_bytes_sandwich(N), spec, g, gstride, hc, ny, kern, kstride, elo, ehi, tw);
+  static int occ = 0;
+  if (!occ) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_z_sandwich<N>, NT, (int)smem_bytes_sandwich(N)));
+  const long long total = (long long)((hc + LX - 1) / LX) * ny;
+  LAUNCH(ctx, kc, fft_z_sandwich<N>, dim3((unsigned)std::min<long long>(total, (long long)NUM_SMS * std::max(occ, 1))), dim3(NT), (int)smem_bytes_sandwich(N), spec,
+         g, gstride, hc, ny, kern, kstride, elo, ehi, tw);
   return 0;
 }
 template <int N> int launch_x_c2r_t(cubep3m_b200_ctx* ctx, int kc, const float2* in, float* out, int lo_x, int cnt_x, int lo_y, int cnt_y, int lo_z,

@@ -13,7 +13,7 @@ from .abi import Config, StepOut, Clock, ERRORS, max_np
 from . import tables
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libcubep3m_b200.so")
+SO_PATH = os.environ.get("CUBEP3M_B200_SO", os.path.join(_HERE, "libcubep3m_b200.so"))   # override only for A/B builds
 _LIB = None
 _fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")

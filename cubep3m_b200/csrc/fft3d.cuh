@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(NT) fft_x_r2c(float* __restrict__ data, int nr
 // ---- pass X forward fused with the NGP mass assignment (particle_mesh_threaded.f90:100-151): the tile's density row is not read from
 // memory but produced on the fly from the fine-cell occupancy table, rho = mass_p * (fstart[k+1] - fstart[k]) for tile-local cells
 // [4, n-5] and 0 elsewhere; `deltas` moves the mass of the few particles whose reference cell floor(fl(x+offset)) differs (fine.cuh).
+// One warp handles one row at a time (lanes along x): no per-element divisions, coalesced gathers within a coarse cell.
 template <int N>
 __global__ void __launch_bounds__(NT) fft_x_r2c_ngp(float* __restrict__ data, const int* __restrict__ fstart, int H, int b, int ox, int oy, int oz,
                                                     float mass_p, const int2* __restrict__ deltas, const int* __restrict__ ndelta_ptr, int delta_cap,
@@ -72,22 +73,29 @@ __global__ void __launch_bounds__(NT) fft_x_r2c_ngp(float* __restrict__ data, co
   Smem s = carve<N>(raw, tw_g);
   constexpr int P = N + 2;
   const int r0 = blockIdx.x * (2 * LX);          // first row (= z*N + y) of this CTA; N*N is a multiple of 32
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double msum = 0.0;
-  for (int q = threadIdx.x; q < 2 * LX * N; q += NT) {
-    const int row = q / N, x = q - row * N;
+  for (int row = warp; row < 2 * LX; row += NT / 32) {
     const int gr = r0 + row;
     const int y = gr % N, z = gr / N;
-    float v = 0.f;
-    if (x >= 4 && x <= N - 5 && y >= 4 && y <= N - 5 && z >= 4 && z <= N - 5) {
-      const int gx = x + ox, gy = y + oy, gz = z + oz;
-      const long long k = ((long long)(((gz >> 2) * H + (gy >> 2))) * H + (gx >> 2)) * 64 + (((gz & 3) << 4) | ((gy & 3) << 2) | (gx & 3));
-      v = mass_p * (float)(fstart[k + 1] - fstart[k]);
-      if (x >= b && x < N - b && y >= b && y < N - b && z >= b && z < N - b) msum += (double)v;
+    float* dst = ((row & 1) ? s.im0 : s.re0) + (row >> 1);
+    const bool yz_in = (y >= 4 && y <= N - 5 && z >= 4 && z <= N - 5);
+    const bool yz_phys = (y >= b && y < N - b && z >= b && z < N - b);
+    const int gy = y + oy, gz = z + oz;
+    const long long rowkey = ((long long)((gz >> 2) * H + (gy >> 2)) * H) * 64 + (((gz & 3) << 4) | ((gy & 3) << 2));
+    for (int x = lane; x < N; x += 32) {
+      float v = 0.f;
+      if (yz_in && x >= 4 && x <= N - 5) {
+        const int gx = x + ox;
+        const long long k = rowkey + (long long)(gx >> 2) * 64 + (gx & 3);
+        v = mass_p * (float)(fstart[k + 1] - fstart[k]);
+        if (yz_phys && x >= b && x < N - b) msum += (double)v;
+      }
+      dst[x * LXP] = v;
     }
-    ((row & 1) ? s.im0 : s.re0)[x * LXP + (row >> 1)] = v;
   }
   msum = warp_sum_d(msum);
-  if ((threadIdx.x & 31) == 0 && msum != 0.0) atomicAdd(sum_phys, msum);
+  if (lane == 0 && msum != 0.0) atomicAdd(sum_phys, msum);
   __syncthreads();
   const int nd = min(*ndelta_ptr, delta_cap);
   if (nd > 0) {
@@ -106,21 +114,22 @@ __global__ void __launch_bounds__(NT) fft_x_r2c_ngp(float* __restrict__ data, co
   fft_columns<N, false>(s.re0, s.im0, s.re1, s.im1, s.tw);
   const float* zr = result_buffer<N>() ? s.re1 : s.re0;
   const float* zi = result_buffer<N>() ? s.im1 : s.im0;
-  for (int q = threadIdx.x; q < 2 * LX * P; q += NT) {
-    const int row = q / P, f = q - row * P;
-    const int k = f >> 1, col = row >> 1;
-    const int km = (k == 0) ? 0 : N - k;
-    const float ar = zr[k * LXP + col], ai = zi[k * LXP + col], br = zr[km * LXP + col], bi = zi[km * LXP + col];
-    float v;
-    if ((row & 1) == 0) v = (f & 1) ? 0.5f * (ai - bi) : 0.5f * (ar + br);
-    else                v = (f & 1) ? -0.5f * (ar - br) : 0.5f * (ai + bi);
-    data[(long long)(r0 + row) * P + f] = v;
+  // untangle the two real rows of each column: A = (Z[k] + conj Z[N-k]) / 2, B = (Z[k] - conj Z[N-k]) / (2i); one warp per row
+  for (int row = warp; row < 2 * LX; row += NT / 32) {
+    float2* orow = reinterpret_cast<float2*>(data + (long long)(r0 + row) * P);
+    const int col = row >> 1;
+    for (int k = lane; k < N / 2 + 1; k += 32) {
+      const int km = (k == 0) ? 0 : N - k;
+      const float ar = zr[k * LXP + col], ai = zi[k * LXP + col], br = zr[km * LXP + col], bi = zi[km * LXP + col];
+      orow[k] = (row & 1) ? make_float2(0.5f * (ai + bi), -0.5f * (ar - br)) : make_float2(0.5f * (ar + br), 0.5f * (ai - bi));
+    }
   }
 }
 
 // ---- pass Y / Z: strided complex columns. Persistent CTAs: each loops over work items (kx block, outer index, batch) and
 // prefetches the NEXT item's column block into registers while the current one is transformed, so the global/L2 latency
-// (the dominant stall in the first version: ~50 % long_scoreboard) overlaps the butterflies.
+// (the dominant stall in the first version: ~50 % long_scoreboard) overlaps the butterflies. Shared-memory layout is AoS
+// float2 [N][16] (fft_smem.cuh: stage_aos) — one 64-bit access per point and constant offsets from one base per thread.
 // element e of column c of item (bx, by, bz): in[bz*bstride + (by + outer0)*ostride + bx*LX + e*estride + c]
 // MUL: multiply the loaded value by i*kern[e*kes + (by+outer0)*kos + kx]   (Z pass: e=z, outer=y; kern = one component)
 // stores only elements e in [elo, ehi]
@@ -128,39 +137,44 @@ template <int N> struct StridedCfg {
   static constexpr int EPT = (N + (NT / LX) - 1) / (NT / LX);   // elements per thread (11 for N=176)
   static constexpr bool PREFETCH = EPT <= 19;                  // keep the prefetch registers bounded (N <= 304)
 };
-
 #ifndef FFTK_MINB
 #define FFTK_MINB 2
 #endif
+
 template <int N, bool INV, bool MUL>
 __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) fft_strided(const float2* __restrict__ in, float2* __restrict__ out, int hc,
                                                   long long estride, long long ostride, int outer0, int nouter, int nbatch,
                                                   const float* __restrict__ kern, long long kes, long long kos,
                                                   int elo, int ehi, const float2* __restrict__ tw_g, long long bstride) {
   extern __shared__ __align__(16) unsigned char raw[];
-  Smem s = carve<N>(raw, tw_g);
+  float2* b0 = reinterpret_cast<float2*>(raw);
+  float2* b1 = b0 + N * LX;
+  float2* tw = b1 + N * LX;
+  for (int t = threadIdx.x; t < N; t += NT) tw[t] = tw_g[t];
   constexpr int EPT = StridedCfg<N>::EPT;
   constexpr bool PF = StridedCfg<N>::PREFETCH;
+  constexpr int ES = NT / LX;                      // element step between a thread's consecutive elements
   const int nbx = (hc + LX - 1) / LX;
   const long long total = (long long)nbx * nouter * nbatch;
   const int col = threadIdx.x % LX, e0 = threadIdx.x / LX;
+  const int sidx = e0 * LX + col;
+  const long long gstep = (long long)ES * estride, kstep = (long long)ES * kes;
   float2 pf[PF ? EPT : 1];
   auto decode = [&](long long item, long long& base, long long& kbase, bool& colok) {
     const int bx = (int)(item % nbx);
     const long long t = item / nbx;
     const int outer = (int)(t % nouter) + outer0, bz = (int)(t / nouter);
     const int kx0 = bx * LX;
-    base = (long long)bz * bstride + (long long)outer * ostride + kx0;
-    kbase = (long long)outer * kos + kx0;
+    base = (long long)bz * bstride + (long long)outer * ostride + kx0 + (long long)e0 * estride + col;
+    kbase = (long long)outer * kos + kx0 + (long long)e0 * kes + col;
     colok = (kx0 + col) < hc;
   };
   auto fetch = [&](long long base, long long kbase, bool colok, int it) -> float2 {
-    const int e = e0 + it * (NT / LX);
     float2 v = make_float2(0.f, 0.f);
-    if (colok && e < N) {
-      v = in[base + (long long)e * estride + col];
+    if (colok && e0 + it * ES < N) {
+      v = in[base + it * gstep];
       if (MUL) {
-        const float kv = kern[(long long)e * kes + kbase + col];
+        const float kv = kern[kbase + it * kstep];
         v = make_float2(-v.y * kv, v.x * kv);
       }
     }
@@ -175,12 +189,12 @@ __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) f
       for (int it = 0; it < EPT; ++it) pf[it] = fetch(base, kbase, colok, it);
     }
   }
+  const float2* res = result_buffer<N>() ? b1 : b0;
   while (item < total) {
 #pragma unroll
     for (int it = 0; it < EPT; ++it) {
-      const int e = e0 + it * (NT / LX);
       const float2 v = PF ? pf[it] : fetch(base, kbase, colok, it);
-      if (e < N) { s.re0[e * LXP + col] = v.x; s.im0[e * LXP + col] = v.y; }
+      if (e0 + it * ES < N) b0[sidx + it * ES * LX] = v;
     }
     __syncthreads();
     const long long cur_base = base; const bool cur_ok = colok;
@@ -192,11 +206,15 @@ __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) f
         for (int it = 0; it < EPT; ++it) pf[it] = fetch(base, kbase, colok, it);
       }
     }
-    fft_columns<N, INV>(s.re0, s.im0, s.re1, s.im1, s.tw);
-    const float* zr = result_buffer<N>() ? s.re1 : s.re0;
-    const float* zi = result_buffer<N>() ? s.im1 : s.im0;
-    if (cur_ok)
-      for (int e = elo + e0; e <= ehi; e += NT / LX) out[cur_base + (long long)e * estride + col] = make_float2(zr[e * LXP + col], zi[e * LXP + col]);
+    fft_columns_aos<N, INV>(b0, b1, tw);
+    if (cur_ok) {
+      float2* op = out + cur_base;
+#pragma unroll
+      for (int it = 0; it < EPT; ++it) {
+        const int e = e0 + it * ES;
+        if (e >= elo && e <= ehi) op[it * gstep] = res[sidx + it * ES * LX];
+      }
+    }
     __syncthreads();
     item = next;
   }
@@ -205,47 +223,42 @@ __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) f
 // ---- fused pass Z: forward FFT along z, then for each of the three force components: multiply by i*kern_f(comp)
 // (particle_mesh_threaded.f90:183-192) and inverse FFT along z, storing only the cropped z range. One load of the spectrum
 // column block feeds four transforms; the forward-z result never goes back to memory. Persistent CTAs with register prefetch of
-// the next block's spectrum and of the next component's Green's function values.
+// the next block's spectrum and of the next component's Green's function values. AoS float2 shared-memory layout.
 template <int N>
 __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) fft_z_sandwich(const float2* __restrict__ spec, float2* __restrict__ g, long long gstride, int hc, int ny,
                                                      const float* __restrict__ kern, long long kstride, int elo, int ehi,
                                                      const float2* __restrict__ tw_g) {
   extern __shared__ __align__(16) unsigned char raw[];
-  float* b0r = reinterpret_cast<float*>(raw);
-  float* b0i = b0r + N * LXP;
-  float* b1r = b0i + N * LXP;
-  float* b1i = b1r + N * LXP;
-  float* b2r = b1i + N * LXP;
-  float* b2i = b2r + N * LXP;
-  float2* tw = reinterpret_cast<float2*>(b2i + N * LXP);
+  float2* b0 = reinterpret_cast<float2*>(raw);
+  float2* b1 = b0 + N * LX;
+  float2* b2 = b1 + N * LX;
+  float2* tw = b2 + N * LX;
   for (int t = threadIdx.x; t < N; t += NT) tw[t] = tw_g[t];
   constexpr int EPT = StridedCfg<N>::EPT;
   constexpr bool PF = StridedCfg<N>::PREFETCH;
+  constexpr int ES = NT / LX;
   const int nbx = (hc + LX - 1) / LX;
   const long long total = (long long)nbx * ny;
   const long long estride = (long long)ny * hc;
+  const long long gstep = (long long)ES * estride;
   const int col = threadIdx.x % LX, e0 = threadIdx.x / LX;
+  const int sidx = e0 * LX + col;
   // S = forward result, X = the other of {b0,b1}; the inverse transforms ping-pong between X and b2
-  const float* sr = result_buffer<N>() ? b1r : b0r;
-  const float* si = result_buffer<N>() ? b1i : b0i;
-  float* xr = result_buffer<N>() ? b0r : b1r;
-  float* xi = result_buffer<N>() ? b0i : b1i;
-  const float* rr = result_buffer<N>() ? b2r : xr;
-  const float* ri = result_buffer<N>() ? b2i : xi;
+  const float2* S = result_buffer<N>() ? b1 : b0;
+  float2* X = result_buffer<N>() ? b0 : b1;
+  const float2* Rr = result_buffer<N>() ? b2 : X;
   float2 pf[PF ? EPT : 1];
   float kf[PF ? EPT : 1];
   auto decode = [&](long long item, long long& base, bool& colok) {
     const int bx = (int)(item % nbx), y = (int)(item / nbx);
-    base = (long long)y * hc + bx * LX;
+    base = (long long)y * hc + bx * LX + (long long)e0 * estride + col;
     colok = (bx * LX + col) < hc;
   };
   auto fetch = [&](long long base, bool colok, int it) -> float2 {
-    const int e = e0 + it * (NT / LX);
-    return (colok && e < N) ? spec[base + (long long)e * estride + col] : make_float2(0.f, 0.f);
+    return (colok && e0 + it * ES < N) ? spec[base + it * gstep] : make_float2(0.f, 0.f);
   };
   auto fetchk = [&](long long base, bool colok, int comp, int it) -> float {
-    const int e = e0 + it * (NT / LX);
-    return (colok && e < N) ? kern[(long long)comp * kstride + base + (long long)e * estride + col] : 0.f;
+    return (colok && e0 + it * ES < N) ? kern[(long long)comp * kstride + base + it * gstep] : 0.f;
   };
   long long item = blockIdx.x, base = 0; bool colok = false;
   if (item < total) {
@@ -258,9 +271,8 @@ __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) f
   while (item < total) {
 #pragma unroll
     for (int it = 0; it < EPT; ++it) {
-      const int e = e0 + it * (NT / LX);
       const float2 v = PF ? pf[it] : fetch(base, colok, it);
-      if (e < N) { b0r[e * LXP + col] = v.x; b0i[e * LXP + col] = v.y; }
+      if (e0 + it * ES < N) b0[sidx + it * ES * LX] = v;
     }
     __syncthreads();
     const long long cur_base = base; const bool cur_ok = colok;
@@ -268,15 +280,14 @@ __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) f
 #pragma unroll
       for (int it = 0; it < EPT; ++it) kf[it] = fetchk(cur_base, cur_ok, 0, it);
     }
-    fft_columns<N, false>(b0r, b0i, b1r, b1i, tw);
+    fft_columns_aos<N, false>(b0, b1, tw);
     const long long next = item + gridDim.x;
 #pragma unroll 1
     for (int comp = 0; comp < 3; ++comp) {
 #pragma unroll
       for (int it = 0; it < EPT; ++it) {
-        const int e = e0 + it * (NT / LX);
         const float kv = PF ? kf[it] : fetchk(cur_base, cur_ok, comp, it);
-        if (e < N) { const int idx = e * LXP + col; xr[idx] = -si[idx] * kv; xi[idx] = sr[idx] * kv; }
+        if (e0 + it * ES < N) { const float2 sv = S[sidx + it * ES * LX]; X[sidx + it * ES * LX] = make_float2(-sv.y * kv, sv.x * kv); }
       }
       __syncthreads();
       if (PF) {
@@ -289,10 +300,14 @@ __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) f
           for (int it = 0; it < EPT; ++it) pf[it] = fetch(base, colok, it);
         }
       }
-      fft_columns<N, true>(xr, xi, b2r, b2i, tw);
+      fft_columns_aos<N, true>(X, b2, tw);
       if (cur_ok) {
         float2* go = g + (long long)comp * gstride + cur_base;
-        for (int e = elo + e0; e <= ehi; e += NT / LX) go[(long long)e * estride + col] = make_float2(rr[e * LXP + col], ri[e * LXP + col]);
+#pragma unroll
+        for (int it = 0; it < EPT; ++it) {
+          const int e = e0 + it * ES;
+          if (e >= elo && e <= ehi) go[it * gstep] = Rr[sidx + it * ES * LX];
+        }
       }
       __syncthreads();
     }
@@ -300,7 +315,7 @@ __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) f
     item = next;
   }
 }
-constexpr size_t smem_bytes_sandwich(int n) { return (size_t)6 * n * LXP * sizeof(float) + (size_t)n * sizeof(float2); }
+constexpr size_t smem_bytes_sandwich(int n) { return smem_bytes_aos(n, 3); }
 
 // ---- pass X backward: half spectra -> real rows with crop + scale.
 // Row index space: ridx in [0, cnt_z*cnt_y): zc = ridx / cnt_y, yc = ridx % cnt_y, source row (z = zc+lo_z, y = yc+lo_y) of an
@@ -329,14 +344,16 @@ __global__ void __launch_bounds__(NT) fft_x_c2r(const float2* __restrict__ in, f
     srow[threadIdx.x] = so; drow[threadIdx.x] = dof;
   }
   __syncthreads();
-  // stage A (even rows) into buffer 0, B (odd rows) into buffer 1
-  for (int q = threadIdx.x; q < 2 * LX * HC; q += NT) {
-    const int row = q / HC, k = q - row * HC;
+  // stage A (even rows) into buffer 0, B (odd rows) into buffer 1; one warp per row, lanes along k
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int row = warp; row < 2 * LX; row += NT / 32) {
     const long long so = srow[row];
-    const float2 v = (so >= 0) ? in[so + k] : make_float2(0.f, 0.f);
-    const int col = row >> 1;
-    if (row & 1) { s.re1[k * LXP + col] = v.x; s.im1[k * LXP + col] = v.y; }
-    else         { s.re0[k * LXP + col] = v.x; s.im0[k * LXP + col] = v.y; }
+    float* dr = ((row & 1) ? s.re1 : s.re0) + (row >> 1);
+    float* di = ((row & 1) ? s.im1 : s.im0) + (row >> 1);
+    for (int k = lane; k < HC; k += 32) {
+      const float2 v = (so >= 0) ? in[so + k] : make_float2(0.f, 0.f);
+      dr[k * LXP] = v.x; di[k * LXP] = v.y;
+    }
   }
   __syncthreads();
   // Z[k] = A[k] + i B[k];  Z[N-k] = conj(A[k]) + i conj(B[k]);  imaginary parts of the k=0 and k=N/2 bins are dropped (c2r)
@@ -356,7 +373,6 @@ __global__ void __launch_bounds__(NT) fft_x_c2r(const float2* __restrict__ in, f
   const float* zr = result_buffer<N>() ? s.re1 : s.re0;
   const float* zi = result_buffer<N>() ? s.im1 : s.im0;
   // one warp per output row at a time: lanes run along x (coalesced stores, stride-17 conflict-free smem reads)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int row = warp; row < 2 * LX; row += NT / 32) {
     const long long dof = drow[row];
     if (dof < 0) continue;
@@ -422,7 +438,7 @@ template <int N> int launch_strided_t(cubep3m_b200_ctx* ctx, int kc, bool inv, c
                                       long long ostride, int outer0, int nouter, const float* kern, long long kes, long long kos, int elo,
                                       int ehi, const float2* tw, int nbatch, long long bstride) {
   if (int st = set_smem_attr<N>()) return st;
-  const int sm = (int)smem_bytes(N);
+  const int sm = (int)smem_bytes_aos(N, 2);
   static int occ[3] = {0, 0, 0};    // resident CTAs per SM of the three instantiations
   if (!occ[0]) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], (fft_strided<N, false, false>), NT, sm));

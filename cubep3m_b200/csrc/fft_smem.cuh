@@ -180,6 +180,59 @@ FFTK_HD void fft_columns(float* re0, float* im0, float* re1, float* im1, const f
 #endif
 }
 
+
+// ---- AoS variant for the strided passes: columns live as float2 buf[N][LX] (no padding). Lanes run along the 16 columns, so a
+// warp touches two 128-byte rows per 64-bit access: conflict-free, and one LDS.64/STS.64 per point instead of two 32-bit ones.
+template <int N, int R, int NS, bool INV>
+FFTK_HD void stage_aos(const float2* __restrict__ in, float2* __restrict__ out, const float2* __restrict__ tw, int tid) {
+  constexpr int NB = N / R;
+  for (int w = tid; w < NB * LX; w += NT) {
+    const int col = w % LX, j = w / LX;
+    const int k = j % NS;
+    const float2* p = in + (j * LX + col);
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = p[r * NB * LX];
+    if (NS > 1) {
+      constexpr int TS = N / (NS * R);
+      const float2* t0 = tw + k * TS;
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        float2 t = t0[(r - 1) * k * TS];      // tw[r*k*TS]
+        if (INV) t.y = -t.y;
+        v[r] = cmul(v[r], t);
+      }
+    }
+    Radix<R, INV>::run(v);
+    float2* q = out + (((j / NS) * NS * R + k) * LX + col);
+#pragma unroll
+    for (int r = 0; r < R; ++r) q[r * NS * LX] = v[r];
+  }
+}
+
+template <int N, bool INV>
+FFTK_HD void fft_columns_aos(float2* b0, float2* b1, const float2* tw) {
+  using F = Factors<N>;
+#ifdef __CUDA_ARCH__
+  const int tid = threadIdx.x;
+  stage_aos<N, F::r0, 1, INV>(b0, b1, tw, tid);
+  __syncthreads();
+  if (F::r1 > 1) {
+    stage_aos<N, F::r1, F::r0, INV>(b1, b0, tw, tid);
+    __syncthreads();
+  }
+  if (F::r2 > 1) {
+    stage_aos<N, F::r2, F::r0 * F::r1, INV>(b0, b1, tw, tid);
+    __syncthreads();
+  }
+#else
+  for (int tid = 0; tid < NT; ++tid) stage_aos<N, F::r0, 1, INV>(b0, b1, tw, tid);
+  if (F::r1 > 1) for (int tid = 0; tid < NT; ++tid) stage_aos<N, F::r1, F::r0, INV>(b1, b0, tw, tid);
+  if (F::r2 > 1) for (int tid = 0; tid < NT; ++tid) stage_aos<N, F::r2, F::r0 * F::r1, INV>(b0, b1, tw, tid);
+#endif
+}
+constexpr size_t smem_bytes_aos(int n, int nbuf) { return (size_t)nbuf * n * LX * sizeof(float2) + (size_t)n * sizeof(float2); }
+
 constexpr size_t smem_bytes(int n) { return (size_t)4 * n * LXP * sizeof(float) + (size_t)n * sizeof(float2); }
 
 }  // namespace fftk

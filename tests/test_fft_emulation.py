@@ -28,6 +28,18 @@ template<int N> double test() {
       double err=std::abs(s-std::complex<double>(rr[k*LXP+c],ri[k*LXP+c])); if(err>maxerr)maxerr=err; if(std::abs(s)>maxv)maxv=std::abs(s);
     }
   }
+  // AoS float2 variant used by the strided passes
+  std::vector<float2> a0(N*LX), a1(N*LX);
+  for (int inv=0; inv<2; ++inv) {
+    for (int e=0;e<N;++e) for(int c=0;c<LX;++c) a0[e*LX+c]=make_float2((float)x[e*LX+c].real(),(float)x[e*LX+c].imag());
+    if (inv) fft_columns_aos<N,true>(a0.data(),a1.data(),tw.data());
+    else fft_columns_aos<N,false>(a0.data(),a1.data(),tw.data());
+    float2* r = result_buffer<N>() ? a1.data() : a0.data();
+    for (int c=1;c<LX;c+=5) for (int k=0;k<N;++k) {
+      std::complex<double> s=0; for (int e=0;e<N;++e){ double a=(inv?2:-2)*M_PI*(double)e*k/N; s+=x[e*LX+c]*std::complex<double>(cos(a),sin(a)); }
+      double err=std::abs(s-std::complex<double>(r[k*LX+c].x,r[k*LX+c].y)); if(err>maxerr)maxerr=err;
+    }
+  }
   printf("N=%d rel_err=%.3e\n", N, maxerr/maxv); return maxerr/maxv;
 }
 int main(){

@@ -382,6 +382,109 @@ __global__ void __launch_bounds__(NT) fft_x_c2r(const float2* __restrict__ in, f
   }
 }
 
+// ---- pass X backward for the three force components of a fine tile, fused with the crop, the 1/n^3 scale and the max |F|^2
+// (particle_mesh_threaded.f90:202-223). One CTA owns 32 cropped rows and loops over the components; the next component's rows
+// are prefetched into registers during the current FFT; |F|^2 is accumulated per output element in registers.
+template <int N>
+__global__ void __launch_bounds__(NT, 2) fft_x_c2r3(const float2* __restrict__ in, float* __restrict__ out, int lo, int cnt, long long in_bstride,
+                                                    long long out_bstride, float scale, unsigned int* __restrict__ fmax_bits,
+                                                    const float2* __restrict__ tw_g) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  Smem s = carve<N>(raw, tw_g);
+  constexpr int HC = N / 2 + 1;
+  constexpr int KIT = (HC + 31) / 32;          // k iterations per lane
+  constexpr int RPW = 2 * LX / (NT / 32);      // rows per warp (4)
+  constexpr int XIT_MAX = (N + 31) / 32;
+  const long long nrows = (long long)cnt * cnt;
+  const long long r0 = (long long)blockIdx.x * (2 * LX);
+  __shared__ long long srow[2 * LX], drow[2 * LX];
+  if (threadIdx.x < 2 * LX) {
+    const long long ridx = r0 + threadIdx.x;
+    long long so = -1, dof = -1;
+    if (ridx < nrows) {
+      const int zc = (int)(ridx / cnt), yc = (int)(ridx - (long long)zc * cnt);
+      so = ((long long)(zc + lo) * N + (yc + lo)) * HC;
+      dof = ((long long)zc * cnt + yc) * cnt;
+    }
+    srow[threadIdx.x] = so; drow[threadIdx.x] = dof;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2 pf[RPW * KIT];
+  float fsq[RPW * XIT_MAX];
+#pragma unroll
+  for (int i = 0; i < RPW * XIT_MAX; ++i) fsq[i] = 0.f;
+  auto prefetch = [&](int comp) {
+    const float2* src = in + (long long)comp * in_bstride;
+#pragma unroll
+    for (int ri = 0; ri < RPW; ++ri) {
+      const long long so = srow[warp + ri * (NT / 32)];
+#pragma unroll
+      for (int ki = 0; ki < KIT; ++ki) {
+        const int k = lane + 32 * ki;
+        pf[ri * KIT + ki] = (so >= 0 && k < HC) ? src[so + k] : make_float2(0.f, 0.f);
+      }
+    }
+  };
+  prefetch(0);
+  const float* zr = result_buffer<N>() ? s.re1 : s.re0;
+  const float* zi = result_buffer<N>() ? s.im1 : s.im0;
+#pragma unroll 1
+  for (int comp = 0; comp < 3; ++comp) {
+    // stage A (even rows) into buffer 0, B (odd rows) into buffer 1
+#pragma unroll
+    for (int ri = 0; ri < RPW; ++ri) {
+      const int row = warp + ri * (NT / 32);
+      float* dr = ((row & 1) ? s.re1 : s.re0) + (row >> 1);
+      float* di = ((row & 1) ? s.im1 : s.im0) + (row >> 1);
+#pragma unroll
+      for (int ki = 0; ki < KIT; ++ki) {
+        const int k = lane + 32 * ki;
+        if (k < HC) { dr[k * LXP] = pf[ri * KIT + ki].x; di[k * LXP] = pf[ri * KIT + ki].y; }
+      }
+    }
+    __syncthreads();
+    if (comp < 2) prefetch(comp + 1);
+    // Z[k] = A[k] + i B[k];  Z[N-k] = conj(A[k]) + i conj(B[k]);  imaginary parts of the k=0 and k=N/2 bins are dropped (c2r)
+    for (int q = threadIdx.x; q < LX * HC; q += NT) {
+      const int k = q / LX, col = q - k * LX;
+      float ar = s.re0[k * LXP + col], ai = s.im0[k * LXP + col], br = s.re1[k * LXP + col], bi = s.im1[k * LXP + col];
+      if (k == 0 || 2 * k == N) { ai = 0.f; bi = 0.f; }
+      s.re0[k * LXP + col] = ar - bi;
+      s.im0[k * LXP + col] = ai + br;
+      if (k != 0 && 2 * k != N) {
+        s.re0[(N - k) * LXP + col] = ar + bi;
+        s.im0[(N - k) * LXP + col] = br - ai;
+      }
+    }
+    __syncthreads();
+    fft_columns<N, true>(s.re0, s.im0, s.re1, s.im1, s.tw);
+    float* o = out + (long long)comp * out_bstride;
+#pragma unroll
+    for (int ri = 0; ri < RPW; ++ri) {
+      const int row = warp + ri * (NT / 32);
+      const long long dof = drow[row];
+      const float* src = (row & 1) ? zi : zr;
+      const int col = row >> 1;
+#pragma unroll
+      for (int xi = 0; xi < XIT_MAX; ++xi) {
+        const int xc = lane + 32 * xi;
+        if (dof >= 0 && xc < cnt) {
+          const float v = src[(xc + lo) * LXP + col] * scale;
+          o[dof + xc] = v;
+          fsq[ri * XIT_MAX + xi] = fmaf(v, v, fsq[ri * XIT_MAX + xi]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float mx = 0.f;
+#pragma unroll
+  for (int i = 0; i < RPW * XIT_MAX; ++i) mx = fmaxf(mx, fsq[i]);
+  mx = warp_max(mx);
+  if (lane == 0 && mx > 0.f) atomic_max_float_nonneg(fmax_bits, mx);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-side dispatch on N (each axis of a mesh may have its own length: the fine tile is cubic, the global coarse mesh of a
 // (Dx,Dy,Dz) rank grid need not be)
@@ -405,6 +508,7 @@ template <int N> int set_smem_attr() {
   CK(cudaFuncSetAttribute(fft_x_r2c<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute(fft_x_r2c_ngp<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute(fft_x_c2r<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CK(cudaFuncSetAttribute(fft_x_c2r3<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute((fft_strided<N, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute((fft_strided<N, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute((fft_strided<N, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -471,6 +575,13 @@ template <int N> int launch_x_c2r_t(cubep3m_b200_ctx* ctx, int kc, const float2*
          lo_z, cnt_z, ny_src, opx, opy, scale, tw, ibs, obs);
   return 0;
 }
+template <int N> int launch_x_c2r3_t(cubep3m_b200_ctx* ctx, int kc, const float2* in, float* out, int lo, int cnt, long long ibs, long long obs, float scale,
+                                     unsigned int* fmax_bits, const float2* tw) {
+  if (int st = set_smem_attr<N>()) return st;
+  const long long nrows = (long long)cnt * cnt;
+  LAUNCH(ctx, kc, fft_x_c2r3<N>, dim3((unsigned)((nrows + 2 * LX - 1) / (2 * LX))), dim3(NT), (int)smem_bytes(N), in, out, lo, cnt, ibs, obs, scale, fmax_bits, tw);
+  return 0;
+}
 #define FFTK_SWITCH(N_, CALL)                                 \
   switch (N_) {                                               \
     FFTK_FOR_ALL_N(CALL)                                      \
@@ -508,12 +619,19 @@ inline int launch_x_c2r(cubep3m_b200_ctx* ctx, int kc, int n, const float2* in, 
 #undef X
 }
 
+inline int launch_x_c2r3(cubep3m_b200_ctx* ctx, int kc, int n, const float2* in, float* out, int lo, int cnt, long long ibs, long long obs, float scale,
+                         unsigned int* fmax_bits, const float2* tw) {
+#define X(N) case N: return launch_x_c2r3_t<N>(ctx, kc, in, out, lo, cnt, ibs, obs, scale, fmax_bits, tw);
+  FFTK_SWITCH(n, X)
+#undef X
+}
+
 // Fine-tile solve after the density is in `data` (n+2,n,n): forward x, y; fused z (forward, 3 x kernel multiply + inverse);
 // then inverse y and inverse x (crop + scale) for the three components in one launch each.
 // g3: scratch of 3 complex tiles; force3: 3 x cnt^3 outputs (component-major).
 // If ngp != nullptr the density is generated inside the first pass (data is then only written).
 inline int fine_solve(cubep3m_b200_ctx* ctx, const Mesh3& m, float* data, float* g3, const float* kern3, float* force3, int lo, int cnt, float scale,
-                      const NgpSource* ngp = nullptr) {
+                      unsigned int* fmax_bits, const NgpSource* ngp = nullptr) {
   const int n = m.nx, hc = m.hc();
   const long long cplx = (long long)hc * n * n;     // complex elements per tile
   float2* c = reinterpret_cast<float2*>(data);
@@ -523,7 +641,7 @@ inline int fine_solve(cubep3m_b200_ctx* ctx, const Mesh3& m, float* data, float*
   if (int st = launch_strided(ctx, KC_FFT_FWD_STRIDED, n, false, c, c, hc, (long long)hc, (long long)n * hc, 0, n, nullptr, 0, 0, 0, n - 1, m.twy)) return st;
   if (int st = launch_sandwich(ctx, KC_FFT_INV_Z_MUL, n, c, g, cplx, hc, n, kern3, cplx, lo, lo + cnt - 1, m.twz)) return st;
   if (int st = launch_strided(ctx, KC_FFT_INV_Y, n, true, g, g, hc, (long long)hc, (long long)n * hc, lo, cnt, nullptr, 0, 0, lo, lo + cnt - 1, m.twy, 3, cplx)) return st;
-  if (int st = launch_x_c2r(ctx, KC_FFT_X_C2R, n, g, force3, lo, cnt, lo, cnt, lo, cnt, n, cnt, cnt, scale, m.twx, 3, cplx, (long long)cnt * cnt * cnt)) return st;
+  if (int st = launch_x_c2r3(ctx, KC_FFT_X_C2R, n, g, force3, lo, cnt, cplx, (long long)cnt * cnt * cnt, scale, fmax_bits, m.twx)) return st;
   CK(cudaGetLastError());
   return 0;
 }

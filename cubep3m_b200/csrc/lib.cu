@@ -421,8 +421,11 @@ int do_delete(cubep3m_b200_ctx* ctx) {
 
 // fine-mesh solve of one tile: (density fused into) forward FFT -> fused z pass with the Green's functions -> inverse y, x + crop.
 // materialise = true writes rho_f to tile_rho first with the stand-alone deposit kernels (debug getter / reference ordering).
-int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, bool materialise, int* scratch_count) {
+int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, bool materialise, int* scratch_count, int set = 0) {
   const Dims& d = ctx->d;
+  float* t_rho = set ? ctx->tile_rho2 : ctx->tile_rho;
+  float* t_g = set ? ctx->tile_g2 : ctx->tile_g;
+  float* t_force = set ? ctx->force_f2[0] : ctx->force_f[0];
   const int T = d.T, n = d.n;
   const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;   // particle_mesh_threaded.f90:86-90 (cur_tile-1, x fastest)
   const float scale = 1.0f / (((float)n * (float)n) * (float)n);       // fft_fine.f90:51
@@ -432,16 +435,15 @@ int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, bool material
     if (ctx->hcnt->n_cand > 0)
       LAUNCH(ctx, KC_DENSITY, fine::ngp_fixup_kernel, std::min(NUM_SMS, (std::min(ctx->hcnt->n_cand, ctx->cand_cap) + fine::TPB - 1) / fine::TPB), fine::TPB, 0,
              ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, ctx->tile_rho, n, d.b, d.m, tx, ty, tz, mass_p, &ctx->dcnt->sum_rho_f);
-    return fftk::fine_solve(ctx, fine_mesh(ctx), ctx->tile_rho, ctx->tile_g, ctx->kern_f, ctx->force_f[0], d.b - 2, d.fdim, scale);
+    return fftk::fine_solve(ctx, fine_mesh(ctx), ctx->tile_rho, ctx->tile_g, ctx->kern_f, ctx->force_f[0], d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits);
   }
   fftk::NgpSource src{ctx->fstart, d.H, d.b, tx * d.m, ty * d.m, tz * d.m, mass_p, ctx->deltas + (size_t)tile * fine::DELTA_CAP, ctx->ndelta + tile,
                       fine::DELTA_CAP, &ctx->dcnt->sum_rho_f};
-  return fftk::fine_solve(ctx, fine_mesh(ctx), ctx->tile_rho, ctx->tile_g, ctx->kern_f, ctx->force_f[0], d.b - 2, d.fdim, scale, &src);
+  return fftk::fine_solve(ctx, fine_mesh(ctx), t_rho, t_g, ctx->kern_f, t_force, d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits, &src);
 }
 
 int do_fine(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p, float* ms_dep_fft, float* ms_kick) {
   const Dims& d = ctx->d;
-  const long long nf = (long long)d.fdim * d.fdim * d.fdim;
   (void)ms_dep_fft; (void)ms_kick;
   // once per step: per-tile particle counts (parity getter) and the per-tile lists of ulp-boundary mass moves
   CK(cudaMemsetAsync(ctx->ndelta, 0, sizeof(int) * d.tiles_node, ctx->stream));
@@ -450,16 +452,24 @@ int do_fine(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p, float* m
   if (ctx->hcnt->n_cand > 0)
     LAUNCH(ctx, KC_DENSITY, fine::build_tile_deltas_kernel, std::min(NUM_SMS, (std::min(ctx->hcnt->n_cand, ctx->cand_cap) + fine::TPB - 1) / fine::TPB), fine::TPB,
            0, ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, d.n, d.b, d.m, d.T, mass_p, ctx->deltas, ctx->ndelta, &ctx->dcnt->sum_rho_f);
-  for (int tile = 0; tile < d.tiles_node; ++tile) {
-    if (int st = fine_tile_solve(ctx, tile, mass_p, false, nullptr)) return st;
-    LAUNCH(ctx, KC_FORCE_MAX, fine::force_max_kernel, NUM_SMS * 4, fine::TPB, 0, ctx->force_f[0], ctx->force_f[1], ctx->force_f[2], nf, &ctx->dcnt->f_force_max2_bits);
-    if (ctx->cfg.ngp_fmesh_force) {
+  const bool two = ctx->tile_streams == 2 && d.tiles_node > 1;
+  if (two) { CK(cudaEventRecord(ctx->ev_fork, ctx->stream_main)); CK(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0)); }
+  int status = 0;
+  for (int tile = 0; tile < d.tiles_node && !status; ++tile) {
+    const int set = two ? (tile & 1) : 0;
+    ctx->stream = set ? ctx->stream_aux : ctx->stream_main;      // LAUNCH() targets ctx->stream
+    status = fine_tile_solve(ctx, tile, mass_p, false, nullptr, set);
+    if (!status && ctx->cfg.ngp_fmesh_force) {
       const int T = d.T;
       const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;
-      LAUNCH(ctx, KC_NGP_KICK, fine::ngp_kick_kernel, d.nc_tile * d.nc_tile, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->force_f[0], ctx->force_f[1],
-             ctx->force_f[2], d.H, d.nc_buf, d.nc_tile, d.b, d.m, d.fdim, tx, ty, tz, a_mid, ctx->cfg.G, dt);
+      float** ff = set ? ctx->force_f2 : ctx->force_f;
+      LAUNCH(ctx, KC_NGP_KICK, fine::ngp_kick_kernel, d.nc_tile * d.nc_tile, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ff[0], ff[1], ff[2], d.H, d.nc_buf,
+             d.nc_tile, d.b, d.m, d.fdim, tx, ty, tz, a_mid, ctx->cfg.G, dt);
     }
   }
+  ctx->stream = ctx->stream_main;
+  if (two) { CK(cudaEventRecord(ctx->ev_join, ctx->stream_aux)); CK(cudaStreamWaitEvent(ctx->stream_main, ctx->ev_join, 0)); }
+  if (status) return status;
   CK(cudaGetLastError());
   return 0;
 }
@@ -609,7 +619,10 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
   if (ctx->comm) ncclCommDestroy(ctx->comm);
 #endif
   F(ctx->cand); F(ctx->deltas); F(ctx->ndelta); F(ctx->tile_counts); F(ctx->key); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
-  F(ctx->kern_f); F(ctx->tile_rho); F(ctx->tile_g); F(ctx->force_f[0]);
+  F(ctx->kern_f); F(ctx->tile_rho); F(ctx->tile_g); F(ctx->force_f[0]); F(ctx->tile_rho2); F(ctx->tile_g2); F(ctx->force_f2[0]);
+  if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->creal); F(ctx->gather); F(ctx->force_c); F(ctx->redbuf); F(ctx->cntbuf); F(ctx->dcnt);
   for (int a = 0; a < 3; ++a) { bool dup = false; for (int b2 = 0; b2 < a; ++b2) dup |= (ctx->tw_c[b2] == ctx->tw_c[a]); if (!dup) F(ctx->tw_c[a]); }
   if (ctx->hcnt) cudaFreeHost(ctx->hcnt);
@@ -669,6 +682,19 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   TRY(dmalloc(&ctx->tile_g, 3 * tile_elems));
   TRY(dmalloc(&ctx->force_f[0], (size_t)3 * d.fdim * d.fdim * d.fdim));
   ctx->force_f[1] = ctx->force_f[0] + (size_t)d.fdim * d.fdim * d.fdim; ctx->force_f[2] = ctx->force_f[1] + (size_t)d.fdim * d.fdim * d.fdim;
+  {
+    const char* e = getenv("CUBEP3M_B200_TILE_STREAMS");
+    ctx->tile_streams = (e && atoi(e) == 1) ? 1 : 2;
+  }
+  ctx->stream_main = ctx->stream;
+  if (ctx->tile_streams == 2) {
+    if (cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
+    TRY(dmalloc(&ctx->tile_rho2, tile_elems));
+    TRY(dmalloc(&ctx->tile_g2, 3 * tile_elems));
+    TRY(dmalloc(&ctx->force_f2[0], (size_t)3 * d.fdim * d.fdim * d.fdim));
+    ctx->force_f2[1] = ctx->force_f2[0] + (size_t)d.fdim * d.fdim * d.fdim; ctx->force_f2[2] = ctx->force_f2[1] + (size_t)d.fdim * d.fdim * d.fdim;
+  }
   TRY(dmalloc(&ctx->kern_f, (size_t)3 * d.hc * d.n * d.n));
   TRY(fftk::make_twiddles(d.n, &ctx->tw_f));
   const int Nx = d.Nc[0], Ny = d.Nc[1], Nz = d.Nc[2];

@@ -130,10 +130,13 @@ struct cubep3m_b200_ctx {
   int cand_cap = 0;
   // fine mesh
   float* kern_f = nullptr;    // [comp][z][y][kx]: the reference's kern_f(3,hc,n,n) (cubep3m.fh:35) de-interleaved
-  int tile_streams = 1;       // 2: consecutive tiles alternate between two streams / buffer sets (hides launch bubbles and tails)
-  cudaStream_t stream_main = nullptr, stream_aux = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  float* tile_rho2 = nullptr; float* tile_g2 = nullptr; float* force_f2[3] = {nullptr, nullptr, nullptr};   // second buffer set
+  static constexpr int MAX_TILE_STREAMS = 4;
+  int tile_streams = 1;       // S > 1: consecutive tiles rotate over S streams / buffer sets (hides launch bubbles, tails, latency)
+  cudaStream_t stream_main = nullptr, stream_aux[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+  float* tile_rho_s[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // buffer sets 1..S-1 (set 0 = tile_rho / tile_g / force_f)
+  float* tile_g_s[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+  float* force_f_s[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
   float* tile_rho = nullptr;  // (n+2,n,n) real / (hc,n,n) complex, in place
   float* tile_g = nullptr;    // work array for one force component
   float* force_f[3] = {nullptr, nullptr, nullptr};  // (fdim^3) each, SoA

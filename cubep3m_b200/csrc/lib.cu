@@ -423,9 +423,9 @@ int do_delete(cubep3m_b200_ctx* ctx) {
 // materialise = true writes rho_f to tile_rho first with the stand-alone deposit kernels (debug getter / reference ordering).
 int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, bool materialise, int* scratch_count, int set = 0) {
   const Dims& d = ctx->d;
-  float* t_rho = set ? ctx->tile_rho2 : ctx->tile_rho;
-  float* t_g = set ? ctx->tile_g2 : ctx->tile_g;
-  float* t_force = set ? ctx->force_f2[0] : ctx->force_f[0];
+  float* t_rho = set ? ctx->tile_rho_s[set] : ctx->tile_rho;
+  float* t_g = set ? ctx->tile_g_s[set] : ctx->tile_g;
+  float* t_force = set ? ctx->force_f_s[set] : ctx->force_f[0];
   const int T = d.T, n = d.n;
   const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;   // particle_mesh_threaded.f90:86-90 (cur_tile-1, x fastest)
   const float scale = 1.0f / (((float)n * (float)n) * (float)n);       // fft_fine.f90:51
@@ -452,23 +452,27 @@ int do_fine(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p, float* m
   if (ctx->hcnt->n_cand > 0)
     LAUNCH(ctx, KC_DENSITY, fine::build_tile_deltas_kernel, std::min(NUM_SMS, (std::min(ctx->hcnt->n_cand, ctx->cand_cap) + fine::TPB - 1) / fine::TPB), fine::TPB,
            0, ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, d.n, d.b, d.m, d.T, mass_p, ctx->deltas, ctx->ndelta, &ctx->dcnt->sum_rho_f);
-  const bool two = ctx->tile_streams == 2 && d.tiles_node > 1;
-  if (two) { CK(cudaEventRecord(ctx->ev_fork, ctx->stream_main)); CK(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0)); }
+  const int S = std::min(ctx->tile_streams, d.tiles_node);
+  const size_t fstride = (size_t)d.fdim * d.fdim * d.fdim;
+  if (S > 1) {
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream_main));
+    for (int q = 1; q < S; ++q) CK(cudaStreamWaitEvent(ctx->stream_aux[q], ctx->ev_fork, 0));
+  }
   int status = 0;
   for (int tile = 0; tile < d.tiles_node && !status; ++tile) {
-    const int set = two ? (tile & 1) : 0;
-    ctx->stream = set ? ctx->stream_aux : ctx->stream_main;      // LAUNCH() targets ctx->stream
+    const int set = tile % S;
+    ctx->stream = set ? ctx->stream_aux[set] : ctx->stream_main;      // LAUNCH() targets ctx->stream
     status = fine_tile_solve(ctx, tile, mass_p, false, nullptr, set);
     if (!status && ctx->cfg.ngp_fmesh_force) {
       const int T = d.T;
       const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;
-      float** ff = set ? ctx->force_f2 : ctx->force_f;
-      LAUNCH(ctx, KC_NGP_KICK, fine::ngp_kick_kernel, d.nc_tile * d.nc_tile, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ff[0], ff[1], ff[2], d.H, d.nc_buf,
+      float* ff = set ? ctx->force_f_s[set] : ctx->force_f[0];
+      LAUNCH(ctx, KC_NGP_KICK, fine::ngp_kick_kernel, d.nc_tile * d.nc_tile, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ff, ff + fstride, ff + 2 * fstride, d.H, d.nc_buf,
              d.nc_tile, d.b, d.m, d.fdim, tx, ty, tz, a_mid, ctx->cfg.G, dt);
     }
   }
   ctx->stream = ctx->stream_main;
-  if (two) { CK(cudaEventRecord(ctx->ev_join, ctx->stream_aux)); CK(cudaStreamWaitEvent(ctx->stream_main, ctx->ev_join, 0)); }
+  for (int q = 1; q < S; ++q) { CK(cudaEventRecord(ctx->ev_join[q], ctx->stream_aux[q])); CK(cudaStreamWaitEvent(ctx->stream_main, ctx->ev_join[q], 0)); }
   if (status) return status;
   CK(cudaGetLastError());
   return 0;
@@ -619,10 +623,13 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
   if (ctx->comm) ncclCommDestroy(ctx->comm);
 #endif
   F(ctx->cand); F(ctx->deltas); F(ctx->ndelta); F(ctx->tile_counts); F(ctx->key); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
-  F(ctx->kern_f); F(ctx->tile_rho); F(ctx->tile_g); F(ctx->force_f[0]); F(ctx->tile_rho2); F(ctx->tile_g2); F(ctx->force_f2[0]);
-  if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
+  F(ctx->kern_f); F(ctx->tile_rho); F(ctx->tile_g); F(ctx->force_f[0]); 
+  for (int q = 1; q < cubep3m_b200_ctx::MAX_TILE_STREAMS; ++q) {
+    F(ctx->tile_rho_s[q]); F(ctx->tile_g_s[q]); F(ctx->force_f_s[q]);
+    if (ctx->stream_aux[q]) cudaStreamDestroy(ctx->stream_aux[q]);
+    if (ctx->ev_join[q]) cudaEventDestroy(ctx->ev_join[q]);
+  }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->creal); F(ctx->gather); F(ctx->force_c); F(ctx->redbuf); F(ctx->cntbuf); F(ctx->dcnt);
   for (int a = 0; a < 3; ++a) { bool dup = false; for (int b2 = 0; b2 < a; ++b2) dup |= (ctx->tw_c[b2] == ctx->tw_c[a]); if (!dup) F(ctx->tw_c[a]); }
   if (ctx->hcnt) cudaFreeHost(ctx->hcnt);
@@ -683,17 +690,19 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   TRY(dmalloc(&ctx->force_f[0], (size_t)3 * d.fdim * d.fdim * d.fdim));
   ctx->force_f[1] = ctx->force_f[0] + (size_t)d.fdim * d.fdim * d.fdim; ctx->force_f[2] = ctx->force_f[1] + (size_t)d.fdim * d.fdim * d.fdim;
   {
-    const char* e = getenv("CUBEP3M_B200_TILE_STREAMS");
-    ctx->tile_streams = (e && atoi(e) == 1) ? 1 : 2;
+    const char* e = getenv("CUBEP3M_B200_TILE_STREAMS");      // tuning knob; default 2
+    ctx->tile_streams = e ? std::max(1, std::min(atoi(e), (int)cubep3m_b200_ctx::MAX_TILE_STREAMS)) : 2;
   }
   ctx->stream_main = ctx->stream;
-  if (ctx->tile_streams == 2) {
-    if (cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
-    TRY(dmalloc(&ctx->tile_rho2, tile_elems));
-    TRY(dmalloc(&ctx->tile_g2, 3 * tile_elems));
-    TRY(dmalloc(&ctx->force_f2[0], (size_t)3 * d.fdim * d.fdim * d.fdim));
-    ctx->force_f2[1] = ctx->force_f2[0] + (size_t)d.fdim * d.fdim * d.fdim; ctx->force_f2[2] = ctx->force_f2[1] + (size_t)d.fdim * d.fdim * d.fdim;
+  if (ctx->tile_streams > 1) {
+    if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
+    for (int q = 1; q < ctx->tile_streams; ++q) {
+      if (cudaStreamCreateWithFlags(&ctx->stream_aux[q], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ctx->ev_join[q], cudaEventDisableTiming) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
+      TRY(dmalloc(&ctx->tile_rho_s[q], tile_elems));
+      TRY(dmalloc(&ctx->tile_g_s[q], 3 * tile_elems));
+      TRY(dmalloc(&ctx->force_f_s[q], (size_t)3 * d.fdim * d.fdim * d.fdim));
+    }
   }
   TRY(dmalloc(&ctx->kern_f, (size_t)3 * d.hc * d.n * d.n));
   TRY(fftk::make_twiddles(d.n, &ctx->tw_f));

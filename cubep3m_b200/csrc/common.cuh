@@ -132,6 +132,8 @@ struct cubep3m_b200_ctx {
   float* kern_f = nullptr;    // [comp][z][y][kx]: the reference's kern_f(3,hc,n,n) (cubep3m.fh:35) de-interleaved
   static constexpr int MAX_TILE_STREAMS = 4;
   int tile_streams = 1;       // S > 1: consecutive tiles rotate over S streams / buffer sets (hides launch bubbles, tails, latency)
+  cudaStream_t stream_coarse = nullptr;   // coarse-mesh solve runs concurrently with the fine-tile loop
+  bool hist_clean = false;     // fcur (the fine-cell histogram) is all zeros
   cudaStream_t stream_main = nullptr, stream_aux[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
   float* tile_rho_s[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // buffer sets 1..S-1 (set 0 = tile_rho / tile_g / force_f)
@@ -154,7 +156,7 @@ struct cubep3m_b200_ctx {
   int* cntbuf = nullptr;      // received pass counts
   DevCounters* dcnt = nullptr;
   DevCounters* hcnt = nullptr; // pinned
-  cudaEvent_t ev[CUBEP3M_B200_ST_COUNT + 2];
+  cudaEvent_t ev[CUBEP3M_B200_ST_COUNT + 4];
   bool ev_ok = false;
   std::vector<float> fine_table, coarse_table;
   int last_tile_counts_valid = 0;

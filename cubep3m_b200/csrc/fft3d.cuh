@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(NT) fft_x_r2c_ngp(float* __restrict__ data, co
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double msum = 0.0;
   for (int row = warp; row < 2 * LX; row += NT / 32) {
+    float rsum = 0.f;                               // per-row partial in fp32 (a handful of small multiples of mass_p), then fp64
     const int gr = r0 + row;
     const int y = gr % N, z = gr / N;
     float* dst = ((row & 1) ? s.im0 : s.re0) + (row >> 1);
@@ -89,10 +90,11 @@ __global__ void __launch_bounds__(NT) fft_x_r2c_ngp(float* __restrict__ data, co
         const int gx = x + ox;
         const long long k = rowkey + (long long)(gx >> 2) * 64 + (gx & 3);
         v = mass_p * (float)(fstart[k + 1] - fstart[k]);
-        if (yz_phys && x >= b && x < N - b) msum += (double)v;
+        if (yz_phys && x >= b && x < N - b) rsum += v;
       }
       dst[x * LXP] = v;
     }
+    msum += (double)rsum;
   }
   msum = warp_sum_d(msum);
   if (lane == 0 && msum != 0.0) atomicAdd(sum_phys, msum);

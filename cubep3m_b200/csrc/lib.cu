@@ -375,7 +375,8 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
   const Dims& d = ctx->d;
   const int np = ctx->np_all;
   const float lo = -(float)d.b, hi = (float)d.mT + (float)d.b;
-  CK(cudaMemsetAsync(ctx->fcur, 0, sizeof(int) * d.NF, ctx->stream));
+  if (!ctx->hist_clean) CK(cudaMemsetAsync(ctx->fcur, 0, sizeof(int) * d.NF, ctx->stream));   // otherwise the last scatter left it zeroed
+  ctx->hist_clean = false;
   CK(cudaMemsetAsync(&ctx->dcnt->np_deleted, 0, sizeof(int), ctx->stream));
   CK(cudaMemsetAsync(&ctx->dcnt->n_multi, 0, 2 * sizeof(int), ctx->stream));
   CK(cudaMemsetAsync(&ctx->dcnt->n_cand, 0, sizeof(int), ctx->stream));
@@ -387,10 +388,11 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
   LAUNCH(ctx, KC_SCAN, part::scan_apply_kernel, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->multi_list,
          ctx->occ_list, ctx->list_cap, ctx->cfg.ppint ? 1 : 0, ctx->cfg.pp_ext ? 1 : 0, ctx->dcnt);
   if (np > 0)
-    LAUNCH(ctx, KC_SCATTER, part::scatter_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->fcur,
+    LAUNCH(ctx, KC_SCATTER, part::scatter_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->fcur, ctx->fstart,
            ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1]);
   CK(cudaGetLastError());
   if (int st = fetch_counters(ctx)) return st;
+  ctx->hist_clean = true;
   ctx->cur ^= 1;
   ctx->np_all = np - ctx->hcnt->np_deleted;
   if (!ctx->passed) ctx->np_local = ctx->np_all;
@@ -630,6 +632,7 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
     if (ctx->ev_join[q]) cudaEventDestroy(ctx->ev_join[q]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->stream_coarse) cudaStreamDestroy(ctx->stream_coarse);
   F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->creal); F(ctx->gather); F(ctx->force_c); F(ctx->redbuf); F(ctx->cntbuf); F(ctx->dcnt);
   for (int a = 0; a < 3; ++a) { bool dup = false; for (int b2 = 0; b2 < a; ++b2) dup |= (ctx->tw_c[b2] == ctx->tw_c[a]); if (!dup) F(ctx->tw_c[a]); }
   if (ctx->hcnt) cudaFreeHost(ctx->hcnt);
@@ -694,6 +697,7 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
     ctx->tile_streams = e ? std::max(1, std::min(atoi(e), (int)cubep3m_b200_ctx::MAX_TILE_STREAMS)) : 2;
   }
   ctx->stream_main = ctx->stream;
+  if (cudaStreamCreateWithFlags(&ctx->stream_coarse, cudaStreamNonBlocking) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   if (ctx->tile_streams > 1) {
     if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
     for (int q = 1; q < ctx->tile_streams; ++q) {
@@ -841,16 +845,25 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   if (int st = do_sort(ctx, &ndel)) return st;                                            // :61 link_list as a cell sort
   const int np_ghost = ctx->np_all;
   CK(cudaEventRecord(ev[3], ctx->stream));
+  // The coarse-mesh density and force solve only need the sorted positions: run them on their own stream, concurrently with
+  // the fine-tile loop (the reference cannot: rho_f/rho_c and force_f/force_c are EQUIVALENCEd, cubep3m.fh:134-135).
+  CK(cudaStreamWaitEvent(ctx->stream_coarse, ev[3], 0));
+  ctx->stream = ctx->stream_coarse;
+  CK(cudaEventRecord(ev[6], ctx->stream));
+  int cst = do_coarse_mass(ctx, mass_p);                                                  // coarse_mesh.f90:28
+  CK(cudaEventRecord(ev[7], ctx->stream));
+  if (!cst) cst = do_coarse_force(ctx);                                                   // coarse_mesh.f90:84-100
+  CK(cudaEventRecord(ev[8], ctx->stream));
+  ctx->stream = ctx->stream_main;
+  if (cst) return cst;
   if (int st = do_fine(ctx, a_mid, dt, mass_p, nullptr, nullptr)) return st;              // :84-368 (mesh part)
   CK(cudaEventRecord(ev[4], ctx->stream));
   if (int st = do_pp(ctx, a_mid, dt, mass_p)) return st;                                  // :274-361
   CK(cudaEventRecord(ev[5], ctx->stream));
   if (int st = do_pp_ext(ctx, a_mid, dt, mass_p)) return st;                              // :378-624
-  CK(cudaEventRecord(ev[6], ctx->stream));
-  if (int st = do_coarse_mass(ctx, mass_p)) return st;                                    // coarse_mesh.f90:28
-  CK(cudaEventRecord(ev[7], ctx->stream));
-  if (int st = do_coarse_force(ctx)) return st;                                           // coarse_mesh.f90:84-100
-  CK(cudaEventRecord(ev[8], ctx->stream));
+  CK(cudaEventRecord(ev[11], ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->stream, ev[8], 0));                                         // join the coarse stream
+  CK(cudaEventRecord(ev[12], ctx->stream));
   if (c.coarse_vel_update) { if (int st = do_coarse_vel(ctx, a_mid, dt)) return st; }     // coarse_mesh.f90:106
   CK(cudaEventRecord(ev[9], ctx->stream));
   if (int st = fetch_counters(ctx)) return st;
@@ -882,10 +895,10 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   out->stage_ms[CUBEP3M_B200_ST_LINK] = ev_ms(ev[2], ev[3]);
   out->stage_ms[CUBEP3M_B200_ST_FINE_FFT] = ev_ms(ev[3], ev[4]);
   out->stage_ms[CUBEP3M_B200_ST_PP] = ev_ms(ev[4], ev[5]);
-  out->stage_ms[CUBEP3M_B200_ST_PP_EXT] = ev_ms(ev[5], ev[6]);
+  out->stage_ms[CUBEP3M_B200_ST_PP_EXT] = ev_ms(ev[5], ev[11]);
   out->stage_ms[CUBEP3M_B200_ST_COARSE_MASS] = ev_ms(ev[6], ev[7]);
   out->stage_ms[CUBEP3M_B200_ST_COARSE_FORCE] = ev_ms(ev[7], ev[8]);
-  out->stage_ms[CUBEP3M_B200_ST_COARSE_VEL] = ev_ms(ev[8], ev[9]);
+  out->stage_ms[CUBEP3M_B200_ST_COARSE_VEL] = ev_ms(ev[12], ev[9]);
   out->stage_ms[CUBEP3M_B200_ST_DELETE] = ev_ms(ev[9], ev[10]);
   out->stage_ms[CUBEP3M_B200_ST_TOTAL] = ev_ms(ev[0], ev[10]);
   ctx->last_tile_counts_valid = 1;

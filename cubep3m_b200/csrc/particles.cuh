@@ -203,9 +203,9 @@ __global__ void __launch_bounds__(1024) scan_blocksums_kernel(int* __restrict__ 
   }
 }
 
-// block scan + offset; writes fstart (exclusive) and re-initialises the cursors; also emits the PP work lists:
+// block scan + offset; writes fstart (exclusive); also emits the PP work lists:
 // physical fine cells (coarse cell in 1..nc_node on all axes) with >= 2 particles (PPINT) / >= 1 (PP_EXT).
-__global__ void __launch_bounds__(TPB) scan_apply_kernel(int* __restrict__ hist_cur, long long n, const int* __restrict__ blocksum,
+__global__ void __launch_bounds__(TPB) scan_apply_kernel(const int* __restrict__ hist_cur, long long n, const int* __restrict__ blocksum,
                                                          int* __restrict__ fstart, int H, int nc_buf, int nc_node,
                                                          int* __restrict__ multi_list, int* __restrict__ occ_list, int list_cap,
                                                          int want_multi, int want_occ, DevCounters* __restrict__ cnt) {
@@ -253,10 +253,9 @@ __global__ void __launch_bounds__(TPB) scan_apply_kernel(int* __restrict__ hist_
     if (base + q + 3 < n) {
       const int4 t = make_int4(o[q], o[q + 1], o[q + 2], o[q + 3]);
       *reinterpret_cast<int4*>(fstart + base + q) = t;
-      *reinterpret_cast<int4*>(hist_cur + base + q) = t;
     } else {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) if (base + q + u < n) { fstart[base + q + u] = o[q + u]; hist_cur[base + q + u] = o[q + u]; }
+      for (int u = 0; u < 4; ++u) if (base + q + u < n) fstart[base + q + u] = o[q + u];
     }
   }
   if (base + SCAN_ITEMS >= n && base < n) fstart[n] = run;   // total
@@ -270,15 +269,17 @@ __global__ void __launch_bounds__(TPB) scan_apply_kernel(int* __restrict__ hist_
 }
 
 __global__ void __launch_bounds__(TPB) scatter_kernel(const float* __restrict__ xv_in, const int64_t* __restrict__ pid_in,
-                                                      const unsigned int* __restrict__ key, int np, int* __restrict__ cursor,
-                                                      float* __restrict__ xv_out, int64_t* __restrict__ pid_out) {
+                                                      const unsigned int* __restrict__ key, int np, int* __restrict__ hist,
+                                                      const int* __restrict__ fstart, float* __restrict__ xv_out, int64_t* __restrict__ pid_out) {
   const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
   if (i >= np) return;
   const unsigned int k = key[i];
   if (k == KEY_DEAD) return;
   float2 a, b, c;
   load_xv(xv_in, i, a, b, c);
-  const int dst = atomicAdd(&cursor[k], 1);
+  // slot = cell start + (remaining count - 1): every particle decrements its cell once, so the histogram is back to all zeros
+  // after the scatter and needs no memset before the next step's key_hist_kernel
+  const int dst = fstart[k] + atomicSub(&hist[k], 1) - 1;
   store_xv(xv_out, dst, a, b, c);
   if (pid_in) pid_out[dst] = pid_in[i];
 }

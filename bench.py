@@ -5,7 +5,7 @@
 
 A "step" is one pass of the hot path (drift -> cell sort -> particle pass -> per-tile fine mesh -> PP -> coarse mesh
 -> ghost deletion) over one synthetic LCDM box.  Workload at N=1 is BASELINE.json configs[1]: 256^3 particles on a
-512^3 fine mesh, PPINT on, nodes_dim=1, tiles_node_dim=4 (nf_tile=176), one B200.
+512^3 fine mesh, PPINT on, nodes_dim=1, tiles_node_dim=2 (nf_tile=304), one B200 (the 64-tile nf_tile=176 variant is `--workload c1a`).
 `value`  : particles / device-seconds per step with the particles resident in HBM (CUDA events on the library's stream).
 `e2e`    : the same step through the C ABI in strict drop-in mode: pinned-host xv -> H2D, particle_mesh, D2H.
 `roofline`: dominant kernel class, algorithmic bytes per launch / its mean device time (events around every launch).
@@ -32,8 +32,10 @@ from cubep3m_b200 import topology as topo  # noqa: E402
 
 WORKLOADS = {
     # name: (nf_tile, tiles_node_dim, ppint, pp_ext, box Mpc/h, z_i, description)
-    "c1": (176, 4, 1, 0, 200.0, 100.0, "BASELINE configs[1]: 256^3 particles, 512^3 fine mesh, PPINT on, nodes_dim=1, tiles_node_dim=4 (nf_tile=176)"),
+    "c1": (304, 2, 1, 0, 200.0, 100.0, "BASELINE configs[1]: 256^3 particles, 512^3 fine mesh, PPINT on, nodes_dim=1, tiles_node_dim=2 (nf_tile=304)"),
+    "c1a": (176, 4, 1, 0, 200.0, 100.0, "BASELINE configs[1] variant: 256^3 particles, 512^3 fine mesh, PPINT on, tiles_node_dim=4 (nf_tile=176)"),
     "c0": (176, 2, 0, 0, 200.0, 100.0, "BASELINE configs[0]: 128^3 particles, 256^3 fine mesh, PM only, tiles_node_dim=2 (nf_tile=176)"),
+    "c1c": (560, 1, 1, 0, 200.0, 100.0, "BASELINE configs[1] variant: 256^3 particles, 512^3 fine mesh, PPINT on, tiles_node_dim=1 (nf_tile=560)"),
     "tiny": (112, 2, 1, 0, 50.0, 20.0, "dev smoke: 64^3 particles, 128^3 fine mesh"),
 }
 

@@ -80,6 +80,82 @@ __global__ void __launch_bounds__(TPB) ngp_fixup_kernel(const float* __restrict_
   }
 }
 
+// ---- fine CIC (the reference's non -DNGP builds: fine_cic_mass.f90:12-42, fine_cic_mass_buffer.f90, particle_mesh_threaded.f90:123-124,154-160).
+// Gather formulation on the cell-sorted array: grid point g receives (g+1-x) from the particles of cell g and (x-(g-1)) from those
+// of cell g-1 on each axis, i.e. it visits the 8 cells (g-1..g)^3. No atomics, deterministic for a given array order; the boundary
+// routine's bounds checks are implicit (grid points outside [0,n) do not exist). Particles outside the tile's coarse-cell range
+// cic_l..cic_h = tile-local fine cells [0, n-1] never reach it.
+__global__ void __launch_bounds__(TPB) cic_density_kernel(const float* __restrict__ xv, const int* __restrict__ fstart, float* __restrict__ rho, int n, int b,
+                                                          int m, int H, int tx, int ty, int tz, float mass_p, double* __restrict__ sum_phys,
+                                                          int* __restrict__ tile_count) {
+  const long long total = (long long)n * n * n;
+  const float offx = (float)(b - tx * m), offy = (float)(b - ty * m), offz = (float)(b - tz * m);
+  double msum = 0.0;
+  int pcount = 0;
+  for (long long t = (long long)blockIdx.x * TPB + threadIdx.x; t < total; t += (long long)gridDim.x * TPB) {
+    const int x = (int)(t % n), y = (int)((t / n) % n), z = (int)(t / ((long long)n * n));
+    float acc = 0.f;
+    for (int dz = -1; dz <= 0; ++dz)
+      for (int dy = -1; dy <= 0; ++dy)
+        for (int dx = -1; dx <= 0; ++dx) {
+          const int cx = x + dx, cy = y + dy, cz = z + dz;
+          if (cx < 0 || cy < 0 || cz < 0) continue;
+          const long long k = cell_key(cx + tx * m, cy + ty * m, cz + tz * m, H);
+          const int s0 = fstart[k], s1 = fstart[k + 1];
+          if (dx == 0 && dy == 0 && dz == 0) pcount += s1 - s0;
+          for (int i = s0; i < s1; ++i) {
+            const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * i;
+            const float2 a = p[0];
+            const float pz = p[1].x;
+            const float xt = __fadd_rn(a.x, offx), yt = __fadd_rn(a.y, offy), zt = __fadd_rn(pz, offz);
+            // weights as the reference forms them: dx1 = i1 - x (lower point), dx2 = 1 - dx1 (upper point); mass_p folded into the x weight
+            const float dx1 = (float)(cx + 1) - xt, dy1 = (float)(cy + 1) - yt, dz1 = (float)(cz + 1) - zt;
+            const float wx = mass_p * (dx == 0 ? dx1 : 1.0f - dx1), wy = (dy == 0 ? dy1 : 1.0f - dy1), wz = (dz == 0 ? dz1 : 1.0f - dz1);
+            acc += (wx * wy) * wz;
+          }
+        }
+    rho[((long long)z * n + y) * (n + 2) + x] = acc;
+    if (x >= b && x < n - b && y >= b && y < n - b && z >= b && z < n - b) msum += (double)acc;
+  }
+  msum = warp_sum_d(msum);
+  pcount = warp_sum_i(pcount);
+  if ((threadIdx.x & 31) == 0) {
+    if (msum != 0.0) atomicAdd(sum_phys, msum);
+    if (pcount && tile_count) atomicAdd(tile_count, pcount);
+  }
+}
+
+// CIC force interpolation + kick, particle_mesh_threaded.f90:289-316 (sequential adds in the reference's corner order)
+__global__ void __launch_bounds__(TPB) cic_fine_kick_kernel(float* __restrict__ xv, const int* __restrict__ fstart, const float* __restrict__ fx,
+                                                            const float* __restrict__ fy, const float* __restrict__ fz, int H, int nc_buf, int nc_tile,
+                                                            int b, int m, int fdim, int tx, int ty, int tz, float a_mid, float G, float dt) {
+  const int ry = blockIdx.x % nc_tile, rz = blockIdx.x / nc_tile;
+  const int cy = nc_buf + ty * nc_tile + ry, cz = nc_buf + tz * nc_tile + rz, cx0 = nc_buf + tx * nc_tile;
+  const long long k0 = ((long long)(cz * H + cy) * H + cx0) * 64;
+  const int s0 = fstart[k0], s1 = fstart[k0 + (long long)nc_tile * 64];
+  const float offx = (float)b - (float)(tx * m), offy = (float)b - (float)(ty * m), offz = (float)b - (float)(tz * m);
+  const float agd = (a_mid * G) * dt;
+  for (int i = s0 + threadIdx.x; i < s1; i += TPB) {
+    float2* p = reinterpret_cast<float2*>(xv) + 3LL * i;
+    const float2 a = p[0];
+    float2 bb = p[1], c = p[2];
+    const float xt = __fadd_rn(a.x, offx), yt = __fadd_rn(a.y, offy), zt = __fadd_rn(bb.x, offz);
+    const int i1x = (int)floorf(xt) + 1, i1y = (int)floorf(yt) + 1, i1z = (int)floorf(zt) + 1;     // 1-based lower grid point
+    const float dx1 = (float)i1x - xt, dy1 = (float)i1y - yt, dz1 = (float)i1z - zt;
+    const float dx2 = 1.0f - dx1, dy2 = 1.0f - dy1, dz2 = 1.0f - dz1;
+    float vx = bb.y, vy = c.x, vz = c.y;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int jx = i1x + (q & 1) - (b - 1), jy = i1y + ((q >> 1) & 1) - (b - 1), jz = i1z + (q >> 2) - (b - 1);   // index into the cropped cube
+      const float dVc = ((agd * ((q & 1) ? dx2 : dx1)) * (((q >> 1) & 1) ? dy2 : dy1)) * ((q >> 2) ? dz2 : dz1);
+      const long long o = ((long long)jz * fdim + jy) * fdim + jx;
+      vx += fx[o] * dVc; vy += fy[o] * dVc; vz += fz[o] * dVc;
+    }
+    bb.y = vx; c.x = vy; c.y = vz;
+    p[1] = bb; p[2] = c;
+  }
+}
+
 // ---- the same fix-up for the fused density + r2c kernel (fft_x_r2c_ngp): per-tile lists of (from-cell, to-cell) moves.
 // Built once per step for all tiles; also applies the corresponding +-mass_p to the DIAG mass sum.
 constexpr int DELTA_CAP = 2048;   // moves per tile (expected: a few tens)

@@ -431,6 +431,11 @@ int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, bool material
   const int T = d.T, n = d.n;
   const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;   // particle_mesh_threaded.f90:86-90 (cur_tile-1, x fastest)
   const float scale = 1.0f / (((float)n * (float)n) * (float)n);       // fft_fine.f90:51
+  if (!ctx->cfg.ngp) {   // fine CIC: materialised gather deposit, then the generic solve
+    LAUNCH(ctx, KC_DENSITY, fine::cic_density_kernel, NUM_SMS * 16, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, t_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
+           &ctx->dcnt->sum_rho_f, scratch_count);
+    return fftk::fine_solve(ctx, fine_mesh(ctx), t_rho, t_g, ctx->kern_f, t_force, d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits);
+  }
   if (materialise) {
     LAUNCH(ctx, KC_DENSITY, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
            &ctx->dcnt->sum_rho_f, scratch_count);
@@ -450,8 +455,8 @@ int do_fine(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p, float* m
   // once per step: per-tile particle counts (parity getter) and the per-tile lists of ulp-boundary mass moves
   CK(cudaMemsetAsync(ctx->ndelta, 0, sizeof(int) * d.tiles_node, ctx->stream));
   CK(cudaMemsetAsync(ctx->tile_counts, 0, sizeof(int) * d.tiles_node, ctx->stream));
-  LAUNCH(ctx, KC_DENSITY, fine::tile_counts_kernel, d.tiles_node, fine::TPB, 0, ctx->fstart, d.H, d.nc_buf, d.nc_tile, d.T, ctx->tile_counts);
-  if (ctx->hcnt->n_cand > 0)
+  if (ctx->cfg.ngp) LAUNCH(ctx, KC_DENSITY, fine::tile_counts_kernel, d.tiles_node, fine::TPB, 0, ctx->fstart, d.H, d.nc_buf, d.nc_tile, d.T, ctx->tile_counts);
+  if (ctx->cfg.ngp && ctx->hcnt->n_cand > 0)
     LAUNCH(ctx, KC_DENSITY, fine::build_tile_deltas_kernel, std::min(NUM_SMS, (std::min(ctx->hcnt->n_cand, ctx->cand_cap) + fine::TPB - 1) / fine::TPB), fine::TPB,
            0, ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, d.n, d.b, d.m, d.T, mass_p, ctx->deltas, ctx->ndelta, &ctx->dcnt->sum_rho_f);
   const int S = std::min(ctx->tile_streams, d.tiles_node);
@@ -464,8 +469,14 @@ int do_fine(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p, float* m
   for (int tile = 0; tile < d.tiles_node && !status; ++tile) {
     const int set = tile % S;
     ctx->stream = set ? ctx->stream_aux[set] : ctx->stream_main;      // LAUNCH() targets ctx->stream
-    status = fine_tile_solve(ctx, tile, mass_p, false, nullptr, set);
-    if (!status && ctx->cfg.ngp_fmesh_force) {
+    status = fine_tile_solve(ctx, tile, mass_p, false, ctx->cfg.ngp ? nullptr : ctx->tile_counts + tile, set);
+    if (!status && !ctx->cfg.ngp) {
+      const int T = d.T;
+      const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;
+      float* ff = set ? ctx->force_f_s[set] : ctx->force_f[0];
+      LAUNCH(ctx, KC_NGP_KICK, fine::cic_fine_kick_kernel, d.nc_tile * d.nc_tile, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ff, ff + fstride, ff + 2 * fstride, d.H,
+             d.nc_buf, d.nc_tile, d.b, d.m, d.fdim, tx, ty, tz, a_mid, ctx->cfg.G, dt);
+    } else if (!status && ctx->cfg.ngp_fmesh_force) {
       const int T = d.T;
       const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;
       float* ff = set ? ctx->force_f_s[set] : ctx->force_f[0];
@@ -484,7 +495,7 @@ int do_pp(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
   pp::PPParams P;
   P.mass_p = mass_p; P.rsoft = ctx->cfg.rsoft; P.pp_bias = ctx->cfg.pp_bias; P.a_mid = a_mid; P.G = ctx->cfg.G; P.dt = dt;
   P.cutoff = (float)ctx->cfg.nf_cutoff;
-  if (ctx->cfg.ppint) {
+  if (ctx->cfg.ppint && ctx->cfg.ngp) {      // the llf binning of particle_mesh_threaded.f90:274-285 only exists inside #ifdef NGP
     P.apply = ctx->cfg.pp_force_flag;
     const int n_multi = std::min(ctx->hcnt->n_multi, ctx->list_cap);
     if (n_multi > 0)
@@ -648,7 +659,6 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   if (!cfg || !out) return CUBEP3M_B200_EINVAL;
   Dims d;
   if (int st = derive(*cfg, d)) return st;
-  if (!cfg->ngp) return CUBEP3M_B200_EINVAL;          // fine CIC (non -DNGP builds) is not built yet
   if (d.world > 1 && (!nccl_unique_id || world_size != d.world)) return CUBEP3M_B200_EINVAL;
   if (cfg->tile_split > 1) return CUBEP3M_B200_EINVAL;   // superseded by nodes_dim_xyz (block split of a non-cubic box)
   if ((!kern_f || !kern_c) && (!fine_table || !coarse_table)) return CUBEP3M_B200_EINVAL;
@@ -996,10 +1006,15 @@ int cubep3m_b200_debug_fine_tile(cubep3m_b200_ctx* ctx, int32_t tile, float mass
   int* scratch = ctx->rowoff + d.nc_node * d.nc_node + 4;
   double* dsum = nullptr;
   CK(cudaMalloc(&dsum, sizeof(double)));
-  LAUNCH(ctx, KC_DENSITY, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p, dsum, scratch);
-  if (ctx->hcnt->n_cand > 0)
-    LAUNCH(ctx, KC_DENSITY, fine::ngp_fixup_kernel, NUM_SMS, fine::TPB, 0, ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, ctx->tile_rho, n, d.b, d.m, tx, ty, tz,
-           mass_p, dsum);
+  if (!ctx->cfg.ngp) {
+    LAUNCH(ctx, KC_DENSITY, fine::cic_density_kernel, NUM_SMS * 16, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
+           dsum, scratch);
+  } else {
+    LAUNCH(ctx, KC_DENSITY, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p, dsum, scratch);
+    if (ctx->hcnt->n_cand > 0)
+      LAUNCH(ctx, KC_DENSITY, fine::ngp_fixup_kernel, NUM_SMS, fine::TPB, 0, ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, ctx->tile_rho, n, d.b, d.m, tx, ty, tz,
+             mass_p, dsum);
+  }
   if (rho_f) CK(cudaMemcpyAsync(rho_f, ctx->tile_rho, sizeof(float) * (size_t)(n + 2) * n * n, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(dsum);

@@ -155,6 +155,25 @@ def test_full_step_many_tiles(built):
     _step_compare(cfg, xv, 0.4, 0.4, 0.05, 8.0, (-3.0, 7.75, 0.125), 1e-4)
 
 
+def test_full_step_fine_cic(built, ics112):
+    """The reference's non -DNGP builds (Makefile:13): fine CIC deposit (fine_cic_mass.f90 / fine_cic_mass_buffer.f90) and CIC force
+    interpolation (particle_mesh_threaded.f90:289-316). fp32 summation order differs (gather vs chain order): 1e-4 rms."""
+    cfg = default_config(nf_tile=112, tiles_node_dim=2, ngp=0, pp_ext=0)
+    rms, res = _step_compare(cfg, ics112, 0.5, 0.3, 0.05, 8.0, (1.25, -0.5, 2.0), 1e-4)
+    pm, o = _mk(cfg)
+    x = ics112.copy()
+    pm.upload_particles(x); o.set_particles(x)
+    pm.link_list(); o.link_list()
+    pm.particle_pass(); o.particle_pass()
+    o.set_debug_tile(3)
+    rho_g, _ = pm.fine_tile(2, 8.0, want_force=False)
+    pm.close()
+    o.delete_particles()   # leave the oracle consistent
+    o.close()
+    n = cfg.nf_tile
+    assert rho_g[:, :, :n].sum() == pytest.approx(res["tiles_g"][2] * 8.0, rel=2e-2)   # CIC conserves the deposited mass up to the clipped rim (cell n-1)
+
+
 def test_full_step_pp_ext_clustered(built):
     """PPINT + PP_EXT on the clustered golden input; also checks the frozen golden output of the oracle.
     Tolerance 2e-4: close pairs amplify fp32 summation-order differences (|f| ~ 1/r^2 at r ~ rsoft)."""

@@ -1,0 +1,58 @@
+"""cic_power twin (cubep3m_b200/power.py): sanity against the IC generator's input spectrum, and the north-star's 0.1 % P(k) gate
+between the GPU path and the oracle after a multi-step run (GPU part marked gpu)."""
+import numpy as np
+import pytest
+
+from cubep3m_b200 import default_config, ic, power
+
+
+def test_power_of_zeldovich_ics_matches_input_spectrum():
+    nc, box, z_i = 64, 100.0, 50.0
+    xv = ic.zeldovich_ics(nc, box=box, z_i=z_i, seed=2)
+    k, d2, _ = power.power_spectrum(xv[:, :3], nc, box)
+    a = 1.0 / (1.0 + z_i)
+    lin = ic.delta2(k, a)
+    sel = (k > 4 * 2 * np.pi / box) & (k < 0.25 * np.pi * nc / box)      # away from cosmic variance and from the lattice scale
+    ratio = d2[sel] / lin[sel]
+    assert 0.6 < np.median(ratio) < 1.4, np.median(ratio)
+
+
+def test_uniform_lattice_has_no_power():
+    nc = 32
+    g = (np.arange(0, nc, 2) + 0.5).astype(np.float32)
+    pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    k, d2, _ = power.power_spectrum(pos, nc, 100.0)
+    assert np.abs(d2[: nc // 4 - 1]).max() < 1e-10     # below the lattice frequency a perfect lattice has zero power
+
+
+@pytest.mark.gpu
+def test_pk_gpu_vs_oracle_multistep(built):
+    """North-star gate: the power spectrum after a multi-step run agrees with the reference path to 0.1 % per bin.
+    5 steps from z=20 with the driver twin choosing dt; same shake offsets on both sides."""
+    from cubep3m_b200.lib import ParticleMesh, clock_init, timestep, absorb_limiters
+    from oracle import Oracle
+    cfg = default_config(nf_tile=112, tiles_node_dim=2, pp_ext=0)
+    box, z_i = 50.0, 20.0
+    xv = ic.zeldovich_ics(cfg.nf_physical_dim, box=box, z_i=z_i, seed=7)
+    pm, o = ParticleMesh(cfg), Oracle(cfg)
+    pm.upload_particles(xv); o.set_particles(xv)
+    ca, cb = clock_init(z_i), clock_init(z_i)
+    rng = np.random.default_rng(777)
+    shake = np.zeros(3, np.float32)
+    for step in range(5):
+        timestep(ca); timestep(cb)
+        off = ((rng.random(3, dtype=np.float32) - np.float32(0.5)) * np.float32(16.0) - shake).astype(np.float32)
+        shake = shake + off
+        og = pm.particle_mesh(ca.dt, ca.dt_old, ca.a_mid, 8.0, off)
+        oo = o.particle_mesh(cb.dt, cb.dt_old, cb.a_mid, 8.0, off)
+        absorb_limiters(ca, og); absorb_limiters(cb, oo)
+        assert og.np_total == oo.np_total == len(xv)
+        assert ca.dt == pytest.approx(cb.dt, rel=1e-3)
+    g, r = pm.download_particles(), o.get_particles()
+    pm.close(); o.close()
+    nc = cfg.nf_physical_dim
+    undo = lambda p: np.mod(p[:, :3] - shake, np.float32(nc))      # checkpoint.f90:92 writes xv - shake_offset
+    kg, dg, _ = power.power_spectrum(undo(g), nc, box)
+    kr, dr, _ = power.power_spectrum(undo(r), nc, box)
+    rel = np.abs(dg - dr) / np.maximum(np.abs(dr), 1e-30)
+    assert rel.max() < 1e-3, rel.max()

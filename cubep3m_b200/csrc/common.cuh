@@ -131,6 +131,7 @@ struct cubep3m_b200_ctx {
   // fine mesh
   float* kern_f = nullptr;    // [comp][z][y][kx]: the reference's kern_f(3,hc,n,n) (cubep3m.fh:35) de-interleaved
   static constexpr int MAX_TILE_STREAMS = 4;
+  int tile_streams_max = 1;
   int tile_streams = 1;       // S > 1: consecutive tiles rotate over S streams / buffer sets (hides launch bubbles, tails, latency)
   cudaStream_t stream_coarse = nullptr;   // coarse-mesh solve runs concurrently with the fine-tile loop
   bool hist_clean = false;     // fcur (the fine-cell histogram) is all zeros

@@ -706,6 +706,7 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
     const char* e = getenv("CUBEP3M_B200_TILE_STREAMS");      // tuning knob; default 2
     ctx->tile_streams = e ? std::max(1, std::min(atoi(e), (int)cubep3m_b200_ctx::MAX_TILE_STREAMS)) : 2;
   }
+  ctx->tile_streams_max = ctx->tile_streams;
   ctx->stream_main = ctx->stream;
   if (cudaStreamCreateWithFlags(&ctx->stream_coarse, cudaStreamNonBlocking) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   if (ctx->tile_streams > 1) {
@@ -931,6 +932,11 @@ int cubep3m_b200_set_profiling(cubep3m_b200_ctx* ctx, int on) {
     for (auto& e : ctx->prof_ev) CK(cudaEventCreate(&e));
   }
   ctx->profiling = on != 0;
+  return 0;
+}
+int cubep3m_b200_set_tile_streams(cubep3m_b200_ctx* ctx, int n) {
+  if (!ctx || n < 1 || n > ctx->tile_streams_max) return CUBEP3M_B200_EINVAL;
+  ctx->tile_streams = n;
   return 0;
 }
 int cubep3m_b200_num_kernel_classes(void) { return KC_COUNT; }

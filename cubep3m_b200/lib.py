@@ -26,7 +26,7 @@ SYMBOLS = ["cubep3m_b200_version", "cubep3m_b200_strerror", "cubep3m_b200_defaul
            "cubep3m_b200_move_grid_back", "cubep3m_b200_debug_cell_counts", "cubep3m_b200_debug_tile_counts",
            "cubep3m_b200_debug_sorted_particles", "cubep3m_b200_debug_kern_f", "cubep3m_b200_debug_kern_c",
            "cubep3m_b200_debug_rho_c", "cubep3m_b200_debug_force_c", "cubep3m_b200_debug_fine_tile",
-           "cubep3m_b200_debug_fft3d", "cubep3m_b200_launch_count", "cubep3m_b200_set_profiling",
+           "cubep3m_b200_debug_fft3d", "cubep3m_b200_launch_count", "cubep3m_b200_set_profiling", "cubep3m_b200_set_tile_streams",
            "cubep3m_b200_num_kernel_classes", "cubep3m_b200_kernel_class_name", "cubep3m_b200_get_kernel_times",
            "cubep3m_b200_clock_init",
            "cubep3m_b200_expansion", "cubep3m_b200_timestep"]
@@ -81,6 +81,7 @@ def load_library():
     L.cubep3m_b200_launch_count.argtypes = [C.c_void_p]
     L.cubep3m_b200_launch_count.restype = C.c_int64
     L.cubep3m_b200_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.cubep3m_b200_set_tile_streams.argtypes = [C.c_void_p, C.c_int]
     L.cubep3m_b200_kernel_class_name.restype = C.c_char_p
     L.cubep3m_b200_kernel_class_name.argtypes = [C.c_int]
     L.cubep3m_b200_get_kernel_times.argtypes = [C.c_void_p, _fp, C.c_void_p]
@@ -237,6 +238,9 @@ class ParticleMesh:
 
     def set_profiling(self, on=True):
         _chk(self.lib.cubep3m_b200_set_profiling(self.h, 1 if on else 0))
+
+    def set_tile_streams(self, n):
+        _chk(self.lib.cubep3m_b200_set_tile_streams(self.h, int(n)))
 
     def kernel_times(self):
         """{class name: (ms, launches)} of the last profiled particle_mesh call."""

@@ -176,6 +176,9 @@ int64_t cubep3m_b200_launch_count(cubep3m_b200_ctx* ctx);
 /* Per-kernel-class device time of the last particle_mesh call: when profiling is on every launch is bracketed by
  * CUDA events on the launching stream (the stand-in for the reference's -DMPI_TIME stopwatches, timers.f90:68-77). */
 int cubep3m_b200_set_profiling(cubep3m_b200_ctx* ctx, int on);
+/* Number of fine tiles kept in flight on separate CUDA streams (1..init-time maximum, default 2). Per-kernel timings are only
+ * unambiguous with 1 (no overlap); the reference analogue is the number of OpenMP threads working on tiles (cores, parameters:20). */
+int cubep3m_b200_set_tile_streams(cubep3m_b200_ctx* ctx, int n);
 int cubep3m_b200_num_kernel_classes(void);
 const char* cubep3m_b200_kernel_class_name(int k);
 int cubep3m_b200_get_kernel_times(cubep3m_b200_ctx* ctx, float* ms, int64_t* launches);

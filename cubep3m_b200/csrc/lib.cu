@@ -386,7 +386,7 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
   LAUNCH(ctx, KC_SCAN, part::scan_reduce_kernel, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum);
   LAUNCH(ctx, KC_SCAN, part::scan_blocksums_kernel, 1, 1024, 0, ctx->blocksum, nb);
   LAUNCH(ctx, KC_SCAN, part::scan_apply_kernel, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->multi_list,
-         ctx->occ_list, ctx->list_cap, ctx->cfg.ppint ? 1 : 0, ctx->cfg.pp_ext ? 1 : 0, ctx->dcnt);
+         ctx->occ_list, ctx->list_cap, ctx->cfg.ppint ? 1 : 0, 0, ctx->dcnt);
   if (np > 0)
     LAUNCH(ctx, KC_SCATTER, part::scatter_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->fcur, ctx->fstart,
            ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1]);
@@ -511,10 +511,9 @@ int do_pp_ext(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
   P.cutoff = (float)ctx->cfg.nf_cutoff;
   if (ctx->cfg.pp_ext && ctx->cfg.pp_range > 0) {
     P.apply = ctx->cfg.pp_ext_force_flag;
-    const int n_occ = std::min(ctx->hcnt->n_occ, ctx->list_cap);
-    if (n_occ > 0)
-      LAUNCH(ctx, KC_PPEXT, pp::ppext_kernel, std::min((n_occ + 3) / 4, NUM_SMS * 16), pp::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->occ_list,
-             &ctx->dcnt->n_occ, ctx->list_cap, ctx->d.H, ctx->cfg.pp_range, P, ctx->dcnt);
+    if (ctx->np_all > 0)
+      LAUNCH(ctx, KC_PPEXT, pp::ppext_kernel, (ctx->np_all + pp::EXT_TPB - 1) / pp::EXT_TPB, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->np_all, ctx->d.H,
+             ctx->d.b, ctx->d.nc_buf, ctx->d.nc_node, ctx->cfg.pp_range, P, ctx->dcnt);
   }
   CK(cudaGetLastError());
   return 0;
@@ -691,9 +690,8 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   TRY(dmalloc(&ctx->fcur, (size_t)d.NF + 64));
   ctx->nblocksum = (int)((d.NF + part::SCAN_BLOCK - 1) / part::SCAN_BLOCK);
   TRY(dmalloc(&ctx->blocksum, (size_t)ctx->nblocksum + 1));
-  ctx->list_cap = cfg->pp_ext ? d.max_np : d.max_np / 2 + 1024;
+  ctx->list_cap = d.max_np / 2 + 1024;
   if (cfg->ppint) TRY(dmalloc(&ctx->multi_list, (size_t)ctx->list_cap));
-  if (cfg->pp_ext) TRY(dmalloc(&ctx->occ_list, (size_t)ctx->list_cap));
   const size_t rowoff_n = (size_t)d.nc_node * d.nc_node + 16 + d.tiles_node;
   TRY(dmalloc(&ctx->rowoff, rowoff_n));
   if (cudaMemset(ctx->rowoff, 0, rowoff_n * sizeof(int)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }

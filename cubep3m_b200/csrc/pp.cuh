@@ -76,76 +76,70 @@ __global__ void __launch_bounds__(TPB) ppint_kernel(float* __restrict__ xv, cons
   if (lane == 0 && fmax > 0.f) atomic_max_float_nonneg(&cnt->pp_force_max_bits, fmax);
 }
 
-// one warp per occupied physical fine cell; neighbours = the (2*pr+1)^3 - 1 surrounding fine cells
-__global__ void __launch_bounds__(TPB) ppext_kernel(float* __restrict__ xv, const int* __restrict__ fstart, const int* __restrict__ list,
-                                                    const int* __restrict__ n_list_ptr, int list_cap, int H, int pr, PPParams P,
-                                                    DevCounters* __restrict__ cnt) {
-  const int lane = threadIdx.x & 31;
-  const int nwarps = gridDim.x * (TPB / 32);
-  const int n_list = min(*n_list_ptr, list_cap);
-  const int side = 2 * pr + 1, ncell = side * side * side;
-  float fmax = 0.f;
-  for (int w = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); w < n_list; w += nwarps) {
-    const int k = list[w];
-    const int s0 = fstart[k], s1 = fstart[k + 1];
-    // decode the fine cell
-    const int sub = k & 63;
-    const unsigned int cc = (unsigned int)k >> 6;
-    const int gx = (int)(cc % H) * 4 + (sub & 3), gy = (int)((cc / H) % H) * 4 + ((sub >> 2) & 3), gz = (int)(cc / (H * H)) * 4 + (sub >> 4);
-    // each lane looks up ceil(ncell/32) neighbour cells
-    int nst[4], nen[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int c = r * 32 + lane;
-      nst[r] = 0; nen[r] = 0;
-      if (c < ncell) {
-        const int dx = c % side - pr, dy = (c / side) % side - pr, dz = c / (side * side) - pr;
-        if (dx != 0 || dy != 0 || dz != 0) {
-          const long long kk = fine::cell_key(gx + dx, gy + dy, gz + dz, H);
-          nst[r] = fstart[kk]; nen[r] = fstart[kk + 1];
-        }
-      }
+// PP_EXT, one THREAD per target particle of the cell-sorted array (ghosts and non-physical cells are skipped). At the mean density
+// of 1/8 particle per fine cell a warp-per-cell mapping leaves 31 of 32 lanes idle; here every lane owns a target and walks the
+// (2*pr+1)^2 neighbour fine-cell rows. The cells gx-pr..gx+pr of one row lie in at most two coarse cells, and inside one coarse
+// cell consecutive fx are consecutive keys, so each row is at most two contiguous particle ranges found with two fstart reads each.
+// Neighbouring lanes hold neighbouring particles, so their range lookups and source loads hit the same L1 lines.
+// The same-cell pairs belong to PPINT (:496-523 excludes the cell itself): the centre row is walked as [gx-pr,gx-1] and [gx+1,gx+pr].
+__device__ __forceinline__ void ppext_range(const float* __restrict__ xv, const int* __restrict__ fstart, long long rowkey, int xa, int xb,
+                                            const float3 pi, const PPParams& P, float3& acc) {
+  if (xa > xb) return;
+  const int ca = xa >> 2, cb = xb >> 2;
+#pragma unroll 1
+  for (int c = ca; c <= cb; ++c) {
+    const int f0 = (c == ca) ? (xa & 3) : 0, f1 = (c == cb) ? (xb & 3) : 3;
+    const long long k0 = rowkey + (long long)c * 64;
+    const int s = fstart[k0 + f0], e = fstart[k0 + f1 + 1];
+#pragma unroll 1
+    for (int j = s; j < e; ++j) {
+      const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * j;
+      const float2 a = p[0];
+      pair_force(pi, make_float3(a.x, a.y, p[1].x), P, true, acc);
     }
-    for (int ib = s0; ib < s1; ib += 32) {
-      const int i = ib + lane;
-      const bool vi = i < s1;
-      float3 pi = make_float3(0.f, 0.f, 0.f);
-      if (vi) { const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * i; const float2 a = p[0]; pi = make_float3(a.x, a.y, p[1].x); }
+  }
+}
+
+constexpr int EXT_TPB = 128;
+__global__ void __launch_bounds__(EXT_TPB) ppext_kernel(float* __restrict__ xv, const int* __restrict__ fstart, int np_all, int H, int b, int nc_buf,
+                                                        int nc_node, int pr, PPParams P, DevCounters* __restrict__ cnt) {
+  const int i = blockIdx.x * EXT_TPB + threadIdx.x;
+  float fm = 0.f;
+  if (i < np_all) {
+    float2* p = reinterpret_cast<float2*>(xv) + 3LL * i;
+    const float2 a = p[0];
+    const float z = p[1].x;
+    const int gx = (int)floorf(a.x) + b, gy = (int)floorf(a.y) + b, gz = (int)floorf(z) + b;   // as part::make_key
+    const int lo = nc_buf * 4, hi = (nc_buf + nc_node) * 4;
+    if (gx >= lo && gx < hi && gy >= lo && gy < hi && gz >= lo && gz < hi) {                      // kick only particles of the physical cells (:576-590)
+      const float3 pi = make_float3(a.x, a.y, z);
       float3 acc = make_float3(0.f, 0.f, 0.f);
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        unsigned m = __ballot_sync(0xffffffffu, nen[r] > nst[r]);
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const int t0 = __shfl_sync(0xffffffffu, nst[r], src), t1 = __shfl_sync(0xffffffffu, nen[r], src);
-          for (int jb = t0; jb < t1; jb += 32) {
-            const int j = jb + lane;
-            float3 pj = make_float3(0.f, 0.f, 0.f);
-            if (j < t1) { const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * j; const float2 a = p[0]; pj = make_float3(a.x, a.y, p[1].x); }
-            const int nj = min(32, t1 - jb);
-            for (int l = 0; l < nj; ++l) {
-              const float3 q = make_float3(__shfl_sync(0xffffffffu, pj.x, l), __shfl_sync(0xffffffffu, pj.y, l), __shfl_sync(0xffffffffu, pj.z, l));
-              if (vi) pair_force(pi, q, P, true, acc);
-            }
+#pragma unroll 1
+      for (int dz = -pr; dz <= pr; ++dz) {
+        const int nz = gz + dz;
+#pragma unroll 1
+        for (int dy = -pr; dy <= pr; ++dy) {
+          const int ny = gy + dy;
+          const long long rowkey = ((long long)((nz >> 2) * H + (ny >> 2)) * H) * 64 + (((nz & 3) << 4) | ((ny & 3) << 2));
+          if (dz == 0 && dy == 0) {
+            ppext_range(xv, fstart, rowkey, gx - pr, gx - 1, pi, P, acc);
+            ppext_range(xv, fstart, rowkey, gx + 1, gx + pr, pi, P, acc);
+          } else {
+            ppext_range(xv, fstart, rowkey, gx - pr, gx + pr, pi, P, acc);
           }
         }
       }
-      if (vi) {
-        fmax = fmaxf(fmax, sqrtf(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z));   // :617
-        if (P.apply) {
-          float2* p = reinterpret_cast<float2*>(xv) + 3LL * i;
-          const float s = P.a_mid * P.G * P.dt;
-          float2 b = p[1], c = p[2];
-          b.y += acc.x * s; c.x += acc.y * s; c.y += acc.z * s;
-          p[1] = b; p[2] = c;
-        }
+      fm = sqrtf(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z);   // :617
+      if (P.apply) {
+        const float s = P.a_mid * P.G * P.dt;
+        float2 bq = p[1], c = p[2];
+        bq.y += acc.x * s; c.x += acc.y * s; c.y += acc.z * s;
+        p[1] = bq; p[2] = c;
       }
-      __syncwarp();
     }
   }
-  fmax = warp_max(fmax);
-  if (lane == 0 && fmax > 0.f) atomic_max_float_nonneg(&cnt->pp_ext_force_max_bits, fmax);
+  fm = warp_max(fm);
+  if ((threadIdx.x & 31) == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_ext_force_max_bits, fm);
 }
 
 }  // namespace pp

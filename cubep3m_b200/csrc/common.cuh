@@ -129,7 +129,9 @@ struct cubep3m_b200_ctx {
   int* tile_counts = nullptr; // per-tile deposited-particle counts (parity getter)
   int cand_cap = 0;
   // fine mesh
-  float* kern_f = nullptr;    // [comp][z][y][kx]: the reference's kern_f(3,hc,n,n) (cubep3m.fh:35) de-interleaved
+  float* kern_f = nullptr;    // [comp][z][y][kf_pitch]: the reference's kern_f(3,hc,n,n) (cubep3m.fh:35) de-interleaved, rows padded to 16 floats
+  int kf_pitch = 0;           // row pitch of kern_f (floats), multiple of 16
+  long long kf_stride = 0;    // component stride of kern_f (floats)
   static constexpr int MAX_TILE_STREAMS = 4;
   int tile_streams_max = 1;
   int tile_streams = 1;       // S > 1: consecutive tiles rotate over S streams / buffer sets (hides launch bubbles, tails, latency)

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) f
 // the next block's spectrum and of the next component's Green's function values. AoS float2 shared-memory layout.
 template <int N>
 __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) fft_z_sandwich(const float2* __restrict__ spec, float2* __restrict__ g, long long gstride, int hc, int ny,
-                                                     const float* __restrict__ kern, long long kstride, int elo, int ehi,
+                                                     const float* __restrict__ kern, long long kstride, int kp, int elo, int ehi,
                                                      const float2* __restrict__ tw_g) {
   extern __shared__ __align__(16) unsigned char raw[];
   float2* b0 = reinterpret_cast<float2*>(raw);
@@ -259,8 +259,10 @@ __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) f
   auto fetch = [&](long long base, bool colok, int it) -> float2 {
     return (colok && e0 + it * ES < N) ? spec[base + it * gstep] : make_float2(0.f, 0.f);
   };
+  const long long kestride = (long long)ny * kp, kgstep = (long long)ES * kestride;   // the Green's function table has row pitch kp
   auto fetchk = [&](long long base, bool colok, int comp, int it) -> float {
-    return (colok && e0 + it * ES < N) ? kern[(long long)comp * kstride + base + it * gstep] : 0.f;
+    const long long y = (base % estride) / hc, kx = (base % estride) % hc;   // base = y*hc + kx + e0*estride
+    return (colok && e0 + it * ES < N) ? kern[(long long)comp * kstride + y * kp + kx + (long long)e0 * kestride + it * kgstep] : 0.f;
   };
   long long item = blockIdx.x, base = 0; bool colok = false;
   if (item < total) {
@@ -487,6 +489,10 @@ __global__ void __launch_bounds__(NT, 2) fft_x_c2r3(const float2* __restrict__ i
   if (lane == 0 && mx > 0.f) atomic_max_float_nonneg(fmax_bits, mx);
 }
 
+}  // namespace fftk
+#include "fft3d2.cuh"
+namespace fftk {
+
 // ------------------------------------------------------------------------------------------------
 // host-side dispatch on N (each axis of a mesh may have its own length: the fine tile is cubic, the global coarse mesh of a
 // (Dx,Dy,Dz) rank grid need not be)
@@ -515,6 +521,15 @@ template <int N> int set_smem_attr() {
   CK(cudaFuncSetAttribute((fft_strided<N, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute((fft_strided<N, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute(fft_z_sandwich<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_sandwich(N)));
+  if constexpr (Plan2<N>::ok) {
+    const int b2 = (int)smem_bytes2(N, 2, LX);
+    CK(cudaFuncSetAttribute((fft_strided2<N, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, b2));
+    CK(cudaFuncSetAttribute((fft_strided2<N, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, b2));
+    CK(cudaFuncSetAttribute((fft_strided2<N, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b2));
+    CK(cudaFuncSetAttribute(fft_z_sandwich2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_sandwich2(N)));
+    CK(cudaFuncSetAttribute(fft_x_r2c_ngp2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes2(N, 1, XP)));
+    CK(cudaFuncSetAttribute(fft_x_c2r3_v2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_c2r3_v2(N)));
+  }
   done = true;
   return 0;
 }
@@ -536,6 +551,11 @@ struct NgpSource {            // what fft_x_r2c_ngp needs to produce the tile's 
 template <int N> int launch_x_r2c_ngp_t(cubep3m_b200_ctx* ctx, int kc, float* data, const NgpSource& g, const float2* tw) {
   if (int st = set_smem_attr<N>()) return st;
   static_assert((N * N) % (2 * LX) == 0, "rows per tile must be a multiple of the rows per CTA");
+  if constexpr (Plan2<N>::ok && N % 4 == 0) {
+    LAUNCH(ctx, kc, fft_x_r2c_ngp2<N>, dim3(N * N / (2 * LX)), dim3(Plan2<N>::NT), (int)smem_bytes2(N, 1, XP), data, g.fstart, g.H, g.b, g.ox, g.oy, g.oz, g.mass_p,
+           g.deltas, g.ndelta, g.delta_cap, g.sum_phys, tw);
+    return 0;
+  }
   LAUNCH(ctx, kc, fft_x_r2c_ngp<N>, dim3(N * N / (2 * LX)), dim3(NT), (int)smem_bytes(N), data, g.fstart, g.H, g.b, g.ox, g.oy, g.oz, g.mass_p, g.deltas,
          g.ndelta, g.delta_cap, g.sum_phys, tw);
   return 0;
@@ -544,6 +564,27 @@ template <int N> int launch_strided_t(cubep3m_b200_ctx* ctx, int kc, bool inv, c
                                       long long ostride, int outer0, int nouter, const float* kern, long long kes, long long kos, int elo,
                                       int ehi, const float2* tw, int nbatch, long long bstride) {
   if (int st = set_smem_attr<N>()) return st;
+  if constexpr (Plan2<N>::ok) {
+    const int sm2 = (int)smem_bytes2(N, 2, LX);
+    static int occ2[3] = {0, 0, 0};
+    if (!occ2[0]) {
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[0], (fft_strided2<N, false, false>), Plan2<N>::NT, sm2));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[1], (fft_strided2<N, true, true>), Plan2<N>::NT, sm2));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[2], (fft_strided2<N, true, false>), Plan2<N>::NT, sm2));
+    }
+    const long long total2 = (long long)((hc + LX - 1) / LX) * nouter * nbatch;
+    auto grid2 = [&](int o) { return dim3((unsigned)std::min<long long>(total2, (long long)NUM_SMS * std::max(o, 1))); };
+    const dim3 blk(Plan2<N>::NT);
+    // 32-bit element offsets inside the kernel: the largest offset touched must stay below 2^31
+    const long long span = (long long)(nbatch - 1) * bstride + (long long)(outer0 + nouter) * ostride + (long long)N * estride + hc;
+    const long long kspan = kern ? (long long)(outer0 + nouter) * kos + (long long)N * kes + hc : 0;
+    if (span >= (1LL << 31) || kspan >= (1LL << 31) || total2 >= (1LL << 31)) return CUBEP3M_B200_EINVAL;
+    const int es = (int)estride, os = (int)ostride, bs = (int)bstride, ke = (int)kes, ko = (int)kos;
+    if (!inv) LAUNCH(ctx, kc, (fft_strided2<N, false, false>), grid2(occ2[0]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, nullptr, 0, 0, elo, ehi, tw, bs);
+    else if (kern) LAUNCH(ctx, kc, (fft_strided2<N, true, true>), grid2(occ2[1]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, kern, ke, ko, elo, ehi, tw, bs);
+    else LAUNCH(ctx, kc, (fft_strided2<N, true, false>), grid2(occ2[2]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, nullptr, 0, 0, elo, ehi, tw, bs);
+    return 0;
+  }
   const int sm = (int)smem_bytes_aos(N, 2);
   static int occ[3] = {0, 0, 0};    // resident CTAs per SM of the three instantiations
   if (!occ[0]) {
@@ -559,13 +600,23 @@ template <int N> int launch_strided_t(cubep3m_b200_ctx* ctx, int kc, bool inv, c
   return 0;
 }
 template <int N> int launch_sandwich_t(cubep3m_b200_ctx* ctx, int kc, const float2* spec, float2* g, long long gstride, int hc, int ny, const float* kern,
-                                       long long kstride, int elo, int ehi, const float2* tw) {
+                                       long long kstride, int kp, int elo, int ehi, const float2* tw) {
   if (int st = set_smem_attr<N>()) return st;
+  if constexpr (Plan2<N>::ok) {
+    const int sm2 = (int)smem_bytes_sandwich2(N);
+    static int occ2 = 0;
+    if (!occ2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fft_z_sandwich2<N>, Plan2<N>::NT, sm2));
+    const long long total2 = (long long)((hc + LX - 1) / LX) * ny;
+    if (kp % 16 != 0 || 3 * gstride >= (1LL << 31)) return CUBEP3M_B200_EINVAL;
+    LAUNCH(ctx, kc, fft_z_sandwich2<N>, dim3((unsigned)std::min<long long>(total2, (long long)NUM_SMS * std::max(occ2, 1))), dim3(Plan2<N>::NT), sm2, spec, g, (int)gstride,
+           hc, ny, kern, kstride, kp, elo, ehi, tw);
+    return 0;
+  }
   static int occ = 0;
   if (!occ) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_z_sandwich<N>, NT, (int)smem_bytes_sandwich(N)));
   const long long total = (long long)((hc + LX - 1) / LX) * ny;
   LAUNCH(ctx, kc, fft_z_sandwich<N>, dim3((unsigned)std::min<long long>(total, (long long)NUM_SMS * std::max(occ, 1))), dim3(NT), (int)smem_bytes_sandwich(N), spec,
-         g, gstride, hc, ny, kern, kstride, elo, ehi, tw);
+         g, gstride, hc, ny, kern, kstride, kp, elo, ehi, tw);
   return 0;
 }
 template <int N> int launch_x_c2r_t(cubep3m_b200_ctx* ctx, int kc, const float2* in, float* out, int lo_x, int cnt_x, int lo_y, int cnt_y, int lo_z,
@@ -577,10 +628,19 @@ template <int N> int launch_x_c2r_t(cubep3m_b200_ctx* ctx, int kc, const float2*
          lo_z, cnt_z, ny_src, opx, opy, scale, tw, ibs, obs);
   return 0;
 }
+#ifndef FFTK_C2R3_V2
+#define FFTK_C2R3_V2 0   // measured on B200 (n = 304): first-generation fft_x_c2r3 175 us, fft_x_c2r3_v2 222 us per tile
+#endif
 template <int N> int launch_x_c2r3_t(cubep3m_b200_ctx* ctx, int kc, const float2* in, float* out, int lo, int cnt, long long ibs, long long obs, float scale,
                                      unsigned int* fmax_bits, const float2* tw) {
   if (int st = set_smem_attr<N>()) return st;
   const long long nrows = (long long)cnt * cnt;
+  if constexpr (Plan2<N>::ok && FFTK_C2R3_V2) {
+    if (3 * ibs >= (1LL << 31) || 3 * obs >= (1LL << 31)) return CUBEP3M_B200_EINVAL;
+    LAUNCH(ctx, kc, fft_x_c2r3_v2<N>, dim3((unsigned)((nrows + 2 * LX - 1) / (2 * LX))), dim3(Plan2<N>::NT), (int)smem_bytes_c2r3_v2(N), in, out, lo, cnt, (int)ibs, (int)obs,
+           scale, fmax_bits, tw);
+    return 0;
+  }
   LAUNCH(ctx, kc, fft_x_c2r3<N>, dim3((unsigned)((nrows + 2 * LX - 1) / (2 * LX))), dim3(NT), (int)smem_bytes(N), in, out, lo, cnt, ibs, obs, scale, fmax_bits, tw);
   return 0;
 }
@@ -608,8 +668,8 @@ inline int launch_strided(cubep3m_b200_ctx* ctx, int kc, int n, bool inv, const 
 #undef X
 }
 inline int launch_sandwich(cubep3m_b200_ctx* ctx, int kc, int n, const float2* spec, float2* g, long long gstride, int hc, int ny, const float* kern,
-                           long long kstride, int elo, int ehi, const float2* tw) {
-#define X(N) case N: return launch_sandwich_t<N>(ctx, kc, spec, g, gstride, hc, ny, kern, kstride, elo, ehi, tw);
+                           long long kstride, int kp, int elo, int ehi, const float2* tw) {
+#define X(N) case N: return launch_sandwich_t<N>(ctx, kc, spec, g, gstride, hc, ny, kern, kstride, kp, elo, ehi, tw);
   FFTK_SWITCH(n, X)
 #undef X
 }
@@ -632,8 +692,8 @@ inline int launch_x_c2r3(cubep3m_b200_ctx* ctx, int kc, int n, const float2* in,
 // then inverse y and inverse x (crop + scale) for the three components in one launch each.
 // g3: scratch of 3 complex tiles; force3: 3 x cnt^3 outputs (component-major).
 // If ngp != nullptr the density is generated inside the first pass (data is then only written).
-inline int fine_solve(cubep3m_b200_ctx* ctx, const Mesh3& m, float* data, float* g3, const float* kern3, float* force3, int lo, int cnt, float scale,
-                      unsigned int* fmax_bits, const NgpSource* ngp = nullptr) {
+inline int fine_solve(cubep3m_b200_ctx* ctx, const Mesh3& m, float* data, float* g3, const float* kern3, long long kstride, int kp, float* force3, int lo, int cnt,
+                      float scale, unsigned int* fmax_bits, const NgpSource* ngp = nullptr) {
   const int n = m.nx, hc = m.hc();
   const long long cplx = (long long)hc * n * n;     // complex elements per tile
   float2* c = reinterpret_cast<float2*>(data);
@@ -641,7 +701,7 @@ inline int fine_solve(cubep3m_b200_ctx* ctx, const Mesh3& m, float* data, float*
   if (ngp) { if (int st = launch_x_r2c_ngp(ctx, KC_FFT_X_R2C, n, data, *ngp, m.twx)) return st; }
   else if (int st = launch_x_r2c(ctx, KC_FFT_X_R2C, n, data, n * n, m.twx)) return st;
   if (int st = launch_strided(ctx, KC_FFT_FWD_STRIDED, n, false, c, c, hc, (long long)hc, (long long)n * hc, 0, n, nullptr, 0, 0, 0, n - 1, m.twy)) return st;
-  if (int st = launch_sandwich(ctx, KC_FFT_INV_Z_MUL, n, c, g, cplx, hc, n, kern3, cplx, lo, lo + cnt - 1, m.twz)) return st;
+  if (int st = launch_sandwich(ctx, KC_FFT_INV_Z_MUL, n, c, g, cplx, hc, n, kern3, kstride, kp, lo, lo + cnt - 1, m.twz)) return st;
   if (int st = launch_strided(ctx, KC_FFT_INV_Y, n, true, g, g, hc, (long long)hc, (long long)n * hc, lo, cnt, nullptr, 0, 0, lo, lo + cnt - 1, m.twy, 3, cplx)) return st;
   if (int st = launch_x_c2r3(ctx, KC_FFT_X_C2R, n, g, force3, lo, cnt, cplx, (long long)cnt * cnt * cnt, scale, fmax_bits, m.twx)) return st;
   CK(cudaGetLastError());

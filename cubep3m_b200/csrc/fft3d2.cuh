@@ -1,0 +1,459 @@
+// Second-generation FFT pass kernels (see fft2.cuh for the core): used for every two-factor N (Plan2<N>::ok); the first-generation
+// kernels of fft3d.cuh remain for N = 16 and the three-factor sizes (512, 560).
+//
+//   fft_strided2     Y / Z pass. The next work item's column block is staged with cp.async (8-byte, the spectrum pitch hc*8 B is not
+//                    16-byte aligned so TMA/bulk copies cannot be used) into the other of two buffers while the current one is
+//                    transformed IN PLACE; stage-B results go straight from registers to global memory (128 B per half-warp).
+//   fft_z_sandwich2  forward z + 3 x (multiply by i*kern_f(comp), inverse z), two buffers: the forward result stays in the landing
+//                    buffer, components 0 and 1 run A: L -> W, B: W -> global, component 2 runs in place on L, which frees W for
+//                    the cp.async prefetch of the next item during the whole third inverse transform. The Green's-function block of
+//                    the NEXT component is staged with 16-byte cp.async into a third, small buffer (kern_f is stored with a pitch of
+//                    a multiple of 16 floats for this) while the current component is transformed.
+//   Addressing is 32-bit and incremental (one decode per item, pointer stepping, crop tests as a per-thread bitmask): the first
+//   version of these kernels spent 75 % of its issue slots on integer work (profiles/r1_ncu_v2_first_try.txt).
+//   fft_x_r2c_ngp2   NGP density from the fine-cell table + r2c along x. One thread produces a whole coarse cell's (fz fixed) 4x4 block
+//                    of densities from 17 consecutive table entries (four 16-byte loads + one), all loads in flight before first use.
+//   fft_x_c2r3_v2    c2r along x for the 3 force components with crop + 1/n^3 + max |F|^2; half-spectrum rows are staged with cp.async
+//                    (next component prefetched during the current FFT).
+#pragma once
+#include "fft2.cuh"
+// (included from the middle of fft3d.cuh, after the first-generation kernels and before the host-side dispatch)
+
+namespace fftk {
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async8(unsigned sdst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(unsigned sdst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// bit r set iff stage-B output e = j + r*R0 lies in [elo, ehi]
+template <int N> __device__ __forceinline__ unsigned crop_mask(int j, int elo, int ehi) {
+  unsigned m = 0;
+#pragma unroll
+  for (int r = 0; r < Plan2<N>::R1; ++r) { const int e = j + r * Plan2<N>::R0; if (e >= elo && e <= ehi) m |= 1u << r; }
+  return m;
+}
+
+// stage one column block (N rows of 16 float2, row stride `estride` elements) into dst[N][16]; thread (j, col) copies rows j, j+ES, ...
+template <int N, int ES> __device__ __forceinline__ void stage_block(const float2* __restrict__ src, int estride, bool ok, unsigned sdst, float2* __restrict__ dgen, int j) {
+#pragma unroll
+  for (int it = 0; it < (N + ES - 1) / ES; ++it) {
+    if (j + it * ES < N) {
+      if (ok) cp_async8(sdst + it * ES * LX * 8, src);
+      else dgen[it * ES * LX] = make_float2(0.f, 0.f);
+      src += (long long)ES * estride;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- strided pass
+// element e of column c of item (bx, outer, bz): in[bz*bstride + (outer + outer0)*ostride + bx*16 + e*estride + c]   (all offsets < 2^31)
+template <int N, bool INV, bool MUL>
+__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_strided2(const float2* __restrict__ in, float2* __restrict__ out, int hc, int estride, int ostride,
+                                                                int outer0, int nouter, int nbatch, const float* __restrict__ kern, int kes, int kos,
+                                                                int elo, int ehi, const float2* __restrict__ tw_g, int bstride) {
+  using P = Plan2<N>;
+  constexpr int NT2 = P::NT, R0 = P::R0, R1 = P::R1, ES = NT2 / LX;
+  extern __shared__ __align__(16) unsigned char raw[];
+  float2* buf0 = reinterpret_cast<float2*>(raw);
+  float2* buf1 = buf0 + N * LX;
+  float2* tw = buf1 + N * LX;
+  for (int t = threadIdx.x; t < N; t += NT2) tw[t] = tw_g[t];
+  const int col = threadIdx.x % LX, j = threadIdx.x / LX;
+  const unsigned nbx = (hc + LX - 1) / LX;
+  const int total = (int)nbx * nouter * nbatch;
+  const unsigned mask = crop_mask<N>(j, elo, ehi);
+  const int slot = j * LX + col;
+  const unsigned s0 = smem_u32(buf0 + slot), s1 = smem_u32(buf1 + slot);
+  const int joff = j * estride;
+  auto decode = [&](int item, int& off, int& koff, bool& ok) {
+    const unsigned bx = (unsigned)item % nbx, t = (unsigned)item / nbx;
+    const unsigned o = t % (unsigned)nouter, bz = t / (unsigned)nouter;
+    const int kx = (int)bx * LX + col;
+    off = (int)bz * bstride + ((int)o + outer0) * ostride + kx;
+    koff = ((int)o + outer0) * kos + kx;
+    ok = kx < hc;
+  };
+  int item = blockIdx.x, off = 0, koff = 0;
+  bool ok = false;
+  int p = 0;
+  if (item < total) {
+    decode(item, off, koff, ok);
+    stage_block<N, ES>(in + off + joff, estride, ok, s0, buf0 + slot, j);
+    cp_async_commit();
+  }
+  while (item < total) {
+    float2* buf = p ? buf1 : buf0;
+    const int next = item + gridDim.x;
+    int noff = 0, nkoff = 0;
+    bool nok = false;
+    cp_async_wait_all();
+    __syncthreads();                               // item landed; every thread is done with the other buffer
+    if (next < total) {
+      decode(next, noff, nkoff, nok);
+      stage_block<N, ES>(in + noff + joff, estride, nok, p ? s0 : s1, (p ? buf0 : buf1) + slot, j);
+      cp_async_commit();
+    }
+    float2 v[R0];
+    if (threadIdx.x < P::NA) {
+      stageA_load<N, INV, LX>(buf, j, col, v);
+      if (MUL) {
+        const float* kp = kern + koff + j * kes;
+#pragma unroll
+        for (int r = 0; r < R0; ++r) {
+          const float kv = ok ? kp[(long long)r * R1 * kes] : 0.f;
+          v[r] = make_float2(-v[r].y * kv, v[r].x * kv);
+        }
+      }
+      PRadix<R0, INV>::run(v);
+    }
+    __syncthreads();
+    if (threadIdx.x < P::NA) stageA_store<N, LX>(buf, j, col, v);
+    __syncthreads();
+    if (threadIdx.x < P::NB) {
+      float2* op = out + off + joff;
+      const unsigned m = ok ? mask : 0u;
+      const int step = R0 * estride;
+      stageB<N, INV, LX>(buf, tw, j, col, [&](int r, float2 val) {
+        if (m & (1u << r)) op[(long long)r * step] = val;
+      });
+    }
+    item = next; off = noff; koff = nkoff; ok = nok;
+    p ^= 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- fused z pass
+// kern: [comp][z][y][kp] floats, kp a multiple of 16 (64-byte aligned 16-column blocks), comp stride kstride.
+template <int N>
+__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_z_sandwich2(const float2* __restrict__ spec, float2* __restrict__ g, int gstride, int hc, int ny,
+                                                                   const float* __restrict__ kern, long long kstride, int kp, int elo, int ehi,
+                                                                   const float2* __restrict__ tw_g) {
+  using P = Plan2<N>;
+  constexpr int NT2 = P::NT, R0 = P::R0, R1 = P::R1, ES = NT2 / LX;
+  extern __shared__ __align__(16) unsigned char raw[];
+  float2* L = reinterpret_cast<float2*>(raw);
+  float2* W = L + N * LX;
+  float* K = reinterpret_cast<float*>(W + N * LX);
+  float2* tw = reinterpret_cast<float2*>(K + N * LX);
+  for (int t = threadIdx.x; t < N; t += NT2) tw[t] = tw_g[t];
+  const int col = threadIdx.x % LX, j = threadIdx.x / LX;
+  const unsigned nbx = (hc + LX - 1) / LX;
+  const int total = (int)nbx * ny;
+  const int estride = ny * hc;
+  const long long kes = (long long)ny * kp;         // z stride of the Green's function table
+  const unsigned mask = crop_mask<N>(j, elo, ehi);
+  const int slot = j * LX + col, joff = j * estride;
+  unsigned sL = smem_u32(L + slot), sW = smem_u32(W + slot);
+  const unsigned sK = smem_u32(K);
+  const bool actA = threadIdx.x < P::NA, actB = threadIdx.x < P::NB;
+  auto decode = [&](int item, int& off, int& kb, bool& ok) {
+    const unsigned bx = (unsigned)item % nbx, y = (unsigned)item / nbx;
+    off = (int)y * hc + (int)bx * LX + col;
+    kb = (int)y * kp + (int)bx * LX;
+    ok = (int)bx * LX + col < hc;
+  };
+  auto issueK = [&](int comp, int kb) {             // N rows of 16 floats = 4 x 16 bytes each
+    const float* src = kern + comp * kstride + kb;
+#pragma unroll
+    for (int it = 0; it < (4 * N + NT2 - 1) / NT2; ++it) {
+      const int t = threadIdx.x + it * NT2;
+      if (t < 4 * N) cp_async16(sK + t * 16, src + (long long)(t >> 2) * kes + (t & 3) * 4);
+    }
+    cp_async_commit();
+  };
+  auto stageA_inv = [&](float2 (&v)[R0]) {          // gather S, multiply by i*kern_f (:188-189), radix R0
+    stageA_load<N, true, LX>(L, j, col, v);
+    const float* kq = K + slot;
+#pragma unroll
+    for (int r = 0; r < R0; ++r) { const float kv = kq[r * R1 * LX]; v[r] = make_float2(-v[r].y * kv, v[r].x * kv); }
+    PRadix<R0, true>::run(v);
+  };
+  int item = blockIdx.x, off = 0, kb = 0;
+  bool ok = false;
+  if (item < total) {
+    decode(item, off, kb, ok);
+    stage_block<N, ES>(spec + off + joff, estride, ok, sL, L + slot, j);
+    issueK(0, kb);
+  }
+  const int step = R0 * estride;
+  while (item < total) {
+    const int next = item + gridDim.x;
+    int noff = 0, nkb = 0;
+    bool nok = false;
+    if (next < total) decode(next, noff, nkb, nok);
+    const unsigned m = ok ? mask : 0u;
+    cp_async_wait_all();
+    __syncthreads();                                // spectrum block and kern_f(0) block landed
+    float2 v[R0];
+    // ---- forward transform in place on L
+    if (actA) { stageA_load<N, false, LX>(L, j, col, v); PRadix<R0, false>::run(v); }
+    __syncthreads();
+    if (actA) stageA_store<N, LX>(L, j, col, v);
+    __syncthreads();
+    if (actB) {
+      float2* sp = L + slot;
+      stageB<N, false, LX>(L, tw, j, col, [&](int r, float2 val) { sp[r * R0 * LX] = val; });   // same slots this thread read
+    }
+    __syncthreads();
+    // ---- components 0 and 1: A: L -> W, B: W -> global
+#pragma unroll
+    for (int comp = 0; comp < 2; ++comp) {
+      if (actA) { stageA_inv(v); stageA_store<N, LX>(W, j, col, v); }
+      __syncthreads();                              // W complete; K consumed
+      issueK(comp + 1, kb);
+      if (actB) {
+        float2* go = g + comp * gstride + off + joff;
+        stageB<N, true, LX>(W, tw, j, col, [&](int r, float2 val) { if (m & (1u << r)) go[(long long)r * step] = val; });
+      }
+      cp_async_wait_all();
+      __syncthreads();                              // next kern_f block landed; W free
+    }
+    if (next < total) { stage_block<N, ES>(spec + noff + joff, estride, nok, sW, W + slot, j); cp_async_commit(); }
+    // ---- component 2 in place on L
+    if (actA) stageA_inv(v);
+    __syncthreads();                                // all gathers from L and K precede the scatter / the next kern_f block
+    if (next < total) issueK(0, nkb);
+    if (actA) stageA_store<N, LX>(L, j, col, v);
+    __syncthreads();
+    if (actB) {
+      float2* go = g + 2 * gstride + off + joff;
+      stageB<N, true, LX>(L, tw, j, col, [&](int r, float2 val) { if (m & (1u << r)) go[(long long)r * step] = val; });
+    }
+    { float2* t = L; L = W; W = t; const unsigned u = sL; sL = sW; sW = u; }
+    item = next; off = noff; kb = nkb; ok = nok;
+  }
+}
+constexpr size_t smem_bytes_sandwich2(int n) { return (size_t)2 * n * LX * sizeof(float2) + (size_t)n * LX * sizeof(float) + (size_t)n * sizeof(float2); }
+
+// ---------------------------------------------------------------------------------------------- x pass forward + NGP density
+constexpr int XP = LX + 1;   // pitch (float2) of the contiguous-axis passes
+
+template <int N>
+__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_r2c_ngp2(float* __restrict__ data, const int* __restrict__ fstart, int H, int b, int ox, int oy, int oz,
+                                                                  float mass_p, const int2* __restrict__ deltas, const int* __restrict__ ndelta_ptr,
+                                                                  int delta_cap, double* __restrict__ sum_phys, const float2* __restrict__ tw_g) {
+  using P = Plan2<N>;
+  constexpr int NT2 = P::NT, NW = NT2 / 32, R0 = P::R0, PW = N + 2, NCX = N / 4, UNITS = 8 * NCX, UPT = (UNITS + NT2 - 1) / NT2;
+  constexpr int HC = N / 2 + 1, KCH = (HC + 31) / 32;
+  extern __shared__ __align__(16) unsigned char raw[];
+  float2* Z = reinterpret_cast<float2*>(raw);
+  float2* tw = Z + N * XP;
+  for (int t = threadIdx.x; t < N; t += NT2) tw[t] = tw_g[t];
+  const int r0 = blockIdx.x * (2 * LX);          // first row (= z*N + y) of this CTA; N*N is a multiple of 32
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- density: unit u = (cyl, ccx): rows r0+4*cyl .. +3 (one coarse-cell row group, fy = 0..3), x cells 4*ccx .. +3
+  int4 q[UPT][4];
+  int qe[UPT];
+  bool live[UPT];
+#pragma unroll
+  for (int s = 0; s < UPT; ++s) {
+    const int u = threadIdx.x + s * NT2;
+    live[s] = false;
+    if (u < UNITS) {
+      const int cyl = u & 7, ccx = u >> 3;            // lanes run over the 8 row groups first: 64-bit stores of a half-warp are 2-way conflicted at worst
+      const int gr = r0 + 4 * cyl, y0 = gr % N, z = gr / N;
+      if (z >= 4 && z <= N - 5 && y0 >= 4 && y0 <= N - 8 && ccx >= 1 && ccx <= NCX - 2) {   // deposit range [4, N-5] on every axis (:120-121)
+        const int gz = z + oz, gy = y0 + oy, gx = 4 * ccx + ox;
+        const long long k = ((long long)((gz >> 2) * H + (gy >> 2)) * H + (gx >> 2)) * 64 + ((gz & 3) << 4);
+        const int4* src = reinterpret_cast<const int4*>(fstart + k);
+        q[s][0] = src[0]; q[s][1] = src[1]; q[s][2] = src[2]; q[s][3] = src[3];
+        qe[s] = fstart[k + 16];
+        live[s] = true;
+      }
+    }
+  }
+  double msum = 0.0;
+#pragma unroll
+  for (int s = 0; s < UPT; ++s) {
+    const int u = threadIdx.x + s * NT2;
+    if (u < UNITS) {
+      const int cyl = u & 7, ccx = u >> 3;
+      float val[16];
+      if (live[s]) {
+        const int e[17] = {q[s][0].x, q[s][0].y, q[s][0].z, q[s][0].w, q[s][1].x, q[s][1].y, q[s][1].z, q[s][1].w, q[s][2].x,
+                           q[s][2].y, q[s][2].z, q[s][2].w, q[s][3].x, q[s][3].y, q[s][3].z, q[s][3].w, qe[s]};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) val[i] = mass_p * (float)(e[i + 1] - e[i]);
+        const int gr = r0 + 4 * cyl, y0 = gr % N, z = gr / N, x0 = 4 * ccx;
+        if (z >= b && z < N - b && y0 >= b && y0 < N - b && x0 >= b && x0 < N - b)           // b % 4 == 0; the 16 values are small multiples of mass_p
+          msum += (double)(mass_p * (float)(e[16] - e[0]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) val[i] = 0.f;
+      }
+      // rows 4*cyl + 2h (real part) and 4*cyl + 2h + 1 (imaginary part) -> column 2*cyl + h
+      float2* zq = Z + (4 * ccx) * XP + 2 * cyl;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int fx = 0; fx < 4; ++fx) zq[fx * XP + h] = make_float2(val[8 * h + fx], val[8 * h + 4 + fx]);
+    }
+  }
+  msum = warp_sum_d(msum);
+  if (lane == 0 && msum != 0.0) atomicAdd(sum_phys, msum);
+  __syncthreads();
+  const int nd = min(*ndelta_ptr, delta_cap);
+  if (nd > 0) {
+    for (int i = threadIdx.x; i < nd; i += NT2) {
+      const int2 d = deltas[i];
+      const int c[2] = {d.x, d.y};
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int x = c[u] % N, gr = c[u] / N;     // gr = z*N + y
+        const int row = gr - r0;
+        if (row >= 0 && row < 2 * LX) atomicAdd(reinterpret_cast<float*>(Z + x * XP + (row >> 1)) + (row & 1), u == 0 ? -mass_p : mass_p);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- FFT of the 16 packed columns, in place
+  const int col = threadIdx.x % LX, j = threadIdx.x / LX;
+  {
+    float2 v[R0];
+    if (threadIdx.x < P::NA) { stageA_load<N, false, XP>(Z, j, col, v); PRadix<R0, false>::run(v); }
+    __syncthreads();
+    if (threadIdx.x < P::NA) stageA_store<N, XP>(Z, j, col, v);
+    __syncthreads();
+    if (threadIdx.x < P::NB) {
+      float2* sp = Z + j * XP + col;
+      stageB<N, false, XP>(Z, tw, j, col, [&](int r, float2 val) { sp[r * R0 * XP] = val; });
+    }
+    __syncthreads();
+  }
+  // ---- untangle the two real rows of each column: A = (Z[k] + conj Z[N-k]) / 2, B = (Z[k] - conj Z[N-k]) / (2i).
+  // Work unit = (column, chunk of 32 k): 16*KCH units dealt round-robin to the warps; each unit stores 256 contiguous bytes to two rows.
+#pragma unroll
+  for (int s = 0; s < (LX * KCH + NW - 1) / NW; ++s) {
+    const int unit = warp + s * NW;
+    if (unit < LX * KCH) {
+      const int c = unit / KCH, k = (unit - c * KCH) * 32 + lane;
+      if (k < HC) {
+        const int km = (k == 0) ? 0 : N - k;
+        const float2 zk = Z[k * XP + c], zm = Z[km * XP + c];
+        const float2 sm = padd(zk, zm), df = psub(zk, zm);
+        float2* rowA = reinterpret_cast<float2*>(data + (long long)(r0 + 2 * c) * PW);
+        rowA[k] = make_float2(0.5f * sm.x, 0.5f * df.y);
+        reinterpret_cast<float2*>(reinterpret_cast<float*>(rowA) + PW)[k] = make_float2(0.5f * sm.y, -0.5f * df.x);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- x pass backward, 3 components
+// Row staging buffer: Rw[32][HC] float2, filled with cp.async from the cropped rows of component `comp`.
+template <int N>
+__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v2(const float2* __restrict__ in, float* __restrict__ out, int lo, int cnt, int in_bstride,
+                                                                 int out_bstride, float scale, unsigned int* __restrict__ fmax_bits,
+                                                                 const float2* __restrict__ tw_g) {
+  using P = Plan2<N>;
+  constexpr int NT2 = P::NT, NW = NT2 / 32, R0 = P::R0, HC = N / 2 + 1, KCH = (HC + 31) / 32;
+  extern __shared__ __align__(16) unsigned char raw[];
+  float2* Z = reinterpret_cast<float2*>(raw);
+  float2* Rw = Z + N * XP;
+  float2* tw = Rw + 2 * LX * HC;
+  __shared__ int srow[2 * LX], drow[2 * LX];
+  for (int t = threadIdx.x; t < N; t += NT2) tw[t] = tw_g[t];
+  const int nrows = cnt * cnt;
+  const int r0 = blockIdx.x * (2 * LX);
+  if (threadIdx.x < 2 * LX) {
+    const int ridx = r0 + threadIdx.x;
+    int so = -1, dof = -1;
+    if (ridx < nrows) {
+      const int zc = ridx / cnt, yc = ridx - zc * cnt;
+      so = ((zc + lo) * N + (yc + lo)) * HC;
+      dof = (zc * cnt + yc) * cnt;
+    }
+    srow[threadIdx.x] = so; drow[threadIdx.x] = dof;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned sR = smem_u32(Rw);
+  auto issue = [&](int comp) {                     // unit = (row, chunk of 32 k)
+    const float2* src = in + (long long)comp * in_bstride + lane;
+#pragma unroll
+    for (int s = 0; s < (2 * LX * KCH + NW - 1) / NW; ++s) {
+      const int unit = warp + s * NW;
+      if (unit < 2 * LX * KCH) {
+        const int row = unit / KCH, k = (unit - row * KCH) * 32 + lane;
+        if (k < HC) {
+          const int so = srow[row];
+          if (so >= 0) cp_async8(sR + (row * HC + k) * 8, src + so + (k - lane));
+          else Rw[row * HC + k] = make_float2(0.f, 0.f);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  const int col = threadIdx.x % LX, j = threadIdx.x / LX;
+  constexpr int XCH = (N + 31) / 32, SU = (LX * XCH + NW - 1) / NW;
+  float2 fsq[SU];
+#pragma unroll
+  for (int s = 0; s < SU; ++s) fsq[s] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int comp = 0; comp < 3; ++comp) {
+    cp_async_wait_all();
+    __syncthreads();                               // rows of `comp` landed; Z is free (previous store phase done)
+    // Z[k] = A[k] + i B[k];  Z[N-k] = conj(A[k]) + i conj(B[k]);  imaginary parts of the k=0 and k=N/2 bins are dropped (c2r)
+#pragma unroll
+    for (int s = 0; s < (LX * KCH + NW - 1) / NW; ++s) {
+      const int unit = warp + s * NW;
+      if (unit < LX * KCH) {
+        const int c = unit / KCH, k = (unit - c * KCH) * 32 + lane;
+        if (k < HC) {
+          float2 a = Rw[(2 * c) * HC + k], bq = Rw[(2 * c + 1) * HC + k];
+          const bool edge = (k == 0 || 2 * k == N);
+          if (edge) { a.y = 0.f; bq.y = 0.f; }
+          Z[k * XP + c] = add_irot(a, bq);                               // (ar - bi, ai + br)
+          if (!edge) Z[(N - k) * XP + c] = make_float2(a.x + bq.y, bq.x - a.y);
+        }
+      }
+    }
+    __syncthreads();                               // Rw consumed
+    if (comp < 2) issue(comp + 1);
+    {
+      float2 v[R0];
+      if (threadIdx.x < P::NA) { stageA_load<N, true, XP>(Z, j, col, v); PRadix<R0, true>::run(v); }
+      __syncthreads();
+      if (threadIdx.x < P::NA) stageA_store<N, XP>(Z, j, col, v);
+      __syncthreads();
+      if (threadIdx.x < P::NB) {
+        float2* sp = Z + j * XP + col;
+        stageB<N, true, XP>(Z, tw, j, col, [&](int r, float2 val) { sp[r * R0 * XP] = val; });
+      }
+      __syncthreads();
+    }
+    // unit = (column, chunk of 32 x): a column holds two output rows (real part -> even row, imaginary part -> odd row); one 64-bit
+    // conflict-free shared load and two coalesced 32-bit stores per element. |F|^2 of the thread's elements accumulates in fsq (the
+    // unit -> thread map is the same for the three components).
+    float* o = out + (long long)comp * out_bstride;
+#pragma unroll
+    for (int s = 0; s < SU; ++s) {
+      const int unit = warp + s * NW;
+      if (unit < LX * XCH) {
+        const int c = unit / XCH, xc = (unit - c * XCH) * 32 + lane;
+        const int dofA = drow[2 * c], dofB = drow[2 * c + 1];
+        if (dofA >= 0 && xc < cnt) {
+          const float2 zz = pmul_s(scale, Z[(xc + lo) * XP + c]);
+          o[dofA + xc] = zz.x;
+          if (dofB >= 0) o[dofB + xc] = zz.y;
+          fsq[s] = pfma_v(zz, zz, fsq[s]);
+        }
+      }
+    }
+  }
+  float mx = 0.f;
+#pragma unroll
+  for (int s = 0; s < SU; ++s) mx = fmaxf(mx, fmaxf(fsq[s].x, fsq[s].y));   // rows beyond the crop contribute 0 (their inputs were zero-filled)
+  mx = warp_max(mx);
+  if (lane == 0 && mx > 0.f) atomic_max_float_nonneg(fmax_bits, mx);
+}
+constexpr size_t smem_bytes_c2r3_v2(int n) { return (size_t)n * XP * sizeof(float2) + (size_t)2 * LX * (n / 2 + 1) * sizeof(float2) + (size_t)n * sizeof(float2); }
+
+}  // namespace fftk

@@ -63,23 +63,30 @@ template <typename T> int dmalloc(T** p, size_t count) {
   return 0;
 }
 
-__global__ void extract_imag_kernel(const float2* __restrict__ spec, long long n, float* __restrict__ kern, int comp) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) kern[(long long)comp * n + i] = spec[i].y;
+// kern_f(comp) = Im(spectrum), stored with row pitch kp >= hc (rows = (z, y))
+__global__ void extract_imag_kernel(const float2* __restrict__ spec, long long n, int hc, int kp, float* __restrict__ kern) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / hc;
+    kern[row * kp + (i - row * hc)] = spec[i].y;
+  }
 }
 
-// host (3, n) interleaved -> device [comp][stride] planes, elements [off, off+count)
-int upload_interleaved(float* dev, const float* host, size_t plane, size_t off, size_t count) {
+// host (3, n) interleaved -> device [comp][stride] planes, elements [off, off+count); rows of `width` elements are stored with row
+// pitch `pitch` on the device (pitch == width: dense)
+int upload_interleaved(float* dev, const float* host, size_t plane, size_t off, size_t count, size_t width = 0, size_t pitch = 0) {
   std::vector<float> tmp(count);
   for (int comp = 0; comp < 3; ++comp) {
     for (size_t i = 0; i < count; ++i) tmp[i] = host[3 * i + comp];
-    CK(cudaMemcpy(dev + (size_t)comp * plane + off, tmp.data(), count * sizeof(float), cudaMemcpyHostToDevice));
+    if (width && pitch != width) CK(cudaMemcpy2D(dev + (size_t)comp * plane, pitch * sizeof(float), tmp.data(), width * sizeof(float), width * sizeof(float), count / width, cudaMemcpyHostToDevice));
+    else CK(cudaMemcpy(dev + (size_t)comp * plane + off, tmp.data(), count * sizeof(float), cudaMemcpyHostToDevice));
   }
   return 0;
 }
-int download_interleaved(float* host, const float* dev, size_t plane, size_t off, size_t count) {
+int download_interleaved(float* host, const float* dev, size_t plane, size_t off, size_t count, size_t width = 0, size_t pitch = 0) {
   std::vector<float> tmp(count);
   for (int comp = 0; comp < 3; ++comp) {
-    CK(cudaMemcpy(tmp.data(), dev + (size_t)comp * plane + off, count * sizeof(float), cudaMemcpyDeviceToHost));
+    if (width && pitch != width) CK(cudaMemcpy2D(tmp.data(), width * sizeof(float), dev + (size_t)comp * plane, pitch * sizeof(float), width * sizeof(float), count / width, cudaMemcpyDeviceToHost));
+    else CK(cudaMemcpy(tmp.data(), dev + (size_t)comp * plane + off, count * sizeof(float), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < count; ++i) host[3 * i + comp] = tmp[i];
   }
   return 0;
@@ -125,7 +132,7 @@ int build_kern_f(cubep3m_b200_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->tile_rho, rho.data(), rho.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     if (int st = fftk::forward3d(ctx, fine_mesh(ctx), ctx->tile_rho)) return st;   // :89
     const long long ns = (long long)d.hc * n * n;
-    LAUNCH(ctx, KC_MISC, extract_imag_kernel, grid_for(ns, 256), 256, 0, reinterpret_cast<const float2*>(ctx->tile_rho), ns, ctx->kern_f, comp);   // :93-99
+    LAUNCH(ctx, KC_MISC, extract_imag_kernel, grid_for(ns, 256), 256, 0, reinterpret_cast<const float2*>(ctx->tile_rho), ns, d.hc, ctx->kf_pitch, ctx->kern_f + (size_t)comp * ctx->kf_stride);   // :93-99
     CK(cudaStreamSynchronize(ctx->stream));
   }
   return 0;
@@ -434,7 +441,7 @@ int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, bool material
   if (!ctx->cfg.ngp) {   // fine CIC: materialised gather deposit, then the generic solve
     LAUNCH(ctx, KC_DENSITY, fine::cic_density_kernel, NUM_SMS * 16, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, t_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
            &ctx->dcnt->sum_rho_f, scratch_count);
-    return fftk::fine_solve(ctx, fine_mesh(ctx), t_rho, t_g, ctx->kern_f, t_force, d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits);
+    return fftk::fine_solve(ctx, fine_mesh(ctx), t_rho, t_g, ctx->kern_f, ctx->kf_stride, ctx->kf_pitch, t_force, d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits);
   }
   if (materialise) {
     LAUNCH(ctx, KC_DENSITY, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
@@ -442,11 +449,11 @@ int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, bool material
     if (ctx->hcnt->n_cand > 0)
       LAUNCH(ctx, KC_DENSITY, fine::ngp_fixup_kernel, std::min(NUM_SMS, (std::min(ctx->hcnt->n_cand, ctx->cand_cap) + fine::TPB - 1) / fine::TPB), fine::TPB, 0,
              ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, ctx->tile_rho, n, d.b, d.m, tx, ty, tz, mass_p, &ctx->dcnt->sum_rho_f);
-    return fftk::fine_solve(ctx, fine_mesh(ctx), ctx->tile_rho, ctx->tile_g, ctx->kern_f, ctx->force_f[0], d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits);
+    return fftk::fine_solve(ctx, fine_mesh(ctx), ctx->tile_rho, ctx->tile_g, ctx->kern_f, ctx->kf_stride, ctx->kf_pitch, ctx->force_f[0], d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits);
   }
   fftk::NgpSource src{ctx->fstart, d.H, d.b, tx * d.m, ty * d.m, tz * d.m, mass_p, ctx->deltas + (size_t)tile * fine::DELTA_CAP, ctx->ndelta + tile,
                       fine::DELTA_CAP, &ctx->dcnt->sum_rho_f};
-  return fftk::fine_solve(ctx, fine_mesh(ctx), t_rho, t_g, ctx->kern_f, t_force, d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits, &src);
+  return fftk::fine_solve(ctx, fine_mesh(ctx), t_rho, t_g, ctx->kern_f, ctx->kf_stride, ctx->kf_pitch, t_force, d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits, &src);
 }
 
 int do_fine(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p, float* ms_dep_fft, float* ms_kick) {
@@ -701,10 +708,12 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   TRY(dmalloc(&ctx->force_f[0], (size_t)3 * d.fdim * d.fdim * d.fdim));
   ctx->force_f[1] = ctx->force_f[0] + (size_t)d.fdim * d.fdim * d.fdim; ctx->force_f[2] = ctx->force_f[1] + (size_t)d.fdim * d.fdim * d.fdim;
   {
-    const char* e = getenv("CUBEP3M_B200_TILE_STREAMS");      // tuning knob; default 2
-    ctx->tile_streams = e ? std::max(1, std::min(atoi(e), (int)cubep3m_b200_ctx::MAX_TILE_STREAMS)) : 2;
+    // tuning knob. The second-generation FFT kernels are persistent and fill all SMs, so one tile in flight is fastest (measured:
+    // 8.21 ms/step with 1, 8.84 with 2, 8.81 with 3 at 256^3 particles); the first generation gained ~25 % from 2.
+    const char* e = getenv("CUBEP3M_B200_TILE_STREAMS");
+    ctx->tile_streams_max = e ? std::max(1, std::min(atoi(e), (int)cubep3m_b200_ctx::MAX_TILE_STREAMS)) : 1;
+    ctx->tile_streams = ctx->tile_streams_max;
   }
-  ctx->tile_streams_max = ctx->tile_streams;
   ctx->stream_main = ctx->stream;
   if (cudaStreamCreateWithFlags(&ctx->stream_coarse, cudaStreamNonBlocking) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   if (ctx->tile_streams > 1) {
@@ -717,7 +726,10 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
       TRY(dmalloc(&ctx->force_f_s[q], (size_t)3 * d.fdim * d.fdim * d.fdim));
     }
   }
-  TRY(dmalloc(&ctx->kern_f, (size_t)3 * d.hc * d.n * d.n));
+  ctx->kf_pitch = (d.hc + 15) / 16 * 16;     // 16-column blocks of kern_f start on 64-byte boundaries (16-byte cp.async in fft_z_sandwich2)
+  ctx->kf_stride = (long long)ctx->kf_pitch * d.n * d.n;
+  TRY(dmalloc(&ctx->kern_f, (size_t)3 * ctx->kf_stride));
+  if (cudaMemset(ctx->kern_f, 0, (size_t)3 * ctx->kf_stride * sizeof(float)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   TRY(fftk::make_twiddles(d.n, &ctx->tw_f));
   const int Nx = d.Nc[0], Ny = d.Nc[1], Nz = d.Nc[2];
   const size_t ncs = (size_t)(Nx / 2 + 1) * Ny * Nz;
@@ -752,7 +764,7 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   if (cudaMemset(ctx->dcnt, 0, sizeof(DevCounters)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   if (cudaMallocHost((void**)&ctx->hcnt, sizeof(DevCounters)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   memset(ctx->hcnt, 0, sizeof(DevCounters));
-  if (kern_f) TRY(upload_interleaved(ctx->kern_f, kern_f, (size_t)d.hc * d.n * d.n, 0, (size_t)d.hc * d.n * d.n));
+  if (kern_f) TRY(upload_interleaved(ctx->kern_f, kern_f, (size_t)ctx->kf_stride, 0, (size_t)d.hc * d.n * d.n, (size_t)d.hc, (size_t)ctx->kf_pitch));
   else TRY(build_kern_f(ctx));
   // a host kern_c is this rank's slab kern_c(3,hc,nc_dim,nc_slab) (cubep3m.fh:56): it is the whole mesh only when there is one rank;
   // with more ranks the library rebuilds the global table itself (every rank needs all of it for the replicated solve)
@@ -975,7 +987,7 @@ int cubep3m_b200_debug_kern_f(cubep3m_b200_ctx* ctx, float* kern_f) {
   if (!ctx) return CUBEP3M_B200_EINVAL;
   CK(cudaSetDevice(ctx->device));
   const size_t plane = (size_t)ctx->d.hc * ctx->d.n * ctx->d.n;
-  return download_interleaved(kern_f, ctx->kern_f, plane, 0, plane);
+  return download_interleaved(kern_f, ctx->kern_f, (size_t)ctx->kf_stride, 0, plane, (size_t)ctx->d.hc, (size_t)ctx->kf_pitch);
 }
 int cubep3m_b200_debug_kern_c(cubep3m_b200_ctx* ctx, float* kern_c) {
   if (!ctx) return CUBEP3M_B200_EINVAL;

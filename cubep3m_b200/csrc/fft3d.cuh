@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(NT) fft_x_r2c(float* __restrict__ data, int nr
 // [4, n-5] and 0 elsewhere; `deltas` moves the mass of the few particles whose reference cell floor(fl(x+offset)) differs (fine.cuh).
 // One warp handles one row at a time (lanes along x): no per-element divisions, coalesced gathers within a coarse cell.
 template <int N>
-__global__ void __launch_bounds__(NT) fft_x_r2c_ngp(float* __restrict__ data, const int* __restrict__ fstart, int H, int b, int ox, int oy, int oz,
+__global__ void __launch_bounds__(NT) fft_x_r2c_ngp(float2* __restrict__ data, int cp, const int* __restrict__ fstart, int H, int b, int ox, int oy, int oz,
                                                     float mass_p, const int2* __restrict__ deltas, const int* __restrict__ ndelta_ptr, int delta_cap,
                                                     double* __restrict__ sum_phys, const float2* __restrict__ tw_g) {
   extern __shared__ __align__(16) unsigned char raw[];
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(NT) fft_x_r2c_ngp(float* __restrict__ data, co
   const float* zi = result_buffer<N>() ? s.im1 : s.im0;
   // untangle the two real rows of each column: A = (Z[k] + conj Z[N-k]) / 2, B = (Z[k] - conj Z[N-k]) / (2i); one warp per row
   for (int row = warp; row < 2 * LX; row += NT / 32) {
-    float2* orow = reinterpret_cast<float2*>(data + (long long)(r0 + row) * P);
+    float2* orow = data + (long long)(r0 + row) * cp;
     const int col = row >> 1;
     for (int k = lane; k < N / 2 + 1; k += 32) {
       const int km = (k == 0) ? 0 : N - k;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) f
 // column block feeds four transforms; the forward-z result never goes back to memory. Persistent CTAs with register prefetch of
 // the next block's spectrum and of the next component's Green's function values. AoS float2 shared-memory layout.
 template <int N>
-__global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) fft_z_sandwich(const float2* __restrict__ spec, float2* __restrict__ g, long long gstride, int hc, int ny,
+__global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) fft_z_sandwich(const float2* __restrict__ spec, float2* __restrict__ g, long long gstride, int hc, int cp, int ny,
                                                      const float* __restrict__ kern, long long kstride, int kp, int elo, int ehi,
                                                      const float2* __restrict__ tw_g) {
   extern __shared__ __align__(16) unsigned char raw[];
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) f
   constexpr int ES = NT / LX;
   const int nbx = (hc + LX - 1) / LX;
   const long long total = (long long)nbx * ny;
-  const long long estride = (long long)ny * hc;
+  const long long estride = (long long)ny * cp;
   const long long gstep = (long long)ES * estride;
   const int col = threadIdx.x % LX, e0 = threadIdx.x / LX;
   const int sidx = e0 * LX + col;
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) f
   float kf[PF ? EPT : 1];
   auto decode = [&](long long item, long long& base, bool& colok) {
     const int bx = (int)(item % nbx), y = (int)(item / nbx);
-    base = (long long)y * hc + bx * LX + (long long)e0 * estride + col;
+    base = (long long)y * cp + bx * LX + (long long)e0 * estride + col;
     colok = (bx * LX + col) < hc;
   };
   auto fetch = [&](long long base, bool colok, int it) -> float2 {
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(NT, StridedCfg<N>::PREFETCH ? FFTK_MINB : 1) f
   };
   const long long kestride = (long long)ny * kp, kgstep = (long long)ES * kestride;   // the Green's function table has row pitch kp
   auto fetchk = [&](long long base, bool colok, int comp, int it) -> float {
-    const long long y = (base % estride) / hc, kx = (base % estride) % hc;   // base = y*hc + kx + e0*estride
+    const long long y = (base % estride) / cp, kx = (base % estride) % cp;   // base = y*cp + kx + e0*estride
     return (colok && e0 + it * ES < N) ? kern[(long long)comp * kstride + y * kp + kx + (long long)e0 * kestride + it * kgstep] : 0.f;
   };
   long long item = blockIdx.x, base = 0; bool colok = false;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(NT) fft_x_c2r(const float2* __restrict__ in, f
 // (particle_mesh_threaded.f90:202-223). One CTA owns 32 cropped rows and loops over the components; the next component's rows
 // are prefetched into registers during the current FFT; |F|^2 is accumulated per output element in registers.
 template <int N>
-__global__ void __launch_bounds__(NT, 2) fft_x_c2r3(const float2* __restrict__ in, float* __restrict__ out, int lo, int cnt, long long in_bstride,
+__global__ void __launch_bounds__(NT, 2) fft_x_c2r3(const float2* __restrict__ in, int cp, float* __restrict__ out, int lo, int cnt, long long in_bstride,
                                                     long long out_bstride, float scale, unsigned int* __restrict__ fmax_bits,
                                                     const float2* __restrict__ tw_g) {
   extern __shared__ __align__(16) unsigned char raw[];
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(NT, 2) fft_x_c2r3(const float2* __restrict__ i
     long long so = -1, dof = -1;
     if (ridx < nrows) {
       const int zc = (int)(ridx / cnt), yc = (int)(ridx - (long long)zc * cnt);
-      so = ((long long)(zc + lo) * N + (yc + lo)) * HC;
+      so = ((long long)(zc + lo) * N + (yc + lo)) * cp;
       dof = ((long long)zc * cnt + yc) * cnt;
     }
     srow[threadIdx.x] = so; drow[threadIdx.x] = dof;
@@ -523,12 +523,16 @@ template <int N> int set_smem_attr() {
   CK(cudaFuncSetAttribute(fft_z_sandwich<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_sandwich(N)));
   if constexpr (Plan2<N>::ok) {
     const int b2 = (int)smem_bytes2(N, 2, LX);
-    CK(cudaFuncSetAttribute((fft_strided2<N, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, b2));
-    CK(cudaFuncSetAttribute((fft_strided2<N, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, b2));
-    CK(cudaFuncSetAttribute((fft_strided2<N, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b2));
-    CK(cudaFuncSetAttribute(fft_z_sandwich2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_sandwich2(N)));
+    CK(cudaFuncSetAttribute((fft_strided2<N, false, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, b2));
+    CK(cudaFuncSetAttribute((fft_strided2<N, true, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, b2));
+    CK(cudaFuncSetAttribute((fft_strided2<N, true, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, b2));
+    CK(cudaFuncSetAttribute((fft_strided2<N, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b2));
+    CK(cudaFuncSetAttribute((fft_strided2<N, true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b2));
+    CK(cudaFuncSetAttribute((fft_z_sandwich2<N, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_sandwich2(N)));
+    CK(cudaFuncSetAttribute((fft_z_sandwich2<N, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_sandwich2(N)));
     CK(cudaFuncSetAttribute(fft_x_r2c_ngp2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes2(N, 1, XP)));
     CK(cudaFuncSetAttribute(fft_x_c2r3_v2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_c2r3_v2(N)));
+    CK(cudaFuncSetAttribute(fft_x_c2r3_v3<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2R3<N>::smem));
   }
   done = true;
   return 0;
@@ -548,15 +552,15 @@ template <int N> int launch_x_r2c_t(cubep3m_b200_ctx* ctx, int kc, float* data, 
 struct NgpSource {            // what fft_x_r2c_ngp needs to produce the tile's density rows itself
   const int* fstart; int H, b, ox, oy, oz; float mass_p; const int2* deltas; const int* ndelta; int delta_cap; double* sum_phys;
 };
-template <int N> int launch_x_r2c_ngp_t(cubep3m_b200_ctx* ctx, int kc, float* data, const NgpSource& g, const float2* tw) {
+template <int N> int launch_x_r2c_ngp_t(cubep3m_b200_ctx* ctx, int kc, float2* data, int cp, const NgpSource& g, const float2* tw) {
   if (int st = set_smem_attr<N>()) return st;
   static_assert((N * N) % (2 * LX) == 0, "rows per tile must be a multiple of the rows per CTA");
   if constexpr (Plan2<N>::ok && N % 4 == 0) {
-    LAUNCH(ctx, kc, fft_x_r2c_ngp2<N>, dim3(N * N / (2 * LX)), dim3(Plan2<N>::NT), (int)smem_bytes2(N, 1, XP), data, g.fstart, g.H, g.b, g.ox, g.oy, g.oz, g.mass_p,
+    LAUNCH(ctx, kc, fft_x_r2c_ngp2<N>, dim3(N * N / (2 * LX)), dim3(Plan2<N>::NT), (int)smem_bytes2(N, 1, XP), data, cp, g.fstart, g.H, g.b, g.ox, g.oy, g.oz, g.mass_p,
            g.deltas, g.ndelta, g.delta_cap, g.sum_phys, tw);
     return 0;
   }
-  LAUNCH(ctx, kc, fft_x_r2c_ngp<N>, dim3(N * N / (2 * LX)), dim3(NT), (int)smem_bytes(N), data, g.fstart, g.H, g.b, g.ox, g.oy, g.oz, g.mass_p, g.deltas,
+  LAUNCH(ctx, kc, fft_x_r2c_ngp<N>, dim3(N * N / (2 * LX)), dim3(NT), (int)smem_bytes(N), data, cp, g.fstart, g.H, g.b, g.ox, g.oy, g.oz, g.mass_p, g.deltas,
          g.ndelta, g.delta_cap, g.sum_phys, tw);
   return 0;
 }
@@ -568,10 +572,13 @@ template <int N> int launch_strided_t(cubep3m_b200_ctx* ctx, int kc, bool inv, c
     const int sm2 = (int)smem_bytes2(N, 2, LX);
     static int occ2[3] = {0, 0, 0};
     if (!occ2[0]) {
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[0], (fft_strided2<N, false, false>), Plan2<N>::NT, sm2));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[1], (fft_strided2<N, true, true>), Plan2<N>::NT, sm2));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[2], (fft_strided2<N, true, false>), Plan2<N>::NT, sm2));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[0], (fft_strided2<N, false, false, false>), Plan2<N>::NT, sm2));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[1], (fft_strided2<N, true, true, false>), Plan2<N>::NT, sm2));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[2], (fft_strided2<N, true, false, false>), Plan2<N>::NT, sm2));
     }
+    // 16-byte staging needs 128-byte aligned column blocks: even strides (the padded spectra of the fused fine-tile path)
+    const bool a16 = !kern && estride % 2 == 0 && ostride % 2 == 0 && bstride % 2 == 0 && ((uintptr_t)in & 15) == 0 &&
+                     std::min(estride, ostride) >= (long long)((hc + LX - 1) / LX) * LX;   // the row pitch covers whole 16-column blocks
     const long long total2 = (long long)((hc + LX - 1) / LX) * nouter * nbatch;
     auto grid2 = [&](int o) { return dim3((unsigned)std::min<long long>(total2, (long long)NUM_SMS * std::max(o, 1))); };
     const dim3 blk(Plan2<N>::NT);
@@ -580,9 +587,11 @@ template <int N> int launch_strided_t(cubep3m_b200_ctx* ctx, int kc, bool inv, c
     const long long kspan = kern ? (long long)(outer0 + nouter) * kos + (long long)N * kes + hc : 0;
     if (span >= (1LL << 31) || kspan >= (1LL << 31) || total2 >= (1LL << 31)) return CUBEP3M_B200_EINVAL;
     const int es = (int)estride, os = (int)ostride, bs = (int)bstride, ke = (int)kes, ko = (int)kos;
-    if (!inv) LAUNCH(ctx, kc, (fft_strided2<N, false, false>), grid2(occ2[0]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, nullptr, 0, 0, elo, ehi, tw, bs);
-    else if (kern) LAUNCH(ctx, kc, (fft_strided2<N, true, true>), grid2(occ2[1]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, kern, ke, ko, elo, ehi, tw, bs);
-    else LAUNCH(ctx, kc, (fft_strided2<N, true, false>), grid2(occ2[2]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, nullptr, 0, 0, elo, ehi, tw, bs);
+    if (!inv && a16) LAUNCH(ctx, kc, (fft_strided2<N, false, false, true>), grid2(occ2[0]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, nullptr, 0, 0, elo, ehi, tw, bs);
+    else if (!inv) LAUNCH(ctx, kc, (fft_strided2<N, false, false, false>), grid2(occ2[0]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, nullptr, 0, 0, elo, ehi, tw, bs);
+    else if (kern) LAUNCH(ctx, kc, (fft_strided2<N, true, true, false>), grid2(occ2[1]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, kern, ke, ko, elo, ehi, tw, bs);
+    else if (a16) LAUNCH(ctx, kc, (fft_strided2<N, true, false, true>), grid2(occ2[2]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, nullptr, 0, 0, elo, ehi, tw, bs);
+    else LAUNCH(ctx, kc, (fft_strided2<N, true, false, false>), grid2(occ2[2]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, nullptr, 0, 0, elo, ehi, tw, bs);
     return 0;
   }
   const int sm = (int)smem_bytes_aos(N, 2);
@@ -599,24 +608,26 @@ template <int N> int launch_strided_t(cubep3m_b200_ctx* ctx, int kc, bool inv, c
   else LAUNCH(ctx, kc, (fft_strided<N, true, false>), grid(occ[2]), dim3(NT), sm, in, out, hc, estride, ostride, outer0, nouter, nbatch, nullptr, 0LL, 0LL, elo, ehi, tw, bstride);
   return 0;
 }
-template <int N> int launch_sandwich_t(cubep3m_b200_ctx* ctx, int kc, const float2* spec, float2* g, long long gstride, int hc, int ny, const float* kern,
+template <int N> int launch_sandwich_t(cubep3m_b200_ctx* ctx, int kc, const float2* spec, float2* g, long long gstride, int hc, int cp, int ny, const float* kern,
                                        long long kstride, int kp, int elo, int ehi, const float2* tw) {
   if (int st = set_smem_attr<N>()) return st;
   if constexpr (Plan2<N>::ok) {
     const int sm2 = (int)smem_bytes_sandwich2(N);
     static int occ2 = 0;
-    if (!occ2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fft_z_sandwich2<N>, Plan2<N>::NT, sm2));
+    if (!occ2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, (fft_z_sandwich2<N, false>), Plan2<N>::NT, sm2));
     const long long total2 = (long long)((hc + LX - 1) / LX) * ny;
     if (kp % 16 != 0 || 3 * gstride >= (1LL << 31)) return CUBEP3M_B200_EINVAL;
-    LAUNCH(ctx, kc, fft_z_sandwich2<N>, dim3((unsigned)std::min<long long>(total2, (long long)NUM_SMS * std::max(occ2, 1))), dim3(Plan2<N>::NT), sm2, spec, g, (int)gstride,
-           hc, ny, kern, kstride, kp, elo, ehi, tw);
+    const dim3 grd((unsigned)std::min<long long>(total2, (long long)NUM_SMS * std::max(occ2, 1)));
+    const bool a16 = cp % 2 == 0 && cp >= (hc + LX - 1) / LX * LX && ((uintptr_t)spec & 15) == 0;
+    if (a16) LAUNCH(ctx, kc, (fft_z_sandwich2<N, true>), grd, dim3(Plan2<N>::NT), sm2, spec, g, (int)gstride, hc, cp, ny, kern, kstride, kp, elo, ehi, tw);
+    else LAUNCH(ctx, kc, (fft_z_sandwich2<N, false>), grd, dim3(Plan2<N>::NT), sm2, spec, g, (int)gstride, hc, cp, ny, kern, kstride, kp, elo, ehi, tw);
     return 0;
   }
   static int occ = 0;
   if (!occ) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_z_sandwich<N>, NT, (int)smem_bytes_sandwich(N)));
   const long long total = (long long)((hc + LX - 1) / LX) * ny;
   LAUNCH(ctx, kc, fft_z_sandwich<N>, dim3((unsigned)std::min<long long>(total, (long long)NUM_SMS * std::max(occ, 1))), dim3(NT), (int)smem_bytes_sandwich(N), spec,
-         g, gstride, hc, ny, kern, kstride, kp, elo, ehi, tw);
+         g, gstride, hc, cp, ny, kern, kstride, kp, elo, ehi, tw);
   return 0;
 }
 template <int N> int launch_x_c2r_t(cubep3m_b200_ctx* ctx, int kc, const float2* in, float* out, int lo_x, int cnt_x, int lo_y, int cnt_y, int lo_z,
@@ -628,20 +639,34 @@ template <int N> int launch_x_c2r_t(cubep3m_b200_ctx* ctx, int kc, const float2*
          lo_z, cnt_z, ny_src, opx, opy, scale, tw, ibs, obs);
   return 0;
 }
+#ifndef FFTK_C2R3_V3
+#define FFTK_C2R3_V3 1
+#endif
 #ifndef FFTK_C2R3_V2
 #define FFTK_C2R3_V2 0   // measured on B200 (n = 304): first-generation fft_x_c2r3 175 us, fft_x_c2r3_v2 222 us per tile
 #endif
-template <int N> int launch_x_c2r3_t(cubep3m_b200_ctx* ctx, int kc, const float2* in, float* out, int lo, int cnt, long long ibs, long long obs, float scale,
+template <int N> int launch_x_c2r3_t(cubep3m_b200_ctx* ctx, int kc, const float2* in, int cp, float* out, int lo, int cnt, long long ibs, long long obs, float scale,
                                      unsigned int* fmax_bits, const float2* tw) {
   if (int st = set_smem_attr<N>()) return st;
   const long long nrows = (long long)cnt * cnt;
+  if constexpr (Plan2<N>::ok) {
+    // bulk-copy (TMA engine) staging needs 16-byte aligned rows of at least RP elements
+    if (FFTK_C2R3_V3 && cp % 2 == 0 && cp >= C2R3<N>::RP && ((uintptr_t)in & 15) == 0 && ibs % 2 == 0 && 3 * ibs < (1LL << 31) && 3 * obs < (1LL << 31)) {
+      static int occ3 = 0;
+      if (!occ3) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, fft_x_c2r3_v3<N>, Plan2<N>::NT, (int)C2R3<N>::smem));
+      const long long nblk = (nrows + 2 * LX - 1) / (2 * LX);
+      LAUNCH(ctx, kc, fft_x_c2r3_v3<N>, dim3((unsigned)std::min<long long>(nblk, (long long)NUM_SMS * std::max(occ3, 1))), dim3(Plan2<N>::NT), (int)C2R3<N>::smem, in, cp, out,
+             lo, cnt, (int)ibs, (int)obs, scale, fmax_bits, tw);
+      return 0;
+    }
+  }
   if constexpr (Plan2<N>::ok && FFTK_C2R3_V2) {
     if (3 * ibs >= (1LL << 31) || 3 * obs >= (1LL << 31)) return CUBEP3M_B200_EINVAL;
-    LAUNCH(ctx, kc, fft_x_c2r3_v2<N>, dim3((unsigned)((nrows + 2 * LX - 1) / (2 * LX))), dim3(Plan2<N>::NT), (int)smem_bytes_c2r3_v2(N), in, out, lo, cnt, (int)ibs, (int)obs,
+    LAUNCH(ctx, kc, fft_x_c2r3_v2<N>, dim3((unsigned)((nrows + 2 * LX - 1) / (2 * LX))), dim3(Plan2<N>::NT), (int)smem_bytes_c2r3_v2(N), in, cp, out, lo, cnt, (int)ibs, (int)obs,
            scale, fmax_bits, tw);
     return 0;
   }
-  LAUNCH(ctx, kc, fft_x_c2r3<N>, dim3((unsigned)((nrows + 2 * LX - 1) / (2 * LX))), dim3(NT), (int)smem_bytes(N), in, out, lo, cnt, ibs, obs, scale, fmax_bits, tw);
+  LAUNCH(ctx, kc, fft_x_c2r3<N>, dim3((unsigned)((nrows + 2 * LX - 1) / (2 * LX))), dim3(NT), (int)smem_bytes(N), in, cp, out, lo, cnt, ibs, obs, scale, fmax_bits, tw);
   return 0;
 }
 #define FFTK_SWITCH(N_, CALL)                                 \
@@ -655,8 +680,8 @@ inline int launch_x_r2c(cubep3m_b200_ctx* ctx, int kc, int n, float* data, int n
   FFTK_SWITCH(n, X)
 #undef X
 }
-inline int launch_x_r2c_ngp(cubep3m_b200_ctx* ctx, int kc, int n, float* data, const NgpSource& g, const float2* tw) {
-#define X(N) case N: return launch_x_r2c_ngp_t<N>(ctx, kc, data, g, tw);
+inline int launch_x_r2c_ngp(cubep3m_b200_ctx* ctx, int kc, int n, float2* data, int cp, const NgpSource& g, const float2* tw) {
+#define X(N) case N: return launch_x_r2c_ngp_t<N>(ctx, kc, data, cp, g, tw);
   FFTK_SWITCH(n, X)
 #undef X
 }
@@ -667,9 +692,9 @@ inline int launch_strided(cubep3m_b200_ctx* ctx, int kc, int n, bool inv, const 
   FFTK_SWITCH(n, X)
 #undef X
 }
-inline int launch_sandwich(cubep3m_b200_ctx* ctx, int kc, int n, const float2* spec, float2* g, long long gstride, int hc, int ny, const float* kern,
+inline int launch_sandwich(cubep3m_b200_ctx* ctx, int kc, int n, const float2* spec, float2* g, long long gstride, int hc, int cp, int ny, const float* kern,
                            long long kstride, int kp, int elo, int ehi, const float2* tw) {
-#define X(N) case N: return launch_sandwich_t<N>(ctx, kc, spec, g, gstride, hc, ny, kern, kstride, kp, elo, ehi, tw);
+#define X(N) case N: return launch_sandwich_t<N>(ctx, kc, spec, g, gstride, hc, cp, ny, kern, kstride, kp, elo, ehi, tw);
   FFTK_SWITCH(n, X)
 #undef X
 }
@@ -681,29 +706,32 @@ inline int launch_x_c2r(cubep3m_b200_ctx* ctx, int kc, int n, const float2* in, 
 #undef X
 }
 
-inline int launch_x_c2r3(cubep3m_b200_ctx* ctx, int kc, int n, const float2* in, float* out, int lo, int cnt, long long ibs, long long obs, float scale,
+inline int launch_x_c2r3(cubep3m_b200_ctx* ctx, int kc, int n, const float2* in, int cp, float* out, int lo, int cnt, long long ibs, long long obs, float scale,
                          unsigned int* fmax_bits, const float2* tw) {
-#define X(N) case N: return launch_x_c2r3_t<N>(ctx, kc, in, out, lo, cnt, ibs, obs, scale, fmax_bits, tw);
+#define X(N) case N: return launch_x_c2r3_t<N>(ctx, kc, in, cp, out, lo, cnt, ibs, obs, scale, fmax_bits, tw);
   FFTK_SWITCH(n, X)
 #undef X
 }
 
-// Fine-tile solve after the density is in `data` (n+2,n,n): forward x, y; fused z (forward, 3 x kernel multiply + inverse);
-// then inverse y and inverse x (crop + scale) for the three components in one launch each.
-// g3: scratch of 3 complex tiles; force3: 3 x cnt^3 outputs (component-major).
-// If ngp != nullptr the density is generated inside the first pass (data is then only written).
-inline int fine_solve(cubep3m_b200_ctx* ctx, const Mesh3& m, float* data, float* g3, const float* kern3, long long kstride, int kp, float* force3, int lo, int cnt,
+// Fine-tile solve: forward x, y; fused z (forward, 3 x kernel multiply + inverse); then inverse y and inverse x (crop + scale) for the
+// three components in one launch each.
+// data: the tile's density (n+2,n,n) reals transformed in place (complex pitch cp = hc), or, when ngp != nullptr, only the destination of
+// the spectrum, which the first pass generates from the fine-cell table; then cp may be any pitch >= hc (the library pads it to a multiple
+// of 16 so that every 16-column block starts on a 128-byte boundary). g3: scratch of 3 complex tiles of the same pitch;
+// force3: 3 x cnt^3 outputs (component-major).
+inline int fine_solve(cubep3m_b200_ctx* ctx, const Mesh3& m, float* data, float* g3, int cp, const float* kern3, long long kstride, int kp, float* force3, int lo, int cnt,
                       float scale, unsigned int* fmax_bits, const NgpSource* ngp = nullptr) {
   const int n = m.nx, hc = m.hc();
-  const long long cplx = (long long)hc * n * n;     // complex elements per tile
+  if (!ngp && cp != hc) return CUBEP3M_B200_EINVAL;
+  const long long cplx = (long long)cp * n * n;     // complex elements per tile
   float2* c = reinterpret_cast<float2*>(data);
   float2* g = reinterpret_cast<float2*>(g3);
-  if (ngp) { if (int st = launch_x_r2c_ngp(ctx, KC_FFT_X_R2C, n, data, *ngp, m.twx)) return st; }
+  if (ngp) { if (int st = launch_x_r2c_ngp(ctx, KC_FFT_X_R2C, n, c, cp, *ngp, m.twx)) return st; }
   else if (int st = launch_x_r2c(ctx, KC_FFT_X_R2C, n, data, n * n, m.twx)) return st;
-  if (int st = launch_strided(ctx, KC_FFT_FWD_STRIDED, n, false, c, c, hc, (long long)hc, (long long)n * hc, 0, n, nullptr, 0, 0, 0, n - 1, m.twy)) return st;
-  if (int st = launch_sandwich(ctx, KC_FFT_INV_Z_MUL, n, c, g, cplx, hc, n, kern3, kstride, kp, lo, lo + cnt - 1, m.twz)) return st;
-  if (int st = launch_strided(ctx, KC_FFT_INV_Y, n, true, g, g, hc, (long long)hc, (long long)n * hc, lo, cnt, nullptr, 0, 0, lo, lo + cnt - 1, m.twy, 3, cplx)) return st;
-  if (int st = launch_x_c2r3(ctx, KC_FFT_X_C2R, n, g, force3, lo, cnt, cplx, (long long)cnt * cnt * cnt, scale, fmax_bits, m.twx)) return st;
+  if (int st = launch_strided(ctx, KC_FFT_FWD_STRIDED, n, false, c, c, hc, (long long)cp, (long long)n * cp, 0, n, nullptr, 0, 0, 0, n - 1, m.twy)) return st;
+  if (int st = launch_sandwich(ctx, KC_FFT_INV_Z_MUL, n, c, g, cplx, hc, cp, n, kern3, kstride, kp, lo, lo + cnt - 1, m.twz)) return st;
+  if (int st = launch_strided(ctx, KC_FFT_INV_Y, n, true, g, g, hc, (long long)cp, (long long)n * cp, lo, cnt, nullptr, 0, 0, lo, lo + cnt - 1, m.twy, 3, cplx)) return st;
+  if (int st = launch_x_c2r3(ctx, KC_FFT_X_C2R, n, g, cp, force3, lo, cnt, cplx, (long long)cnt * cnt * cnt, scale, fmax_bits, m.twx)) return st;
   CK(cudaGetLastError());
   return 0;
 }

@@ -39,26 +39,47 @@ template <int N> __device__ __forceinline__ unsigned crop_mask(int j, int elo, i
   return m;
 }
 
-// stage one column block (N rows of 16 float2, row stride `estride` elements) into dst[N][16]; thread (j, col) copies rows j, j+ES, ...
-template <int N, int ES> __device__ __forceinline__ void stage_block(const float2* __restrict__ src, int estride, bool ok, unsigned sdst, float2* __restrict__ dgen, int j) {
+// stage one column block (N rows of 16 float2, row stride `estride` elements) into dst[N][16].
+// A16 = false: thread (j, col) copies element col of rows j, j+ES, ... with 8-byte cp.async (any pitch); columns beyond hc are zero-filled.
+// A16 = true : the block starts on a 128-byte boundary and the pitch is even (padded spectra): 8 threads copy one row with 16-byte cp.async,
+//              half as many copies; columns beyond hc are read from the (zero) padding.
+template <int N, int NTH, bool A16> __device__ __forceinline__ void stage_block(const float2* __restrict__ blk, int estride, bool ok, unsigned sbuf,
+                                                                                float2* __restrict__ gbuf) {
+  if constexpr (A16) {
+    constexpr int RPP = NTH / 8;                   // rows per pass
+    const int row = threadIdx.x >> 3, q = threadIdx.x & 7;
+    const float2* src = blk + (long long)row * estride + q * 2;
+    const unsigned sd = sbuf + (row * LX + q * 2) * 8;
 #pragma unroll
-  for (int it = 0; it < (N + ES - 1) / ES; ++it) {
-    if (j + it * ES < N) {
-      if (ok) cp_async8(sdst + it * ES * LX * 8, src);
-      else dgen[it * ES * LX] = make_float2(0.f, 0.f);
-      src += (long long)ES * estride;
+    for (int it = 0; it < (N + RPP - 1) / RPP; ++it) {
+      if (row + it * RPP < N) cp_async16(sd + it * RPP * LX * 8, src);
+      src += (long long)RPP * estride;
+    }
+  } else {
+    constexpr int ES = NTH / LX;
+    const int col = threadIdx.x % LX, j = threadIdx.x / LX;
+    const float2* src = blk + (long long)j * estride + col;
+    const unsigned sd = sbuf + (j * LX + col) * 8;
+    float2* dgen = gbuf + j * LX + col;
+#pragma unroll
+    for (int it = 0; it < (N + ES - 1) / ES; ++it) {
+      if (j + it * ES < N) {
+        if (ok) cp_async8(sd + it * ES * LX * 8, src);
+        else dgen[it * ES * LX] = make_float2(0.f, 0.f);
+        src += (long long)ES * estride;
+      }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------- strided pass
 // element e of column c of item (bx, outer, bz): in[bz*bstride + (outer + outer0)*ostride + bx*16 + e*estride + c]   (all offsets < 2^31)
-template <int N, bool INV, bool MUL>
+template <int N, bool INV, bool MUL, bool A16>
 __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_strided2(const float2* __restrict__ in, float2* __restrict__ out, int hc, int estride, int ostride,
                                                                 int outer0, int nouter, int nbatch, const float* __restrict__ kern, int kes, int kos,
                                                                 int elo, int ehi, const float2* __restrict__ tw_g, int bstride) {
   using P = Plan2<N>;
-  constexpr int NT2 = P::NT, R0 = P::R0, R1 = P::R1, ES = NT2 / LX;
+  constexpr int NT2 = P::NT, R0 = P::R0, R1 = P::R1;
   extern __shared__ __align__(16) unsigned char raw[];
   float2* buf0 = reinterpret_cast<float2*>(raw);
   float2* buf1 = buf0 + N * LX;
@@ -68,23 +89,22 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_strided2(const float2* __
   const unsigned nbx = (hc + LX - 1) / LX;
   const int total = (int)nbx * nouter * nbatch;
   const unsigned mask = crop_mask<N>(j, elo, ehi);
-  const int slot = j * LX + col;
-  const unsigned s0 = smem_u32(buf0 + slot), s1 = smem_u32(buf1 + slot);
-  const int joff = j * estride;
-  auto decode = [&](int item, int& off, int& koff, bool& ok) {
+  const unsigned s0 = smem_u32(buf0), s1 = smem_u32(buf1);
+  const int joff = j * estride + col;
+  auto decode = [&](int item, int& off, int& koff, bool& ok) {      // off: offset of the block's first element (column 0, element 0)
     const unsigned bx = (unsigned)item % nbx, t = (unsigned)item / nbx;
     const unsigned o = t % (unsigned)nouter, bz = t / (unsigned)nouter;
-    const int kx = (int)bx * LX + col;
+    const int kx = (int)bx * LX;
     off = (int)bz * bstride + ((int)o + outer0) * ostride + kx;
-    koff = ((int)o + outer0) * kos + kx;
-    ok = kx < hc;
+    koff = ((int)o + outer0) * kos + kx + col;
+    ok = kx + col < hc;
   };
   int item = blockIdx.x, off = 0, koff = 0;
   bool ok = false;
   int p = 0;
   if (item < total) {
     decode(item, off, koff, ok);
-    stage_block<N, ES>(in + off + joff, estride, ok, s0, buf0 + slot, j);
+    stage_block<N, NT2, A16>(in + off, estride, ok, s0, buf0);
     cp_async_commit();
   }
   while (item < total) {
@@ -96,7 +116,7 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_strided2(const float2* __
     __syncthreads();                               // item landed; every thread is done with the other buffer
     if (next < total) {
       decode(next, noff, nkoff, nok);
-      stage_block<N, ES>(in + noff + joff, estride, nok, p ? s0 : s1, (p ? buf0 : buf1) + slot, j);
+      stage_block<N, NT2, A16>(in + noff, estride, nok, p ? s0 : s1, p ? buf0 : buf1);
       cp_async_commit();
     }
     float2 v[R0];
@@ -130,12 +150,13 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_strided2(const float2* __
 
 // ---------------------------------------------------------------------------------------------- fused z pass
 // kern: [comp][z][y][kp] floats, kp a multiple of 16 (64-byte aligned 16-column blocks), comp stride kstride.
-template <int N>
-__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_z_sandwich2(const float2* __restrict__ spec, float2* __restrict__ g, int gstride, int hc, int ny,
+// spec / g: complex rows of pitch cp (>= hc) float2.
+template <int N, bool A16>
+__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_z_sandwich2(const float2* __restrict__ spec, float2* __restrict__ g, int gstride, int hc, int cp, int ny,
                                                                    const float* __restrict__ kern, long long kstride, int kp, int elo, int ehi,
                                                                    const float2* __restrict__ tw_g) {
   using P = Plan2<N>;
-  constexpr int NT2 = P::NT, R0 = P::R0, R1 = P::R1, ES = NT2 / LX;
+  constexpr int NT2 = P::NT, R0 = P::R0, R1 = P::R1;
   extern __shared__ __align__(16) unsigned char raw[];
   float2* L = reinterpret_cast<float2*>(raw);
   float2* W = L + N * LX;
@@ -145,16 +166,16 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_z_sandwich2(const float2*
   const int col = threadIdx.x % LX, j = threadIdx.x / LX;
   const unsigned nbx = (hc + LX - 1) / LX;
   const int total = (int)nbx * ny;
-  const int estride = ny * hc;
+  const int estride = ny * cp;
   const long long kes = (long long)ny * kp;         // z stride of the Green's function table
   const unsigned mask = crop_mask<N>(j, elo, ehi);
-  const int slot = j * LX + col, joff = j * estride;
-  unsigned sL = smem_u32(L + slot), sW = smem_u32(W + slot);
+  const int slot = j * LX + col, joff = j * estride + col;
+  unsigned sL = smem_u32(L), sW = smem_u32(W);
   const unsigned sK = smem_u32(K);
   const bool actA = threadIdx.x < P::NA, actB = threadIdx.x < P::NB;
   auto decode = [&](int item, int& off, int& kb, bool& ok) {
     const unsigned bx = (unsigned)item % nbx, y = (unsigned)item / nbx;
-    off = (int)y * hc + (int)bx * LX + col;
+    off = (int)y * cp + (int)bx * LX;
     kb = (int)y * kp + (int)bx * LX;
     ok = (int)bx * LX + col < hc;
   };
@@ -178,7 +199,7 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_z_sandwich2(const float2*
   bool ok = false;
   if (item < total) {
     decode(item, off, kb, ok);
-    stage_block<N, ES>(spec + off + joff, estride, ok, sL, L + slot, j);
+    stage_block<N, NT2, A16>(spec + off, estride, ok, sL, L);
     issueK(0, kb);
   }
   const int step = R0 * estride;
@@ -214,7 +235,7 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_z_sandwich2(const float2*
       cp_async_wait_all();
       __syncthreads();                              // next kern_f block landed; W free
     }
-    if (next < total) { stage_block<N, ES>(spec + noff + joff, estride, nok, sW, W + slot, j); cp_async_commit(); }
+    if (next < total) { stage_block<N, NT2, A16>(spec + noff, estride, nok, sW, W); cp_async_commit(); }
     // ---- component 2 in place on L
     if (actA) stageA_inv(v);
     __syncthreads();                                // all gathers from L and K precede the scatter / the next kern_f block
@@ -235,11 +256,11 @@ constexpr size_t smem_bytes_sandwich2(int n) { return (size_t)2 * n * LX * sizeo
 constexpr int XP = LX + 1;   // pitch (float2) of the contiguous-axis passes
 
 template <int N>
-__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_r2c_ngp2(float* __restrict__ data, const int* __restrict__ fstart, int H, int b, int ox, int oy, int oz,
+__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_r2c_ngp2(float2* __restrict__ data, int cp, const int* __restrict__ fstart, int H, int b, int ox, int oy, int oz,
                                                                   float mass_p, const int2* __restrict__ deltas, const int* __restrict__ ndelta_ptr,
                                                                   int delta_cap, double* __restrict__ sum_phys, const float2* __restrict__ tw_g) {
   using P = Plan2<N>;
-  constexpr int NT2 = P::NT, NW = NT2 / 32, R0 = P::R0, PW = N + 2, NCX = N / 4, UNITS = 8 * NCX, UPT = (UNITS + NT2 - 1) / NT2;
+  constexpr int NT2 = P::NT, NW = NT2 / 32, R0 = P::R0, NCX = N / 4, UNITS = 8 * NCX, UPT = (UNITS + NT2 - 1) / NT2;
   constexpr int HC = N / 2 + 1, KCH = (HC + 31) / 32;
   extern __shared__ __align__(16) unsigned char raw[];
   float2* Z = reinterpret_cast<float2*>(raw);
@@ -337,9 +358,9 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_r2c_ngp2(float* __restr
         const int km = (k == 0) ? 0 : N - k;
         const float2 zk = Z[k * XP + c], zm = Z[km * XP + c];
         const float2 sm = padd(zk, zm), df = psub(zk, zm);
-        float2* rowA = reinterpret_cast<float2*>(data + (long long)(r0 + 2 * c) * PW);
+        float2* rowA = data + (long long)(r0 + 2 * c) * cp;     // complex rows of pitch cp
         rowA[k] = make_float2(0.5f * sm.x, 0.5f * df.y);
-        reinterpret_cast<float2*>(reinterpret_cast<float*>(rowA) + PW)[k] = make_float2(0.5f * sm.y, -0.5f * df.x);
+        rowA[cp + k] = make_float2(0.5f * sm.y, -0.5f * df.x);
       }
     }
   }
@@ -348,7 +369,7 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_r2c_ngp2(float* __restr
 // ---------------------------------------------------------------------------------------------- x pass backward, 3 components
 // Row staging buffer: Rw[32][HC] float2, filled with cp.async from the cropped rows of component `comp`.
 template <int N>
-__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v2(const float2* __restrict__ in, float* __restrict__ out, int lo, int cnt, int in_bstride,
+__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v2(const float2* __restrict__ in, int cp, float* __restrict__ out, int lo, int cnt, int in_bstride,
                                                                  int out_bstride, float scale, unsigned int* __restrict__ fmax_bits,
                                                                  const float2* __restrict__ tw_g) {
   using P = Plan2<N>;
@@ -366,7 +387,7 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v2(const float2* _
     int so = -1, dof = -1;
     if (ridx < nrows) {
       const int zc = ridx / cnt, yc = ridx - zc * cnt;
-      so = ((zc + lo) * N + (yc + lo)) * HC;
+      so = ((zc + lo) * N + (yc + lo)) * cp;
       dof = (zc * cnt + yc) * cnt;
     }
     srow[threadIdx.x] = so; drow[threadIdx.x] = dof;
@@ -455,5 +476,139 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v2(const float2* _
   if (lane == 0 && mx > 0.f) atomic_max_float_nonneg(fmax_bits, mx);
 }
 constexpr size_t smem_bytes_c2r3_v2(int n) { return (size_t)n * XP * sizeof(float2) + (size_t)2 * LX * (n / 2 + 1) * sizeof(float2) + (size_t)n * sizeof(float2); }
+
+// ---------------------------------------------------------------------------------------------- x pass backward, 3 components, v3
+// Persistent CTAs; the 32 half-spectrum rows of the next (row block, component) are fetched by the TMA engine as 32 bulk copies
+// (cp.async.bulk, one per lane of warp 0, completion on an mbarrier) while the current one is transformed: no per-element staging
+// instructions at all. Needs rows that start on 16-byte boundaries and a pitch >= RP (the padded spectra of the fused path).
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+template <int N> struct C2R3 {
+  static constexpr int HC = N / 2 + 1;
+  static constexpr int RP = (HC + 1) / 2 * 2;      // staged row length (float2): even, so that a row is a multiple of 16 bytes
+  static constexpr size_t smem = (size_t)N * XP * sizeof(float2) + (size_t)2 * LX * RP * sizeof(float2) + (size_t)N * sizeof(float2) + 2 * 2 * LX * sizeof(int) + 16;
+};
+
+template <int N>
+__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v3(const float2* __restrict__ in, int cp, float* __restrict__ out, int lo, int cnt, int in_bstride,
+                                                                 int out_bstride, float scale, unsigned int* __restrict__ fmax_bits,
+                                                                 const float2* __restrict__ tw_g) {
+  using P = Plan2<N>;
+  constexpr int NT2 = P::NT, NW = NT2 / 32, R0 = P::R0, HC = C2R3<N>::HC, RP = C2R3<N>::RP, KCH = (HC + 31) / 32;
+  constexpr int XCH = (N + 31) / 32, SU = (LX * XCH + NW - 1) / NW;
+  extern __shared__ __align__(16) unsigned char raw[];
+  float2* Z = reinterpret_cast<float2*>(raw);
+  float2* Rw = Z + N * XP;
+  float2* tw = Rw + 2 * LX * RP;
+  int* drow = reinterpret_cast<int*>(tw + N);        // [2][32]
+  const unsigned bar = smem_u32(drow + 2 * 2 * LX);  // 8-byte aligned: every array before it is a multiple of 8 bytes
+  for (int t = threadIdx.x; t < N; t += NT2) tw[t] = tw_g[t];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = threadIdx.x % LX, j = threadIdx.x / LX;
+  const int nrows = cnt * cnt, nblk = (nrows + 2 * LX - 1) / (2 * LX);
+  const unsigned sR = smem_u32(Rw);
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  // warp 0: fetch the rows of (blk, comp); for comp 0 also publish the block's output offsets in drow[slot]
+  auto issue = [&](int blk, int comp, int slot) {
+    const int ridx = blk * (2 * LX) + lane;
+    const bool valid = ridx < nrows;
+    const int rr = valid ? ridx : nrows - 1;         // rows beyond the crop re-read the last row; their results are never stored
+    const int zc = rr / cnt, yc = rr - zc * cnt;
+    if (comp == 0) drow[slot * 2 * LX + lane] = valid ? (zc * cnt + yc) * cnt : -1;
+    const float2* src = in + (long long)comp * in_bstride + ((zc + lo) * N + (yc + lo)) * cp;
+    if (lane == 0) mbar_expect_tx(bar, 2 * LX * RP * 8);
+    __syncwarp();
+    bulk_g2s(sR + lane * RP * 8, src, RP * 8, bar);
+  };
+  int blk = blockIdx.x, slot = 0;
+  unsigned parity = 0;
+  if (warp == 0 && blk < nblk) issue(blk, 0, 0);
+  for (; blk < nblk; blk += gridDim.x, slot ^= 1) {
+    float2 fsq[SU];
+#pragma unroll
+    for (int s = 0; s < SU; ++s) fsq[s] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int comp = 0; comp < 3; ++comp) {
+      mbar_wait(bar, parity);
+      parity ^= 1;
+      // Z[k] = A[k] + i B[k];  Z[N-k] = conj(A[k]) + i conj(B[k]);  imaginary parts of the k=0 and k=N/2 bins are dropped (c2r)
+#pragma unroll
+      for (int s = 0; s < (LX * KCH + NW - 1) / NW; ++s) {
+        const int unit = warp + s * NW;
+        if (unit < LX * KCH) {
+          const int c = unit / KCH, k = (unit - c * KCH) * 32 + lane;
+          if (k < HC) {
+            float2 a = Rw[(2 * c) * RP + k], bq = Rw[(2 * c + 1) * RP + k];
+            const bool edge = (k == 0 || 2 * k == N);
+            if (edge) { a.y = 0.f; bq.y = 0.f; }
+            Z[k * XP + c] = add_irot(a, bq);                               // (ar - bi, ai + br)
+            if (!edge) Z[(N - k) * XP + c] = make_float2(a.x + bq.y, bq.x - a.y);
+          }
+        }
+      }
+      fence_proxy_async();                           // generic reads of Rw are ordered before the async-proxy writes of the next fetch
+      __syncthreads();                               // Rw consumed, Z complete
+      if (warp == 0) {
+        if (comp < 2) issue(blk, comp + 1, slot);
+        else if (blk + (int)gridDim.x < nblk) issue(blk + gridDim.x, 0, slot ^ 1);
+      }
+      {
+        float2 v[R0];
+        if (threadIdx.x < P::NA) { stageA_load<N, true, XP>(Z, j, col, v); PRadix<R0, true>::run(v); }
+        __syncthreads();
+        if (threadIdx.x < P::NA) stageA_store<N, XP>(Z, j, col, v);
+        __syncthreads();
+        if (threadIdx.x < P::NB) {
+          float2* sp = Z + j * XP + col;
+          stageB<N, true, XP>(Z, tw, j, col, [&](int r, float2 val) { sp[r * R0 * XP] = val; });
+        }
+        __syncthreads();
+      }
+      // unit = (column, chunk of 32 x): a column holds two output rows (real part -> even row, imaginary part -> odd row)
+      float* o = out + (long long)comp * out_bstride;
+      const int* dr = drow + slot * 2 * LX;
+#pragma unroll
+      for (int s = 0; s < SU; ++s) {
+        const int unit = warp + s * NW;
+        if (unit < LX * XCH) {
+          const int c = unit / XCH, xc = (unit - c * XCH) * 32 + lane;
+          const int dofA = dr[2 * c], dofB = dr[2 * c + 1];
+          if (dofA >= 0 && xc < cnt) {
+            float2 zz = pmul_s(scale, Z[(xc + lo) * XP + c]);
+            o[dofA + xc] = zz.x;
+            if (dofB >= 0) o[dofB + xc] = zz.y; else zz.y = 0.f;
+            fsq[s] = pfma_v(zz, zz, fsq[s]);
+          }
+        }
+      }
+      __syncthreads();                               // Z is free for the next item
+    }
+    float mx = 0.f;
+#pragma unroll
+    for (int s = 0; s < SU; ++s) mx = fmaxf(mx, fmaxf(fsq[s].x, fsq[s].y));   // max |F|^2 (:208-223)
+    mx = warp_max(mx);
+    if (lane == 0 && mx > 0.f) atomic_max_float_nonneg(fmax_bits, mx);
+  }
+}
 
 }  // namespace fftk

@@ -441,7 +441,7 @@ int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, bool material
   if (!ctx->cfg.ngp) {   // fine CIC: materialised gather deposit, then the generic solve
     LAUNCH(ctx, KC_DENSITY, fine::cic_density_kernel, NUM_SMS * 16, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, t_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
            &ctx->dcnt->sum_rho_f, scratch_count);
-    return fftk::fine_solve(ctx, fine_mesh(ctx), t_rho, t_g, ctx->kern_f, ctx->kf_stride, ctx->kf_pitch, t_force, d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits);
+    return fftk::fine_solve(ctx, fine_mesh(ctx), t_rho, t_g, d.hc, ctx->kern_f, ctx->kf_stride, ctx->kf_pitch, t_force, d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits);
   }
   if (materialise) {
     LAUNCH(ctx, KC_DENSITY, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
@@ -449,11 +449,11 @@ int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, bool material
     if (ctx->hcnt->n_cand > 0)
       LAUNCH(ctx, KC_DENSITY, fine::ngp_fixup_kernel, std::min(NUM_SMS, (std::min(ctx->hcnt->n_cand, ctx->cand_cap) + fine::TPB - 1) / fine::TPB), fine::TPB, 0,
              ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, ctx->tile_rho, n, d.b, d.m, tx, ty, tz, mass_p, &ctx->dcnt->sum_rho_f);
-    return fftk::fine_solve(ctx, fine_mesh(ctx), ctx->tile_rho, ctx->tile_g, ctx->kern_f, ctx->kf_stride, ctx->kf_pitch, ctx->force_f[0], d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits);
+    return fftk::fine_solve(ctx, fine_mesh(ctx), ctx->tile_rho, ctx->tile_g, d.hc, ctx->kern_f, ctx->kf_stride, ctx->kf_pitch, ctx->force_f[0], d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits);
   }
   fftk::NgpSource src{ctx->fstart, d.H, d.b, tx * d.m, ty * d.m, tz * d.m, mass_p, ctx->deltas + (size_t)tile * fine::DELTA_CAP, ctx->ndelta + tile,
                       fine::DELTA_CAP, &ctx->dcnt->sum_rho_f};
-  return fftk::fine_solve(ctx, fine_mesh(ctx), t_rho, t_g, ctx->kern_f, ctx->kf_stride, ctx->kf_pitch, t_force, d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits, &src);
+  return fftk::fine_solve(ctx, fine_mesh(ctx), t_rho, t_g, ctx->kf_pitch, ctx->kern_f, ctx->kf_stride, ctx->kf_pitch, t_force, d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits, &src);
 }
 
 int do_fine(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p, float* ms_dep_fft, float* ms_kick) {
@@ -702,9 +702,11 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   const size_t rowoff_n = (size_t)d.nc_node * d.nc_node + 16 + d.tiles_node;
   TRY(dmalloc(&ctx->rowoff, rowoff_n));
   if (cudaMemset(ctx->rowoff, 0, rowoff_n * sizeof(int)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
-  const size_t tile_elems = (size_t)(d.n + 2) * d.n * d.n;
+  // spectra of the fused NGP path use a row pitch of a multiple of 16 complex (128-byte aligned 16-column blocks): size for it
+  const size_t tile_elems = (size_t)2 * ((d.hc + 15) / 16 * 16) * d.n * d.n;
   TRY(dmalloc(&ctx->tile_rho, tile_elems));
   TRY(dmalloc(&ctx->tile_g, 3 * tile_elems));
+  if (cudaMemset(ctx->tile_rho, 0, tile_elems * sizeof(float)) != cudaSuccess || cudaMemset(ctx->tile_g, 0, 3 * tile_elems * sizeof(float)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   TRY(dmalloc(&ctx->force_f[0], (size_t)3 * d.fdim * d.fdim * d.fdim));
   ctx->force_f[1] = ctx->force_f[0] + (size_t)d.fdim * d.fdim * d.fdim; ctx->force_f[2] = ctx->force_f[1] + (size_t)d.fdim * d.fdim * d.fdim;
   {
@@ -723,6 +725,7 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
           cudaEventCreateWithFlags(&ctx->ev_join[q], cudaEventDisableTiming) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
       TRY(dmalloc(&ctx->tile_rho_s[q], tile_elems));
       TRY(dmalloc(&ctx->tile_g_s[q], 3 * tile_elems));
+      if (cudaMemset(ctx->tile_rho_s[q], 0, tile_elems * sizeof(float)) != cudaSuccess || cudaMemset(ctx->tile_g_s[q], 0, 3 * tile_elems * sizeof(float)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
       TRY(dmalloc(&ctx->force_f_s[q], (size_t)3 * d.fdim * d.fdim * d.fdim));
     }
   }

@@ -37,6 +37,7 @@ WORKLOADS = {
     "c2": (304, 4, 1, 1, 200.0, 100.0, "BASELINE configs[2]: 512^3 particles, 1024^3 fine mesh, PPINT + PP_EXT, nodes_dim=1, tiles_node_dim=4 (nf_tile=304); ICs = 2x2x2 periodic replication of the 256^3-particle box"),
     "c0": (176, 2, 0, 0, 200.0, 100.0, "BASELINE configs[0]: 128^3 particles, 256^3 fine mesh, PM only, tiles_node_dim=2 (nf_tile=176)"),
     "c1c": (560, 1, 1, 0, 200.0, 100.0, "BASELINE configs[1] variant: 256^3 particles, 512^3 fine mesh, PPINT on, tiles_node_dim=1 (nf_tile=560)"),
+    "c0x": (176, 2, 1, 1, 200.0, 100.0, "profiling aid: BASELINE configs[0] box (128^3 particles, 256^3 fine mesh) with PPINT + PP_EXT on"),
     "tiny": (112, 2, 1, 0, 50.0, 20.0, "dev smoke: 64^3 particles, 128^3 fine mesh"),
 }
 
@@ -372,6 +373,10 @@ def run_ours(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything libraries print while the run is set up (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

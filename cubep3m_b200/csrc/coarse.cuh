@@ -168,4 +168,43 @@ __global__ void __launch_bounds__(TPB) cic_kick_kernel(float* __restrict__ xv, c
   }
 }
 
+// coarse kick fused with delete_particles' compaction (delete_particles.f90:14-50): the physical particles are exactly the coarse-cell rows
+// 1..nc_node of the sorted array, so the kick's row loop can write each kicked record straight to its compacted place (rowoff = exclusive scan
+// of the row lengths) instead of updating it in place and copying it afterwards: one read and one write of the particle array instead of two.
+__global__ void __launch_bounds__(TPB) cic_kick_compact_kernel(const float* __restrict__ xv, const int64_t* __restrict__ pid_in, const int* __restrict__ fstart,
+                                                               const int* __restrict__ rowoff, const float* __restrict__ force_c, int H, int nc_buf, int nc_node,
+                                                               float a_mid, float G, float dt, int coarse_ngp, int kick, float* __restrict__ xv_out,
+                                                               int64_t* __restrict__ pid_out) {
+  const int ry = blockIdx.x % nc_node, rz = blockIdx.x / nc_node;
+  const int cy = nc_buf + ry, cz = nc_buf + rz;
+  const long long k0 = ((long long)(cz * H + cy) * H + nc_buf) * 64;
+  const int s0 = fstart[k0], s1 = fstart[k0 + (long long)nc_node * 64];
+  const int dst0 = rowoff[blockIdx.x] - s0;
+  const int fc = nc_node + 2;
+  const float agd = (a_mid * G) * dt;
+  for (int i = s0 + threadIdx.x; i < s1; i += TPB) {
+    const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * i;
+    const float2 a = p[0];
+    float2 b = p[1], c = p[2];
+    if (kick) {
+      int ix, iy, iz; float dx1, dx2, dy1, dy2, dz1, dz2;
+      cic_setup(a.x, coarse_ngp, ix, dx1, dx2);
+      cic_setup(a.y, coarse_ngp, iy, dy1, dy2);
+      cic_setup(b.x, coarse_ngp, iz, dz1, dz2);
+      float vx = b.y, vy = c.x, vz = c.y;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int jx = ix + (q & 1), jy = iy + ((q >> 1) & 1), jz = iz + (q >> 2);
+        const float dV = ((agd * ((q & 1) ? dx2 : dx1)) * (((q >> 1) & 1) ? dy2 : dy1)) * ((q >> 2) ? dz2 : dz1);
+        const float* f = force_c + (((long long)jz * fc + jy) * fc + jx) * 3;
+        vx += f[0] * dV; vy += f[1] * dV; vz += f[2] * dV;
+      }
+      b.y = vx; c.x = vy; c.y = vz;
+    }
+    float2* o = reinterpret_cast<float2*>(xv_out) + 3LL * (dst0 + i);
+    o[0] = a; o[1] = b; o[2] = c;
+    if (pid_in) pid_out[dst0 + i] = pid_in[i];
+  }
+}
+
 }  // namespace coarse

@@ -81,6 +81,7 @@ struct DevCounters {
   unsigned int c_force_max_bits;
   int np_phys;           // after delete_particles
   int n_cand;            // particles within half an ulp below a fine-cell boundary (see fine::ngp_fixup_kernel)
+  int n_blist;           // particles near a y or z face, listed by the first particle_pass kernel
   double sum_rho_f;
   double sum_rho_c;
 };
@@ -110,7 +111,7 @@ struct cubep3m_b200_ctx {
   bool passed = false;
   unsigned int* key = nullptr;
   int* fstart = nullptr; // exclusive scan of fine-cell counts, NF+1 entries
-  int* fcur = nullptr;   // histogram / scatter cursors, NF entries
+  unsigned int* fcur = nullptr;   // fine-cell histogram, two 16-bit counters per word (NF/2 words); counts itself back to zero in the scatter
   int* blocksum = nullptr;
   int nblocksum = 0;
   int* multi_list = nullptr;  // keys of physical fine cells with >= 2 particles

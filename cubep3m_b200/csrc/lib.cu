@@ -272,7 +272,7 @@ int do_drift(cubep3m_b200_ctx* ctx, float dt, float dt_old, const float off[3]) 
 // particle_pass.f90:69-722 for nodes_dim = 1 (every neighbour is this rank) or over NCCL
 int exchange_axis(cubep3m_b200_ctx* ctx, int axis, int n_plus_out, int n_minus_out, int* n_from_minus, int* n_from_plus);
 
-int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max) {
+int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max, const float* drift = nullptr) {   // drift = {dt+dt_old, ox, oy, oz}: fuse update_position into the first pack
   const Dims& d = ctx->d;
   const float lo = -(float)d.b, hi = (float)d.mT + (float)d.b;
   const float fmT = (float)d.mT, rnf = (float)d.b;
@@ -280,16 +280,30 @@ int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max) {
   const float hi_clamp = (fmT + rnf) - ctx->cfg.eps;
   const int cap = d.max_buf / 6;
   int np = ctx->np_all;
+  const int np_first = np;                          // particles present before the first exchange
+  int nlist = 0;
+  int* blist = reinterpret_cast<int*>(ctx->key);    // the sort's key array is free until do_sort
   *np_buf_max = 0;
+  CK(cudaMemsetAsync(&ctx->dcnt->n_blist, 0, sizeof(int), ctx->stream));
   for (int axis = 0; axis < 3; ++axis) {
     CK(cudaMemsetAsync(&ctx->dcnt->n_send[0], 0, 2 * sizeof(int), ctx->stream));
-    if (np > 0)
-      LAUNCH(ctx, KC_PASS_PACK, part::pass_pack_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], np, axis, lo, hi,
-             cut_hi, cut_lo, ctx->sendbuf[0], ctx->sendbuf[1], ctx->sendpid[0], ctx->sendpid[1], cap, ctx->dcnt);
+    if (np > 0) {
+      const float z4[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* dr = drift ? drift : z4;
+      const long long nvis = axis == 0 ? np : (long long)nlist + (np - np_first);
+      const int grid = (int)((nvis + part::TPB - 1) / part::TPB);
+#define PACK_ARGS ctx->xv[ctx->cur], ctx->pid[ctx->cur], np, axis, lo, hi, cut_hi, cut_lo, ctx->sendbuf[0], ctx->sendbuf[1], ctx->sendpid[0], ctx->sendpid[1], cap, \
+                  ctx->dcnt, dr[0], dr[1], dr[2], dr[3], blist, nlist, np_first
+      if (axis == 0 && drift) LAUNCH(ctx, KC_PASS_PACK, (part::pass_pack_kernel<true, false>), grid, part::TPB, 0, PACK_ARGS);
+      else if (axis == 0) LAUNCH(ctx, KC_PASS_PACK, (part::pass_pack_kernel<false, false>), grid, part::TPB, 0, PACK_ARGS);
+      else if (grid > 0) LAUNCH(ctx, KC_PASS_PACK, (part::pass_pack_kernel<false, true>), grid, part::TPB, 0, PACK_ARGS);
+#undef PACK_ARGS
+    }
     CK(cudaGetLastError());
     if (int st = fetch_counters(ctx)) return st;
     if (int st = overflow_status(ctx->hcnt)) return st;
     const int n_plus = ctx->hcnt->n_send[0], n_minus = ctx->hcnt->n_send[1];
+    if (axis == 0) nlist = ctx->hcnt->n_blist;
     if (n_plus * 6 > d.max_buf || n_minus * 6 > d.max_buf) return CUBEP3M_B200_EPASSBUF;      // particle_pass.f90:96-99
     *np_buf_max = std::max(*np_buf_max, std::max(n_plus, n_minus));
     int r_plus = 0, r_minus = 0;   // r_plus: particles that travelled in + direction (arrive from the - neighbour)
@@ -382,7 +396,7 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
   const Dims& d = ctx->d;
   const int np = ctx->np_all;
   const float lo = -(float)d.b, hi = (float)d.mT + (float)d.b;
-  if (!ctx->hist_clean) CK(cudaMemsetAsync(ctx->fcur, 0, sizeof(int) * d.NF, ctx->stream));   // otherwise the last scatter left it zeroed
+  if (!ctx->hist_clean) CK(cudaMemsetAsync(ctx->fcur, 0, sizeof(unsigned int) * (d.NF / 2), ctx->stream));   // two 16-bit counters per word   // otherwise the last scatter left it zeroed
   ctx->hist_clean = false;
   CK(cudaMemsetAsync(&ctx->dcnt->np_deleted, 0, sizeof(int), ctx->stream));
   CK(cudaMemsetAsync(&ctx->dcnt->n_multi, 0, 2 * sizeof(int), ctx->stream));
@@ -409,14 +423,19 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
 }
 
 // delete_particles.f90:14-50 on the sorted array
-int do_delete(cubep3m_b200_ctx* ctx) {
+// kick != nullptr: {a_mid, dt}: coarse_velocity (coarse_velocity.f90:137-179) is applied on the way (fused kernel, see coarse.cuh)
+int do_delete(cubep3m_b200_ctx* ctx, const float* kick = nullptr) {
   const Dims& d = ctx->d;
   const int rows = d.nc_node * d.nc_node;
   CK(cudaMemsetAsync(ctx->rowoff + rows, 0, sizeof(int), ctx->stream));
   LAUNCH(ctx, KC_COMPACT, part::row_count_kernel, (rows + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->rowoff);
   LAUNCH(ctx, KC_SCAN, part::scan_blocksums_kernel, 1, 1024, 0, ctx->rowoff, rows + 1);   // entry [rows] (initialised to 0) becomes the total
-  LAUNCH(ctx, KC_COMPACT, part::compact_rows_kernel, rows, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->fstart, ctx->rowoff, d.H, d.nc_buf, d.nc_node,
-         ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1]);
+  if (kick)
+    LAUNCH(ctx, KC_CIC_KICK, coarse::cic_kick_compact_kernel, rows, coarse::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->fstart, ctx->rowoff, ctx->force_c, d.H,
+           d.nc_buf, d.nc_node, kick[0], ctx->cfg.G, kick[1], ctx->cfg.coarse_ngp, 1, ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1]);
+  else
+    LAUNCH(ctx, KC_COMPACT, part::compact_rows_kernel, rows, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->fstart, ctx->rowoff, d.H, d.nc_buf, d.nc_node,
+           ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1]);
   CK(cudaGetLastError());
   int total = 0;
   CK(cudaMemcpyAsync(&ctx->hcnt->np_phys, ctx->rowoff + rows, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -694,7 +713,7 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   TRY(dmalloc(&ctx->ndelta, (size_t)d.tiles_node));
   TRY(dmalloc(&ctx->tile_counts, (size_t)d.tiles_node));
   TRY(dmalloc(&ctx->fstart, (size_t)d.NF + 64));
-  TRY(dmalloc(&ctx->fcur, (size_t)d.NF + 64));
+  TRY(dmalloc(&ctx->fcur, (size_t)d.NF / 2 + 64));
   ctx->nblocksum = (int)((d.NF + part::SCAN_BLOCK - 1) / part::SCAN_BLOCK);
   TRY(dmalloc(&ctx->blocksum, (size_t)ctx->nblocksum + 1));
   ctx->list_cap = d.max_np / 2 + 1024;
@@ -861,10 +880,14 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   CK(cudaMemsetAsync(ctx->rowoff + d.nc_node * d.nc_node, 0, sizeof(int) * (16 + d.tiles_node), ctx->stream));
   ctx->prof_n = 0;
   CK(cudaEventRecord(ev[0], ctx->stream));
-  if (int st = do_drift(ctx, dt, dt_old, offset ? offset : zero)) return st;             // particle_mesh_threaded.f90:56
+  // update_position (particle_mesh_threaded.f90:56) is fused into the first pack kernel of particle_pass (:63; range check of :61 folded in)
+  const float* off3 = offset ? offset : zero;
+  const float drift4[4] = {dt + dt_old, off3[0], off3[1], off3[2]};
+  ctx->sorted = false; ctx->passed = false; ctx->np_all = ctx->np_local;
   CK(cudaEventRecord(ev[1], ctx->stream));
   int bufmax = 0, ndel = 0;
-  if (int st = do_pass(ctx, &bufmax)) return st;                                          // :63 (range check of :61 folded in)
+  if (ctx->np_local > 0) { if (int st = do_pass(ctx, &bufmax, drift4)) return st; }
+  else { if (int st = do_drift(ctx, dt, dt_old, off3)) return st; if (int st = do_pass(ctx, &bufmax)) return st; }
   CK(cudaEventRecord(ev[2], ctx->stream));
   if (int st = do_sort(ctx, &ndel)) return st;                                            // :61 link_list as a cell sort
   const int np_ghost = ctx->np_all;
@@ -888,12 +911,13 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   CK(cudaEventRecord(ev[11], ctx->stream));
   CK(cudaStreamWaitEvent(ctx->stream, ev[8], 0));                                         // join the coarse stream
   CK(cudaEventRecord(ev[12], ctx->stream));
-  if (c.coarse_vel_update) { if (int st = do_coarse_vel(ctx, a_mid, dt)) return st; }     // coarse_mesh.f90:106
   CK(cudaEventRecord(ev[9], ctx->stream));
   if (int st = fetch_counters(ctx)) return st;
   const DevCounters hc = *ctx->hcnt;
   if (int st = overflow_status(&hc)) return st;
-  if (int st = do_delete(ctx)) return st;                                                 // particle_mesh_threaded.f90:720
+  // coarse_velocity (coarse_mesh.f90:106) rides on delete_particles' compaction (particle_mesh_threaded.f90:720)
+  const float kick2[2] = {a_mid, dt};
+  if (int st = do_delete(ctx, c.coarse_vel_update ? kick2 : nullptr)) return st;
   CK(cudaEventRecord(ev[10], ctx->stream));
   CK(cudaEventSynchronize(ev[10]));
   // limiters (particle_mesh_threaded.f90:643-696, coarse_max_dt.f90:36)

@@ -53,20 +53,53 @@ __device__ __forceinline__ bool in_hoc_range(float x, float y, float z, float lo
 // particle_pass.f90:73-94 (+ pass) and :173-192 (- pass) for one axis: every chained particle with
 // x >= mT - nf_buf goes to the + neighbour, every one with x < nf_buf to the - neighbour.
 // Both directions read the same pre-axis particle list (the reference relinks only after both).
-__global__ void __launch_bounds__(TPB) pass_pack_kernel(const float* __restrict__ xv, const int64_t* __restrict__ pid, int np, int axis,
+// DRIFT: the first axis' pack also performs update_position (update_position.f90:71) on the record it has just loaded and writes the
+// new position back, which saves the drift kernel's own pass over the particle array inside particle_mesh.
+// The first axis' kernel (LIST = false) scans all np particles and also lists (blist) the chained ones that lie within nf_buf of a y or z
+// face: only those, plus the ghosts received so far (indices >= np_first), can be sent along the later axes, whose kernels (LIST = true) then
+// visit nlist + (np - np_first) records instead of all np.
+template <bool DRIFT, bool LIST>
+__global__ void __launch_bounds__(TPB) pass_pack_kernel(float* __restrict__ xv, const int64_t* __restrict__ pid, int np, int axis,
                                                         float lo, float hi, float cut_hi, float cut_lo,
                                                         float* __restrict__ send_plus, float* __restrict__ send_minus,
                                                         int64_t* __restrict__ pid_plus, int64_t* __restrict__ pid_minus,
-                                                        int cap, DevCounters* __restrict__ cnt) {
-  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+                                                        int cap, DevCounters* __restrict__ cnt, float hdt, float ox, float oy, float oz,
+                                                        int* __restrict__ blist, int nlist, int np_first) {
+  const long long t = (long long)blockIdx.x * TPB + threadIdx.x;
+  long long i = t;
+  bool act = t < np;
+  if (LIST) {
+    act = t < (long long)nlist + (np - np_first);
+    if (act) i = (t < nlist) ? blist[t] : (long long)np_first + (t - nlist);
+  }
   bool gp = false, gm = false;
   float2 a, b, c;
-  if (i < np) {
+  if (act) {
     load_xv(xv, i, a, b, c);
+    if (DRIFT) {
+      a.x = __fadd_rn(__fadd_rn(a.x, __fmul_rn(__fmul_rn(b.y, 0.5f), hdt)), ox);
+      a.y = __fadd_rn(__fadd_rn(a.y, __fmul_rn(__fmul_rn(c.x, 0.5f), hdt)), oy);
+      b.x = __fadd_rn(__fadd_rn(b.x, __fmul_rn(__fmul_rn(c.y, 0.5f), hdt)), oz);
+      float2* p = reinterpret_cast<float2*>(xv) + 3 * i;
+      p[0] = a; p[1] = b;
+    }
+    bool face = false;
     if (in_hoc_range(a.x, a.y, b.x, lo, hi)) {
       const float q = axis == 0 ? a.x : (axis == 1 ? a.y : b.x);
       gp = q >= cut_hi;
       gm = q < cut_lo;
+      if (!LIST) face = a.y >= cut_hi || a.y < cut_lo || b.x >= cut_hi || b.x < cut_lo;
+    }
+    if (!LIST) {                                    // warp-aggregated append to the boundary list
+      const unsigned mf = __ballot_sync(__activemask(), face);
+      if (face) {
+        const int lane_ = threadIdx.x & 31;
+        const int leader = __ffs(mf) - 1;
+        int base = 0;
+        if (lane_ == leader) base = atomicAdd(&cnt->n_blist, __popc(mf));
+        base = __shfl_sync(mf, base, leader);
+        blist[base + __popc(mf & ((1u << lane_) - 1))] = (int)i;
+      }
     }
   }
   // warp-aggregated slot allocation
@@ -128,8 +161,11 @@ __device__ __forceinline__ unsigned int make_key(float x, float y, float z, int 
 
 // Also lists the particles that sit within 2^-15 below an integer coordinate on any axis: only for those can the
 // reference's tile-local cell floor(fl(x + offset)) (particle_mesh_threaded.f90:139-143) differ from floor(x)+offset.
+// The histogram holds two 16-bit counters per 32-bit word (cell k -> word k>>1, half k&1): the table is the largest array the sort touches
+// (H^3*64 cells, ~8 per particle) and every atomic on it is a DRAM sector read-modify-write, so halving its footprint halves that traffic.
+// A fine cell with >= 65535 particles raises the 'exceeded max_llf' flag (max_llf = 100000 in cubepm.par:183 is the same kind of bound).
 __global__ void __launch_bounds__(TPB) key_hist_kernel(const float* __restrict__ xv, int np, float lo, float hi, int b, int H,
-                                                       unsigned int* __restrict__ key, int* __restrict__ hist, float* __restrict__ cand, int cand_cap,
+                                                       unsigned int* __restrict__ key, unsigned int* __restrict__ hist, float* __restrict__ cand, int cand_cap,
                                                        DevCounters* __restrict__ cnt) {
   const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
   if (i >= np) return;
@@ -139,7 +175,9 @@ __global__ void __launch_bounds__(TPB) key_hist_kernel(const float* __restrict__
   unsigned int k = KEY_DEAD;
   if (in_hoc_range(a.x, a.y, z, lo, hi)) {
     k = make_key(a.x, a.y, z, b, H);
-    atomicAdd(&hist[k], 1);
+    const unsigned sh = (k & 1u) << 4;
+    const unsigned old = atomicAdd(&hist[k >> 1], 1u << sh);
+    if (((old >> sh) & 0xffffu) >= 0xfffeu) atomicOr(&cnt->overflow, 4);
     const float th = 3.0517578125e-05f;   // 2^-15 >= half an ulp of any |x + offset| < 1024
     if (ceilf(a.x) - a.x <= th || ceilf(a.y) - a.y <= th || ceilf(z) - z <= th) {
       const int slot = atomicAdd(&cnt->n_cand, 1);
@@ -155,15 +193,16 @@ __global__ void __launch_bounds__(TPB) key_hist_kernel(const float* __restrict__
 constexpr int SCAN_ITEMS = 16;                       // ints per thread
 constexpr int SCAN_BLOCK = TPB * SCAN_ITEMS;         // 4096 ints per block
 
-__global__ void __launch_bounds__(TPB) scan_reduce_kernel(const int* __restrict__ hist, long long n, int* __restrict__ blocksum) {
+__device__ __forceinline__ int pair_sum(unsigned int w) { return (int)(w & 0xffffu) + (int)(w >> 16); }
+// n (cells) is a multiple of 16: the block's SCAN_BLOCK cells are SCAN_BLOCK/2 words
+__global__ void __launch_bounds__(TPB) scan_reduce_kernel(const unsigned int* __restrict__ hist, long long n, int* __restrict__ blocksum) {
   const long long base = (long long)blockIdx.x * SCAN_BLOCK;
   int s = 0;
-  const int4* h4 = reinterpret_cast<const int4*>(hist + base);
+  const uint4* h4 = reinterpret_cast<const uint4*>(hist + (base >> 1));
 #pragma unroll
-  for (int it = 0; it < SCAN_ITEMS / 4; ++it) {
-    const long long e = base + ((long long)it * TPB + threadIdx.x) * 4;
-    if (e + 3 < n) { const int4 v = h4[it * TPB + threadIdx.x]; s += v.x + v.y + v.z + v.w; }
-    else for (int q = 0; q < 4; ++q) if (e + q < n) s += hist[e + q];
+  for (int it = 0; it < SCAN_ITEMS / 8; ++it) {
+    const long long e = base + ((long long)it * TPB + threadIdx.x) * 8;      // first cell of this thread's 4 words
+    if (e + 7 < n) { const uint4 v = h4[it * TPB + threadIdx.x]; s += pair_sum(v.x) + pair_sum(v.y) + pair_sum(v.z) + pair_sum(v.w); }
   }
   __shared__ int ws[TPB / 32];
   s = warp_sum_i(s);
@@ -205,7 +244,7 @@ __global__ void __launch_bounds__(1024) scan_blocksums_kernel(int* __restrict__ 
 
 // block scan + offset; writes fstart (exclusive); also emits the PP work lists:
 // physical fine cells (coarse cell in 1..nc_node on all axes) with >= 2 particles (PPINT) / >= 1 (PP_EXT).
-__global__ void __launch_bounds__(TPB) scan_apply_kernel(const int* __restrict__ hist_cur, long long n, const int* __restrict__ blocksum,
+__global__ void __launch_bounds__(TPB) scan_apply_kernel(const unsigned int* __restrict__ hist_cur, long long n, const int* __restrict__ blocksum,
                                                          int* __restrict__ fstart, int H, int nc_buf, int nc_node,
                                                          int* __restrict__ multi_list, int* __restrict__ occ_list, int list_cap,
                                                          int want_multi, int want_occ, DevCounters* __restrict__ cnt) {
@@ -213,15 +252,13 @@ __global__ void __launch_bounds__(TPB) scan_apply_kernel(const int* __restrict__
   int v[SCAN_ITEMS];
   int s = 0;
 #pragma unroll
-  for (int q = 0; q < SCAN_ITEMS; q += 4) {
-    if (base + q + 3 < n) {
-      const int4 t = *reinterpret_cast<const int4*>(hist_cur + base + q);
-      v[q] = t.x; v[q + 1] = t.y; v[q + 2] = t.z; v[q + 3] = t.w;
-    } else {
+  for (int q = 0; q < SCAN_ITEMS; q += 8) {       // 8 cells = 4 packed words (n is a multiple of 16)
+    uint4 t = make_uint4(0u, 0u, 0u, 0u);
+    if (base + q + 7 < n) t = *reinterpret_cast<const uint4*>(hist_cur + ((base + q) >> 1));
+    v[q] = t.x & 0xffffu; v[q + 1] = t.x >> 16; v[q + 2] = t.y & 0xffffu; v[q + 3] = t.y >> 16;
+    v[q + 4] = t.z & 0xffffu; v[q + 5] = t.z >> 16; v[q + 6] = t.w & 0xffffu; v[q + 7] = t.w >> 16;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[q + u] = (base + q + u < n) ? hist_cur[base + q + u] : 0;
-    }
-    s += v[q] + v[q + 1] + v[q + 2] + v[q + 3];
+    for (int u = 0; u < 8; ++u) s += v[q + u];
   }
   // exclusive scan of s over the block
   __shared__ int ws[TPB / 32];
@@ -269,7 +306,7 @@ __global__ void __launch_bounds__(TPB) scan_apply_kernel(const int* __restrict__
 }
 
 __global__ void __launch_bounds__(TPB) scatter_kernel(const float* __restrict__ xv_in, const int64_t* __restrict__ pid_in,
-                                                      const unsigned int* __restrict__ key, int np, int* __restrict__ hist,
+                                                      const unsigned int* __restrict__ key, int np, unsigned int* __restrict__ hist,
                                                       const int* __restrict__ fstart, float* __restrict__ xv_out, int64_t* __restrict__ pid_out) {
   const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
   if (i >= np) return;
@@ -279,7 +316,8 @@ __global__ void __launch_bounds__(TPB) scatter_kernel(const float* __restrict__ 
   load_xv(xv_in, i, a, b, c);
   // slot = cell start + (remaining count - 1): every particle decrements its cell once, so the histogram is back to all zeros
   // after the scatter and needs no memset before the next step's key_hist_kernel
-  const int dst = fstart[k] + atomicSub(&hist[k], 1) - 1;
+  const unsigned sh = (k & 1u) << 4;
+  const int dst = fstart[k] + (int)((atomicSub(&hist[k >> 1], 1u << sh) >> sh) & 0xffffu) - 1;
   store_xv(xv_out, dst, a, b, c);
   if (pid_in) pid_out[dst] = pid_in[i];
 }

@@ -82,25 +82,18 @@ __global__ void __launch_bounds__(TPB) ppint_kernel(float* __restrict__ xv, cons
 // cell consecutive fx are consecutive keys, so each row is at most two contiguous particle ranges found with two fstart reads each.
 // Neighbouring lanes hold neighbouring particles, so their range lookups and source loads hit the same L1 lines.
 // The same-cell pairs belong to PPINT (:496-523 excludes the cell itself): the centre row is walked as [gx-pr,gx-1] and [gx+1,gx+pr].
-__device__ __forceinline__ void ppext_range(const float* __restrict__ xv, const int* __restrict__ fstart, long long rowkey, int xa, int xb,
-                                            const float3 pi, const PPParams& P, float3& acc) {
-  if (xa > xb) return;
-  const int ca = xa >> 2, cb = xb >> 2;
+// one contiguous range of sources
+__device__ __forceinline__ void ppext_sources(const float* __restrict__ xv, int s, int e, const float3 pi, const PPParams& P, float3& acc) {
 #pragma unroll 1
-  for (int c = ca; c <= cb; ++c) {
-    const int f0 = (c == ca) ? (xa & 3) : 0, f1 = (c == cb) ? (xb & 3) : 3;
-    const long long k0 = rowkey + (long long)c * 64;
-    const int s = fstart[k0 + f0], e = fstart[k0 + f1 + 1];
-#pragma unroll 1
-    for (int j = s; j < e; ++j) {
-      const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * j;
-      const float2 a = p[0];
-      pair_force(pi, make_float3(a.x, a.y, p[1].x), P, true, acc);
-    }
+  for (int j = s; j < e; ++j) {
+    const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * j;
+    const float2 a = p[0];
+    pair_force(pi, make_float3(a.x, a.y, p[1].x), P, true, acc);
   }
 }
 
 constexpr int EXT_TPB = 128;
+constexpr int EXT_MAXR = 2;    // largest pp_range (cubepm.par:92 uses 2)
 __global__ void __launch_bounds__(EXT_TPB) ppext_kernel(float* __restrict__ xv, const int* __restrict__ fstart, int np_all, int H, int b, int nc_buf,
                                                         int nc_node, int pr, PPParams P, DevCounters* __restrict__ cnt) {
   const int i = blockIdx.x * EXT_TPB + threadIdx.x;
@@ -114,18 +107,46 @@ __global__ void __launch_bounds__(EXT_TPB) ppext_kernel(float* __restrict__ xv, 
     if (gx >= lo && gx < hi && gy >= lo && gy < hi && gz >= lo && gz < hi) {                      // kick only particles of the physical cells (:576-590)
       const float3 pi = make_float3(a.x, a.y, z);
       float3 acc = make_float3(0.f, 0.f, 0.f);
+      // x cells gx-pr..gx+pr lie in coarse cells ca (fine cells fa0..fa1) and, if the window straddles a coarse boundary, cb (0..fb1)
+      const int xa = gx - pr, xb = gx + pr;
+      const int ca = xa >> 2, cb = xb >> 2;
+      const bool two = cb != ca;
+      const int fa0 = xa & 3, fa1 = two ? 3 : (xb & 3), fb1 = xb & 3;
 #pragma unroll 1
       for (int dz = -pr; dz <= pr; ++dz) {
         const int nz = gz + dz;
+        // all table look-ups of this z plane first (up to 4 per row, independent loads), then the pair loops
+        int rs[2 * EXT_MAXR + 1][2], re[2 * EXT_MAXR + 1][2];
+#pragma unroll
+        for (int q = 0; q < 2 * EXT_MAXR + 1; ++q) {
+          const int dy = q - EXT_MAXR;
+          rs[q][0] = re[q][0] = rs[q][1] = re[q][1] = 0;
+          if (dy >= -pr && dy <= pr) {
+            const int ny = gy + dy;
+            const long long rowkey = ((long long)((nz >> 2) * H + (ny >> 2)) * H) * 64 + (((nz & 3) << 4) | ((ny & 3) << 2));
+            const long long ka = rowkey + (long long)ca * 64;
+            rs[q][0] = fstart[ka + fa0]; re[q][0] = fstart[ka + fa1 + 1];
+            if (two) { const long long kb = rowkey + (long long)cb * 64; rs[q][1] = fstart[kb]; re[q][1] = fstart[kb + fb1 + 1]; }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 2 * EXT_MAXR + 1; ++q) {
+          if (dz == 0 && q == EXT_MAXR) continue;       // the centre row is handled below (own cell excluded)
+          ppext_sources(xv, rs[q][0], re[q][0], pi, P, acc);
+          ppext_sources(xv, rs[q][1], re[q][1], pi, P, acc);
+        }
+      }
+      {   // centre row: cells [gx-pr, gx-1] and [gx+1, gx+pr]; the pairs inside the own cell belong to PPINT (:496-523)
+        const long long rowkey = ((long long)((gz >> 2) * H + (gy >> 2)) * H) * 64 + (((gz & 3) << 4) | ((gy & 3) << 2));
 #pragma unroll 1
-        for (int dy = -pr; dy <= pr; ++dy) {
-          const int ny = gy + dy;
-          const long long rowkey = ((long long)((nz >> 2) * H + (ny >> 2)) * H) * 64 + (((nz & 3) << 4) | ((ny & 3) << 2));
-          if (dz == 0 && dy == 0) {
-            ppext_range(xv, fstart, rowkey, gx - pr, gx - 1, pi, P, acc);
-            ppext_range(xv, fstart, rowkey, gx + 1, gx + pr, pi, P, acc);
-          } else {
-            ppext_range(xv, fstart, rowkey, gx - pr, gx + pr, pi, P, acc);
+        for (int side = 0; side < 2; ++side) {
+          const int x0 = side ? gx + 1 : gx - pr, x1 = side ? gx + pr : gx - 1;
+          if (x0 > x1) continue;
+          const int c0 = x0 >> 2, c1 = x1 >> 2;
+          for (int cc = c0; cc <= c1; ++cc) {
+            const int f0 = (cc == c0) ? (x0 & 3) : 0, f1 = (cc == c1) ? (x1 & 3) : 3;
+            const long long k0 = rowkey + (long long)cc * 64;
+            ppext_sources(xv, fstart[k0 + f0], fstart[k0 + f1 + 1], pi, P, acc);
           }
         }
       }

@@ -158,6 +158,16 @@ struct cubep3m_b200_ctx {
   float2* tw_c[3] = {nullptr, nullptr, nullptr};   // twiddles for Nx, Ny, Nz
   float* redbuf = nullptr;    // small device scratch for cross-rank reductions
   int* cntbuf = nullptr;      // received pass counts
+  // particle_pass over NVLink peer memory (multi-rank, inside particle_mesh): the pack kernel stores straight into the neighbour's receive
+  // buffer; counts and completion flags travel through small mailboxes in peer memory (lib.cu: p2p_init / do_pass)
+  bool p2p = false;
+  int p2p_cap = 0;                 // particles per (axis, direction) region of a receive buffer
+  unsigned int p2p_epoch = 0;      // one per particle_mesh call; flags carry it, so they never need resetting
+  int* mailbox = nullptr;          // own: [3 axes][2 directions][count, flag]
+  float* peer_recv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // where MY (axis, direction)-going particles land
+  int* peer_box[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  std::vector<void*> ipc_opened;
+  int* hbox = nullptr;             // pinned: received counts + time-out flag
   DevCounters* dcnt = nullptr;
   DevCounters* hcnt = nullptr; // pinned
   cudaEvent_t ev[CUBEP3M_B200_ST_COUNT + 4];

@@ -246,6 +246,72 @@ int build_kern_c(cubep3m_b200_ctx* ctx) {
   } while (0)
 #endif
 
+// Peer-memory set-up for particle_pass: every rank exports its two receive buffers and its mailbox with cudaIpc, the handles are
+// all-gathered over NCCL, and each rank maps the buffers of its (up to six) neighbours. Falls back to the NCCL send/recv path (p2p stays
+// false) if any step is unavailable; CUBEP3M_B200_P2P=0 forces the fallback.
+int p2p_init(cubep3m_b200_ctx* ctx) {
+#ifdef CUBEP3M_WITH_NCCL
+  const Dims& d = ctx->d;
+  const char* e = getenv("CUBEP3M_B200_P2P");
+  if (e && atoi(e) == 0) return 0;
+  if (ctx->cfg.pid) return 0;
+  CK(cudaMalloc((void**)&ctx->mailbox, 3 * 2 * 2 * sizeof(int)));
+  CK(cudaMemset(ctx->mailbox, 0, 3 * 2 * 2 * sizeof(int)));
+  CK(cudaMallocHost((void**)&ctx->hbox, 4 * sizeof(int)));
+  struct Handles { cudaIpcMemHandle_t h[3]; int ok; int pad[3]; };
+  Handles mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.ok = cudaIpcGetMemHandle(&mine.h[0], ctx->recvbuf_own[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine.h[1], ctx->recvbuf_own[1]) == cudaSuccess &&
+            cudaIpcGetMemHandle(&mine.h[2], ctx->mailbox) == cudaSuccess;
+  cudaGetLastError();
+  Handles* dall = nullptr;
+  CK(cudaMalloc((void**)&dall, sizeof(Handles) * d.world));
+  CK(cudaMemcpy(dall + ctx->cfg.rank, &mine, sizeof(Handles), cudaMemcpyHostToDevice));
+  NCK(ncclAllGather(dall + ctx->cfg.rank, dall, sizeof(Handles), ncclChar, ctx->comm, ctx->stream));
+  std::vector<Handles> all(d.world);
+  CK(cudaMemcpyAsync(all.data(), dall, sizeof(Handles) * d.world, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dall);
+  bool ok = true;
+  for (int r = 0; r < d.world; ++r) ok = ok && all[r].ok;
+  std::vector<float*> rb0(d.world, nullptr), rb1(d.world, nullptr);
+  std::vector<int*> mb(d.world, nullptr);
+  ctx->p2p_cap = d.max_buf / 6 / 3;
+  for (int axis = 0; axis < 3 && ok; ++axis) {
+    if (d.Dg[axis] == 1) continue;
+    for (int dir = 0; dir < 2 && ok; ++dir) {
+      const int peer = dir == 0 ? d.nbr[2 * axis + 1] : d.nbr[2 * axis];    // "+"-going particles land at the + neighbour
+      if (peer == ctx->cfg.rank) { rb0[peer] = ctx->recvbuf_own[0]; rb1[peer] = ctx->recvbuf_own[1]; mb[peer] = ctx->mailbox; }
+      if (!mb[peer]) {
+        void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+        ok = cudaIpcOpenMemHandle(&p0, all[peer].h[0], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+             cudaIpcOpenMemHandle(&p1, all[peer].h[1], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+             cudaIpcOpenMemHandle(&p2, all[peer].h[2], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        if (p0) ctx->ipc_opened.push_back(p0);
+        if (p1) ctx->ipc_opened.push_back(p1);
+        if (p2) ctx->ipc_opened.push_back(p2);
+        if (!ok) { cudaGetLastError(); break; }
+        rb0[peer] = (float*)p0; rb1[peer] = (float*)p1; mb[peer] = (int*)p2;
+      }
+      // my "+"-going particles are what the peer receives "from its - neighbour": its buffer 0, mailbox entry (axis, 0); "-"-going: 1
+      ctx->peer_recv[axis][dir] = (dir == 0 ? rb0[peer] : rb1[peer]) + (size_t)axis * ctx->p2p_cap * 6;
+      ctx->peer_box[axis][dir] = mb[peer] + (axis * 2 + dir) * 2;
+    }
+  }
+  // every rank must take the same path: agree on it
+  int* dflag = ctx->cntbuf;
+  const int mine_ok = ok ? 1 : 0;
+  CK(cudaMemcpy(dflag, &mine_ok, sizeof(int), cudaMemcpyHostToDevice));
+  NCK(ncclAllReduce(dflag, dflag, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
+  int all_ok = 0;
+  CK(cudaMemcpyAsync(&all_ok, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->p2p = all_ok == 1;
+  if (!ctx->p2p && ctx->cfg.rank == 0) fprintf(stderr, "cubep3m_b200: peer-memory particle_pass unavailable, using NCCL send/recv\n");
+#endif
+  return 0;
+}
+
 int fetch_counters(cubep3m_b200_ctx* ctx) {
   CK(cudaMemcpyAsync(ctx->hcnt, ctx->dcnt, sizeof(DevCounters), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -272,7 +338,7 @@ int do_drift(cubep3m_b200_ctx* ctx, float dt, float dt_old, const float off[3]) 
 // particle_pass.f90:69-722 for nodes_dim = 1 (every neighbour is this rank) or over NCCL
 int exchange_axis(cubep3m_b200_ctx* ctx, int axis, int n_plus_out, int n_minus_out, int* n_from_minus, int* n_from_plus);
 
-int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max, const float* drift = nullptr) {   // drift = {dt+dt_old, ox, oy, oz}: fuse update_position into the first pack
+int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max, const float* drift = nullptr, bool in_step = false) {   // drift = {dt+dt_old, ox, oy, oz}: fuse update_position into the first pack
   const Dims& d = ctx->d;
   const float lo = -(float)d.b, hi = (float)d.mT + (float)d.b;
   const float fmT = (float)d.mT, rnf = (float)d.b;
@@ -287,12 +353,18 @@ int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max, const float* drift = nullptr
   CK(cudaMemsetAsync(&ctx->dcnt->n_blist, 0, sizeof(int), ctx->stream));
   for (int axis = 0; axis < 3; ++axis) {
     CK(cudaMemsetAsync(&ctx->dcnt->n_send[0], 0, 2 * sizeof(int), ctx->stream));
+    // peer-memory path: only inside particle_mesh (its end-of-step all-reduce is what keeps a fast rank from overwriting a region the
+    // neighbour has not consumed yet) and without PIDs
+    const bool p2p = ctx->p2p && in_step && d.Dg[axis] > 1 && !ctx->cfg.pid;
+    float* dst_plus = p2p ? ctx->peer_recv[axis][0] : ctx->sendbuf[0];
+    float* dst_minus = p2p ? ctx->peer_recv[axis][1] : ctx->sendbuf[1];
+    const int cap_axis = p2p ? ctx->p2p_cap : cap;
     if (np > 0) {
       const float z4[4] = {0.f, 0.f, 0.f, 0.f};
       const float* dr = drift ? drift : z4;
       const long long nvis = axis == 0 ? np : (long long)nlist + (np - np_first);
       const int grid = (int)((nvis + part::TPB - 1) / part::TPB);
-#define PACK_ARGS ctx->xv[ctx->cur], ctx->pid[ctx->cur], np, axis, lo, hi, cut_hi, cut_lo, ctx->sendbuf[0], ctx->sendbuf[1], ctx->sendpid[0], ctx->sendpid[1], cap, \
+#define PACK_ARGS ctx->xv[ctx->cur], ctx->pid[ctx->cur], np, axis, lo, hi, cut_hi, cut_lo, dst_plus, dst_minus, ctx->sendpid[0], ctx->sendpid[1], cap_axis, \
                   ctx->dcnt, dr[0], dr[1], dr[2], dr[3], blist, nlist, np_first
       if (axis == 0 && drift) LAUNCH(ctx, KC_PASS_PACK, (part::pass_pack_kernel<true, false>), grid, part::TPB, 0, PACK_ARGS);
       else if (axis == 0) LAUNCH(ctx, KC_PASS_PACK, (part::pass_pack_kernel<false, false>), grid, part::TPB, 0, PACK_ARGS);
@@ -300,6 +372,15 @@ int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max, const float* drift = nullptr
 #undef PACK_ARGS
     }
     CK(cudaGetLastError());
+    if (p2p) {
+      // one kernel publishes counts + flags into the neighbours' mailboxes, one waits for both of ours: no NCCL call and a single
+      // host synchronisation per axis (the NCCL path needs two groups and two synchronisations)
+      ctx->hbox[0] = ctx->hbox[1] = ctx->hbox[2] = 0;
+      CK(cudaMemsetAsync(ctx->cntbuf, 0, 4 * sizeof(int), ctx->stream));
+      LAUNCH(ctx, KC_PASS_PACK, part::pass_publish_kernel, 1, 32, 0, ctx->dcnt, ctx->peer_box[axis][0], ctx->peer_box[axis][1], (int)ctx->p2p_epoch);
+      LAUNCH(ctx, KC_PASS_UNPACK, part::pass_wait_kernel, 1, 32, 0, ctx->mailbox + axis * 4, (int)ctx->p2p_epoch, ctx->cntbuf, 10000000000LL);
+      CK(cudaMemcpyAsync(ctx->hbox, ctx->cntbuf, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (int st = fetch_counters(ctx)) return st;
     if (int st = overflow_status(ctx->hcnt)) return st;
     const int n_plus = ctx->hcnt->n_send[0], n_minus = ctx->hcnt->n_send[1];
@@ -307,7 +388,13 @@ int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max, const float* drift = nullptr
     if (n_plus * 6 > d.max_buf || n_minus * 6 > d.max_buf) return CUBEP3M_B200_EPASSBUF;      // particle_pass.f90:96-99
     *np_buf_max = std::max(*np_buf_max, std::max(n_plus, n_minus));
     int r_plus = 0, r_minus = 0;   // r_plus: particles that travelled in + direction (arrive from the - neighbour)
-    if (int st = exchange_axis(ctx, axis, n_plus, n_minus, &r_plus, &r_minus)) return st;
+    if (p2p) {
+      if (ctx->hbox[2]) { fprintf(stderr, "cubep3m_b200: particle_pass timed out waiting for a neighbour (axis %d)\n", axis); return CUBEP3M_B200_ENCCL; }
+      r_plus = ctx->hbox[0]; r_minus = ctx->hbox[1];
+      if (r_plus > ctx->p2p_cap || r_minus > ctx->p2p_cap) return CUBEP3M_B200_EPASSBUF;       // the sender flagged the overflow too
+      ctx->recvbuf[0] = ctx->recvbuf_own[0] + (size_t)axis * ctx->p2p_cap * 6;
+      ctx->recvbuf[1] = ctx->recvbuf_own[1] + (size_t)axis * ctx->p2p_cap * 6;
+    } else if (int st = exchange_axis(ctx, axis, n_plus, n_minus, &r_plus, &r_minus)) return st;
     if ((long long)np + r_plus + r_minus > d.max_np) return CUBEP3M_B200_EMAXNP;              // particle_pass.f90:136-139
     const int nr = r_plus + r_minus;
     if (nr > 0)
@@ -657,6 +744,9 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   auto F = [](void* p) { if (p) cudaFree(p); };
   for (int i = 0; i < 2; ++i) { F(ctx->xv[i]); F(ctx->pid[i]); F(ctx->sendbuf[i]); F(ctx->sendpid[i]); F(ctx->recvbuf_own[i]); F(ctx->recvpid_own[i]); }
+  for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
+  if (ctx->mailbox) cudaFree(ctx->mailbox);
+  if (ctx->hbox) cudaFreeHost(ctx->hbox);
 #ifdef CUBEP3M_WITH_NCCL
   if (ctx->comm) ncclCommDestroy(ctx->comm);
 #endif
@@ -778,6 +868,7 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
     ncclUniqueId id;
     memcpy(&id, nccl_unique_id, sizeof(id));
     if (ncclCommInitRank(&ctx->comm, d.world, id, cfg->rank) != ncclSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ENCCL; }
+    if (int st = p2p_init(ctx)) { cubep3m_b200_finalize(ctx); return st; }
 #else
     cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ENCCL;
 #endif
@@ -886,8 +977,9 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   ctx->sorted = false; ctx->passed = false; ctx->np_all = ctx->np_local;
   CK(cudaEventRecord(ev[1], ctx->stream));
   int bufmax = 0, ndel = 0;
-  if (ctx->np_local > 0) { if (int st = do_pass(ctx, &bufmax, drift4)) return st; }
-  else { if (int st = do_drift(ctx, dt, dt_old, off3)) return st; if (int st = do_pass(ctx, &bufmax)) return st; }
+  ctx->p2p_epoch++;
+  if (ctx->np_local > 0) { if (int st = do_pass(ctx, &bufmax, drift4, true)) return st; }
+  else { if (int st = do_drift(ctx, dt, dt_old, off3)) return st; if (int st = do_pass(ctx, &bufmax, nullptr, true)) return st; }
   CK(cudaEventRecord(ev[2], ctx->stream));
   if (int st = do_sort(ctx, &ndel)) return st;                                            // :61 link_list as a cell sort
   const int np_ghost = ctx->np_all;

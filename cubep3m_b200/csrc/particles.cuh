@@ -124,6 +124,35 @@ __global__ void __launch_bounds__(TPB) pass_pack_kernel(float* __restrict__ xv, 
   }
 }
 
+// ---- peer-memory exchange (multi-GPU, NVLink): after the pack kernel has stored this rank's outgoing particles straight into the two
+// neighbours' receive regions, one thread publishes the counts and raises the neighbours' flags; the receiver spins on its own two flags.
+__global__ void pass_publish_kernel(const DevCounters* __restrict__ cnt, int* box_plus, int* box_minus, int epoch) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(box_plus) = cnt->n_send[0];
+    *reinterpret_cast<volatile int*>(box_minus) = cnt->n_send[1];
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(box_plus + 1) = epoch;
+    *reinterpret_cast<volatile int*>(box_minus + 1) = epoch;
+  }
+}
+// mybox: [2 directions][count, flag]; out: {count from the - neighbour ("+" going), count from the + neighbour, time-out}
+__global__ void pass_wait_kernel(const int* mybox, int epoch, int* __restrict__ out, long long timeout_cycles) {
+  const int d = threadIdx.x;
+  if (d < 2) {
+    const volatile int* flag = mybox + 2 * d + 1;
+    const long long t0 = clock64();
+    bool ok = true;
+    while (*flag != epoch) {
+      if (clock64() - t0 > timeout_cycles) { ok = false; break; }
+      __nanosleep(200);
+    }
+    __threadfence_system();
+    out[d] = ok ? *reinterpret_cast<const volatile int*>(mybox + 2 * d) : 0;
+    if (!ok) out[2] = 1;
+  }
+}
+
 // receive side: shift + clamp, append at xv[np0 ...]
 //   from the - neighbour's "+" buffer:  x = max(x - mT, -nf_buf)                          particle_pass.f90:162
 //   from the + neighbour's "-" buffer:  |x|<eps -> +-eps ; x = min(x + mT, mT+nf_buf-eps)   particle_pass.f90:257-265

@@ -8,6 +8,7 @@
 #include "fine.cuh"
 #include "pp.cuh"
 #include "coarse.cuh"
+#include "power.cuh"
 
 namespace {
 
@@ -1187,6 +1188,61 @@ int cubep3m_b200_debug_fft3d(cubep3m_b200_ctx* ctx, int32_t n, float* data, int3
   return 0;
 }
 int64_t cubep3m_b200_launch_count(cubep3m_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------- cic_power on the device (utils/cic_power/cic_power.f90)
+int cubep3m_b200_cic_power(cubep3m_b200_ctx* ctx, const float shake_offset[3], double box, int32_t ngp_binning, double* k_out, double* delta2_out,
+                           double* sigma_out, int32_t nshells) {
+  if (!ctx || !k_out || !delta2_out) return CUBEP3M_B200_EINVAL;
+  const Dims& d = ctx->d;
+  if (d.world != 1) return CUBEP3M_B200_EINVAL;             // the mesh lives on one GPU; the distributed transform is listed under "next"
+  const int nc = d.mT;                                        // nf_physical_dim
+  if (!fftk::supported(nc) || nshells != nc / 2) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  const int np = ctx->np_local;
+  if (np <= 0 || ctx->passed) return CUBEP3M_B200_ENOTREADY;   // needs the physical particles only (after delete_particles / upload)
+  const size_t nreal = (size_t)(nc + 2) * nc * nc;
+  const int nb = nc / 2 + 2, stride = nb + 2;
+  float* rho = nullptr; float2* tw = nullptr; double *dsinc = nullptr, *dsums = nullptr;
+  auto cleanup = [&]() { if (rho) cudaFree(rho); if (tw) cudaFree(tw); if (dsinc) cudaFree(dsinc); if (dsums) cudaFree(dsums); };
+#define PCK(x) do { if ((x) != cudaSuccess) { cleanup(); return CUBEP3M_B200_ECUDA; } } while (0)
+  PCK(cudaMalloc((void**)&rho, nreal * sizeof(float)));
+  PCK(cudaMalloc((void**)&dsinc, nc * sizeof(double)));
+  PCK(cudaMalloc((void**)&dsums, 4 * stride * sizeof(double)));
+  if (fftk::make_twiddles(nc, &tw)) { cleanup(); return CUBEP3M_B200_ECUDA; }
+  PCK(cudaMemsetAsync(rho, 0, nreal * sizeof(float), ctx->stream));
+  PCK(cudaMemsetAsync(dsums, 0, 4 * stride * sizeof(double), ctx->stream));
+  std::vector<double> sinc4(nc);
+  for (int i = 0; i < nc; ++i) {
+    const int k = i < nc / 2 ? i : i - nc;
+    const double x = M_PI * (double)k / (double)nc, sc = (k == 0) ? 1.0 : sin(x) / x;
+    sinc4[i] = sc * sc * sc * sc;
+  }
+  PCK(cudaMemcpyAsync(dsinc, sinc4.data(), nc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const float zero[3] = {0.f, 0.f, 0.f};
+  const float* so = shake_offset ? shake_offset : zero;
+  const float mp = (float)(((double)nc * nc * nc) / (double)np);
+  LAUNCH(ctx, KC_MISC, power::cic_density_kernel, (np + power::TPB - 1) / power::TPB, power::TPB, 0, ctx->xv[ctx->cur], np, nc, so[0], so[1], so[2], mp, rho);
+  const fftk::Mesh3 g{nc, nc, nc, tw, tw, tw};
+  if (int st = fftk::forward3d(ctx, g, rho)) { cleanup(); return st; }
+  PCK(cudaFuncSetAttribute(power::shell_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * stride * sizeof(double))));
+  LAUNCH(ctx, KC_MISC, power::shell_bin_kernel, NUM_SMS * 4, power::TPB, 4 * stride * sizeof(double), reinterpret_cast<const float2*>(rho), nc, dsinc, ngp_binning, nb, dsums);
+  std::vector<double> sums(4 * stride);
+  PCK(cudaMemcpyAsync(sums.data(), dsums, sums.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PCK(cudaStreamSynchronize(ctx->stream));
+  PCK(cudaGetLastError());
+#undef PCK
+  cleanup();
+  const double* P = sums.data(); const double* P2 = P + stride; const double* W = P2 + stride; const double* K = W + stride;
+  for (int sh = 1; sh <= nc / 2; ++sh) {                      // cic_power.f90:1649-1660
+    const double Wn = std::max(W[sh], 1e-300), kavg = K[sh] / Wn, Pm = P[sh] / Wn;
+    const double var = std::max(P2[sh] / Wn - Pm * Pm, 0.0);
+    const double keff = ngp_binning ? kavg : kavg - 1.0;
+    k_out[sh - 1] = 2.0 * M_PI * kavg / box;
+    delta2_out[sh - 1] = 4.0 * M_PI * keff * keff * keff * Pm;
+    if (sigma_out) sigma_out[sh - 1] = 4.0 * M_PI * keff * keff * keff * sqrt(var / std::max(W[sh] - 1.0, 1.0));
+  }
+  return 0;
+}
 
 // ---------------------------------------------------------------- driver twin (host): timestep.f90
 void cubep3m_b200_expansion(float a0, float dt0, float omega_m, float omega_l, float wde, float* da1, float* da2) {

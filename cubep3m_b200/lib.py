@@ -28,7 +28,7 @@ SYMBOLS = ["cubep3m_b200_version", "cubep3m_b200_strerror", "cubep3m_b200_defaul
            "cubep3m_b200_debug_rho_c", "cubep3m_b200_debug_force_c", "cubep3m_b200_debug_fine_tile",
            "cubep3m_b200_debug_fft3d", "cubep3m_b200_launch_count", "cubep3m_b200_set_profiling", "cubep3m_b200_set_tile_streams",
            "cubep3m_b200_num_kernel_classes", "cubep3m_b200_kernel_class_name", "cubep3m_b200_get_kernel_times",
-           "cubep3m_b200_clock_init",
+           "cubep3m_b200_cic_power", "cubep3m_b200_clock_init",
            "cubep3m_b200_expansion", "cubep3m_b200_timestep"]
 
 
@@ -82,6 +82,8 @@ def load_library():
     L.cubep3m_b200_launch_count.restype = C.c_int64
     L.cubep3m_b200_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.cubep3m_b200_set_tile_streams.argtypes = [C.c_void_p, C.c_int]
+    L.cubep3m_b200_cic_power.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_double, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double), C.c_int32]
     L.cubep3m_b200_kernel_class_name.restype = C.c_char_p
     L.cubep3m_b200_kernel_class_name.argtypes = [C.c_int]
     L.cubep3m_b200_get_kernel_times.argtypes = [C.c_void_p, _fp, C.c_void_p]
@@ -235,6 +237,16 @@ class ParticleMesh:
         assert a.shape == (n, n, n + 2)
         _chk(self.lib.cubep3m_b200_debug_fft3d(self.h, n, a.reshape(-1), 1 if inverse else 0))
         return a
+
+    def cic_power(self, box, shake=(0.0, 0.0, 0.0), ngp_binning=True):
+        """Device twin of utils/cic_power (cic_power.f90:840-954): returns (k [h/Mpc], Delta^2, sigma) for shells 1..nc/2 of the resident
+        physical particles after subtracting the accumulated shake offset (checkpoint.f90:92)."""
+        n = self.cfg.nf_physical_dim // 2
+        k, d2, sg = (np.empty(n, np.float64) for _ in range(3))
+        off = (C.c_float * 3)(*[float(v) for v in shake])
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        _chk(self.lib.cubep3m_b200_cic_power(self.h, off, C.c_double(box), 1 if ngp_binning else 0, dp(k), dp(d2), dp(sg), n))
+        return k, d2, sg
 
     def set_profiling(self, on=True):
         _chk(self.lib.cubep3m_b200_set_profiling(self.h, 1 if on else 0))

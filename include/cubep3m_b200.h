@@ -184,6 +184,16 @@ const char* cubep3m_b200_kernel_class_name(int k);
 int cubep3m_b200_get_kernel_times(cubep3m_b200_ctx* ctx, float* ms, int64_t* launches);
 
 /*
+ * cic_power on the device (utils/cic_power/cic_power.f90:840-954 driver, :1496-1539 CIC deposit, :1583-1615 mode weights and shells,
+ * :1649-1660 output columns): power spectrum of the resident physical particles on the global nf_physical_dim^3 mesh, single rank.
+ * shake_offset is subtracted first, as checkpoint.f90:92 does before the particles reach cic_power. nshells must be nf_physical_dim/2;
+ * k [h/Mpc], Delta^2(k) and its standard error (may be NULL) are written for shells 1..nshells. ngp_binning = 1 is the build
+ * COMPILE_cic_power.csh:20 uses (w1 = 1, w2 = 0), 0 the CIC shell weights.
+ */
+int cubep3m_b200_cic_power(cubep3m_b200_ctx* ctx, const float shake_offset[3], double box, int32_t ngp_binning,
+                           double* k, double* delta2, double* sigma, int32_t nshells);
+
+/*
  * Driver twin (host C++): restatement of timestep / expansion (timestep.f90:2-293) so the harness can
  * run multi-step parity without the Fortran driver. Not needed when the Fortran driver is present.
  */

@@ -82,6 +82,7 @@ struct DevCounters {
   int np_phys;           // after delete_particles
   int n_cand;            // particles within half an ulp below a fine-cell boundary (see fine::ngp_fixup_kernel)
   int n_blist;           // particles near a y or z face, listed by the first particle_pass kernel
+  int n_ppext_fallback;  // PP_EXT blocks whose source region exceeded the shared-memory capacity (walked directly instead)
   double sum_rho_f;
   double sum_rho_c;
 };
@@ -137,6 +138,8 @@ struct cubep3m_b200_ctx {
   int tile_streams_max = 1;
   int tile_streams = 1;       // S > 1: consecutive tiles rotate over S streams / buffer sets (hides launch bubbles, tails, latency)
   cudaStream_t stream_coarse = nullptr;   // coarse-mesh solve runs concurrently with the fine-tile loop
+  int ppext_mode = 1;          // 1: tiled shared-memory kernel (pp::ppext_tiled_kernel), 0: direct one-thread-per-target kernel (CUBEP3M_B200_PPEXT=direct)
+  int ppext_blocks = 0, ppext_fallback = 0;   // of the last step (debug getter)
   bool hist_clean = false;     // fcur (the fine-cell histogram) is all zeros
   cudaStream_t stream_main = nullptr, stream_aux[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};

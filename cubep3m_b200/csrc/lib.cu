@@ -625,9 +625,17 @@ int do_pp_ext(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
   P.cutoff = (float)ctx->cfg.nf_cutoff;
   if (ctx->cfg.pp_ext && ctx->cfg.pp_range > 0) {
     P.apply = ctx->cfg.pp_ext_force_flag;
-    if (ctx->np_all > 0)
+    ctx->ppext_blocks = 0;
+    if (ctx->np_all > 0 && ctx->ppext_mode == 1 && ctx->cfg.pp_range <= pp::TB_HALO) {
+      const int nc = ctx->d.nc_node;
+      const int nbx = (nc + pp::TB_X - 1) / pp::TB_X, nby = (nc + pp::TB_Y - 1) / pp::TB_Y, nbz = (nc + pp::TB_Z - 1) / pp::TB_Z;
+      ctx->ppext_blocks = nbx * nby * nbz;
+      LAUNCH(ctx, KC_PPEXT, pp::ppext_tiled_kernel, ctx->ppext_blocks, pp::TB_NT, pp::TB_SMEM, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->d.b, ctx->d.nc_buf, nc, nbx, nby,
+             ctx->cfg.pp_range, P, ctx->dcnt, &ctx->dcnt->n_ppext_fallback);
+    } else if (ctx->np_all > 0) {
       LAUNCH(ctx, KC_PPEXT, pp::ppext_kernel, (ctx->np_all + pp::EXT_TPB - 1) / pp::EXT_TPB, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->np_all, ctx->d.H,
              ctx->d.b, ctx->d.nc_buf, ctx->d.nc_node, ctx->cfg.pp_range, P, ctx->dcnt);
+    }
   }
   CK(cudaGetLastError());
   return 0;
@@ -826,6 +834,11 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
     ctx->tile_streams_max = e ? std::max(1, std::min(atoi(e), (int)cubep3m_b200_ctx::MAX_TILE_STREAMS)) : 1;
     ctx->tile_streams = ctx->tile_streams_max;
   }
+  {
+    const char* e = getenv("CUBEP3M_B200_PPEXT");       // "direct": the one-thread-per-target kernel (A/B measurements); default: tiled
+    ctx->ppext_mode = (e && !strcmp(e, "direct")) ? 0 : 1;
+    if (cudaFuncSetAttribute(pp::ppext_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp::TB_SMEM) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
+  }
   ctx->stream_main = ctx->stream;
   if (cudaStreamCreateWithFlags(&ctx->stream_coarse, cudaStreamNonBlocking) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   if (ctx->tile_streams > 1) {
@@ -1007,6 +1020,7 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   CK(cudaEventRecord(ev[9], ctx->stream));
   if (int st = fetch_counters(ctx)) return st;
   const DevCounters hc = *ctx->hcnt;
+  ctx->ppext_fallback = hc.n_ppext_fallback;
   if (int st = overflow_status(&hc)) return st;
   // coarse_velocity (coarse_mesh.f90:106) rides on delete_particles' compaction (particle_mesh_threaded.f90:720)
   const float kick2[2] = {a_mid, dt};
@@ -1067,6 +1081,12 @@ int cubep3m_b200_set_profiling(cubep3m_b200_ctx* ctx, int on) {
 int cubep3m_b200_set_tile_streams(cubep3m_b200_ctx* ctx, int n) {
   if (!ctx || n < 1 || n > ctx->tile_streams_max) return CUBEP3M_B200_EINVAL;
   ctx->tile_streams = n;
+  return 0;
+}
+int cubep3m_b200_debug_ppext_blocks(cubep3m_b200_ctx* ctx, int32_t* blocks, int32_t* fallback) {
+  if (!ctx) return CUBEP3M_B200_EINVAL;
+  if (blocks) *blocks = ctx->ppext_blocks;
+  if (fallback) *fallback = ctx->ppext_fallback;
   return 0;
 }
 int cubep3m_b200_num_kernel_classes(void) { return KC_COUNT; }

@@ -94,6 +94,69 @@ __device__ __forceinline__ void ppext_sources(const float* __restrict__ xv, int 
 
 constexpr int EXT_TPB = 128;
 constexpr int EXT_MAXR = 2;    // largest pp_range (cubepm.par:92 uses 2)
+
+// force on the target particle i (a physical-cell particle at position pi, fine cell (gx,gy,gz) of the hoc range) from every particle of the
+// cells within pr, looked up in the global fine-cell table
+__device__ __forceinline__ float3 ppext_direct(const float* __restrict__ xv, const int* __restrict__ fstart, int H, int pr, const float3 pi, int gx, int gy,
+                                               int gz, const PPParams& P) {
+  float3 acc = make_float3(0.f, 0.f, 0.f);
+  // x cells gx-pr..gx+pr lie in coarse cells ca (fine cells fa0..fa1) and, if the window straddles a coarse boundary, cb (0..fb1)
+  const int xa = gx - pr, xb = gx + pr;
+  const int ca = xa >> 2, cb = xb >> 2;
+  const bool two = cb != ca;
+  const int fa0 = xa & 3, fa1 = two ? 3 : (xb & 3), fb1 = xb & 3;
+#pragma unroll 1
+  for (int dz = -pr; dz <= pr; ++dz) {
+    const int nz = gz + dz;
+    // all table look-ups of this z plane first (up to 4 per row, independent loads), then the pair loops
+    int rs[2 * EXT_MAXR + 1][2], re[2 * EXT_MAXR + 1][2];
+#pragma unroll
+    for (int q = 0; q < 2 * EXT_MAXR + 1; ++q) {
+      const int dy = q - EXT_MAXR;
+      rs[q][0] = re[q][0] = rs[q][1] = re[q][1] = 0;
+      if (dy >= -pr && dy <= pr) {
+        const int ny = gy + dy;
+        const long long rowkey = ((long long)((nz >> 2) * H + (ny >> 2)) * H) * 64 + (((nz & 3) << 4) | ((ny & 3) << 2));
+        const long long ka = rowkey + (long long)ca * 64;
+        rs[q][0] = fstart[ka + fa0]; re[q][0] = fstart[ka + fa1 + 1];
+        if (two) { const long long kb = rowkey + (long long)cb * 64; rs[q][1] = fstart[kb]; re[q][1] = fstart[kb + fb1 + 1]; }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2 * EXT_MAXR + 1; ++q) {
+      if (dz == 0 && q == EXT_MAXR) continue;       // the centre row is handled below (own cell excluded)
+      ppext_sources(xv, rs[q][0], re[q][0], pi, P, acc);
+      ppext_sources(xv, rs[q][1], re[q][1], pi, P, acc);
+    }
+  }
+  {   // centre row: cells [gx-pr, gx-1] and [gx+1, gx+pr]; the pairs inside the own cell belong to PPINT (:496-523)
+    const long long rowkey = ((long long)((gz >> 2) * H + (gy >> 2)) * H) * 64 + (((gz & 3) << 4) | ((gy & 3) << 2));
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+      const int x0 = side ? gx + 1 : gx - pr, x1 = side ? gx + pr : gx - 1;
+      if (x0 > x1) continue;
+      const int c0 = x0 >> 2, c1 = x1 >> 2;
+      for (int cc = c0; cc <= c1; ++cc) {
+        const int f0 = (cc == c0) ? (x0 & 3) : 0, f1 = (cc == c1) ? (x1 & 3) : 3;
+        const long long k0 = rowkey + (long long)cc * 64;
+        ppext_sources(xv, fstart[k0 + f0], fstart[k0 + f1 + 1], pi, P, acc);
+      }
+    }
+  }
+  return acc;
+}
+
+// kick of pp_ext_force_accum (:576-590) on the record at p; returns |F| for pp_ext_force_max (:617)
+__device__ __forceinline__ float ppext_apply(float2* __restrict__ p, const float3 acc, const PPParams& P) {
+  if (P.apply) {
+    const float s = P.a_mid * P.G * P.dt;
+    float2 bq = p[1], c = p[2];
+    bq.y += acc.x * s; c.x += acc.y * s; c.y += acc.z * s;
+    p[1] = bq; p[2] = c;
+  }
+  return sqrtf(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z);
+}
+
 __global__ void __launch_bounds__(EXT_TPB) ppext_kernel(float* __restrict__ xv, const int* __restrict__ fstart, int np_all, int H, int b, int nc_buf,
                                                         int nc_node, int pr, PPParams P, DevCounters* __restrict__ cnt) {
   const int i = blockIdx.x * EXT_TPB + threadIdx.x;
@@ -104,63 +167,191 @@ __global__ void __launch_bounds__(EXT_TPB) ppext_kernel(float* __restrict__ xv, 
     const float z = p[1].x;
     const int gx = (int)floorf(a.x) + b, gy = (int)floorf(a.y) + b, gz = (int)floorf(z) + b;   // as part::make_key
     const int lo = nc_buf * 4, hi = (nc_buf + nc_node) * 4;
-    if (gx >= lo && gx < hi && gy >= lo && gy < hi && gz >= lo && gz < hi) {                      // kick only particles of the physical cells (:576-590)
-      const float3 pi = make_float3(a.x, a.y, z);
-      float3 acc = make_float3(0.f, 0.f, 0.f);
-      // x cells gx-pr..gx+pr lie in coarse cells ca (fine cells fa0..fa1) and, if the window straddles a coarse boundary, cb (0..fb1)
-      const int xa = gx - pr, xb = gx + pr;
-      const int ca = xa >> 2, cb = xb >> 2;
-      const bool two = cb != ca;
-      const int fa0 = xa & 3, fa1 = two ? 3 : (xb & 3), fb1 = xb & 3;
-#pragma unroll 1
-      for (int dz = -pr; dz <= pr; ++dz) {
-        const int nz = gz + dz;
-        // all table look-ups of this z plane first (up to 4 per row, independent loads), then the pair loops
-        int rs[2 * EXT_MAXR + 1][2], re[2 * EXT_MAXR + 1][2];
-#pragma unroll
-        for (int q = 0; q < 2 * EXT_MAXR + 1; ++q) {
-          const int dy = q - EXT_MAXR;
-          rs[q][0] = re[q][0] = rs[q][1] = re[q][1] = 0;
-          if (dy >= -pr && dy <= pr) {
-            const int ny = gy + dy;
-            const long long rowkey = ((long long)((nz >> 2) * H + (ny >> 2)) * H) * 64 + (((nz & 3) << 4) | ((ny & 3) << 2));
-            const long long ka = rowkey + (long long)ca * 64;
-            rs[q][0] = fstart[ka + fa0]; re[q][0] = fstart[ka + fa1 + 1];
-            if (two) { const long long kb = rowkey + (long long)cb * 64; rs[q][1] = fstart[kb]; re[q][1] = fstart[kb + fb1 + 1]; }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 2 * EXT_MAXR + 1; ++q) {
-          if (dz == 0 && q == EXT_MAXR) continue;       // the centre row is handled below (own cell excluded)
-          ppext_sources(xv, rs[q][0], re[q][0], pi, P, acc);
-          ppext_sources(xv, rs[q][1], re[q][1], pi, P, acc);
-        }
-      }
-      {   // centre row: cells [gx-pr, gx-1] and [gx+1, gx+pr]; the pairs inside the own cell belong to PPINT (:496-523)
-        const long long rowkey = ((long long)((gz >> 2) * H + (gy >> 2)) * H) * 64 + (((gz & 3) << 4) | ((gy & 3) << 2));
-#pragma unroll 1
-        for (int side = 0; side < 2; ++side) {
-          const int x0 = side ? gx + 1 : gx - pr, x1 = side ? gx + pr : gx - 1;
-          if (x0 > x1) continue;
-          const int c0 = x0 >> 2, c1 = x1 >> 2;
-          for (int cc = c0; cc <= c1; ++cc) {
-            const int f0 = (cc == c0) ? (x0 & 3) : 0, f1 = (cc == c1) ? (x1 & 3) : 3;
-            const long long k0 = rowkey + (long long)cc * 64;
-            ppext_sources(xv, fstart[k0 + f0], fstart[k0 + f1 + 1], pi, P, acc);
-          }
-        }
-      }
-      fm = sqrtf(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z);   // :617
-      if (P.apply) {
-        const float s = P.a_mid * P.G * P.dt;
-        float2 bq = p[1], c = p[2];
-        bq.y += acc.x * s; c.x += acc.y * s; c.y += acc.z * s;
-        p[1] = bq; p[2] = c;
-      }
-    }
+    if (gx >= lo && gx < hi && gy >= lo && gy < hi && gz >= lo && gz < hi)                        // kick only particles of the physical cells (:576-590)
+      fm = ppext_apply(p, ppext_direct(xv, fstart, H, pr, make_float3(a.x, a.y, z), gx, gy, gz, P), P);
   }
   fm = warp_max(fm);
   if ((threadIdx.x & 31) == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_ext_force_max_bits, fm);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// PP_EXT, tiled: one CTA per block of TB_X x TB_Y x TB_Z coarse cells (the targets) and the TB_HALO fine cells around it (the sources).
+// The direct kernel above spends its time on table look-ups (up to 100 global fstart reads per target: the 4^3 fine cells of a coarse
+// cell are stored (fz,fy,fx)-major, so a 5-cell x window of one (y,z) row is split over two coarse cells) and on divergence. Here the
+// block's source particles are RE-SORTED IN SHARED MEMORY by the dense region cell index (z,y,x) with x running over the whole region
+// width: every neighbour row of a target is then exactly ONE contiguous range between two adjacent-table entries, both in shared memory.
+//   1. count : the (TB_Y+2) x (TB_Z+2) coarse x-rows that cover the region are contiguous ranges of the sorted particle array
+//              (key = (cz*H+cy)*H+cx major): coalesced reads, shared-memory histogram over the region's fine cells
+//   2. scan  : exclusive scan of the histogram (one chunk per thread, warp shuffles)
+//   3. fill  : second read of the same ranges (L1/L2 hits), positions + global index scattered to their sorted place as float4
+//   4. list  : warp-ballot compaction of the targets (sources whose cell is inside the block and physical), in cell order
+//   5. walk  : one thread per target; (2 pr + 1)^2 rows, two shared-memory table reads per row, pair loop over float4 sources
+// A block whose region holds more than TB_CAP particles (density contrast > ~5 over the region) falls back to the direct walk for its
+// targets: there the per-cell ranges are long, neighbouring lanes share them, and the direct kernel is efficient.
+// The pair weight uses the fast reciprocal (MUFU.RCP, 2 ulp) instead of two IEEE divisions: |error| ~ 3e-7 relative, far inside the 1e-4 gate.
+constexpr int TB_X = 4, TB_Y = 2, TB_Z = 2, TB_HALO = EXT_MAXR;
+constexpr int TB_RX = 4 * TB_X + 2 * TB_HALO, TB_RY = 4 * TB_Y + 2 * TB_HALO, TB_RZ = 4 * TB_Z + 2 * TB_HALO;   // 20 x 12 x 12 fine cells
+constexpr int TB_NCELL = TB_RX * TB_RY * TB_RZ;
+constexpr int TB_NT = 128;
+constexpr int TB_CAP = 2048;                    // source particles per block held in shared memory
+constexpr int TB_NROW = (TB_Y + 2) * (TB_Z + 2);   // coarse x-rows read per block
+constexpr int TB_CHUNK = (TB_NCELL + TB_NT - 1) / TB_NT;
+constexpr size_t TB_SMEM = (size_t)TB_CAP * sizeof(float4) + (size_t)(TB_NCELL + 1) * sizeof(int) + (size_t)TB_CAP * sizeof(unsigned short);
+
+__device__ __forceinline__ void pair_force_fast(const float3 pi, const float4 pj, const PPParams& P, float inv_cut, float3& acc) {
+  const float sx = pi.x - pj.x, sy = pi.y - pj.y, sz = pi.z - pj.z;
+  const float r = sqrtf(sx * sx + sy * sy + sz * sz);
+  if (r > P.rsoft) {
+    const float rb = r * P.pp_bias;
+    float w = __fdividef(P.mass_p, rb * rb * rb);
+    if (!(r > P.cutoff + 1.7320508f)) {
+      const float u = rb * inv_cut, u2 = u * u, u3 = u2 * u;
+      w *= (1.0f - 1.75f * u3 + 0.75f * u3 * u2);
+    }
+    acc.x -= sx * w; acc.y -= sy * w; acc.z -= sz * w;
+  }
+}
+
+__global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ xv, const int* __restrict__ fstart, int H, int b, int nc_buf, int nc_node, int nbx,
+                                                            int nby, int pr, PPParams P, DevCounters* __restrict__ cnt, int* __restrict__ n_fallback) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  float4* src = reinterpret_cast<float4*>(raw);
+  int* tab = reinterpret_cast<int*>(src + TB_CAP);                       // [TB_NCELL + 1]: counts -> starts
+  unsigned short* tl = reinterpret_cast<unsigned short*>(tab + TB_NCELL + 1);
+  __shared__ int row_g0[TB_NROW], row_pre[TB_NROW + 1], wsum[TB_NT / 32], s_nt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bx = blockIdx.x % nbx, by = (blockIdx.x / nbx) % nby, bz = blockIdx.x / (nbx * nby);
+  const int cx0 = nc_buf + bx * TB_X, cy0 = nc_buf + by * TB_Y, cz0 = nc_buf + bz * TB_Z;      // first coarse cell of the block (hoc-range coordinates)
+  const int phys_hi = nc_buf + nc_node;                                                        // first non-physical coarse cell
+  const int ox = 4 * cx0 - TB_HALO, oy = 4 * cy0 - TB_HALO, oz = 4 * cz0 - TB_HALO;            // fine cell (0,0,0) of the region
+  for (int t = tid; t <= TB_NCELL; t += TB_NT) tab[t] = 0;
+  if (tid < TB_NROW) {
+    const int cy = min(cy0 - 1 + tid % (TB_Y + 2), H - 1), cz = min(cz0 - 1 + tid / (TB_Y + 2), H - 1);
+    const int ca = cx0 - 1, cb = min(cx0 + TB_X, H - 1);
+    const long long rk = (long long)(cz * H + cy) * H;
+    // a row clamped at the upper edge of the hoc range repeats its neighbour: give it an empty range
+    const bool dup = (cy0 - 1 + tid % (TB_Y + 2) > H - 1) || (cz0 - 1 + tid / (TB_Y + 2) > H - 1);
+    const int g0 = fstart[(rk + ca) * 64], g1 = dup ? g0 : fstart[(rk + cb) * 64 + 64];
+    row_g0[tid] = g0;
+    row_pre[tid + 1] = g1 - g0;
+  }
+  if (tid == 0) { row_pre[0] = 0; s_nt = 0; }
+  __syncthreads();
+  if (tid == 0) for (int r = 0; r < TB_NROW; ++r) row_pre[r + 1] += row_pre[r];
+  __syncthreads();
+  const int nraw = row_pre[TB_NROW];
+  const float2* xv2 = reinterpret_cast<const float2*>(xv);
+  // region cell of the record f of the flattened row ranges (or -1), and its global index
+  auto locate = [&](int f, int& gi, float3& q) -> int {
+    int r = 0;
+#pragma unroll
+    for (int s = TB_NROW / 2; s >= 1; s >>= 1) if (r + s < TB_NROW && row_pre[r + s] <= f) r += s;   // TB_NROW = 16: binary search
+    gi = row_g0[r] + (f - row_pre[r]);
+    const float2* p = xv2 + 3LL * gi;
+    const float2 a = p[0];
+    q = make_float3(a.x, a.y, p[1].x);
+    const int lx = (int)floorf(q.x) + b - ox, ly = (int)floorf(q.y) + b - oy, lz = (int)floorf(q.z) + b - oz;
+    if ((unsigned)lx >= (unsigned)TB_RX || (unsigned)ly >= (unsigned)TB_RY || (unsigned)lz >= (unsigned)TB_RZ) return -1;
+    return (lz * TB_RY + ly) * TB_RX + lx;
+  };
+  // ---- 1. count
+  for (int f = tid; f < nraw; f += TB_NT) {
+    int gi; float3 q;
+    const int c = locate(f, gi, q);
+    if (c >= 0) atomicAdd(&tab[c + 1], 1);
+  }
+  __syncthreads();
+  // ---- 2. exclusive scan of tab[1..NCELL] in place: tab[c + 1] = start of cell c (tab[0] = 0 = start of cell 0 after the fill)
+  {
+    const int c0 = 1 + tid * TB_CHUNK, c1 = min(c0 + TB_CHUNK, TB_NCELL + 1);
+    int s = 0;
+    for (int c = c0; c < c1; ++c) s += tab[c];
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int base = inc - s;
+    for (int w = 0; w < warp; ++w) base += wsum[w];
+    for (int c = c0; c < c1; ++c) { const int v = tab[c]; tab[c] = base; base += v; }
+  }
+  int total = 0;
+#pragma unroll
+  for (int w = 0; w < TB_NT / 32; ++w) total += wsum[w];
+  __syncthreads();
+  float fm = 0.f;
+  const int plo = 4 * nc_buf, phi = 4 * phys_hi;
+  if (total > TB_CAP) {
+    // ---- fallback: direct walk for the block's physical targets (TB_Y x TB_Z coarse x-rows, contiguous ranges)
+    if (tid == 0) atomicAdd(n_fallback, 1);
+    for (int rr = 0; rr < TB_Y * TB_Z; ++rr) {
+      const int cy = cy0 + rr % TB_Y, cz = cz0 + rr / TB_Y;
+      if (cy >= phys_hi || cz >= phys_hi) continue;
+      const long long rk = (long long)(cz * H + cy) * H;
+      const int g0 = fstart[(rk + cx0) * 64], g1 = fstart[(rk + min(cx0 + TB_X, phys_hi) - 1) * 64 + 64];
+      for (int i = g0 + tid; i < g1; i += TB_NT) {
+        float2* p = reinterpret_cast<float2*>(xv) + 3LL * i;
+        const float2 a = p[0];
+        const float z = p[1].x;
+        const int gx = (int)floorf(a.x) + b, gy = (int)floorf(a.y) + b, gz = (int)floorf(z) + b;
+        fm = fmaxf(fm, ppext_apply(p, ppext_direct(xv, fstart, H, pr, make_float3(a.x, a.y, z), gx, gy, gz, P), P));
+      }
+    }
+  } else {
+    // ---- 3. fill
+    for (int f = tid; f < nraw; f += TB_NT) {
+      int gi; float3 q;
+      const int c = locate(f, gi, q);
+      if (c >= 0) { const int slot = atomicAdd(&tab[c + 1], 1); src[slot] = make_float4(q.x, q.y, q.z, __int_as_float(gi)); }
+    }
+    __syncthreads();                                   // now tab[c] = start of cell c, c = 0..NCELL
+    // ---- 4. target list in cell order (chunks of 32 sorted entries keep their order)
+    for (int base = 0; base < total; base += TB_NT) {
+      const int i = base + tid;
+      bool tgt = false;
+      if (i < total) {
+        const float4 q = src[i];
+        const int gx = (int)floorf(q.x) + b, gy = (int)floorf(q.y) + b, gz = (int)floorf(q.z) + b;
+        const int lx = gx - ox - TB_HALO, ly = gy - oy - TB_HALO, lz = gz - oz - TB_HALO;
+        tgt = (unsigned)lx < (unsigned)(4 * TB_X) && (unsigned)ly < (unsigned)(4 * TB_Y) && (unsigned)lz < (unsigned)(4 * TB_Z) && gx < phi && gy < phi && gz < phi &&
+              gx >= plo && gy >= plo && gz >= plo;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, tgt);
+      int slot = 0;
+      if (lane == 0 && m) slot = atomicAdd(&s_nt, __popc(m));
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      if (tgt) tl[slot + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
+    }
+    __syncthreads();
+    // ---- 5. walk
+    const int nt = s_nt;
+    const float inv_cut = 1.0f / P.cutoff;
+    for (int t = tid; t < nt; t += TB_NT) {
+      const float4 me = src[tl[t]];
+      const float3 pi = make_float3(me.x, me.y, me.z);
+      const int lx = (int)floorf(me.x) + b - ox, ly = (int)floorf(me.y) + b - oy, lz = (int)floorf(me.z) + b - oz;
+      const int own = (lz * TB_RY + ly) * TB_RX + lx;
+      const int own_s = tab[own], own_e = tab[own + 1];            // the own cell's pairs belong to PPINT (:496-523)
+      float3 acc = make_float3(0.f, 0.f, 0.f);
+      int dy = -pr - 1, dz = -pr, s = 0, e = 0;
+      for (;;) {
+        if (s == own_s) s = own_e;
+        while (s >= e) {                                 // next neighbour row
+          if (++dy > pr) { dy = -pr; ++dz; }
+          if (dz > pr) break;
+          const int rb = own + (dz * TB_RY + dy) * TB_RX;
+          s = tab[rb - pr]; e = tab[rb + pr + 1];
+          if (s == own_s) s = own_e;
+        }
+        if (dz > pr) break;
+        pair_force_fast(pi, src[s], P, inv_cut, acc);
+        ++s;
+      }
+      fm = fmaxf(fm, ppext_apply(reinterpret_cast<float2*>(xv) + 3LL * __float_as_int(me.w), acc, P));
+    }
+  }
+  fm = warp_max(fm);
+  if (lane == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_ext_force_max_bits, fm);
 }
 
 }  // namespace pp

@@ -26,7 +26,7 @@ SYMBOLS = ["cubep3m_b200_version", "cubep3m_b200_strerror", "cubep3m_b200_defaul
            "cubep3m_b200_move_grid_back", "cubep3m_b200_debug_cell_counts", "cubep3m_b200_debug_tile_counts",
            "cubep3m_b200_debug_sorted_particles", "cubep3m_b200_debug_kern_f", "cubep3m_b200_debug_kern_c",
            "cubep3m_b200_debug_rho_c", "cubep3m_b200_debug_force_c", "cubep3m_b200_debug_fine_tile",
-           "cubep3m_b200_debug_fft3d", "cubep3m_b200_launch_count", "cubep3m_b200_set_profiling", "cubep3m_b200_set_tile_streams",
+           "cubep3m_b200_debug_fft3d", "cubep3m_b200_debug_ppext_blocks", "cubep3m_b200_launch_count", "cubep3m_b200_set_profiling", "cubep3m_b200_set_tile_streams",
            "cubep3m_b200_num_kernel_classes", "cubep3m_b200_kernel_class_name", "cubep3m_b200_get_kernel_times",
            "cubep3m_b200_cic_power", "cubep3m_b200_clock_init",
            "cubep3m_b200_expansion", "cubep3m_b200_timestep"]
@@ -196,6 +196,12 @@ class ParticleMesh:
         a = np.empty(self.cfg.tiles_node, np.int32)
         _chk(self.lib.cubep3m_b200_debug_tile_counts(self.h, a))
         return a
+
+    def ppext_blocks(self):
+        """(target blocks of the tiled PP_EXT kernel, blocks that fell back to the direct walk) of the last particle_mesh call."""
+        nb, nf = C.c_int32(), C.c_int32()
+        _chk(self.lib.cubep3m_b200_debug_ppext_blocks(self.h, C.byref(nb), C.byref(nf)))
+        return nb.value, nf.value
 
     def sorted_particles(self):
         n = C.c_int32()

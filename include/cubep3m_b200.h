@@ -171,6 +171,9 @@ int cubep3m_b200_debug_force_c(cubep3m_b200_ctx* ctx, float* force_c);
 int cubep3m_b200_debug_fine_tile(cubep3m_b200_ctx* ctx, int32_t tile, float mass_p, float* rho_f, float* force_f);
 /* in-place 3-D r2c / c2r of a (n+2,n,n) padded array with the library's own FFT (parity vs. the FFTW call sites) */
 int cubep3m_b200_debug_fft3d(cubep3m_b200_ctx* ctx, int32_t n, float* data, int32_t inverse);
+/* PP_EXT of the last particle_mesh call (particle_mesh_threaded.f90:378-624): target blocks launched by the tiled shared-memory kernel and
+ * how many of them exceeded the shared-memory source capacity and were walked through the global cell table instead */
+int cubep3m_b200_debug_ppext_blocks(cubep3m_b200_ctx* ctx, int32_t* blocks, int32_t* fallback);
 /* number of kernels this context launched so far (bench.py's gpu_launches) */
 int64_t cubep3m_b200_launch_count(cubep3m_b200_ctx* ctx);
 /* Per-kernel-class device time of the last particle_mesh call: when profiling is on every launch is bracketed by

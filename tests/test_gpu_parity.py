@@ -195,6 +195,73 @@ def test_full_step_pp_ext_clustered(built):
     assert np.array_equal(pm_tile_counts_safe(cfg, g), g["tile_counts"])
 
 
+def test_pp_ext_tiled_lcdm(built, ics112):
+    """PP_EXT through the tiled shared-memory kernel (pp::ppext_tiled_kernel) on the near-lattice LCDM input (the regime of the benchmark
+    boxes: ~1/8 particle per fine cell, every target walks 25 neighbour rows): 1e-4 rms against the oracle's half-stencil pair loops
+    (particle_mesh_threaded.f90:496-590); no block may fall back to the global-table walk at this density."""
+    cfg = default_config(nf_tile=112, tiles_node_dim=2, pp_ext=1)
+    from cubep3m_b200.lib import ParticleMesh
+    from oracle import Oracle
+    x = ics112.copy()
+    x[:, 3:] = 0
+    pm, o = ParticleMesh(cfg), Oracle(cfg)
+    pm.upload_particles(x); o.set_particles(x)
+    args = (0.5, 0.3, 0.05, 8.0, (1.25, -0.5, 2.0))
+    og, oo = pm.particle_mesh(*args), o.particle_mesh(*args)
+    nb, nf = pm.ppext_blocks()
+    g, r = sort_records(pm.download_particles()), sort_records(o.get_particles())
+    pm.close(); o.close()
+    assert nb == (cfg.nc_node // 4) * (cfg.nc_node // 2) ** 2 and nf == 0, (nb, nf)
+    assert np.array_equal(g[:, :3], r[:, :3])
+    rel = np.sqrt(((g[:, 3:] - r[:, 3:]) ** 2).sum(1)) / np.maximum(np.sqrt((r[:, 3:] ** 2).sum(1)), 1e-30)
+    assert np.sqrt(np.mean(rel ** 2)) < 1e-4, (np.sqrt(np.mean(rel ** 2)), rel.max())
+    assert og.dt_pp_ext_acc == pytest.approx(oo.dt_pp_ext_acc, rel=2e-4)
+    assert og.pp_ext_force_max > 0
+
+
+def _clumpy(cfg, n_bg, n_clump, seed):
+    rng = np.random.default_rng(seed)
+    bg = rng.random((n_bg, 3)).astype(np.float32) * np.float32(cfg.mT)
+    centre = np.array([0.37, 0.52, 0.61], np.float32) * np.float32(cfg.mT)
+    cl = (centre + rng.normal(0, 1.5, (n_clump, 3))).astype(np.float32) % np.float32(cfg.mT)
+    edge = (np.array([0.2, 0.0, 0.999], np.float32) * np.float32(cfg.mT) + rng.normal(0, 1.0, (n_clump // 4, 3))).astype(np.float32) % np.float32(cfg.mT)
+    xv = np.zeros((n_bg + n_clump + n_clump // 4, 6), np.float32)
+    xv[:, :3] = np.concatenate([bg, cl, edge])
+    return xv
+
+
+def test_pp_ext_tiled_capacity_fallback_and_direct_agree(built, monkeypatch):
+    """A clump of 3000 particles inside one block region (> pp::TB_CAP = 2048 sources) plus one straddling the periodic box edge: the
+    over-full blocks must take the direct walk (fallback counter > 0), the others the tiled path, and both must agree with the oracle and
+    with the all-direct kernel (CUBEP3M_B200_PPEXT=direct) to the PP tolerance of 2e-4 rms (close pairs, summation order)."""
+    cfg = default_config(nf_tile=112, tiles_node_dim=2, pp_ext=1)
+    from cubep3m_b200.lib import ParticleMesh
+    from oracle import Oracle
+    xv = _clumpy(cfg, 20000, 3000, 5)
+    args = (0.05, 0.05, 0.05, 8.0, (0.5, -1.5, 2.25))
+    o = Oracle(cfg)
+    o.set_particles(xv)
+    oo = o.particle_mesh(*args)
+    r = sort_records(o.get_particles())
+    o.close()
+    res = {}
+    for mode in ("tiled", "direct"):
+        monkeypatch.setenv("CUBEP3M_B200_PPEXT", mode)
+        pm = ParticleMesh(cfg)
+        pm.upload_particles(xv)
+        og = pm.particle_mesh(*args)
+        res[mode] = (sort_records(pm.download_particles()), og, pm.ppext_blocks())
+        pm.close()
+    nb, nf = res["tiled"][2]
+    assert nb > 0 and 0 < nf < nb, (nb, nf)
+    assert res["direct"][2][0] == 0
+    for mode, (g, og, _) in res.items():
+        assert np.array_equal(g[:, :3], r[:, :3]), mode
+        rel = np.sqrt(((g[:, 3:] - r[:, 3:]) ** 2).sum(1)) / np.maximum(np.sqrt((r[:, 3:] ** 2).sum(1)), 1e-30)
+        assert np.sqrt(np.mean(rel ** 2)) < 2e-4, (mode, np.sqrt(np.mean(rel ** 2)), rel.max())
+        assert og.dt_pp_ext_acc == pytest.approx(oo.dt_pp_ext_acc, rel=1e-3), mode
+
+
 def pm_tile_counts_safe(cfg, g):
     from cubep3m_b200.lib import ParticleMesh
     pm = ParticleMesh(cfg)

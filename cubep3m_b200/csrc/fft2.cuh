@@ -265,6 +265,65 @@ FFTK_HD void stageB(const float2* __restrict__ buf, const float2* __restrict__ t
   pradix_emit<R1, INV>(v, emit);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Contiguous-axis (x) c2r with lanes along the SEQUENCE: the half-spectrum rows arrive row-contiguous (bulk copies), so running the lanes
+// of a warp along k makes every shared-memory access of the transform contiguous and removes the separate "tangle" pass (and its two
+// barriers) of the column-major kernels: stage A reads A[k], B[k] of the two real rows packed into one complex column straight from the
+// staged rows, forms x[idx] = A + iB (idx <= N/2) or conj(A) + i conj(B) (idx > N/2) in registers, and stores its radix-16 results to a
+// column-major work buffer Y; stage B reads Y and hands its results to the caller (global stores), so Y is never written twice.
+//   thread (c, j) of stage A: j in [0, R1), elements idx = j + r*R1, r = 0..15; k = idx (r < 8, or r = 8 and j = 0) else N - idx
+//   Y[c][pos(i)], pos(i) = i + (i >> 4): stage A stores y[16 j + r] at 17 j + r, stage B loads y[j + 16 r] at j + 17 r — both run the
+//   lanes along j with a stride of 17 (A) or 1 (B) float2, conflict-free; the column pitch 17*R1 == R1 (mod 16) keeps consecutive
+//   threads on consecutive 8-byte bank slots across a column change.
+template <int N> struct XRow {
+  using P = Plan2<N>;
+  static_assert(P::R0 == 16, "XRow needs N = 16 * R1");
+  static constexpr int R1 = P::R1;
+  static constexpr int HC = N / 2 + 1;
+  static constexpr int RP = (HC + 1) / 2 * 2;      // staged row length (float2): even, so that a row is a multiple of 16 bytes
+  static constexpr int YP = 17 * R1;               // column pitch of Y (float2)
+  static constexpr int NA = LX * R1, NB = LX * 16;
+  static constexpr int NTW = (R1 - 1) * 16;        // transposed twiddles twT[(r-1)*16 + j] = exp(-2 pi i r j / N)
+};
+
+template <int N> FFTK_HD void c2r_stageA_load(const float2* __restrict__ rowA, const float2* __restrict__ rowB, int j, float2 (&v)[16]) {
+  constexpr int R1 = XRow<N>::R1;
+  const bool j0 = (j == 0);
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    if (r < 8) {
+      float2 a = rowA[j + r * R1], b = rowB[j + r * R1];
+      if (r == 0 && j0) { a.y = 0.f; b.y = 0.f; }              // imaginary part of the k = 0 bin is dropped (c2r)
+      v[r] = add_irot(a, b);                                     // A + iB
+    } else if (r == 8) {
+      const int k = j0 ? 8 * R1 : 8 * R1 - j;                    // j = 0: the k = N/2 bin itself (imaginary part dropped)
+      const float2 a = rowA[k], b = rowB[k];
+      v[r] = j0 ? make_float2(a.x, b.x) : make_float2(a.x + b.y, b.x - a.y);
+    } else {
+      const int k = (16 - r) * R1 - j;                           // N - idx
+      const float2 a = rowA[k], b = rowB[k];
+      v[r] = make_float2(a.x + b.y, b.x - a.y);                  // conj(A) + i conj(B)
+    }
+  }
+}
+template <int N> FFTK_HD void c2r_stageA_store(float2* __restrict__ ycol, int j, const float2 (&v)[16]) {
+  float2* q = ycol + 17 * j;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) q[r] = v[r];
+}
+template <int N> FFTK_HD void c2r_stageB_load(const float2* __restrict__ ycol, int j, float2 (&u)[XRow<N>::R1]) {
+#pragma unroll
+  for (int r = 0; r < XRow<N>::R1; ++r) u[r] = ycol[j + 17 * r];
+}
+// inverse twiddles + radix R1; output x = j + 16 r goes to emit(r, value)
+template <int N, typename Emit> FFTK_HD void c2r_stageB_finish(float2 (&u)[XRow<N>::R1], const float2* __restrict__ twT, int j, Emit emit) {
+  constexpr int R1 = XRow<N>::R1;
+#pragma unroll
+  for (int r = 1; r < R1; ++r) u[r] = twmul<true>(u[r], twT[(r - 1) * 16 + j]);
+  pradix_emit<R1, true>(u, emit);
+}
+
 constexpr size_t smem_bytes2(int n, int nbuf, int pitch) { return (size_t)nbuf * n * pitch * sizeof(float2) + (size_t)n * sizeof(float2); }
 
 }  // namespace fftk

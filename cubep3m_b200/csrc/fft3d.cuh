@@ -533,6 +533,7 @@ template <int N> int set_smem_attr() {
     CK(cudaFuncSetAttribute(fft_x_r2c_ngp2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes2(N, 1, XP)));
     CK(cudaFuncSetAttribute(fft_x_c2r3_v2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_c2r3_v2(N)));
     CK(cudaFuncSetAttribute(fft_x_c2r3_v3<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2R3<N>::smem));
+    CK(cudaFuncSetAttribute(fft_x_c2r3_v4<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2R4<N>::smem));
   }
   done = true;
   return 0;
@@ -639,6 +640,9 @@ template <int N> int launch_x_c2r_t(cubep3m_b200_ctx* ctx, int kc, const float2*
          lo_z, cnt_z, ny_src, opx, opy, scale, tw, ibs, obs);
   return 0;
 }
+#ifndef FFTK_C2R3_V4
+#define FFTK_C2R3_V4 1   // row-major lanes, tangle fused into stage A, results stored from registers (fft3d2.cuh)
+#endif
 #ifndef FFTK_C2R3_V3
 #define FFTK_C2R3_V3 1
 #endif
@@ -651,6 +655,15 @@ template <int N> int launch_x_c2r3_t(cubep3m_b200_ctx* ctx, int kc, const float2
   const long long nrows = (long long)cnt * cnt;
   if constexpr (Plan2<N>::ok) {
     // bulk-copy (TMA engine) staging needs 16-byte aligned rows of at least RP elements
+    static const bool use_v4 = [] { const char* e = getenv("CUBEP3M_B200_C2R"); return !(e && !strcmp(e, "v3")); }();   // A/B knob
+    if (FFTK_C2R3_V4 && use_v4 && cp % 2 == 0 && cp >= C2R4<N>::X::RP && ((uintptr_t)in & 15) == 0 && ibs % 2 == 0 && 3 * ibs < (1LL << 31) && 3 * obs < (1LL << 31)) {
+      static int occ4 = 0;
+      if (!occ4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, fft_x_c2r3_v4<N>, Plan2<N>::NT, (int)C2R4<N>::smem));
+      const long long nblk = (nrows + 2 * LX - 1) / (2 * LX);
+      LAUNCH(ctx, kc, fft_x_c2r3_v4<N>, dim3((unsigned)std::min<long long>(nblk, (long long)NUM_SMS * std::max(occ4, 1))), dim3(Plan2<N>::NT), (int)C2R4<N>::smem, in, cp, out,
+             lo, cnt, (int)ibs, (int)obs, scale, fmax_bits, tw);
+      return 0;
+    }
     if (FFTK_C2R3_V3 && cp % 2 == 0 && cp >= C2R3<N>::RP && ((uintptr_t)in & 15) == 0 && ibs % 2 == 0 && 3 * ibs < (1LL << 31) && 3 * obs < (1LL << 31)) {
       static int occ3 = 0;
       if (!occ3) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, fft_x_c2r3_v3<N>, Plan2<N>::NT, (int)C2R3<N>::smem));

@@ -611,4 +611,103 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v3(const float2* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------- x pass backward, 3 components, v4
+// As v3 (persistent CTAs, rows fetched by the TMA engine as bulk copies signalled on an mbarrier), but with the lanes of a warp along the
+// SEQUENCE instead of along the 16 columns (fft2.cuh, XRow): the Hermitian tangle happens in the registers of stage A, read straight from
+// the staged rows, and stage B's results go from registers to global memory (each half-warp writes 64 contiguous bytes of one output row).
+// Per item: 2 block barriers and ~5 N shared-memory accesses instead of 5 barriers and ~8 N (v3: tangle -> A -> B in place -> store pass).
+template <int N> struct C2R4 {
+  using X = XRow<N>;
+  static constexpr size_t smem = (size_t)2 * LX * X::RP * sizeof(float2) + (size_t)LX * X::YP * sizeof(float2) + (size_t)X::NTW * sizeof(float2) + 2 * 2 * LX * sizeof(int) + 16;
+};
+
+template <int N>
+__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v4(const float2* __restrict__ in, int cp, float* __restrict__ out, int lo, int cnt, int in_bstride,
+                                                                 int out_bstride, float scale, unsigned int* __restrict__ fmax_bits,
+                                                                 const float2* __restrict__ tw_g) {
+  using P = Plan2<N>;
+  using X = XRow<N>;
+  constexpr int NT2 = P::NT, R1 = X::R1, RP = X::RP, YP = X::YP;
+  extern __shared__ __align__(16) unsigned char raw[];
+  float2* Rw = reinterpret_cast<float2*>(raw);
+  float2* Y = Rw + 2 * LX * RP;
+  float2* twT = Y + LX * YP;
+  int* drow = reinterpret_cast<int*>(twT + X::NTW);  // [2][32]
+  const unsigned bar = smem_u32(drow + 2 * 2 * LX);  // 8-byte aligned: every array before it is a multiple of 8 bytes
+  for (int t = threadIdx.x; t < X::NTW; t += NT2) twT[t] = tw_g[((t >> 4) + 1) * (t & 15)];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cA = threadIdx.x / R1, jA = threadIdx.x - cA * R1;     // stage A: lanes along k
+  const int cB = threadIdx.x >> 4, jB = threadIdx.x & 15;          // stage B: lanes along x
+  const bool actA = threadIdx.x < X::NA, actB = threadIdx.x < X::NB;
+  const unsigned mask = crop_mask<N>(jB, lo, lo + cnt - 1);
+  const int nrows = cnt * cnt, nblk = (nrows + 2 * LX - 1) / (2 * LX);
+  const unsigned sR = smem_u32(Rw);
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  // warp 0: fetch the rows of (blk, comp); for comp 0 also publish the block's output offsets in drow[slot]
+  auto issue = [&](int blk, int comp, int slot) {
+    const int ridx = blk * (2 * LX) + lane;
+    const bool valid = ridx < nrows;
+    const int rr = valid ? ridx : nrows - 1;         // rows beyond the crop re-read the last row; their results are never stored
+    const int zc = rr / cnt, yc = rr - zc * cnt;
+    if (comp == 0) drow[slot * 2 * LX + lane] = valid ? (zc * cnt + yc) * cnt : -1;
+    const float2* src = in + (long long)comp * in_bstride + ((zc + lo) * N + (yc + lo)) * cp;
+    if (lane == 0) mbar_expect_tx(bar, 2 * LX * RP * 8);
+    __syncwarp();
+    bulk_g2s(sR + lane * RP * 8, src, RP * 8, bar);
+  };
+  int blk = blockIdx.x, slot = 0;
+  unsigned parity = 0;
+  if (warp == 0 && blk < nblk) issue(blk, 0, 0);
+  const float2* rowA = Rw + (2 * cA) * RP;
+  float2* ycolA = Y + cA * YP;
+  const float2* ycolB = Y + cB * YP;
+  for (; blk < nblk; blk += gridDim.x, slot ^= 1) {
+    float2 fsq[R1];
+#pragma unroll
+    for (int r = 0; r < R1; ++r) fsq[r] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int comp = 0; comp < 3; ++comp) {
+      mbar_wait(bar, parity);
+      parity ^= 1;
+      if (actA) {
+        float2 v[16];
+        c2r_stageA_load<N>(rowA, rowA + RP, jA, v);
+        PRadix<16, true>::run(v);
+        c2r_stageA_store<N>(ycolA, jA, v);           // Y is free: every stage-B load of the previous item precedes its second barrier
+      }
+      fence_proxy_async();                           // generic reads of Rw are ordered before the async-proxy writes of the next fetch
+      __syncthreads();                               // Rw consumed, Y complete
+      if (warp == 0) {
+        if (comp < 2) issue(blk, comp + 1, slot);
+        else if (blk + (int)gridDim.x < nblk) issue(blk + gridDim.x, 0, slot ^ 1);
+      }
+      float2 u[R1];
+      if (actB) c2r_stageB_load<N>(ycolB, jB, u);
+      __syncthreads();                               // Y is free for the next item
+      if (actB) {
+        const int* dr = drow + slot * 2 * LX;
+        const int dofA = dr[2 * cB], dofB = dr[2 * cB + 1];
+        const unsigned m = dofA >= 0 ? mask : 0u;
+        float* oA = out + (long long)comp * out_bstride + dofA + (jB - lo);
+        float* oB = out + (long long)comp * out_bstride + dofB + (jB - lo);
+        const bool hasB = dofB >= 0;
+        c2r_stageB_finish<N>(u, twT, jB, [&](int r, float2 val) {
+          if (m & (1u << r)) {
+            float2 zz = pmul_s(scale, val);
+            oA[16 * r] = zz.x;                       // real part -> even row, imaginary part -> odd row
+            if (hasB) oB[16 * r] = zz.y; else zz.y = 0.f;
+            fsq[r] = pfma_v(zz, zz, fsq[r]);
+          }
+        });
+      }
+    }
+    float mx = 0.f;
+#pragma unroll
+    for (int r = 0; r < R1; ++r) mx = fmaxf(mx, fmaxf(fsq[r].x, fsq[r].y));   // max |F|^2 (:208-223)
+    mx = warp_max(mx);
+    if (lane == 0 && mx > 0.f) atomic_max_float_nonneg(fmax_bits, mx);
+  }
+}
+
 }  // namespace fftk

@@ -200,7 +200,8 @@ constexpr size_t TB_SMEM = (size_t)TB_CAP * sizeof(float4) + (size_t)(TB_NCELL +
 
 __device__ __forceinline__ void pair_force_fast(const float3 pi, const float4 pj, const PPParams& P, float inv_cut, float3& acc) {
   const float sx = pi.x - pj.x, sy = pi.y - pj.y, sz = pi.z - pj.z;
-  const float r = sqrtf(sx * sx + sy * sy + sz * sz);
+  const float r2 = sx * sx + sy * sy + sz * sz;
+  const float r = r2 * rsqrtf(r2);                 // MUFU.RSQ (2 ulp); r2 = 0 gives NaN, which fails the test below like r = 0 does
   if (r > P.rsoft) {
     const float rb = r * P.pp_bias;
     float w = __fdividef(P.mass_p, rb * rb * rb);
@@ -333,17 +334,30 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
       const int own = (lz * TB_RY + ly) * TB_RX + lx;
       const int own_s = tab[own], own_e = tab[own + 1];            // the own cell's pairs belong to PPINT (:496-523)
       float3 acc = make_float3(0.f, 0.f, 0.f);
-      int dy = -pr - 1, dz = -pr, s = 0, e = 0;
+      // pass 1 (uniform over the rows, no divergence): bit q of `rows` = neighbour row q = (dz+pr)*w + (dy+pr) holds a source outside the own cell
+      const int w = 2 * pr + 1, nrow = w * w, qc = (nrow - 1) >> 1;
+      unsigned rows = 0;
+      {
+        int rb = own - pr * (TB_RY + 1) * TB_RX;
+        for (int qz = 0, q = 0; qz < w; ++qz, rb += (TB_RY - w) * TB_RX)
+          for (int qy = 0; qy < w; ++qy, ++q, rb += TB_RX) {
+            const int n = tab[rb + pr + 1] - tab[rb - pr] - (q == qc ? own_e - own_s : 0);
+            rows |= (n > 0 ? 1u : 0u) << q;
+          }
+      }
+      // pass 2: one pair per iteration; a lane whose row is exhausted takes its next non-empty row (a single predicated block, never a loop)
+      int s = 0, e = 0;
       for (;;) {
         if (s == own_s) s = own_e;
-        while (s >= e) {                                 // next neighbour row
-          if (++dy > pr) { dy = -pr; ++dz; }
-          if (dz > pr) break;
-          const int rb = own + (dz * TB_RY + dy) * TB_RX;
+        if (s >= e) {
+          if (!rows) break;
+          const int q = __ffs(rows) - 1;
+          rows &= rows - 1;
+          const int qz = (w == 5) ? (q * 52) >> 8 : (w == 3) ? (q * 86) >> 8 : 0, qy = q - qz * w;
+          const int rb = own + ((qz - pr) * TB_RY + (qy - pr)) * TB_RX;
           s = tab[rb - pr]; e = tab[rb + pr + 1];
           if (s == own_s) s = own_e;
         }
-        if (dz > pr) break;
         pair_force_fast(pi, src[s], P, inv_cut, acc);
         ++s;
       }

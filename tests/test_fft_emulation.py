@@ -96,6 +96,63 @@ int main(){
 '''
 
 
+SRC3 = r"""
+#include "fft2.cuh"
+#include <cstdio>
+#include <cmath>
+#include <vector>
+#include <complex>
+using namespace fftk;
+// host emulation of the row-major c2r x pass (fft_x_c2r3_v4): two real rows per complex column, Hermitian tangle fused into stage A
+template<int N> double test() {
+  using X = XRow<N>;
+  constexpr int R1 = X::R1, RP = X::RP, YP = X::YP, HC = X::HC;
+  std::vector<double> real((size_t)2*LX*N);
+  for (int row=0; row<2*LX; ++row) for (int x=0;x<N;++x) real[(size_t)row*N+x] = sin(0.37*x*(row+1)) + 0.25*cos(1.1*x - row) + 0.01*row;
+  std::vector<float2> Rw((size_t)2*LX*RP, make_float2(7.f,7.f)), Y((size_t)LX*YP, make_float2(9.f,9.f)), twT(X::NTW);
+  for (int row=0; row<2*LX; ++row) for (int k=0;k<HC;++k) {
+    std::complex<double> s=0; for (int x=0;x<N;++x){ double a=-2*M_PI*(double)x*k/N; s+=real[(size_t)row*N+x]*std::complex<double>(cos(a),sin(a)); }
+    // garbage in the imaginary parts of the k = 0 and k = N/2 bins must be ignored (c2r semantics)
+    if (k==0 || 2*k==N) s = {s.real(), 123.0};
+    Rw[(size_t)row*RP+k]=make_float2((float)s.real(),(float)s.imag());
+  }
+  for (int r=1;r<R1;++r) for (int j=0;j<16;++j){ double a=-2*M_PI*(double)(r*j)/N; twT[(r-1)*16+j]=make_float2((float)cos(a),(float)sin(a)); }
+  std::vector<float2> regs((size_t)X::NA*16);
+  for (int tid=0; tid<X::NA; ++tid) { int c=tid/R1, j=tid-c*R1; float2 v[16];
+    c2r_stageA_load<N>(Rw.data()+(size_t)(2*c)*RP, Rw.data()+(size_t)(2*c+1)*RP, j, v); PRadix<16,true>::run(v);
+    for (int r=0;r<16;++r) regs[(size_t)tid*16+r]=v[r]; }
+  for (int tid=0; tid<X::NA; ++tid) { int c=tid/R1, j=tid-c*R1; float2 v[16]; for (int r=0;r<16;++r) v[r]=regs[(size_t)tid*16+r];
+    c2r_stageA_store<N>(Y.data()+(size_t)c*YP, j, v); }
+  double maxerr=0, maxv=0;
+  for (int tid=0; tid<X::NB; ++tid) { int c=tid>>4, j=tid&15; float2 u[R1];
+    c2r_stageB_load<N>(Y.data()+(size_t)c*YP, j, u);
+    c2r_stageB_finish<N>(u, twT.data(), j, [&](int r, float2 val){
+      const int x=j+16*r;
+      const double ea=std::abs(val.x/(double)N-real[(size_t)(2*c)*N+x]), eb=std::abs(val.y/(double)N-real[(size_t)(2*c+1)*N+x]);
+      if (ea>maxerr) maxerr=ea; if (eb>maxerr) maxerr=eb; maxv=1.3; }); }
+  printf("N=%d rowmajor c2r rel_err=%.3e\n", N, maxerr/maxv); return maxerr/maxv;
+}
+int main(){
+  double m=0; double e;
+#define T(N) e=test<N>(); if(e>m)m=e;
+  T(32) T(48) T(64) T(80) T(112) T(128) T(176) T(256) T(304)
+  return m < 2e-6 ? 0 : 1;
+}
+"""
+
+
+def test_rowmajor_c2r_core_on_host(tmp_path):
+    """fft2.cuh XRow helpers (c2r along x with lanes along the sequence, tangle fused into stage A) emulated thread by thread."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cu = tmp_path / "t3.cu"
+    cu.write_text(SRC3)
+    exe = tmp_path / "t3"
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-w", "--expt-relaxed-constexpr", "--extended-lambda", "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(root, "cubep3m_b200", "csrc"), "-o", str(exe), str(cu)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    assert r.stdout.count("rel_err") == 9
+
+
 def test_inplace_two_stage_core_on_host(tmp_path):
     """fft2.cuh (packed butterflies, in-place two-stage Stockham) emulated thread by thread on the host."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -139,6 +139,7 @@ struct cubep3m_b200_ctx {
   int tile_streams = 1;       // S > 1: consecutive tiles rotate over S streams / buffer sets (hides launch bubbles, tails, latency)
   cudaStream_t stream_coarse = nullptr;   // coarse-mesh solve runs concurrently with the fine-tile loop
   int ppext_mode = 1;          // 1: tiled shared-memory kernel (pp::ppext_tiled_kernel), 0: direct one-thread-per-target kernel (CUBEP3M_B200_PPEXT=direct)
+  int* ppext_ovf = nullptr;    // ids of the PP_EXT target blocks that exceeded the tiled kernel's shared-memory capacity
   int ppext_blocks = 0, ppext_fallback = 0;   // of the last step (debug getter)
   bool hist_clean = false;     // fcur (the fine-cell histogram) is all zeros
   cudaStream_t stream_main = nullptr, stream_aux[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused

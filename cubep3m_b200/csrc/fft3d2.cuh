@@ -616,9 +616,19 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v3(const float2* _
 // SEQUENCE instead of along the 16 columns (fft2.cuh, XRow): the Hermitian tangle happens in the registers of stage A, read straight from
 // the staged rows, and stage B's results go from registers to global memory (each half-warp writes 64 contiguous bytes of one output row).
 // Per item: 2 block barriers and ~5 N shared-memory accesses instead of 5 barriers and ~8 N (v3: tangle -> A -> B in place -> store pass).
+// |F|^2 of a point needs its three components, which are three consecutive items: each stage-B thread accumulates them for its own R1 x 2
+// outputs. Holding all of them in registers (38 for R1 = 19, next to the 38 of the radix-19 butterfly) spilled 264 bytes per thread and made
+// every accumulation a local-memory round trip (ncu: long-scoreboard 37 %); only the first FSR stay in registers, the rest live in shared
+// memory as fs[(r - FSR) * NB + tid] (each thread touches only its own entries: no synchronisation).
+#ifndef FFTK_C2R4_FSR
+#define FFTK_C2R4_FSR 6
+#endif
 template <int N> struct C2R4 {
   using X = XRow<N>;
-  static constexpr size_t smem = (size_t)2 * LX * X::RP * sizeof(float2) + (size_t)LX * X::YP * sizeof(float2) + (size_t)X::NTW * sizeof(float2) + 2 * 2 * LX * sizeof(int) + 16;
+  static constexpr int FSR = X::R1 < FFTK_C2R4_FSR ? X::R1 : FFTK_C2R4_FSR;
+  static constexpr int FSS = X::R1 - FSR;            // accumulators per thread kept in shared memory
+  static constexpr size_t smem = (size_t)2 * LX * X::RP * sizeof(float2) + (size_t)LX * X::YP * sizeof(float2) + (size_t)X::NTW * sizeof(float2) +
+                                 (size_t)FSS * X::NB * sizeof(float2) + 2 * 2 * LX * sizeof(int) + 16;
 };
 
 template <int N>
@@ -632,7 +642,9 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v4(const float2* _
   float2* Rw = reinterpret_cast<float2*>(raw);
   float2* Y = Rw + 2 * LX * RP;
   float2* twT = Y + LX * YP;
-  int* drow = reinterpret_cast<int*>(twT + X::NTW);  // [2][32]
+  constexpr int FSR = C2R4<N>::FSR, FSS = C2R4<N>::FSS;
+  float2* fs = twT + X::NTW;                         // [FSS][NB]
+  int* drow = reinterpret_cast<int*>(fs + FSS * X::NB);  // [2][32]
   const unsigned bar = smem_u32(drow + 2 * 2 * LX);  // 8-byte aligned: every array before it is a multiple of 8 bytes
   for (int t = threadIdx.x; t < X::NTW; t += NT2) twT[t] = tw_g[((t >> 4) + 1) * (t & 15)];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -662,10 +674,15 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v4(const float2* _
   const float2* rowA = Rw + (2 * cA) * RP;
   float2* ycolA = Y + cA * YP;
   const float2* ycolB = Y + cB * YP;
+  float2* fsme = fs + threadIdx.x;
   for (; blk < nblk; blk += gridDim.x, slot ^= 1) {
-    float2 fsq[R1];
+    float2 fsq[FSR > 0 ? FSR : 1];
 #pragma unroll
-    for (int r = 0; r < R1; ++r) fsq[r] = make_float2(0.f, 0.f);
+    for (int r = 0; r < FSR; ++r) fsq[r] = make_float2(0.f, 0.f);
+    if (actB) {
+#pragma unroll
+      for (int r = 0; r < FSS; ++r) fsme[r * X::NB] = make_float2(0.f, 0.f);
+    }
 #pragma unroll 1
     for (int comp = 0; comp < 3; ++comp) {
       mbar_wait(bar, parity);
@@ -697,14 +714,19 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v4(const float2* _
             float2 zz = pmul_s(scale, val);
             oA[16 * r] = zz.x;                       // real part -> even row, imaginary part -> odd row
             if (hasB) oB[16 * r] = zz.y; else zz.y = 0.f;
-            fsq[r] = pfma_v(zz, zz, fsq[r]);
+            if (r < FSR) fsq[r < FSR ? r : 0] = pfma_v(zz, zz, fsq[r < FSR ? r : 0]);
+            else fsme[(r - FSR) * X::NB] = pfma_v(zz, zz, fsme[(r - FSR) * X::NB]);
           }
         });
       }
     }
     float mx = 0.f;
 #pragma unroll
-    for (int r = 0; r < R1; ++r) mx = fmaxf(mx, fmaxf(fsq[r].x, fsq[r].y));   // max |F|^2 (:208-223)
+    for (int r = 0; r < FSR; ++r) mx = fmaxf(mx, fmaxf(fsq[r].x, fsq[r].y));   // max |F|^2 (:208-223)
+    if (actB) {
+#pragma unroll
+      for (int r = 0; r < FSS; ++r) { const float2 q = fsme[r * X::NB]; mx = fmaxf(mx, fmaxf(q.x, q.y)); }
+    }
     mx = warp_max(mx);
     if (lane == 0 && mx > 0.f) atomic_max_float_nonneg(fmax_bits, mx);
   }

@@ -631,7 +631,9 @@ int do_pp_ext(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
       const int nbx = (nc + pp::TB_X - 1) / pp::TB_X, nby = (nc + pp::TB_Y - 1) / pp::TB_Y, nbz = (nc + pp::TB_Z - 1) / pp::TB_Z;
       ctx->ppext_blocks = nbx * nby * nbz;
       LAUNCH(ctx, KC_PPEXT, pp::ppext_tiled_kernel, ctx->ppext_blocks, pp::TB_NT, pp::TB_SMEM, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->d.b, ctx->d.nc_buf, nc, nbx, nby,
-             ctx->cfg.pp_range, P, ctx->dcnt, &ctx->dcnt->n_ppext_fallback);
+             ctx->cfg.pp_range, P, ctx->dcnt, &ctx->dcnt->n_ppext_fallback, ctx->ppext_ovf);
+      LAUNCH(ctx, KC_PPEXT, pp::ppext_blocklist_kernel, std::min(ctx->ppext_blocks, NUM_SMS * 8), pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->d.b, ctx->d.nc_buf, nc,
+             nbx, nby, ctx->cfg.pp_range, P, ctx->dcnt, &ctx->dcnt->n_ppext_fallback, ctx->ppext_ovf);
     } else if (ctx->np_all > 0) {
       LAUNCH(ctx, KC_PPEXT, pp::ppext_kernel, (ctx->np_all + pp::EXT_TPB - 1) / pp::EXT_TPB, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->np_all, ctx->d.H,
              ctx->d.b, ctx->d.nc_buf, ctx->d.nc_node, ctx->cfg.pp_range, P, ctx->dcnt);
@@ -768,7 +770,7 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->stream_coarse) cudaStreamDestroy(ctx->stream_coarse);
-  F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->creal); F(ctx->gather); F(ctx->force_c); F(ctx->redbuf); F(ctx->cntbuf); F(ctx->dcnt);
+  F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->creal); F(ctx->gather); F(ctx->force_c); F(ctx->redbuf); F(ctx->cntbuf); F(ctx->dcnt); F(ctx->ppext_ovf);
   for (int a = 0; a < 3; ++a) { bool dup = false; for (int b2 = 0; b2 < a; ++b2) dup |= (ctx->tw_c[b2] == ctx->tw_c[a]); if (!dup) F(ctx->tw_c[a]); }
   if (ctx->hcnt) cudaFreeHost(ctx->hcnt);
   if (ctx->ev_ok) for (auto& e : ctx->ev) cudaEventDestroy(e);
@@ -817,6 +819,10 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   TRY(dmalloc(&ctx->blocksum, (size_t)ctx->nblocksum + 1));
   ctx->list_cap = d.max_np / 2 + 1024;
   if (cfg->ppint) TRY(dmalloc(&ctx->multi_list, (size_t)ctx->list_cap));
+  if (cfg->pp_ext) {
+    const int nc = ctx->d.nc_node;
+    TRY(dmalloc(&ctx->ppext_ovf, (size_t)((nc + pp::TB_X - 1) / pp::TB_X) * ((nc + pp::TB_Y - 1) / pp::TB_Y) * ((nc + pp::TB_Z - 1) / pp::TB_Z)));
+  }
   const size_t rowoff_n = (size_t)d.nc_node * d.nc_node + 16 + d.tiles_node;
   TRY(dmalloc(&ctx->rowoff, rowoff_n));
   if (cudaMemset(ctx->rowoff, 0, rowoff_n * sizeof(int)) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }

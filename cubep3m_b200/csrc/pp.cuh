@@ -186,14 +186,16 @@ __global__ void __launch_bounds__(EXT_TPB) ppext_kernel(float* __restrict__ xv, 
 //   3. fill  : second read of the same ranges (L1/L2 hits), positions + global index scattered to their sorted place as float4
 //   4. list  : warp-ballot compaction of the targets (sources whose cell is inside the block and physical), in cell order
 //   5. walk  : one thread per target; (2 pr + 1)^2 rows, two shared-memory table reads per row, pair loop over float4 sources
-// A block whose region holds more than TB_CAP particles (density contrast > ~5 over the region) falls back to the direct walk for its
-// targets: there the per-cell ranges are long, neighbouring lanes share them, and the direct kernel is efficient.
+// A block whose region holds more than TB_CAP particles (density contrast > ~3 over the region) is appended to an overflow list and walked
+// by ppext_blocklist_kernel through the global table: there the per-cell ranges are long, neighbouring lanes share them, and the direct
+// walk is efficient. Keeping that path out of this kernel also keeps its register count (and so its occupancy) low.
 // The pair weight uses the fast reciprocal (MUFU.RCP, 2 ulp) instead of two IEEE divisions: |error| ~ 3e-7 relative, far inside the 1e-4 gate.
 constexpr int TB_X = 4, TB_Y = 2, TB_Z = 2, TB_HALO = EXT_MAXR;
 constexpr int TB_RX = 4 * TB_X + 2 * TB_HALO, TB_RY = 4 * TB_Y + 2 * TB_HALO, TB_RZ = 4 * TB_Z + 2 * TB_HALO;   // 20 x 12 x 12 fine cells
 constexpr int TB_NCELL = TB_RX * TB_RY * TB_RZ;
 constexpr int TB_NT = 128;
-constexpr int TB_CAP = 2048;                    // source particles per block held in shared memory
+constexpr int TB_CAP = 1024;                    // source particles per block held in shared memory (mean: 360 at 1/8 particle per fine cell);
+                                                // 30 KB per CTA -> 7 CTAs (28 warps) per SM: the walk is latency-bound, occupancy is what it needs
 constexpr int TB_NROW = (TB_Y + 2) * (TB_Z + 2);   // coarse x-rows read per block
 constexpr int TB_CHUNK = (TB_NCELL + TB_NT - 1) / TB_NT;
 constexpr size_t TB_SMEM = (size_t)TB_CAP * sizeof(float4) + (size_t)(TB_NCELL + 1) * sizeof(int) + (size_t)TB_CAP * sizeof(unsigned short);
@@ -214,7 +216,7 @@ __device__ __forceinline__ void pair_force_fast(const float3 pi, const float4 pj
 }
 
 __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ xv, const int* __restrict__ fstart, int H, int b, int nc_buf, int nc_node, int nbx,
-                                                            int nby, int pr, PPParams P, DevCounters* __restrict__ cnt, int* __restrict__ n_fallback) {
+                                                            int nby, int pr, PPParams P, DevCounters* __restrict__ cnt, int* __restrict__ n_fallback, int* __restrict__ ovf_list) {
   extern __shared__ __align__(16) unsigned char raw[];
   float4* src = reinterpret_cast<float4*>(raw);
   int* tab = reinterpret_cast<int*>(src + TB_CAP);                       // [TB_NCELL + 1]: counts -> starts
@@ -283,21 +285,7 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
   float fm = 0.f;
   const int plo = 4 * nc_buf, phi = 4 * phys_hi;
   if (total > TB_CAP) {
-    // ---- fallback: direct walk for the block's physical targets (TB_Y x TB_Z coarse x-rows, contiguous ranges)
-    if (tid == 0) atomicAdd(n_fallback, 1);
-    for (int rr = 0; rr < TB_Y * TB_Z; ++rr) {
-      const int cy = cy0 + rr % TB_Y, cz = cz0 + rr / TB_Y;
-      if (cy >= phys_hi || cz >= phys_hi) continue;
-      const long long rk = (long long)(cz * H + cy) * H;
-      const int g0 = fstart[(rk + cx0) * 64], g1 = fstart[(rk + min(cx0 + TB_X, phys_hi) - 1) * 64 + 64];
-      for (int i = g0 + tid; i < g1; i += TB_NT) {
-        float2* p = reinterpret_cast<float2*>(xv) + 3LL * i;
-        const float2 a = p[0];
-        const float z = p[1].x;
-        const int gx = (int)floorf(a.x) + b, gy = (int)floorf(a.y) + b, gz = (int)floorf(z) + b;
-        fm = fmaxf(fm, ppext_apply(p, ppext_direct(xv, fstart, H, pr, make_float3(a.x, a.y, z), gx, gy, gz, P), P));
-      }
-    }
+    if (tid == 0) ovf_list[atomicAdd(n_fallback, 1)] = blockIdx.x;     // walked by ppext_blocklist_kernel
   } else {
     // ---- 3. fill
     for (int f = tid; f < nraw; f += TB_NT) {
@@ -366,6 +354,35 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
   }
   fm = warp_max(fm);
   if (lane == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_ext_force_max_bits, fm);
+}
+
+// direct walk for the targets of the blocks the tiled kernel could not hold (same block decode)
+__global__ void __launch_bounds__(TB_NT) ppext_blocklist_kernel(float* __restrict__ xv, const int* __restrict__ fstart, int H, int b, int nc_buf, int nc_node, int nbx,
+                                                                int nby, int pr, PPParams P, DevCounters* __restrict__ cnt, const int* __restrict__ n_list,
+                                                                const int* __restrict__ list) {
+  const int n = *n_list, tid = threadIdx.x;
+  const int phys_hi = nc_buf + nc_node;
+  float fm = 0.f;
+  for (int k = blockIdx.x; k < n; k += gridDim.x) {
+    const int blk = list[k];
+    const int bx = blk % nbx, by = (blk / nbx) % nby, bz = blk / (nbx * nby);
+    const int cx0 = nc_buf + bx * TB_X, cy0 = nc_buf + by * TB_Y, cz0 = nc_buf + bz * TB_Z;
+    for (int rr = 0; rr < TB_Y * TB_Z; ++rr) {      // TB_Y x TB_Z coarse x-rows, each a contiguous range of the sorted array
+      const int cy = cy0 + rr % TB_Y, cz = cz0 + rr / TB_Y;
+      if (cy >= phys_hi || cz >= phys_hi) continue;
+      const long long rk = (long long)(cz * H + cy) * H;
+      const int g0 = fstart[(rk + cx0) * 64], g1 = fstart[(rk + min(cx0 + TB_X, phys_hi) - 1) * 64 + 64];
+      for (int i = g0 + tid; i < g1; i += TB_NT) {
+        float2* p = reinterpret_cast<float2*>(xv) + 3LL * i;
+        const float2 a = p[0];
+        const float z = p[1].x;
+        const int gx = (int)floorf(a.x) + b, gy = (int)floorf(a.y) + b, gz = (int)floorf(z) + b;
+        fm = fmaxf(fm, ppext_apply(p, ppext_direct(xv, fstart, H, pr, make_float3(a.x, a.y, z), gx, gy, gz, P), P));
+      }
+    }
+  }
+  fm = warp_max(fm);
+  if ((tid & 31) == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_ext_force_max_bits, fm);
 }
 
 }  // namespace pp

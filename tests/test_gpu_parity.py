@@ -232,7 +232,7 @@ def _clumpy(cfg, n_bg, n_clump, seed):
 
 
 def test_pp_ext_tiled_capacity_fallback_and_direct_agree(built, monkeypatch):
-    """A clump of 3000 particles inside one block region (> pp::TB_CAP = 2048 sources) plus one straddling the periodic box edge: the
+    """A clump of 3000 particles inside one block region (> pp::TB_CAP = 1024 sources) plus one straddling the periodic box edge: the
     over-full blocks must take the direct walk (fallback counter > 0), the others the tiled path, and both must agree with the oracle and
     with the all-direct kernel (CUBEP3M_B200_PPEXT=direct) to the PP tolerance of 2e-4 rms (close pairs, summation order)."""
     cfg = default_config(nf_tile=112, tiles_node_dim=2, pp_ext=1)

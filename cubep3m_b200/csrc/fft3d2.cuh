@@ -256,7 +256,7 @@ constexpr size_t smem_bytes_sandwich2(int n) { return (size_t)2 * n * LX * sizeo
 constexpr int XP = LX + 1;   // pitch (float2) of the contiguous-axis passes
 
 template <int N>
-__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_r2c_ngp2(float2* __restrict__ data, int cp, const int* __restrict__ fstart, int H, int b, int ox, int oy, int oz,
+__global__ void __launch_bounds__(Plan2<N>::NT, 3) fft_x_r2c_ngp2(float2* __restrict__ data, int cp, const int* __restrict__ fstart, int H, int b, int ox, int oy, int oz,
                                                                   float mass_p, const int2* __restrict__ deltas, const int* __restrict__ ndelta_ptr,
                                                                   int delta_cap, double* __restrict__ sum_phys, const float2* __restrict__ tw_g) {
   using P = Plan2<N>;

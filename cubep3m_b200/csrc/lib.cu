@@ -630,8 +630,12 @@ int do_pp_ext(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
       const int nc = ctx->d.nc_node;
       const int nbx = (nc + pp::TB_X - 1) / pp::TB_X, nby = (nc + pp::TB_Y - 1) / pp::TB_Y, nbz = (nc + pp::TB_Z - 1) / pp::TB_Z;
       ctx->ppext_blocks = nbx * nby * nbz;
-      LAUNCH(ctx, KC_PPEXT, pp::ppext_tiled_kernel, ctx->ppext_blocks, pp::TB_NT, pp::TB_SMEM, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->d.b, ctx->d.nc_buf, nc, nbx, nby,
-             ctx->cfg.pp_range, P, ctx->dcnt, &ctx->dcnt->n_ppext_fallback, ctx->ppext_ovf);
+      if (ctx->cfg.pp_range == 2)
+        LAUNCH(ctx, KC_PPEXT, pp::ppext_tiled_kernel<2>, ctx->ppext_blocks, pp::TB_NT, pp::TB_SMEM, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->d.b, ctx->d.nc_buf, nc, nbx, nby,
+               2, P, ctx->dcnt, &ctx->dcnt->n_ppext_fallback, ctx->ppext_ovf);
+      else
+        LAUNCH(ctx, KC_PPEXT, pp::ppext_tiled_kernel<-1>, ctx->ppext_blocks, pp::TB_NT, pp::TB_SMEM, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->d.b, ctx->d.nc_buf, nc, nbx, nby,
+               ctx->cfg.pp_range, P, ctx->dcnt, &ctx->dcnt->n_ppext_fallback, ctx->ppext_ovf);
       LAUNCH(ctx, KC_PPEXT, pp::ppext_blocklist_kernel, std::min(ctx->ppext_blocks, NUM_SMS * 8), pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->d.b, ctx->d.nc_buf, nc,
              nbx, nby, ctx->cfg.pp_range, P, ctx->dcnt, &ctx->dcnt->n_ppext_fallback, ctx->ppext_ovf);
     } else if (ctx->np_all > 0) {
@@ -843,7 +847,8 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   {
     const char* e = getenv("CUBEP3M_B200_PPEXT");       // "direct": the one-thread-per-target kernel (A/B measurements); default: tiled
     ctx->ppext_mode = (e && !strcmp(e, "direct")) ? 0 : 1;
-    if (cudaFuncSetAttribute(pp::ppext_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp::TB_SMEM) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
+    if (cudaFuncSetAttribute(pp::ppext_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp::TB_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(pp::ppext_tiled_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp::TB_SMEM) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   }
   ctx->stream_main = ctx->stream;
   if (cudaStreamCreateWithFlags(&ctx->stream_coarse, cudaStreamNonBlocking) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }

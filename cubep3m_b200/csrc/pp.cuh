@@ -200,13 +200,23 @@ constexpr int TB_NROW = (TB_Y + 2) * (TB_Z + 2);   // coarse x-rows read per blo
 constexpr int TB_CHUNK = (TB_NCELL + TB_NT - 1) / TB_NT;
 constexpr size_t TB_SMEM = (size_t)TB_CAP * sizeof(float4) + (size_t)(TB_NCELL + 1) * sizeof(int) + (size_t)TB_CAP * sizeof(unsigned short);
 
+__device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// shared-memory loads through 32-bit window addresses computed once (the generic-pointer form made the compiler rebuild the
+// window base from SR_CgaCtaId in front of every access inside the walk: 4-5 issue slots per load)
+__device__ __forceinline__ int lds_i32(unsigned a) { int v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ float4 lds_f4(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ void pair_force_fast(const float3 pi, const float4 pj, const PPParams& P, float inv_cut, float3& acc) {
   const float sx = pi.x - pj.x, sy = pi.y - pj.y, sz = pi.z - pj.z;
   const float r2 = sx * sx + sy * sy + sz * sz;
-  const float r = r2 * rsqrtf(r2);                 // MUFU.RSQ (2 ulp); r2 = 0 gives NaN, which fails the test below like r = 0 does
+  const float r = r2 * rsqrt_ftz(r2);              // one MUFU.RSQ (2 ulp); r2 = 0 gives NaN, which fails the test below like r = 0 does
   if (r > P.rsoft) {
     const float rb = r * P.pp_bias;
-    float w = __fdividef(P.mass_p, rb * rb * rb);
+    float w = P.mass_p * rcp_ftz(rb * rb * rb);    // one MUFU.RCP (1 ulp); rb^3 > rsoft^3 is far from the denormal range
     if (!(r > P.cutoff + 1.7320508f)) {
       const float u = rb * inv_cut, u2 = u * u, u3 = u2 * u;
       w *= (1.0f - 1.75f * u3 + 0.75f * u3 * u2);
@@ -215,14 +225,20 @@ __device__ __forceinline__ void pair_force_fast(const float3 pi, const float4 pj
   }
 }
 
+// PRT: compile-time pp_range (2 = cubepm.par:92, every loop of the walk unrolls and the row decode folds to constants) or -1 = run-time pr_rt
+template <int PRT>
 __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ xv, const int* __restrict__ fstart, int H, int b, int nc_buf, int nc_node, int nbx,
-                                                            int nby, int pr, PPParams P, DevCounters* __restrict__ cnt, int* __restrict__ n_fallback, int* __restrict__ ovf_list) {
+                                                            int nby, int pr_rt, PPParams P, DevCounters* __restrict__ cnt, int* __restrict__ n_fallback, int* __restrict__ ovf_list) {
   extern __shared__ __align__(16) unsigned char raw[];
   float4* src = reinterpret_cast<float4*>(raw);
   int* tab = reinterpret_cast<int*>(src + TB_CAP);                       // [TB_NCELL + 1]: counts -> starts
   unsigned short* tl = reinterpret_cast<unsigned short*>(tab + TB_NCELL + 1);
   __shared__ int row_g0[TB_NROW], row_pre[TB_NROW + 1], wsum[TB_NT / 32], s_nt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pr = PRT >= 0 ? PRT : pr_rt;
+  unsigned a_src = (unsigned)__cvta_generic_to_shared(src), a_tab = (unsigned)__cvta_generic_to_shared(tab);
+  asm volatile("mov.u32 %0, %0;" : "+r"(a_src));   // opaque copies: otherwise the window base (SR_CgaCtaId arithmetic, 4 issue slots) is
+  asm volatile("mov.u32 %0, %0;" : "+r"(a_tab));   // rematerialised in front of every shared-memory access of the walk
   const int bx = blockIdx.x % nbx, by = (blockIdx.x / nbx) % nby, bz = blockIdx.x / (nbx * nby);
   const int cx0 = nc_buf + bx * TB_X, cy0 = nc_buf + by * TB_Y, cz0 = nc_buf + bz * TB_Z;      // first coarse cell of the block (hoc-range coordinates)
   const int phys_hi = nc_buf + nc_node;                                                        // first non-physical coarse cell
@@ -320,12 +336,23 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
       const float3 pi = make_float3(me.x, me.y, me.z);
       const int lx = (int)floorf(me.x) + b - ox, ly = (int)floorf(me.y) + b - oy, lz = (int)floorf(me.z) + b - oz;
       const int own = (lz * TB_RY + ly) * TB_RX + lx;
-      const int own_s = tab[own], own_e = tab[own + 1];            // the own cell's pairs belong to PPINT (:496-523)
+      const unsigned a_own = a_tab + 4u * (unsigned)own;          // address of tab[own]
+      const int own_s = lds_i32(a_own), own_e = lds_i32(a_own + 4);   // the own cell's pairs belong to PPINT (:496-523)
       float3 acc = make_float3(0.f, 0.f, 0.f);
       // pass 1 (uniform over the rows, no divergence): bit q of `rows` = neighbour row q = (dz+pr)*w + (dy+pr) holds a source outside the own cell
-      const int w = 2 * pr + 1, nrow = w * w, qc = (nrow - 1) >> 1;
+      const int w = 2 * pr + 1, qc = (w * w - 1) >> 1;
       unsigned rows = 0;
-      {
+      if constexpr (PRT >= 0) {
+#pragma unroll
+        for (int qz = 0; qz < 2 * PRT + 1; ++qz)
+#pragma unroll
+          for (int qy = 0; qy < 2 * PRT + 1; ++qy) {
+            constexpr int W = 2 * PRT + 1;
+            const int q = qz * W + qy, off = 4 * (((qz - PRT) * TB_RY + (qy - PRT)) * TB_RX);
+            const int n = lds_i32(a_own + off + 4 * (PRT + 1)) - lds_i32(a_own + off - 4 * PRT) - (q == (W * W - 1) / 2 ? own_e - own_s : 0);
+            rows |= (n > 0 ? 1u : 0u) << q;
+          }
+      } else {
         int rb = own - pr * (TB_RY + 1) * TB_RX;
         for (int qz = 0, q = 0; qz < w; ++qz, rb += (TB_RY - w) * TB_RX)
           for (int qy = 0; qy < w; ++qy, ++q, rb += TB_RX) {
@@ -342,11 +369,11 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
           const int q = __ffs(rows) - 1;
           rows &= rows - 1;
           const int qz = (w == 5) ? (q * 52) >> 8 : (w == 3) ? (q * 86) >> 8 : 0, qy = q - qz * w;
-          const int rb = own + ((qz - pr) * TB_RY + (qy - pr)) * TB_RX;
-          s = tab[rb - pr]; e = tab[rb + pr + 1];
+          const unsigned a_rb = a_own + 4 * (((qz - pr) * TB_RY + (qy - pr)) * TB_RX);
+          s = lds_i32(a_rb - 4 * pr); e = lds_i32(a_rb + 4 * (pr + 1));
           if (s == own_s) s = own_e;
         }
-        pair_force_fast(pi, src[s], P, inv_cut, acc);
+        pair_force_fast(pi, lds_f4(a_src + 16u * (unsigned)s), P, inv_cut, acc);
         ++s;
       }
       fm = fmaxf(fm, ppext_apply(reinterpret_cast<float2*>(xv) + 3LL * __float_as_int(me.w), acc, P));

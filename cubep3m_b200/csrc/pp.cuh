@@ -181,10 +181,11 @@ __global__ void __launch_bounds__(EXT_TPB) ppext_kernel(float* __restrict__ xv, 
 // block's source particles are RE-SORTED IN SHARED MEMORY by the dense region cell index (z,y,x) with x running over the whole region
 // width: every neighbour row of a target is then exactly ONE contiguous range between two adjacent-table entries, both in shared memory.
 //   1. count : the (TB_Y+2) x (TB_Z+2) coarse x-rows that cover the region are contiguous ranges of the sorted particle array
-//              (key = (cz*H+cy)*H+cx major): coalesced reads, shared-memory histogram over the region's fine cells
+//              (key = (cz*H+cy)*H+cx major): one warp per row, lanes along the range, shared-memory histogram over the region's fine cells
 //   2. scan  : exclusive scan of the histogram (one chunk per thread, warp shuffles)
 //   3. fill  : second read of the same ranges (L1/L2 hits), positions + global index scattered to their sorted place as float4
-//   4. list  : warp-ballot compaction of the targets (sources whose cell is inside the block and physical), in cell order
+//   4. list  : the targets (particles of the block's own physical cells) are one contiguous range of the re-sorted array per interior
+//              (z,y) row: a 64-entry row table built by one warp replaces a per-particle list
 //   5. walk  : one thread per target; (2 pr + 1)^2 rows, two shared-memory table reads per row, pair loop over float4 sources
 // A block whose region holds more than TB_CAP particles (density contrast > ~3 over the region) is appended to an overflow list and walked
 // by ppext_blocklist_kernel through the global table: there the per-cell ranges are long, neighbouring lanes share them, and the direct
@@ -198,7 +199,10 @@ constexpr int TB_CAP = 1024;                    // source particles per block he
                                                 // 30 KB per CTA -> 7 CTAs (28 warps) per SM: the walk is latency-bound, occupancy is what it needs
 constexpr int TB_NROW = (TB_Y + 2) * (TB_Z + 2);   // coarse x-rows read per block
 constexpr int TB_CHUNK = (TB_NCELL + TB_NT - 1) / TB_NT;
-constexpr size_t TB_SMEM = (size_t)TB_CAP * sizeof(float4) + (size_t)(TB_NCELL + 1) * sizeof(int) + (size_t)TB_CAP * sizeof(unsigned short);
+constexpr int TB_TAB = (TB_NCELL + 1 + 3) / 4 * 4;   // table entries, padded for 16-byte zeroing
+constexpr int TB_NTROW = 16 * TB_Y * TB_Z;           // interior (z,y) fine rows of a block
+static_assert(TB_NTROW == 64 && TB_NROW == 16 && TB_NT == 128, "the row tables assume 64 target rows (2 per lane of one warp) and 4 warps");
+constexpr size_t TB_SMEM = (size_t)TB_CAP * sizeof(float4) + (size_t)TB_TAB * sizeof(int);
 
 __device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -231,9 +235,8 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
                                                             int nby, int pr_rt, PPParams P, DevCounters* __restrict__ cnt, int* __restrict__ n_fallback, int* __restrict__ ovf_list) {
   extern __shared__ __align__(16) unsigned char raw[];
   float4* src = reinterpret_cast<float4*>(raw);
-  int* tab = reinterpret_cast<int*>(src + TB_CAP);                       // [TB_NCELL + 1]: counts -> starts
-  unsigned short* tl = reinterpret_cast<unsigned short*>(tab + TB_NCELL + 1);
-  __shared__ int row_g0[TB_NROW], row_pre[TB_NROW + 1], wsum[TB_NT / 32], s_nt;
+  int* tab = reinterpret_cast<int*>(src + TB_CAP);                       // [TB_NCELL + 1] (padded to TB_TAB): counts -> starts
+  __shared__ int wsum[TB_NT / 32], trow_pre[TB_NTROW + 1], trow_s[TB_NTROW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pr = PRT >= 0 ? PRT : pr_rt;
   unsigned a_src = (unsigned)__cvta_generic_to_shared(src), a_tab = (unsigned)__cvta_generic_to_shared(tab);
@@ -243,42 +246,30 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
   const int cx0 = nc_buf + bx * TB_X, cy0 = nc_buf + by * TB_Y, cz0 = nc_buf + bz * TB_Z;      // first coarse cell of the block (hoc-range coordinates)
   const int phys_hi = nc_buf + nc_node;                                                        // first non-physical coarse cell
   const int ox = 4 * cx0 - TB_HALO, oy = 4 * cy0 - TB_HALO, oz = 4 * cz0 - TB_HALO;            // fine cell (0,0,0) of the region
-  for (int t = tid; t <= TB_NCELL; t += TB_NT) tab[t] = 0;
-  if (tid < TB_NROW) {
-    const int cy = min(cy0 - 1 + tid % (TB_Y + 2), H - 1), cz = min(cz0 - 1 + tid / (TB_Y + 2), H - 1);
-    const int ca = cx0 - 1, cb = min(cx0 + TB_X, H - 1);
-    const long long rk = (long long)(cz * H + cy) * H;
-    // a row clamped at the upper edge of the hoc range repeats its neighbour: give it an empty range
-    const bool dup = (cy0 - 1 + tid % (TB_Y + 2) > H - 1) || (cz0 - 1 + tid / (TB_Y + 2) > H - 1);
-    const int g0 = fstart[(rk + ca) * 64], g1 = dup ? g0 : fstart[(rk + cb) * 64 + 64];
-    row_g0[tid] = g0;
-    row_pre[tid + 1] = g1 - g0;
-  }
-  if (tid == 0) { row_pre[0] = 0; s_nt = 0; }
+  for (int t = tid; t < TB_TAB / 4; t += TB_NT) reinterpret_cast<int4*>(tab)[t] = make_int4(0, 0, 0, 0);
   __syncthreads();
-  if (tid == 0) for (int r = 0; r < TB_NROW; ++r) row_pre[r + 1] += row_pre[r];
-  __syncthreads();
-  const int nraw = row_pre[TB_NROW];
   const float2* xv2 = reinterpret_cast<const float2*>(xv);
-  // region cell of the record f of the flattened row ranges (or -1), and its global index
-  auto locate = [&](int f, int& gi, float3& q) -> int {
-    int r = 0;
-#pragma unroll
-    for (int s = TB_NROW / 2; s >= 1; s >>= 1) if (r + s < TB_NROW && row_pre[r + s] <= f) r += s;   // TB_NROW = 16: binary search
-    gi = row_g0[r] + (f - row_pre[r]);
-    const float2* p = xv2 + 3LL * gi;
-    const float2 a = p[0];
-    q = make_float3(a.x, a.y, p[1].x);
-    const int lx = (int)floorf(q.x) + b - ox, ly = (int)floorf(q.y) + b - oy, lz = (int)floorf(q.z) + b - oz;
-    if ((unsigned)lx >= (unsigned)TB_RX || (unsigned)ly >= (unsigned)TB_RY || (unsigned)lz >= (unsigned)TB_RZ) return -1;
-    return (lz * TB_RY + ly) * TB_RX + lx;
+  // The region is covered by TB_NROW coarse x-rows, each ONE contiguous range of the sorted array: warp w walks rows w, w + 4, ... with its
+  // lanes along the range. visit(cell, position, global index) is called for every particle inside the region.
+  auto for_region = [&](auto visit) {
+#pragma unroll 1
+    for (int r = warp; r < TB_NROW; r += TB_NT / 32) {
+      const int cy = cy0 - 1 + r % (TB_Y + 2), cz = cz0 - 1 + r / (TB_Y + 2);
+      if (cy > H - 1 || cz > H - 1) continue;
+      const long long rk = (long long)(cz * H + cy) * H;
+      const int g0 = fstart[(rk + cx0 - 1) * 64], g1 = fstart[(rk + min(cx0 + TB_X, H - 1)) * 64 + 64];
+      for (int gi = g0 + lane; gi < g1; gi += 32) {
+        const float2* p = xv2 + 3LL * gi;
+        const float2 a = p[0];
+        const float z = p[1].x;
+        const int lx = (int)floorf(a.x) + b - ox, ly = (int)floorf(a.y) + b - oy, lz = (int)floorf(z) + b - oz;
+        if ((unsigned)lx < (unsigned)TB_RX && (unsigned)ly < (unsigned)TB_RY && (unsigned)lz < (unsigned)TB_RZ)
+          visit((lz * TB_RY + ly) * TB_RX + lx, a.x, a.y, z, gi);
+      }
+    }
   };
   // ---- 1. count
-  for (int f = tid; f < nraw; f += TB_NT) {
-    int gi; float3 q;
-    const int c = locate(f, gi, q);
-    if (c >= 0) atomicAdd(&tab[c + 1], 1);
-  }
+  for_region([&](int c, float, float, float, int) { atomicAdd(&tab[c + 1], 1); });
   __syncthreads();
   // ---- 2. exclusive scan of tab[1..NCELL] in place: tab[c + 1] = start of cell c (tab[0] = 0 = start of cell 0 after the fill)
   {
@@ -304,35 +295,38 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
     if (tid == 0) ovf_list[atomicAdd(n_fallback, 1)] = blockIdx.x;     // walked by ppext_blocklist_kernel
   } else {
     // ---- 3. fill
-    for (int f = tid; f < nraw; f += TB_NT) {
-      int gi; float3 q;
-      const int c = locate(f, gi, q);
-      if (c >= 0) { const int slot = atomicAdd(&tab[c + 1], 1); src[slot] = make_float4(q.x, q.y, q.z, __int_as_float(gi)); }
-    }
+    for_region([&](int c, float x, float y, float z, int gi) { src[atomicAdd(&tab[c + 1], 1)] = make_float4(x, y, z, __int_as_float(gi)); });
     __syncthreads();                                   // now tab[c] = start of cell c, c = 0..NCELL
-    // ---- 4. target list in cell order (chunks of 32 sorted entries keep their order)
-    for (int base = 0; base < total; base += TB_NT) {
-      const int i = base + tid;
-      bool tgt = false;
-      if (i < total) {
-        const float4 q = src[i];
-        const int gx = (int)floorf(q.x) + b, gy = (int)floorf(q.y) + b, gz = (int)floorf(q.z) + b;
-        const int lx = gx - ox - TB_HALO, ly = gy - oy - TB_HALO, lz = gz - oz - TB_HALO;
-        tgt = (unsigned)lx < (unsigned)(4 * TB_X) && (unsigned)ly < (unsigned)(4 * TB_Y) && (unsigned)lz < (unsigned)(4 * TB_Z) && gx < phi && gy < phi && gz < phi &&
-              gx >= plo && gy >= plo && gz >= plo;
+    // ---- 4. targets = the particles of the block's own physical cells: in every interior (z,y) row they are ONE contiguous range of the
+    //         re-sorted array, so the target list is a 64-entry table (first target, targets before the row), built by warp 0
+    if (warp == 0) {
+      const int xl = max(TB_HALO, plo - ox), xh = min(TB_HALO + 4 * TB_X, phi - ox);
+      int cnt2[2], st2[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = 2 * lane + h, ly = TB_HALO + row % (4 * TB_Y), lz = TB_HALO + row / (4 * TB_Y);
+        const bool live = xh > xl && ly + oy >= plo && ly + oy < phi && lz + oz >= plo && lz + oz < phi;
+        const int rb = (lz * TB_RY + ly) * TB_RX;
+        st2[h] = live ? tab[rb + xl] : 0;
+        cnt2[h] = live ? tab[rb + xh] - st2[h] : 0;
       }
-      const unsigned m = __ballot_sync(0xffffffffu, tgt);
-      int slot = 0;
-      if (lane == 0 && m) slot = atomicAdd(&s_nt, __popc(m));
-      slot = __shfl_sync(0xffffffffu, slot, 0);
-      if (tgt) tl[slot + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
+      const int s2 = cnt2[0] + cnt2[1];
+      int inc = s2;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+      trow_pre[2 * lane] = inc - s2; trow_pre[2 * lane + 1] = inc - s2 + cnt2[0];
+      trow_s[2 * lane] = st2[0]; trow_s[2 * lane + 1] = st2[1];
+      if (lane == 31) trow_pre[TB_NTROW] = inc;
     }
     __syncthreads();
     // ---- 5. walk
-    const int nt = s_nt;
+    const int nt = trow_pre[TB_NTROW];
     const float inv_cut = 1.0f / P.cutoff;
     for (int t = tid; t < nt; t += TB_NT) {
-      const float4 me = src[tl[t]];
+      int r = 0;
+#pragma unroll
+      for (int h = TB_NTROW / 2; h >= 1; h >>= 1) if (trow_pre[r + h] <= t) r += h;       // row of target t (largest r with pre[r] <= t)
+      const float4 me = src[trow_s[r] + (t - trow_pre[r])];
       const float3 pi = make_float3(me.x, me.y, me.z);
       const int lx = (int)floorf(me.x) + b - ox, ly = (int)floorf(me.y) + b - oy, lz = (int)floorf(me.z) + b - oz;
       const int own = (lz * TB_RY + ly) * TB_RX + lx;

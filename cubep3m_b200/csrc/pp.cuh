@@ -248,24 +248,44 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
   const int ox = 4 * cx0 - TB_HALO, oy = 4 * cy0 - TB_HALO, oz = 4 * cz0 - TB_HALO;            // fine cell (0,0,0) of the region
   for (int t = tid; t < TB_TAB / 4; t += TB_NT) reinterpret_cast<int4*>(tab)[t] = make_int4(0, 0, 0, 0);
   __syncthreads();
-  const float2* xv2 = reinterpret_cast<const float2*>(xv);
-  // The region is covered by TB_NROW coarse x-rows, each ONE contiguous range of the sorted array: warp w walks rows w, w + 4, ... with its
-  // lanes along the range. visit(cell, position, global index) is called for every particle inside the region.
-  auto for_region = [&](auto visit) {
-#pragma unroll 1
-    for (int r = warp; r < TB_NROW; r += TB_NT / 32) {
+  // The region is covered by TB_NROW coarse x-rows, each ONE contiguous range of the sorted array. Warp w owns rows w, w + 4, w + 8, w + 12:
+  // their four ranges are looked up first (8 independent loads), then walked as one flattened range with the lanes along it, two records per
+  // iteration with both loads issued before either is used. visit(cell, x, y, z, global index) is called for every particle inside the region.
+  int rd[4], ro[5];                                   // rd[q] = g0[q] - ro[q]: global index = flattened index + rd[row]
+  {
+    int g0[4], len[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = warp + (TB_NT / 32) * q;
       const int cy = cy0 - 1 + r % (TB_Y + 2), cz = cz0 - 1 + r / (TB_Y + 2);
-      if (cy > H - 1 || cz > H - 1) continue;
-      const long long rk = (long long)(cz * H + cy) * H;
-      const int g0 = fstart[(rk + cx0 - 1) * 64], g1 = fstart[(rk + min(cx0 + TB_X, H - 1)) * 64 + 64];
-      for (int gi = g0 + lane; gi < g1; gi += 32) {
-        const float2* p = xv2 + 3LL * gi;
-        const float2 a = p[0];
-        const float z = p[1].x;
-        const int lx = (int)floorf(a.x) + b - ox, ly = (int)floorf(a.y) + b - oy, lz = (int)floorf(z) + b - oz;
-        if ((unsigned)lx < (unsigned)TB_RX && (unsigned)ly < (unsigned)TB_RY && (unsigned)lz < (unsigned)TB_RZ)
-          visit((lz * TB_RY + ly) * TB_RX + lx, a.x, a.y, z, gi);
-      }
+      const bool ok = cy <= H - 1 && cz <= H - 1;
+      const long long rk = (long long)(min(cz, H - 1) * H + min(cy, H - 1)) * H;
+      g0[q] = fstart[(rk + cx0 - 1) * 64];
+      len[q] = ok ? fstart[(rk + min(cx0 + TB_X, H - 1)) * 64 + 64] - g0[q] : 0;
+    }
+    ro[0] = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { ro[q + 1] = ro[q] + len[q]; rd[q] = g0[q] - ro[q]; }
+  }
+  const float2* xv2 = reinterpret_cast<const float2*>(xv);
+  auto for_region = [&](auto visit) {
+    const int n = ro[4];
+    auto gidx = [&](int f) { return f + (f < ro[1] ? rd[0] : f < ro[2] ? rd[1] : f < ro[3] ? rd[2] : rd[3]); };
+    auto one = [&](float2 a, float z, int gi) {
+      const int lx = (int)floorf(a.x) + b - ox, ly = (int)floorf(a.y) + b - oy, lz = (int)floorf(z) + b - oz;
+      if ((unsigned)lx < (unsigned)TB_RX && (unsigned)ly < (unsigned)TB_RY && (unsigned)lz < (unsigned)TB_RZ)
+        visit((lz * TB_RY + ly) * TB_RX + lx, a.x, a.y, z, gi);
+    };
+#pragma unroll 1
+    for (int f = lane; f < n; f += 64) {
+      const bool two = f + 32 < n;
+      const int ga = gidx(f), gb = two ? gidx(f + 32) : ga;
+      const float2* pa = xv2 + 3LL * ga;
+      const float2* pb = xv2 + 3LL * gb;
+      const float2 a = pa[0], c = pb[0];
+      const float za = pa[1].x, zc = pb[1].x;
+      one(a, za, ga);
+      if (two) one(c, zc, gb);
     }
   };
   // ---- 1. count

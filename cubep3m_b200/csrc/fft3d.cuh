@@ -583,10 +583,10 @@ template <int N> int launch_strided_t(cubep3m_b200_ctx* ctx, int kc, bool inv, c
     const long long total2 = (long long)((hc + LX - 1) / LX) * nouter * nbatch;
     auto grid2 = [&](int o) { return dim3((unsigned)std::min<long long>(total2, (long long)NUM_SMS * std::max(o, 1))); };
     const dim3 blk(Plan2<N>::NT);
-    // 32-bit element offsets inside the kernel: the largest offset touched must stay below 2^31
+    // 32-bit element offsets (loads) and 32-bit BYTE offsets (stage-B stores) inside the kernel: the largest offset touched must stay below 2^29 elements
     const long long span = (long long)(nbatch - 1) * bstride + (long long)(outer0 + nouter) * ostride + (long long)N * estride + hc;
     const long long kspan = kern ? (long long)(outer0 + nouter) * kos + (long long)N * kes + hc : 0;
-    if (span >= (1LL << 31) || kspan >= (1LL << 31) || total2 >= (1LL << 31)) return CUBEP3M_B200_EINVAL;
+    if (span >= (1LL << 29) || kspan >= (1LL << 31) || total2 >= (1LL << 31)) return CUBEP3M_B200_EINVAL;
     const int es = (int)estride, os = (int)ostride, bs = (int)bstride, ke = (int)kes, ko = (int)kos;
     if (!inv && a16) LAUNCH(ctx, kc, (fft_strided2<N, false, false, true>), grid2(occ2[0]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, nullptr, 0, 0, elo, ehi, tw, bs);
     else if (!inv) LAUNCH(ctx, kc, (fft_strided2<N, false, false, false>), grid2(occ2[0]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, nullptr, 0, 0, elo, ehi, tw, bs);
@@ -617,7 +617,7 @@ template <int N> int launch_sandwich_t(cubep3m_b200_ctx* ctx, int kc, const floa
     static int occ2 = 0;
     if (!occ2) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, (fft_z_sandwich2<N, false>), Plan2<N>::NT, sm2));
     const long long total2 = (long long)((hc + LX - 1) / LX) * ny;
-    if (kp % 16 != 0 || 3 * gstride >= (1LL << 31)) return CUBEP3M_B200_EINVAL;
+    if (kp % 16 != 0 || 3 * gstride >= (1LL << 29)) return CUBEP3M_B200_EINVAL;   // stage-B stores use 32-bit byte offsets from g
     const dim3 grd((unsigned)std::min<long long>(total2, (long long)NUM_SMS * std::max(occ2, 1)));
     const bool a16 = cp % 2 == 0 && cp >= (hc + LX - 1) / LX * LX && ((uintptr_t)spec & 15) == 0;
     if (a16) LAUNCH(ctx, kc, (fft_z_sandwich2<N, true>), grd, dim3(Plan2<N>::NT), sm2, spec, g, (int)gstride, hc, cp, ny, kern, kstride, kp, elo, ehi, tw);

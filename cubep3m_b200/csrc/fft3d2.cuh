@@ -136,11 +136,12 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_strided2(const float2* __
     if (threadIdx.x < P::NA) stageA_store<N, LX>(buf, j, col, v);
     __syncthreads();
     if (threadIdx.x < P::NB) {
-      float2* op = out + off + joff;
+      // 32-bit byte offsets from the array base: one IMAD per store instead of a 64-bit address chain rebuilt for every output
+      const unsigned ob = (unsigned)(off + joff) * 8u, stepb = (unsigned)(R0 * estride) * 8u;
+      char* obase = reinterpret_cast<char*>(out);
       const unsigned m = ok ? mask : 0u;
-      const int step = R0 * estride;
       stageB<N, INV, LX>(buf, tw, j, col, [&](int r, float2 val) {
-        if (m & (1u << r)) op[(long long)r * step] = val;
+        if (m & (1u << r)) *reinterpret_cast<float2*>(obase + (ob + (unsigned)r * stepb)) = val;
       });
     }
     item = next; off = noff; koff = nkoff; ok = nok;
@@ -202,7 +203,9 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_z_sandwich2(const float2*
     stage_block<N, NT2, A16>(spec + off, estride, ok, sL, L);
     issueK(0, kb);
   }
-  const int step = R0 * estride;
+  // stage-B stores: 32-bit byte offsets from g (one IMAD per store instead of a 64-bit address chain rebuilt for every output)
+  const unsigned stepb = (unsigned)(R0 * estride) * 8u;
+  char* gbase = reinterpret_cast<char*>(g);
   while (item < total) {
     const int next = item + gridDim.x;
     int noff = 0, nkb = 0;
@@ -229,8 +232,8 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_z_sandwich2(const float2*
       __syncthreads();                              // W complete; K consumed
       issueK(comp + 1, kb);
       if (actB) {
-        float2* go = g + comp * gstride + off + joff;
-        stageB<N, true, LX>(W, tw, j, col, [&](int r, float2 val) { if (m & (1u << r)) go[(long long)r * step] = val; });
+        const unsigned ob = (unsigned)(comp * gstride + off + joff) * 8u;
+        stageB<N, true, LX>(W, tw, j, col, [&](int r, float2 val) { if (m & (1u << r)) *reinterpret_cast<float2*>(gbase + (ob + (unsigned)r * stepb)) = val; });
       }
       cp_async_wait_all();
       __syncthreads();                              // next kern_f block landed; W free
@@ -243,8 +246,8 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_z_sandwich2(const float2*
     if (actA) stageA_store<N, LX>(L, j, col, v);
     __syncthreads();
     if (actB) {
-      float2* go = g + 2 * gstride + off + joff;
-      stageB<N, true, LX>(L, tw, j, col, [&](int r, float2 val) { if (m & (1u << r)) go[(long long)r * step] = val; });
+      const unsigned ob = (unsigned)(2 * gstride + off + joff) * 8u;
+      stageB<N, true, LX>(L, tw, j, col, [&](int r, float2 val) { if (m & (1u << r)) *reinterpret_cast<float2*>(gbase + (ob + (unsigned)r * stepb)) = val; });
     }
     { float2* t = L; L = W; W = t; const unsigned u = sL; sL = sW; sW = u; }
     item = next; off = noff; kb = nkb; ok = nok;

@@ -16,7 +16,7 @@ for m in ("c1","c2"):
     except Exception as e:
         print(m, "failed", e)
 PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"fft_x_c2r3_v4|fft_x_r2c_ngp2" -s 6 -c 2 -o gpurun_out/${T}_fine python bench.py --steps 1 --no-cpu --no-profile > gpurun_out/${T}_ncu1.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"fft_z_sandwich2|fft_strided2" -s 8 -c 3 -o gpurun_out/${T}_fine python bench.py --steps 1 --no-cpu --no-profile > gpurun_out/${T}_ncu1.log 2>&1
 ncu -i gpurun_out/${T}_fine.ncu-rep --page raw --csv > gpurun_out/${T}_fine_raw.csv 2>/dev/null
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ppext_tiled -c 1 -o gpurun_out/${T}_ppext python bench.py --workload c0x --steps 1 --no-cpu --no-profile > gpurun_out/${T}_ncu2.log 2>&1
 ncu -i gpurun_out/${T}_ppext.ncu-rep --page raw --csv > gpurun_out/${T}_ppext_raw.csv 2>/dev/null

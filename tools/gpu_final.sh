@@ -9,6 +9,9 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/$
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${T}_launches_c1.csv python bench.py --steps 1 --no-cpu --no-profile > gpurun_out/${T}_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fft_x_r2c_ngp2|fft_strided2<304|fft_z_sandwich2|fft_x_c2r3_v4|ngp_kick_kernel" -s 12 -c 6 -o gpurun_out/${T}_fine python bench.py --steps 1 --no-cpu --no-profile > gpurun_out/${T}_ncu_fine.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ppext|ppint" -c 3 -o gpurun_out/${T}_pp python bench.py --workload c0x --steps 1 --no-cpu --no-profile > gpurun_out/${T}_ncu_pp.log 2>&1
+timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_run.py > gpurun_out/${T}_sanitizer_memcheck.txt 2>&1
+timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_run.py > gpurun_out/${T}_sanitizer_racecheck.txt 2>&1
+tail -n 2 gpurun_out/${T}_sanitizer_memcheck.txt gpurun_out/${T}_sanitizer_racecheck.txt
 python - <<PY
 import json
 for m in ("c1","c2","c1_reference"):

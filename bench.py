@@ -354,7 +354,7 @@ def run_ours(args):
             "config": {"workload": desc, "particles_per_gpu": int(npart), "particles_with_ghosts": int(np_all),
                        "timing": "host clock around K steps between barrier+synchronize, max over ranks (CUDA-event sum in device_ms_per_step); working set (particles 0.4 GB + cell table 1.4 GB) exceeds the 126 MB L2",
                        "ics": f"Zel'dovich LCDM (EH no-wiggle), z_i={z_i}, box={box} Mpc/h per node, numpy seed 12345 (same box on every rank), generated in {t_ic:.1f}s",
-                       "rank_grid": list(grid), "parallelism": f"{world} rank(s), one cubic node of {cfg.tiles_node} tiles per GPU; NCCL send/recv particle_pass, all-gathered replicated coarse solve",
+                       "rank_grid": list(grid), "parallelism": f"{world} rank(s), one cubic node of {cfg.tiles_node} tiles per GPU; particle_pass packed straight into the neighbour's memory over NVLink (NCCL send/recv fallback), all-gathered replicated coarse solve",
                        "mode": "resident (particles stay in HBM between steps)"},
             "device_ms_per_step": dev_step,
             "e2e": {"value": total_particles / (e2e_ms * 1e-3), "unit": "particles/s", "ms_per_step": e2e_ms,

@@ -220,6 +220,28 @@ def test_pp_ext_tiled_lcdm(built, ics112):
     assert og.pp_ext_force_max > 0 and og.dt_pp_ext_acc >= oo.dt_pp_ext_acc * (1 - 2e-4)
 
 
+def test_pp_ext_range_one(built, ics112):
+    """pp_range = 1 (the run-time-range instantiation pp::ppext_tiled_kernel<-1>, 3x3 neighbour rows; the zeroed near field of the fine
+    kernel shrinks with it, kernel_initialization.f90:38-54): 1e-4 rms against the oracle."""
+    cfg = default_config(nf_tile=112, tiles_node_dim=2, pp_ext=1, pp_range=1)
+    from cubep3m_b200.lib import ParticleMesh
+    from oracle import Oracle
+    x = ics112.copy()
+    x[:, 3:] = 0
+    pm, o = ParticleMesh(cfg), Oracle(cfg)
+    pm.upload_particles(x); o.set_particles(x)
+    args = (0.5, 0.3, 0.05, 8.0, (-2.25, 1.5, 0.75))
+    og, oo = pm.particle_mesh(*args), o.particle_mesh(*args)
+    nb, nf = pm.ppext_blocks()
+    g, r = sort_records(pm.download_particles()), sort_records(o.get_particles())
+    pm.close(); o.close()
+    assert nb > 0 and nf == 0
+    assert np.array_equal(g[:, :3], r[:, :3])
+    rel = np.sqrt(((g[:, 3:] - r[:, 3:]) ** 2).sum(1)) / np.maximum(np.sqrt((r[:, 3:] ** 2).sum(1)), 1e-30)
+    assert np.sqrt(np.mean(rel ** 2)) < 1e-4, (np.sqrt(np.mean(rel ** 2)), rel.max())
+    assert og.pp_ext_force_max > 0
+
+
 def _clumpy(cfg, n_bg, n_clump, seed):
     rng = np.random.default_rng(seed)
     bg = rng.random((n_bg, 3)).astype(np.float32) * np.float32(cfg.mT)

@@ -338,3 +338,37 @@ def test_size_independent_properties_full_config(built):
     a, b = sort_records(outs[0][1][:, :3].copy()), sort_records(outs[1][1][:, :3].copy())
     assert np.array_equal(a, b)
     assert outs[0][0].dt_f_acc == outs[1][0].dt_f_acc
+
+
+def test_pp_ext_momentum_and_mode_agreement_bench_box(built, monkeypatch):
+    """PP_EXT at a benchmark-box size (BASELINE configs[0] box: 128^3 particles on a 256^3 mesh, PPINT + PP_EXT, the `c0x` workload of bench.py),
+    needing no oracle: every force of the step is pairwise antisymmetric (NGP/NGP fine mesh, CIC/CIC coarse mesh, PP pairs — each pair evaluated
+    twice, once per partner, possibly in different CTAs or through the periodic ghost image), so from zeroed velocities the total momentum after the
+    step must vanish to fp32 rounding; and the tiled PP_EXT kernel must reproduce the direct kernel."""
+    from cubep3m_b200.lib import ParticleMesh
+    xv = ic.zeldovich_ics(256, box=200.0, z_i=100.0, seed=12345)
+    xv[:, 3:] = 0
+    # cluster a little so that PPINT and PP_EXT have work at all separations
+    rng = np.random.default_rng(3)
+    sel = rng.choice(len(xv), 200000, replace=False)
+    xv[sel, :3] = (xv[sel, :3] + rng.normal(0, 0.6, (len(sel), 3)).astype(np.float32)) % np.float32(256.0)
+    args = (0.3, 0.0, 0.0101, 8.0, (2.5, -7.0, 0.625))
+    res = {}
+    for mode in ("tiled", "direct"):
+        monkeypatch.setenv("CUBEP3M_B200_PPEXT", mode)
+        cfg = default_config(nf_tile=176, tiles_node_dim=2, pp_ext=1)
+        pm = ParticleMesh(cfg)
+        pm.upload_particles(xv)
+        out = pm.particle_mesh(*args)
+        res[mode] = (sort_records(pm.download_particles()), out, pm.ppext_blocks())
+        pm.close()
+    assert res["tiled"][2][0] == (64 // 4) * (64 // 2) ** 2 and res["direct"][2][0] == 0
+    g, d = res["tiled"][0], res["direct"][0]
+    assert len(g) == len(xv) and np.array_equal(g[:, :3], d[:, :3])
+    v = g[:, 3:].astype(np.float64)
+    assert (np.abs(v.sum(0)) < 1e-4 * np.abs(v).sum(0)).all(), (v.sum(0), np.abs(v).sum(0))
+    assert res["tiled"][1].pp_ext_force_max > 0 and res["tiled"][1].pp_force_max > 0
+    num = np.sqrt(((g[:, 3:] - d[:, 3:]) ** 2).sum(1))
+    den = np.maximum(np.sqrt((d[:, 3:] ** 2).sum(1)), 1e-30)
+    assert np.sqrt(np.mean((num / den) ** 2)) < 2e-5
+    assert res["tiled"][1].dt_pp_ext_acc == pytest.approx(res["direct"][1].dt_pp_ext_acc, rel=1e-5)

@@ -283,6 +283,8 @@ template <int N> struct XRow {
   static constexpr int HC = N / 2 + 1;
   static constexpr int RP = (HC + 1) / 2 * 2;      // staged row length (float2): even, so that a row is a multiple of 16 bytes
   static constexpr int YP = 17 * R1;               // column pitch of Y (float2)
+  template <int CW> static constexpr int NA_ = CW * R1;      // threads with a stage-A / stage-B butterfly for CW columns per item
+  template <int CW> static constexpr int NB_ = CW * 16;
   static constexpr int NA = LX * R1, NB = LX * 16;
   static constexpr int NTW = (R1 - 1) * 16;        // transposed twiddles twT[(r-1)*16 + j] = exp(-2 pi i r j / N)
 };

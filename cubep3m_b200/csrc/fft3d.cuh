@@ -658,9 +658,9 @@ template <int N> int launch_x_c2r3_t(cubep3m_b200_ctx* ctx, int kc, const float2
     static const bool use_v4 = [] { const char* e = getenv("CUBEP3M_B200_C2R"); return !(e && !strcmp(e, "v3")); }();   // A/B knob
     if (FFTK_C2R3_V4 && use_v4 && cp % 2 == 0 && cp >= C2R4<N>::X::RP && ((uintptr_t)in & 15) == 0 && ibs % 2 == 0 && 3 * ibs < (1LL << 31) && 3 * obs < (1LL << 31)) {
       static int occ4 = 0;
-      if (!occ4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, fft_x_c2r3_v4<N>, Plan2<N>::NT, (int)C2R4<N>::smem));
-      const long long nblk = (nrows + 2 * LX - 1) / (2 * LX);
-      LAUNCH(ctx, kc, fft_x_c2r3_v4<N>, dim3((unsigned)std::min<long long>(nblk, (long long)NUM_SMS * std::max(occ4, 1))), dim3(Plan2<N>::NT), (int)C2R4<N>::smem, in, cp, out,
+      if (!occ4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, fft_x_c2r3_v4<N>, C2R4<N>::NT, (int)C2R4<N>::smem));
+      const long long nblk = (nrows + 2 * C2R4<N>::CW - 1) / (2 * C2R4<N>::CW);
+      LAUNCH(ctx, kc, fft_x_c2r3_v4<N>, dim3((unsigned)std::min<long long>(nblk, (long long)NUM_SMS * std::max(occ4, 1))), dim3(C2R4<N>::NT), (int)C2R4<N>::smem, in, cp, out,
              lo, cnt, (int)ibs, (int)obs, scale, fmax_bits, tw);
       return 0;
     }

@@ -626,50 +626,63 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v3(const float2* _
 #ifndef FFTK_C2R4_FSR
 #define FFTK_C2R4_FSR 6
 #endif
+// CW = complex columns (pairs of real rows) per item. 16 columns per 320-thread CTA left a 13 % tail at n = 304 (2097 row blocks over
+// 296 persistent CTAs: 8 vs 7.08 blocks per CTA) and two CTAs per SM at the same phase boundaries; with 8 columns an item costs half, the CTAs are
+// 160 threads and four fit an SM (same warps, same registers, 55 KB of shared memory each).
+#ifndef FFTK_C2R4_CW
+#define FFTK_C2R4_CW 8
+#endif
 template <int N> struct C2R4 {
   using X = XRow<N>;
+  static constexpr int CW = FFTK_C2R4_CW;
+  static constexpr int NA = CW * X::R1, NB = CW * 16;
+  static constexpr int NT = ((NA > NB ? NA : NB) + 31) / 32 * 32;
+  static constexpr int CPS = (N == 304 && CW == 8) ? 4 : 2;     // CTAs per SM the launch bounds ask for
   static constexpr int FSR = X::R1 < FFTK_C2R4_FSR ? X::R1 : FFTK_C2R4_FSR;
   static constexpr int FSS = X::R1 - FSR;            // accumulators per thread kept in shared memory
-  static constexpr size_t smem = (size_t)2 * LX * X::RP * sizeof(float2) + (size_t)LX * X::YP * sizeof(float2) + (size_t)X::NTW * sizeof(float2) +
-                                 (size_t)FSS * X::NB * sizeof(float2) + 2 * 2 * LX * sizeof(int) + 16;
+  static constexpr size_t smem = (size_t)2 * CW * X::RP * sizeof(float2) + (size_t)CW * X::YP * sizeof(float2) + (size_t)X::NTW * sizeof(float2) +
+                                 (size_t)FSS * NB * sizeof(float2) + 2 * 2 * CW * sizeof(int) + 16;
 };
 
 template <int N>
-__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v4(const float2* __restrict__ in, int cp, float* __restrict__ out, int lo, int cnt, int in_bstride,
-                                                                 int out_bstride, float scale, unsigned int* __restrict__ fmax_bits,
-                                                                 const float2* __restrict__ tw_g) {
-  using P = Plan2<N>;
+__global__ void __launch_bounds__(C2R4<N>::NT, C2R4<N>::CPS) fft_x_c2r3_v4(const float2* __restrict__ in, int cp, float* __restrict__ out, int lo, int cnt, int in_bstride,
+                                                                        int out_bstride, float scale, unsigned int* __restrict__ fmax_bits,
+                                                                        const float2* __restrict__ tw_g) {
   using X = XRow<N>;
-  constexpr int NT2 = P::NT, R1 = X::R1, RP = X::RP, YP = X::YP;
+  using C = C2R4<N>;
+  constexpr int NT2 = C::NT, R1 = X::R1, RP = X::RP, YP = X::YP, CW = C::CW, NR = 2 * CW;
+  static_assert(NR <= 32, "one warp issues the row copies of an item");
   extern __shared__ __align__(16) unsigned char raw[];
   float2* Rw = reinterpret_cast<float2*>(raw);
-  float2* Y = Rw + 2 * LX * RP;
-  float2* twT = Y + LX * YP;
-  constexpr int FSR = C2R4<N>::FSR, FSS = C2R4<N>::FSS;
+  float2* Y = Rw + NR * RP;
+  float2* twT = Y + CW * YP;
+  constexpr int FSR = C::FSR, FSS = C::FSS;
   float2* fs = twT + X::NTW;                         // [FSS][NB]
-  int* drow = reinterpret_cast<int*>(fs + FSS * X::NB);  // [2][32]
-  const unsigned bar = smem_u32(drow + 2 * 2 * LX);  // 8-byte aligned: every array before it is a multiple of 8 bytes
+  int* drow = reinterpret_cast<int*>(fs + FSS * C::NB);  // [2][NR]
+  const unsigned bar = smem_u32(drow + 2 * NR);      // 8-byte aligned: every array before it is a multiple of 8 bytes
   for (int t = threadIdx.x; t < X::NTW; t += NT2) twT[t] = tw_g[((t >> 4) + 1) * (t & 15)];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cA = threadIdx.x / R1, jA = threadIdx.x - cA * R1;     // stage A: lanes along k
   const int cB = threadIdx.x >> 4, jB = threadIdx.x & 15;          // stage B: lanes along x
-  const bool actA = threadIdx.x < X::NA, actB = threadIdx.x < X::NB;
+  const bool actA = threadIdx.x < C::NA, actB = threadIdx.x < C::NB;
   const unsigned mask = crop_mask<N>(jB, lo, lo + cnt - 1);
-  const int nrows = cnt * cnt, nblk = (nrows + 2 * LX - 1) / (2 * LX);
+  const int nrows = cnt * cnt, nblk = (nrows + NR - 1) / NR;
   const unsigned sR = smem_u32(Rw);
   if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   __syncthreads();
   // warp 0: fetch the rows of (blk, comp); for comp 0 also publish the block's output offsets in drow[slot]
   auto issue = [&](int blk, int comp, int slot) {
-    const int ridx = blk * (2 * LX) + lane;
-    const bool valid = ridx < nrows;
-    const int rr = valid ? ridx : nrows - 1;         // rows beyond the crop re-read the last row; their results are never stored
-    const int zc = rr / cnt, yc = rr - zc * cnt;
-    if (comp == 0) drow[slot * 2 * LX + lane] = valid ? (zc * cnt + yc) * cnt : -1;
-    const float2* src = in + (long long)comp * in_bstride + ((zc + lo) * N + (yc + lo)) * cp;
-    if (lane == 0) mbar_expect_tx(bar, 2 * LX * RP * 8);
+    if (lane == 0) mbar_expect_tx(bar, NR * RP * 8);
     __syncwarp();
-    bulk_g2s(sR + lane * RP * 8, src, RP * 8, bar);
+    if (lane < NR) {
+      const int ridx = blk * NR + lane;
+      const bool valid = ridx < nrows;
+      const int rr = valid ? ridx : nrows - 1;       // rows beyond the crop re-read the last row; their results are never stored
+      const int zc = rr / cnt, yc = rr - zc * cnt;
+      if (comp == 0) drow[slot * NR + lane] = valid ? (zc * cnt + yc) * cnt : -1;
+      const float2* src = in + (long long)comp * in_bstride + ((zc + lo) * N + (yc + lo)) * cp;
+      bulk_g2s(sR + lane * RP * 8, src, RP * 8, bar);
+    }
   };
   int blk = blockIdx.x, slot = 0;
   unsigned parity = 0;
@@ -684,7 +697,7 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v4(const float2* _
     for (int r = 0; r < FSR; ++r) fsq[r] = make_float2(0.f, 0.f);
     if (actB) {
 #pragma unroll
-      for (int r = 0; r < FSS; ++r) fsme[r * X::NB] = make_float2(0.f, 0.f);
+      for (int r = 0; r < FSS; ++r) fsme[r * C::NB] = make_float2(0.f, 0.f);
     }
 #pragma unroll 1
     for (int comp = 0; comp < 3; ++comp) {
@@ -706,7 +719,7 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v4(const float2* _
       if (actB) c2r_stageB_load<N>(ycolB, jB, u);
       __syncthreads();                               // Y is free for the next item
       if (actB) {
-        const int* dr = drow + slot * 2 * LX;
+        const int* dr = drow + slot * NR;
         const int dofA = dr[2 * cB], dofB = dr[2 * cB + 1];
         const unsigned m = dofA >= 0 ? mask : 0u;
         float* oA = out + (long long)comp * out_bstride + dofA + (jB - lo);
@@ -718,7 +731,7 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v4(const float2* _
             oA[16 * r] = zz.x;                       // real part -> even row, imaginary part -> odd row
             if (hasB) oB[16 * r] = zz.y; else zz.y = 0.f;
             if (r < FSR) fsq[r < FSR ? r : 0] = pfma_v(zz, zz, fsq[r < FSR ? r : 0]);
-            else fsme[(r - FSR) * X::NB] = pfma_v(zz, zz, fsme[(r - FSR) * X::NB]);
+            else fsme[(r - FSR) * C::NB] = pfma_v(zz, zz, fsme[(r - FSR) * C::NB]);
           }
         });
       }
@@ -728,7 +741,7 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_x_c2r3_v4(const float2* _
     for (int r = 0; r < FSR; ++r) mx = fmaxf(mx, fmaxf(fsq[r].x, fsq[r].y));   // max |F|^2 (:208-223)
     if (actB) {
 #pragma unroll
-      for (int r = 0; r < FSS; ++r) { const float2 q = fsme[r * X::NB]; mx = fmaxf(mx, fmaxf(q.x, q.y)); }
+      for (int r = 0; r < FSS; ++r) { const float2 q = fsme[r * C::NB]; mx = fmaxf(mx, fmaxf(q.x, q.y)); }
     }
     mx = warp_max(mx);
     if (lane == 0 && mx > 0.f) atomic_max_float_nonneg(fmax_bits, mx);

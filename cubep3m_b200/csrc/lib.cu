@@ -492,7 +492,7 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
   if (np > 0)
     LAUNCH(ctx, KC_KEY_HIST, part::key_hist_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], np, lo, hi, d.b, d.H, ctx->key, ctx->fcur, ctx->cand, ctx->cand_cap, ctx->dcnt);
   const int nb = (int)((d.NF + part::SCAN_BLOCK - 1) / part::SCAN_BLOCK);
-  LAUNCH(ctx, KC_SCAN, part::scan_reduce_kernel, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum);
+  LAUNCH(ctx, KC_SCAN, part::scan_reduce_kernel, (nb + part::SCAN_RB - 1) / part::SCAN_RB, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum, nb);
   LAUNCH(ctx, KC_SCAN, part::scan_blocksums_kernel, 1, 1024, 0, ctx->blocksum, nb);
   LAUNCH(ctx, KC_SCAN, part::scan_apply_kernel, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->multi_list,
          ctx->occ_list, ctx->list_cap, ctx->cfg.ppint ? 1 : 0, 0, ctx->dcnt);

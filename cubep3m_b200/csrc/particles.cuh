@@ -223,21 +223,37 @@ constexpr int SCAN_ITEMS = 16;                       // ints per thread
 constexpr int SCAN_BLOCK = TPB * SCAN_ITEMS;         // 4096 ints per block
 
 __device__ __forceinline__ int pair_sum(unsigned int w) { return (int)(w & 0xffffu) + (int)(w >> 16); }
-// n (cells) is a multiple of 16: the block's SCAN_BLOCK cells are SCAN_BLOCK/2 words
-__global__ void __launch_bounds__(TPB) scan_reduce_kernel(const unsigned int* __restrict__ hist, long long n, int* __restrict__ blocksum) {
-  const long long base = (long long)blockIdx.x * SCAN_BLOCK;
-  int s = 0;
-  const uint4* h4 = reinterpret_cast<const uint4*>(hist + (base >> 1));
+// n (cells) is a multiple of 16: a scan block's SCAN_BLOCK cells are SCAN_BLOCK/2 words. One CTA reduces SCAN_RB consecutive scan blocks with
+// all of its 2*SCAN_RB 16-byte loads in flight before the first add (two loads per thread left the kernel at half the DRAM bandwidth).
+constexpr int SCAN_RB = 4;
+__global__ void __launch_bounds__(TPB) scan_reduce_kernel(const unsigned int* __restrict__ hist, long long n, int* __restrict__ blocksum, int nb) {
+  const int b0 = blockIdx.x * SCAN_RB;
+  uint4 v[SCAN_RB][SCAN_ITEMS / 8];
 #pragma unroll
-  for (int it = 0; it < SCAN_ITEMS / 8; ++it) {
-    const long long e = base + ((long long)it * TPB + threadIdx.x) * 8;      // first cell of this thread's 4 words
-    if (e + 7 < n) { const uint4 v = h4[it * TPB + threadIdx.x]; s += pair_sum(v.x) + pair_sum(v.y) + pair_sum(v.z) + pair_sum(v.w); }
+  for (int q = 0; q < SCAN_RB; ++q) {
+    const long long base = (long long)(b0 + q) * SCAN_BLOCK;
+    const uint4* h4 = reinterpret_cast<const uint4*>(hist + (base >> 1));
+#pragma unroll
+    for (int it = 0; it < SCAN_ITEMS / 8; ++it) {
+      const long long e = base + ((long long)it * TPB + threadIdx.x) * 8;      // first cell of this thread's 4 words
+      v[q][it] = (b0 + q < nb && e + 7 < n) ? h4[it * TPB + threadIdx.x] : make_uint4(0u, 0u, 0u, 0u);
+    }
   }
-  __shared__ int ws[TPB / 32];
-  s = warp_sum_i(s);
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __shared__ int ws[SCAN_RB][TPB / 32];
+#pragma unroll
+  for (int q = 0; q < SCAN_RB; ++q) {
+    int s = 0;
+#pragma unroll
+    for (int it = 0; it < SCAN_ITEMS / 8; ++it) s += pair_sum(v[q][it].x) + pair_sum(v[q][it].y) + pair_sum(v[q][it].z) + pair_sum(v[q][it].w);
+    s = warp_sum_i(s);
+    if ((threadIdx.x & 31) == 0) ws[q][threadIdx.x >> 5] = s;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < TPB / 32; ++w) t += ws[w]; blocksum[blockIdx.x] = t; }
+  if (threadIdx.x < SCAN_RB && b0 + threadIdx.x < nb) {
+    int t = 0;
+    for (int w = 0; w < TPB / 32; ++w) t += ws[threadIdx.x][w];
+    blocksum[b0 + threadIdx.x] = t;
+  }
 }
 
 // single block: exclusive scan of the block sums in place

@@ -277,7 +277,9 @@ def run_ours(args):
     # ---- timed region B: the same K steps continued with every launch bracketed by CUDA events on its stream -> per-kernel-class
     # durations for the roofline (the instrumentation itself costs ~6 % of a step, which is why `value` comes from region A)
     class_ms, prof_ms = {}, 0.0
+    tile_streams = int(os.environ.get("CUBEP3M_B200_TILE_STREAMS", "2"))
     if not args.no_profile:
+        pm.set_tile_streams(1)         # one fine tile in flight: per-kernel event times are only unambiguous without tile overlap
         pm.set_profiling(True)
         barrier()
         for _ in range(args.steps):
@@ -288,6 +290,7 @@ def run_ours(args):
                 a[0] += ms; a[1] += nl
         barrier()
         pm.set_profiling(False)
+        pm.set_tile_streams(min(tile_streams, cfg.tiles_node))
         prof_ms /= args.steps
     # ---- e2e: strict drop-in mode through the C ABI with host buffers
     host[:npart] = pm.download_particles()
@@ -339,8 +342,9 @@ def run_ours(args):
                     "share_of_step": stages[dom]["share_of_step"], "launches_per_step": stages[dom]["launches_per_step"],
                     "instrumented_ms_per_step": prof_ms,
                     "note": "algorithmic bytes per launch / mean CUDA-event time per launch over K instrumented steps that directly follow the K timed "
-                            "steps (same configuration: one fine tile in flight; the coarse-mesh solve overlaps on its own stream, so a fine-mesh "
-                            "launch's event time can include SM time lent to coarse kernels)"}
+                            "steps (instrumented with ONE fine tile in flight so that a launch's event time is its own; the timed steps keep two tiles "
+                            "in flight; the coarse-mesh solve overlaps on its own stream in both, so a fine-mesh launch's event time can include SM "
+                            "time lent to coarse kernels)"}
         cpu = None
         if world == 1 and not args.no_cpu:
             sec, threads, ost = oracle_run(cfg, xv, z_i, 1, 0)
@@ -355,7 +359,7 @@ def run_ours(args):
                        "timing": "host clock around K steps between barrier+synchronize, max over ranks (CUDA-event sum in device_ms_per_step); working set (particles 0.4 GB + cell table 1.4 GB) exceeds the 126 MB L2",
                        "ics": f"Zel'dovich LCDM (EH no-wiggle), z_i={z_i}, box={box} Mpc/h per node, numpy seed 12345 (same box on every rank), generated in {t_ic:.1f}s",
                        "rank_grid": list(grid), "parallelism": f"{world} rank(s), one cubic node of {cfg.tiles_node} tiles per GPU; particle_pass packed straight into the neighbour's memory over NVLink (NCCL send/recv fallback), all-gathered replicated coarse solve",
-                       "mode": "resident (particles stay in HBM between steps)"},
+                       "mode": "resident (particles stay in HBM between steps)", "fine_tiles_in_flight": min(tile_streams, cfg.tiles_node)},
             "device_ms_per_step": dev_step,
             "e2e": {"value": total_particles / (e2e_ms * 1e-3), "unit": "particles/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(npart) * 24, "d2h_bytes_per_step": int(npart) * 24, "steps": e2e_steps,

@@ -492,10 +492,16 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
   if (np > 0)
     LAUNCH(ctx, KC_KEY_HIST, part::key_hist_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], np, lo, hi, d.b, d.H, ctx->key, ctx->fcur, ctx->cand, ctx->cand_cap, ctx->dcnt);
   const int nb = (int)((d.NF + part::SCAN_BLOCK - 1) / part::SCAN_BLOCK);
-  LAUNCH(ctx, KC_SCAN, part::scan_reduce_kernel, (nb + part::SCAN_RB - 1) / part::SCAN_RB, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum, nb);
-  LAUNCH(ctx, KC_SCAN, part::scan_blocksums_kernel, 1, 1024, 0, ctx->blocksum, nb);
-  LAUNCH(ctx, KC_SCAN, part::scan_apply_kernel, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->multi_list,
-         ctx->occ_list, ctx->list_cap, ctx->cfg.ppint ? 1 : 0, 0, ctx->dcnt);
+  if (ctx->scan_onepass) {
+    CK(cudaMemsetAsync(ctx->scan_status, 0, sizeof(unsigned long long) * ((size_t)nb + 1), ctx->stream));
+    LAUNCH(ctx, KC_SCAN, part::scan_apply_kernel<true>, nb, part::TPB, 0, ctx->fcur, d.NF, nullptr, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->multi_list,
+           ctx->occ_list, ctx->list_cap, ctx->cfg.ppint ? 1 : 0, 0, ctx->dcnt, ctx->scan_status, nb);
+  } else {
+    LAUNCH(ctx, KC_SCAN, part::scan_reduce_kernel, (nb + part::SCAN_RB - 1) / part::SCAN_RB, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum, nb);
+    LAUNCH(ctx, KC_SCAN, part::scan_blocksums_kernel, 1, 1024, 0, ctx->blocksum, nb);
+    LAUNCH(ctx, KC_SCAN, part::scan_apply_kernel<false>, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->multi_list,
+           ctx->occ_list, ctx->list_cap, ctx->cfg.ppint ? 1 : 0, 0, ctx->dcnt, nullptr, nb);
+  }
   if (np > 0)
     LAUNCH(ctx, KC_SCATTER, part::scatter_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->fcur, ctx->fstart,
            ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1]);
@@ -765,7 +771,7 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
 #ifdef CUBEP3M_WITH_NCCL
   if (ctx->comm) ncclCommDestroy(ctx->comm);
 #endif
-  F(ctx->cand); F(ctx->deltas); F(ctx->ndelta); F(ctx->tile_counts); F(ctx->key); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
+  F(ctx->cand); F(ctx->deltas); F(ctx->ndelta); F(ctx->tile_counts); F(ctx->key); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->scan_status); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
   F(ctx->kern_f); F(ctx->tile_rho); F(ctx->tile_g); F(ctx->force_f[0]); 
   for (int q = 1; q < cubep3m_b200_ctx::MAX_TILE_STREAMS; ++q) {
     F(ctx->tile_rho_s[q]); F(ctx->tile_g_s[q]); F(ctx->force_f_s[q]);
@@ -821,6 +827,11 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   TRY(dmalloc(&ctx->fcur, (size_t)d.NF / 2 + 64));
   ctx->nblocksum = (int)((d.NF + part::SCAN_BLOCK - 1) / part::SCAN_BLOCK);
   TRY(dmalloc(&ctx->blocksum, (size_t)ctx->nblocksum + 1));
+  TRY(dmalloc(&ctx->scan_status, (size_t)ctx->nblocksum + 1));
+  {
+    const char* e = getenv("CUBEP3M_B200_SCAN");          // "3pass": reduce / scan of block sums / apply (A/B measurements); default: single pass
+    ctx->scan_onepass = !(e && !strcmp(e, "3pass"));
+  }
   ctx->list_cap = d.max_np / 2 + 1024;
   if (cfg->ppint) TRY(dmalloc(&ctx->multi_list, (size_t)ctx->list_cap));
   if (cfg->pp_ext) {
@@ -838,10 +849,12 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   TRY(dmalloc(&ctx->force_f[0], (size_t)3 * d.fdim * d.fdim * d.fdim));
   ctx->force_f[1] = ctx->force_f[0] + (size_t)d.fdim * d.fdim * d.fdim; ctx->force_f[2] = ctx->force_f[1] + (size_t)d.fdim * d.fdim * d.fdim;
   {
-    // tuning knob. The second-generation FFT kernels are persistent and fill all SMs, so one tile in flight is fastest (measured:
-    // 8.21 ms/step with 1, 8.84 with 2, 8.81 with 3 at 256^3 particles); the first generation gained ~25 % from 2.
+    // tuning knob: fine tiles in flight on separate streams / buffer sets. Two: the second tile's kernels fill the tails of the first tile's
+    // persistent grids (measured at 256^3 particles with the session-5 kernels: 6.16 ms/step with 1, 6.04 with 2; the session-4 kernels, which
+    // were longer and thrashed the L2 with two 113 MB working sets, lost 8 % with 2). Per-kernel timings are only unambiguous with 1, which is
+    // what bench.py switches to for its instrumented region (cubep3m_b200_set_tile_streams).
     const char* e = getenv("CUBEP3M_B200_TILE_STREAMS");
-    ctx->tile_streams_max = e ? std::max(1, std::min(atoi(e), (int)cubep3m_b200_ctx::MAX_TILE_STREAMS)) : 1;
+    ctx->tile_streams_max = e ? std::max(1, std::min(atoi(e), (int)cubep3m_b200_ctx::MAX_TILE_STREAMS)) : 2;
     ctx->tile_streams = ctx->tile_streams_max;
   }
   {

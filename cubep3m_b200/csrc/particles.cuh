@@ -289,11 +289,25 @@ __global__ void __launch_bounds__(1024) scan_blocksums_kernel(int* __restrict__ 
 
 // block scan + offset; writes fstart (exclusive); also emits the PP work lists:
 // physical fine cells (coarse cell in 1..nc_node on all axes) with >= 2 particles (PPINT) / >= 1 (PP_EXT).
+// ONEPASS: single-pass scan with decoupled look-back (one read of the histogram instead of two, one launch instead of three). A CTA takes
+// its tile from an atomic ticket (so every predecessor has started: spinning on them cannot deadlock), publishes its tile's AGGREGATE as soon as
+// the local sums are known, looks back over the predecessors' status words (32 per step, one per lane) until it meets a PREFIX, and publishes
+// its own inclusive PREFIX. status[t] = flag << 32 | value, flag 0 = empty (the array is cleared before the launch), 1 = aggregate, 2 = prefix;
+// status[ntiles] is the ticket counter.
+template <bool ONEPASS>
 __global__ void __launch_bounds__(TPB) scan_apply_kernel(const unsigned int* __restrict__ hist_cur, long long n, const int* __restrict__ blocksum,
                                                          int* __restrict__ fstart, int H, int nc_buf, int nc_node,
                                                          int* __restrict__ multi_list, int* __restrict__ occ_list, int list_cap,
-                                                         int want_multi, int want_occ, DevCounters* __restrict__ cnt) {
-  const long long base = (long long)blockIdx.x * SCAN_BLOCK + (long long)threadIdx.x * SCAN_ITEMS;
+                                                         int want_multi, int want_occ, DevCounters* __restrict__ cnt,
+                                                         unsigned long long* __restrict__ status, int ntiles) {
+  __shared__ int s_tile, s_prefix;
+  int tile = blockIdx.x;
+  if (ONEPASS) {
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(status + ntiles, 1ULL);
+    __syncthreads();
+    tile = s_tile;
+  }
+  const long long base = (long long)tile * SCAN_BLOCK + (long long)threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS];
   int s = 0;
 #pragma unroll
@@ -319,7 +333,38 @@ __global__ void __launch_bounds__(TPB) scan_apply_kernel(const unsigned int* __r
     if (threadIdx.x < TPB / 32) ws[threadIdx.x] = w;
   }
   __syncthreads();
-  int run = blocksum[blockIdx.x] + (x - s) + ((threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0);
+  int tile_prefix;
+  if (ONEPASS) {
+    if (threadIdx.x < 32) {
+      const unsigned lane = threadIdx.x;
+      const unsigned long long total = (unsigned long long)(unsigned)ws[TPB / 32 - 1];
+      volatile unsigned long long* st = status;
+      if (lane == 0) { __threadfence(); st[tile] = ((tile == 0 ? 2ULL : 1ULL) << 32) | total; }
+      int excl = 0;
+      if (tile > 0) {
+        int j0 = tile - 1;                            // lane l inspects tile j0 - l
+        for (;;) {
+          const int j = j0 - (int)lane;
+          unsigned long long w = 2ULL << 32;          // tiles before 0 count as a zero prefix
+          if (j >= 0) { do { w = st[j]; } while ((w >> 32) == 0ULL); }
+          const unsigned pm = __ballot_sync(0xffffffffu, (w >> 32) == 2ULL);   // lanes that found a prefix
+          const int first = pm ? __ffs(pm) - 1 : 32;                             // nearest one
+          int v = (int)lane <= first ? (int)(unsigned)(w & 0xffffffffULL) : 0;  // aggregates up to and including the nearest prefix
+          v = warp_sum_i(v);
+          excl += v;
+          if (pm) break;
+          j0 -= 32;
+        }
+        if (lane == 0) { __threadfence(); st[tile] = (2ULL << 32) | (unsigned long long)(unsigned)(excl + (int)total); }
+      }
+      if (lane == 0) s_prefix = excl;
+    }
+    __syncthreads();
+    tile_prefix = s_prefix;
+  } else {
+    tile_prefix = blocksum[tile];
+  }
+  int run = tile_prefix + (x - s) + ((threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0);
   // the 16 entries of one thread are a quarter of ONE coarse cell (64 fine cells): decode it once
   bool phys = false;
   if (base < n) {

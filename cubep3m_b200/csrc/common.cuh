@@ -115,7 +115,7 @@ struct cubep3m_b200_ctx {
   unsigned int* fcur = nullptr;   // fine-cell histogram, two 16-bit counters per word (NF/2 words); counts itself back to zero in the scatter
   int* blocksum = nullptr;
   unsigned long long* scan_status = nullptr;   // tile status words of the single-pass scan (+ ticket counter)
-  bool scan_onepass = true;
+  bool scan_onepass = false;
   int nblocksum = 0;
   int* multi_list = nullptr;  // keys of physical fine cells with >= 2 particles
   int* occ_list = nullptr;    // keys of occupied physical fine cells

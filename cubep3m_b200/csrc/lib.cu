@@ -829,8 +829,11 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   TRY(dmalloc(&ctx->blocksum, (size_t)ctx->nblocksum + 1));
   TRY(dmalloc(&ctx->scan_status, (size_t)ctx->nblocksum + 1));
   {
-    const char* e = getenv("CUBEP3M_B200_SCAN");          // "3pass": reduce / scan of block sums / apply (A/B measurements); default: single pass
-    ctx->scan_onepass = !(e && !strcmp(e, "3pass"));
+    // "1pass": single-pass scan with decoupled look-back. Measured on B200 it is SLOWER than the three-kernel scan (0.59 vs 0.36 ms over
+    // 175 M cells, 4.0 vs 2.9 ms over 1.2 G cells): with 4096-cell tiles the 43 k-long prefix chain, not the second read of the 16-bit histogram
+    // it saves, sets the pace. Kept as an option (bit-identical results, tests/test_gpu_parity.py::test_scan_variants_agree); default: three kernels.
+    const char* e = getenv("CUBEP3M_B200_SCAN");
+    ctx->scan_onepass = e && !strcmp(e, "1pass");
   }
   ctx->list_cap = d.max_np / 2 + 1024;
   if (cfg->ppint) TRY(dmalloc(&ctx->multi_list, (size_t)ctx->list_cap));

@@ -95,7 +95,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -267,7 +267,6 @@ def run_ours(args):
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     launches = pm.launches - l0
-    clocks = sampler.stop() if sampler else None
     # `ms_per_step` is the host clock around the K steps, bracketed by barrier + cudaDeviceSynchronize on both sides (every step ends with
     # a device->host read of the limiters, so there is no queued work outside the bracket); the sum of the library's own CUDA-event step
     # times is reported beside it as device_ms_per_step (it excludes the host-side timestep logic between steps).
@@ -292,6 +291,8 @@ def run_ours(args):
         pm.set_profiling(False)
         pm.set_tile_streams(min(tile_streams, cfg.tiles_node))
         prof_ms /= args.steps
+    # the clock sampler covers the timed region and the instrumented one (the same steps, back to back, both under load)
+    clocks = sampler.stop() if sampler else None
     # ---- e2e: strict drop-in mode through the C ABI with host buffers
     host[:npart] = pm.download_particles()
     barrier()

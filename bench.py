@@ -4,13 +4,16 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c0|tiny]
 
 A "step" is one pass of the hot path (drift -> cell sort -> particle pass -> per-tile fine mesh -> PP -> coarse mesh
--> ghost deletion) over one synthetic LCDM box.  Workload at N=1 is BASELINE.json configs[1]: 256^3 particles on a
-512^3 fine mesh, PPINT on, nodes_dim=1, tiles_node_dim=2 (nf_tile=304), one B200 (the 64-tile nf_tile=176 variant is `--workload c1a`).
+-> ghost deletion) over one synthetic LCDM box.  Workload at N=1 is BASELINE.json configs[2], the largest single-GPU configuration:
+512^3 particles on a 1024^3 fine mesh, PPINT + PP_EXT, nodes_dim=1, tiles_node_dim=4 (nf_tile=304), one B200; at N>1 every GPU owns one
+such node (configs[4]: weak scaling at 512^3 particles per GPU; N=8 is configs[3]'s 1024^3 particles on a 2048^3 mesh, nodes_dim=2).
+`--workload c1` is configs[1] (256^3 particles, PPINT only), `c0` configs[0].
 `value`  : particles / device-seconds per step with the particles resident in HBM (CUDA events on the library's stream).
 `e2e`    : the same step through the C ABI in strict drop-in mode: pinned-host xv -> H2D, particle_mesh, D2H.
 `roofline`: dominant kernel class, algorithmic bytes per launch / its mean device time (events around every launch).
 `cpu_baseline` / `--impl reference`: the CPU oracle (C++/OpenMP restatement of the reference; the Fortran itself cannot
-be built in this image) timed on this box's host cores.
+be built in this image) timed on this box's host cores, all of them (OMP threads set explicitly: torchrun exports OMP_NUM_THREADS=1).
+Its FFT is a vectorised batched Stockham transform (oracle/fft_ref.h), not FFTW: a stated baseline, not the target.
 """
 import argparse
 import ctypes
@@ -63,12 +66,16 @@ def algorithmic_bytes(cfg, np_local, np_all):
     r = fd / n
     NF = cfg.H ** 3 * 64
     N = cfg.nc_dim
+    ghosts = max(np_all - np_local, 0)
     return {
+        # per-particle figures are SURVEY §8(d)'s: drift 36 B; key + sort 64 B (12 read, 4 key | 24 + 24 permute); pass ~48 B per ghost;
+        # coarse deposit 12 B; compaction 48 B per surviving particle (the coarse kick is fused into it, its 8-point gather hits L2)
         "drift": 36.0 * np_local,                       # 24 B read + 12 B written per particle
-        "key_hist": (12.0 + 4.0 + 8.0) * np_all,        # position read, key write, one 4-byte RMW on the cell table
-        "scan": None,                                    # three kernels of different shape; see stages table
-        "scatter": (4.0 + 24.0 + 24.0 + 8.0) * np_all,   # key, record read, record write, cursor RMW
-        "pass_pack": None, "pass_unpack": None,
+        "key_hist": (12.0 + 4.0) * np_all,              # position read, key written (the cell-table atomics are this design's cost, not the algorithm's)
+        "scan": 2.0 * NF,                               # design-dependent, per launch: 4 launches per step move 8 B per fine cell of the table (2-byte counts read twice, 4-byte starts written)
+        "scatter": (4.0 + 24.0 + 24.0) * np_all,        # key, record read, record written
+        "pass_pack": 36.0 * np_local / 3 + 24.0 * ghosts / 3,   # per launch (3 axes): the fused drift of the first axis + the packed ghosts, averaged
+        "pass_unpack": 48.0 * ghosts / 3,
         "ngp_density": None,                             # tile_counts + delta-list kernels (tiny)
         "fft_x_r2c": 8.0 * (n - 8) ** 3 + A,             # fused NGP deposit: 2 table entries per deposited cell read, half-spectra written
         "fft_fwd_strided": 2.0 * A,                      # y pass in place
@@ -76,13 +83,26 @@ def algorithmic_bytes(cfg, np_local, np_all):
         "fft_inv_y": 3 * (r * A + r * r * A),            # 3 components, cropped planes read, cropped rows written
         "fft_x_c2r": 3 * (r * r * A + 4.0 * fd ** 3),    # 3 components, cropped rows read, force cube written (+ max |F|^2 fused)
         "force_max": None,
-        "ngp_kick": 52.0 * np_local / cfg.tiles_node,   # 24 B record read, 12 B force gather, 16 B velocity written per particle
-        "cic_mass": (12.0 + 8 * 8.0) * np_all * ((cfg.nc_node + 2) / cfg.H) ** 3,
-        "cic_kick": 40.0 * np_local,                    # 24 B record read + 16 B written; the 8-point gather hits the L2-resident force_c
+        "ngp_kick": 48.0 * np_local / cfg.tiles_node,   # §8(d): 12 pos + 12 force gather + 12 + 12 velocity RMW per particle
+        "cic_mass": 12.0 * np_all * ((cfg.nc_node + 2) / cfg.H) ** 3 + 4.0 * cfg.nc_node ** 3,   # §8(d): 12 B per deposited particle (+ rho_c written once)
+        "cic_kick": 48.0 * np_local,                    # fused coarse kick + compaction: 24 B record read + 24 B written
         "compact": None,
-        "coarse_fft": None, "coarse_misc": None, "ppint": None, "ppext": None, "misc": None,
+        "coarse_fft": None, "coarse_misc": None, "coarse_xchg": None, "ppint": None, "ppext": None, "ppext_margin": None, "misc": None,
         "_NF": NF, "_A": A,
     }
+
+
+def fp32_peak():
+    """FFMA peak measured with tools/fp32_peak.cu on this pool's B200 (profiles/r1_fp32_peak.json); nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4."""
+    p = os.path.join(ROOT, "profiles", "r1_fp32_peak.json")
+    try:
+        d = json.load(open(p))
+        for k in ("ffma_tflops", "FFMA", "ffma"):
+            if k in d:
+                return float(d[k]), "measured (profiles/r1_fp32_peak.json)"
+    except Exception:
+        pass
+    return 67.7, "measured in round 1 (tools/fp32_peak.cu, FFMA)"
 
 
 class ClockSampler:
@@ -139,11 +159,20 @@ def make_ics(cfg, box, z_i, seed=12345):
     return xv, time.time() - t
 
 
-def oracle_run(cfg, xv, z_i, steps, warmup, tile_note=""):
-    """Times the CPU oracle (all host threads) on full particle_mesh steps of the given workload."""
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def oracle_run(cfg, xv, z_i, steps, warmup, budget_s=None):
+    """Times the CPU oracle (all host threads) on full particle_mesh steps of the given workload; with budget_s the number of timed steps
+    is cut so that the run stays inside the budget (at least one)."""
     from oracle import Oracle
     from cubep3m_b200.lib import clock_init, timestep, absorb_limiters
-    o = Oracle(cfg)
+    o = Oracle(cfg, threads=host_threads())
+    t_begin = time.perf_counter()
     o.set_particles(xv)
     clk = clock_init(z_i, ppint=cfg.ppint, pp_ext=cfg.pp_ext)
     rng = np.random.default_rng(777)
@@ -161,31 +190,36 @@ def oracle_run(cfg, xv, z_i, steps, warmup, tile_note=""):
         if s >= warmup:
             times.append(dtm)
             stages = out.stages()
+        if budget_s is not None and times and (time.perf_counter() - t_begin) + 1.2 * dtm > budget_s:
+            break
     threads = o.threads
     o.close()
-    return float(np.mean(times)), threads, stages
+    return float(np.mean(times)), threads, stages, len(times)
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port; the Fortran cannot be compiled here), rank 0 only."""
+    """--impl reference: the reference's CPU path (oracle port; the Fortran cannot be compiled here) on the FULL workload box, rank 0 only,
+    all host threads; bounded by running fewer steps (never a smaller box): one warm-up step if a step is short, then as many of the K
+    steps as fit ~150 s."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg, box, z_i, desc = make_cfg(args.workload)
     xv, _ = make_ics(cfg, box, z_i)
     steps, warmup = args.steps, args.warmup
-    # bound the run to a few minutes: one oracle step of c1 takes ~10-20 s on 16 host threads
-    cap_steps = max(1, min(steps, 6))
-    cap_warm = min(warmup, 1)
-    sec, threads, stages = oracle_run(cfg, xv, z_i, cap_steps, cap_warm)
+    big = len(xv) > 64 * 1024 * 1024
+    cap_warm = 0 if big else min(warmup, 1)
+    sec, threads, stages, ran = oracle_run(cfg, xv, z_i, max(1, steps), cap_warm, budget_s=150.0)
     val = len(xv) / sec
     line = {
         "metric": "particle_updates_per_sec", "value": val, "unit": "particles/s", "impl": "reference", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "particles": int(len(xv)), "timed_steps_actually_run": cap_steps, "warmup_actually_run": cap_warm},
+        "config": {"workload": desc, "particles_per_gpu": int(len(xv)), "timed_steps_actually_run": ran, "warmup_actually_run": cap_warm,
+                   "note": "one node of the workload (what one GPU owns) on this box's host cores; the step count, not the box, is what bounds the run"},
         "cpu_baseline": {"value": val, "unit": "particles/s", "cores": threads, "kind": "port",
-                         "sample": f"{cap_steps} full particle_mesh step(s) of the same workload after {cap_warm} warm-up (bounded: the oracle needs ~10-20 s per step)"},
+                         "sample": f"{ran} full particle_mesh step(s) of the whole workload box after {cap_warm} warm-up, {threads} OpenMP threads "
+                                   "(oracle port of the reference; FFT = oracle/fft_ref.h batched Stockham, not FFTW)"},
         "e2e": {"value": val, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "stages_ms": stages,
     }
@@ -276,6 +310,8 @@ def run_ours(args):
     # ---- timed region B: the same K steps continued with every launch bracketed by CUDA events on its stream -> per-kernel-class
     # durations for the roofline (the instrumentation itself costs ~6 % of a step, which is why `value` comes from region A)
     class_ms, prof_ms = {}, 0.0
+    pp_i, pp_e = pm.pair_counts()
+    pair_counts = {"ppint": pp_i, "ppext": pp_e}
     tile_streams = int(os.environ.get("CUBEP3M_B200_TILE_STREAMS", "2"))
     if not args.no_profile:
         pm.set_tile_streams(1)         # one fine tile in flight: per-kernel event times are only unambiguous without tile overlap
@@ -327,6 +363,16 @@ def run_ours(args):
                 e["algorithmic_MB_per_launch"] = ab[k] / 1e6
                 e["achieved_GBs"] = ab[k] / (per * 1e-3) / 1e9
                 e["frac_of_hbm_peak"] = e["achieved_GBs"] / peak
+            if k in pair_counts and pair_counts[k] > 0:
+                # FP32-pipe stages: 20 flop per ordered pair interaction evaluated against the measured FFMA peak
+                fpk, fsrc = fp32_peak()
+                sec = (ms / args.steps) * 1e-3
+                e["ordered_pairs_per_step"] = pair_counts[k]
+                e["pairs_per_s"] = pair_counts[k] / sec
+                e["achieved_TFLOPs"] = 20.0 * pair_counts[k] / sec / 1e12
+                e["frac_of_fp32_peak"] = e["achieved_TFLOPs"] / fpk
+                e["fp32_peak_TFLOPs"] = fpk
+                e["fp32_peak_source"] = fsrc
             stages[k] = e
         if not stages:
             stages = {"fft_inv_z_mul": {"ms_per_step": 0.0, "launches_per_step": 0, "us_per_launch": 0.0, "share_of_step": 0.0, "achieved_GBs": 0.0}}
@@ -348,9 +394,16 @@ def run_ours(args):
                             "time lent to coarse kernels)"}
         cpu = None
         if world == 1 and not args.no_cpu:
-            sec, threads, ost = oracle_run(cfg, xv, z_i, 1, 0)
-            cpu = {"value": npart / sec, "unit": "particles/s", "cores": threads, "kind": "port", "ms_per_step": sec * 1e3,
-                   "sample": "1 full particle_mesh step (first step from the ICs) of the same workload, all host threads",
+            # bounded sample: for boxes beyond 256^3 particles one octant-sized node of the same workload (same tile size, flags, density and
+            # ICs: the 256^3-particle box the workload's ICs replicate), which is 1/8 of the work at the same per-particle cost
+            scfg, sxv, snote = cfg, xv, "the whole workload box"
+            if npart > 64 * 1024 * 1024:
+                scfg = default_config(nf_tile=cfg.nf_tile, tiles_node_dim=cfg.tiles_node_dim // 2, ppint=cfg.ppint, pp_ext=cfg.pp_ext)
+                sxv, _ = make_ics(scfg, box, z_i)
+                snote = f"a {round(len(sxv) ** (1 / 3))}^3-particle node of the same workload (1/8 of the box: same nf_tile, flags, density and ICs)"
+            sec, threads, ost, ran = oracle_run(scfg, sxv, z_i, 3, 0, budget_s=30.0)
+            cpu = {"value": len(sxv) / sec, "unit": "particles/s", "cores": threads, "kind": "port", "ms_per_step": sec * 1e3,
+                   "sample": f"{ran} full particle_mesh step(s) from the ICs on {snote}, {threads} OpenMP threads (oracle FFT: batched Stockham, not FFTW)",
                    "stages_ms": {k: round(v, 1) for k, v in ost.items()}}
         line = {
             "metric": "particle_updates_per_sec", "value": total_particles / (ms_step * 1e-3), "unit": "particles/s",
@@ -387,7 +440,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket launches with events in the timed region (overhead check)")
     args = ap.parse_args()

@@ -28,12 +28,12 @@
 enum KernelClass {
   KC_DRIFT = 0, KC_PASS_PACK, KC_PASS_UNPACK, KC_KEY_HIST, KC_SCAN, KC_SCATTER, KC_DENSITY,
   KC_FFT_X_R2C, KC_FFT_FWD_STRIDED, KC_FFT_INV_Z_MUL, KC_FFT_INV_Y, KC_FFT_X_C2R, KC_FORCE_MAX, KC_NGP_KICK,
-  KC_PPINT, KC_PPEXT, KC_CIC_MASS, KC_COARSE_FFT, KC_COARSE_MISC, KC_CIC_KICK, KC_COMPACT, KC_MISC, KC_COUNT
+  KC_PPINT, KC_PPEXT, KC_PPEXT_MARGIN, KC_CIC_MASS, KC_COARSE_FFT, KC_COARSE_MISC, KC_COARSE_XCHG, KC_CIC_KICK, KC_COMPACT, KC_MISC, KC_COUNT
 };
 static const char* const kKernelClassNames[KC_COUNT] = {
   "drift", "pass_pack", "pass_unpack", "key_hist", "scan", "scatter", "ngp_density",
   "fft_x_r2c", "fft_fwd_strided", "fft_inv_z_mul", "fft_inv_y", "fft_x_c2r", "force_max", "ngp_kick",
-  "ppint", "ppext", "cic_mass", "coarse_fft", "coarse_misc", "cic_kick", "compact", "misc"};
+  "ppint", "ppext", "ppext_margin", "cic_mass", "coarse_fft", "coarse_misc", "coarse_xchg", "cic_kick", "compact", "misc"};
 
 constexpr int PROF_MAX = 8192;   // profiled launches per step
 
@@ -68,6 +68,9 @@ struct Dims {
   long long NF;    // fine cells of the hoc range: H^3 * 64
 };
 
+// every rank's exchange allocation as mapped into THIS process (coarse_slab.cuh); own pointer for the own rank
+struct PeerTable { float* base[8]; };
+
 // device counters written by kernels, mirrored to the host once per step
 struct DevCounters {
   int np_deleted;        // out-of-range particles dropped by link_list
@@ -82,9 +85,12 @@ struct DevCounters {
   int np_phys;           // after delete_particles
   int n_cand;            // particles within half an ulp below a fine-cell boundary (see fine::ngp_fixup_kernel)
   int n_blist;           // particles near a y or z face, listed by the first particle_pass kernel
+  int xchg_timeout;      // a coarse-mesh exchange wait (coarse_slab.cuh) gave up on a peer
   int n_ppext_fallback;  // PP_EXT blocks whose source region exceeded the shared-memory capacity (walked directly instead)
   double sum_rho_f;
   double sum_rho_c;
+  unsigned long long pairs_ppint;   // ordered pair interactions evaluated by PPINT / PP_EXT in this step (margin-only limiter sums not counted)
+  unsigned long long pairs_ppext;
 };
 
 struct cubep3m_b200_ctx {
@@ -142,7 +148,9 @@ struct cubep3m_b200_ctx {
   cudaStream_t stream_coarse = nullptr;   // coarse-mesh solve runs concurrently with the fine-tile loop
   int ppext_mode = 1;          // 1: tiled shared-memory kernel (pp::ppext_tiled_kernel), 0: direct one-thread-per-target kernel (CUBEP3M_B200_PPEXT=direct)
   int* ppext_ovf = nullptr;    // ids of the PP_EXT target blocks that exceeded the tiled kernel's shared-memory capacity
-  int ppext_blocks = 0, ppext_fallback = 0;   // of the last step (debug getter)
+  bool ppext_margin_max = true; // also evaluate the margin particles' partial sums for pp_ext_force_max (particle_mesh_threaded.f90:617); CUBEP3M_B200_PPEXT_MARGIN=0 skips it
+  int ppext_blocks = 0, ppext_fallback = 0;
+  long long pairs_ppint = 0, pairs_ppext = 0;   // of the last step   // of the last step (debug getter)
   bool hist_clean = false;     // fcur (the fine-cell histogram) is all zeros
   cudaStream_t stream_main = nullptr, stream_aux[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
@@ -162,6 +170,17 @@ struct cubep3m_b200_ctx {
   float* gather = nullptr;    // all ranks' rho_c cubes (ncclAllGather target), world * nc_node^3
   float* force_c = nullptr;   // (3, nc_node+2, nc_node+2, nc_node+2) components innermost as cubep3m.fh:59
   float2* tw_c[3] = {nullptr, nullptr, nullptr};   // twiddles for Nx, Ny, Nz
+  // slab-decomposed coarse solve over peer memory (coarse_slab.cuh, lib.cu: cs_init / do_coarse_force_slab)
+  int coarse_mode = 0;         // 0: the whole coarse mesh on this GPU (one rank; or the all-gather + replicated-solve fallback), 1: slab-decomposed
+  int cs_zs = 0, cs_ys = 0;    // z planes per slab (the reference's nc_slab), y rows per pencil block
+  float* cs_xchg = nullptr;    // ONE allocation the peers store into: [slab | pencils T | back[3] | force_c | mailbox], offsets in floats
+  size_t cs_off_slab = 0, cs_off_T = 0, cs_off_back[3] = {0, 0, 0}, cs_off_force = 0, cs_off_mail = 0, cs_floats = 0;
+  PeerTable cs_peers = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
+  float* cs_G = nullptr;       // (Nz, ys, hc) complex: inverse-z result of one component before it is sent back
+  float* cs_real3 = nullptr;   // [comp][zs][Ny][Nx] real-space force of this rank's slab
+  float* cs_kern_rows = nullptr;   // [comp][Nz][ys][hc]: this rank's rows of kern_c
+  unsigned int cs_epoch = 0;
+  std::vector<void*> cs_ipc_opened;
   float* redbuf = nullptr;    // small device scratch for cross-rank reductions
   int* cntbuf = nullptr;      // received pass counts
   // particle_pass over NVLink peer memory (multi-rank, inside particle_mesh): the pack kernel stores straight into the neighbour's receive

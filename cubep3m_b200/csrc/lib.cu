@@ -8,6 +8,7 @@
 #include "fine.cuh"
 #include "pp.cuh"
 #include "coarse.cuh"
+#include "coarse_slab.cuh"
 #include "power.cuh"
 
 namespace {
@@ -311,6 +312,92 @@ int p2p_init(cubep3m_b200_ctx* ctx) {
   if (!ctx->p2p && ctx->cfg.rank == 0) fprintf(stderr, "cubep3m_b200: peer-memory particle_pass unavailable, using NCCL send/recv\n");
 #endif
   return 0;
+}
+
+
+// ---- slab-decomposed coarse solve (coarse_slab.cuh): allocation, peer mapping, the rank's rows of kern_c
+bool cs_supported(const Dims& d) {
+  const int W = d.world;
+  if (W > cslab::MAXW) return false;
+  if (d.Nc[2] % W || d.Nc[1] % W) return false;
+  const int zs = d.Nc[2] / W;
+  return zs >= 1 && d.nc_node % zs == 0;
+}
+int cs_alloc(cubep3m_b200_ctx* ctx) {
+  const Dims& d = ctx->d;
+  const int W = d.world, Nx = d.Nc[0], Ny = d.Nc[1], Nz = d.Nc[2], hc = Nx / 2 + 1;
+  ctx->cs_zs = Nz / W; ctx->cs_ys = Ny / W;
+  auto al = [](size_t n) { return (n + 63) / 64 * 64; };
+  const size_t slab_f = al((size_t)2 * hc * Ny * ctx->cs_zs), pen_f = al((size_t)2 * hc * ctx->cs_ys * Nz);
+  const size_t force_f = al((size_t)3 * (d.nc_node + 2) * (d.nc_node + 2) * (d.nc_node + 2));
+  size_t o = 0;
+  ctx->cs_off_slab = o; o += slab_f;
+  ctx->cs_off_T = o; o += pen_f;
+  for (int c = 0; c < 3; ++c) { ctx->cs_off_back[c] = o; o += slab_f; }
+  ctx->cs_off_force = o; o += force_f;
+  ctx->cs_off_mail = o; o += al((size_t)cslab::PH_COUNT * cslab::MAXW);
+  ctx->cs_floats = o;
+  CK(cudaMalloc((void**)&ctx->cs_xchg, o * sizeof(float)));
+  CK(cudaMemset(ctx->cs_xchg, 0, o * sizeof(float)));
+  CK(cudaMalloc((void**)&ctx->cs_G, pen_f * sizeof(float)));
+  CK(cudaMalloc((void**)&ctx->cs_real3, (size_t)3 * ctx->cs_zs * Ny * Nx * sizeof(float)));
+  CK(cudaMalloc((void**)&ctx->cs_kern_rows, (size_t)3 * Nz * ctx->cs_ys * hc * sizeof(float)));
+  ctx->force_c = ctx->cs_xchg + ctx->cs_off_force;
+  for (int r = 0; r < cslab::MAXW; ++r) ctx->cs_peers.base[r] = nullptr;
+  ctx->cs_peers.base[ctx->cfg.rank] = ctx->cs_xchg;
+  return 0;
+}
+// maps every other rank's exchange allocation (cudaIpc handles all-gathered over NCCL); ok = false if any rank could not
+int cs_map_peers(cubep3m_b200_ctx* ctx, bool* ok_out) {
+  *ok_out = true;
+  if (ctx->d.world == 1) return 0;
+#ifdef CUBEP3M_WITH_NCCL
+  const Dims& d = ctx->d;
+  struct Handle { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+  Handle mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.ok = cudaIpcGetMemHandle(&mine.h, ctx->cs_xchg) == cudaSuccess;
+  cudaGetLastError();
+  Handle* dall = nullptr;
+  CK(cudaMalloc((void**)&dall, sizeof(Handle) * d.world));
+  CK(cudaMemcpy(dall + ctx->cfg.rank, &mine, sizeof(Handle), cudaMemcpyHostToDevice));
+  NCK(ncclAllGather(dall + ctx->cfg.rank, dall, sizeof(Handle), ncclChar, ctx->comm, ctx->stream));
+  std::vector<Handle> all(d.world);
+  CK(cudaMemcpyAsync(all.data(), dall, sizeof(Handle) * d.world, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dall);
+  bool ok = true;
+  for (int r = 0; r < d.world; ++r) ok = ok && all[r].ok;
+  for (int r = 0; r < d.world && ok; ++r) {
+    if (r == ctx->cfg.rank) continue;
+    void* p = nullptr;
+    ok = cudaIpcOpenMemHandle(&p, all[r].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    if (p) ctx->cs_ipc_opened.push_back(p);
+    if (!ok) { cudaGetLastError(); break; }
+    ctx->cs_peers.base[r] = (float*)p;
+  }
+  int* dflag = ctx->cntbuf;
+  const int mine_ok = ok ? 1 : 0;
+  CK(cudaMemcpy(dflag, &mine_ok, sizeof(int), cudaMemcpyHostToDevice));
+  NCK(ncclAllReduce(dflag, dflag, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
+  int all_ok = 0;
+  CK(cudaMemcpyAsync(&all_ok, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *ok_out = all_ok == 1;
+  return 0;
+#else
+  *ok_out = false;
+  return 0;
+#endif
+}
+void cs_free(cubep3m_b200_ctx* ctx) {
+  for (void* q : ctx->cs_ipc_opened) cudaIpcCloseMemHandle(q);
+  ctx->cs_ipc_opened.clear();
+  if (ctx->cs_xchg) { cudaFree(ctx->cs_xchg); if (ctx->force_c == ctx->cs_xchg + ctx->cs_off_force) ctx->force_c = nullptr; ctx->cs_xchg = nullptr; }
+  if (ctx->cs_G) cudaFree(ctx->cs_G);
+  if (ctx->cs_real3) cudaFree(ctx->cs_real3);
+  if (ctx->cs_kern_rows) cudaFree(ctx->cs_kern_rows);
+  ctx->cs_G = ctx->cs_real3 = ctx->cs_kern_rows = nullptr;
 }
 
 int fetch_counters(cubep3m_b200_ctx* ctx) {
@@ -648,6 +735,10 @@ int do_pp_ext(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
       LAUNCH(ctx, KC_PPEXT, pp::ppext_kernel, (ctx->np_all + pp::EXT_TPB - 1) / pp::EXT_TPB, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->np_all, ctx->d.H,
              ctx->d.b, ctx->d.nc_buf, ctx->d.nc_node, ctx->cfg.pp_range, P, ctx->dcnt);
     }
+    // :617 takes the maximum over the margin particles' partial sums as well (limiter only, no kick)
+    if (ctx->np_all > 0 && ctx->ppext_margin_max)
+      LAUNCH(ctx, KC_PPEXT_MARGIN, pp::ppext_margin_max_kernel, (ctx->np_all + pp::EXT_TPB - 1) / pp::EXT_TPB, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->np_all,
+             ctx->d.H, ctx->d.b, ctx->d.m, ctx->d.T, ctx->cfg.pp_range, P, ctx->dcnt);
   }
   CK(cudaGetLastError());
   return 0;
@@ -663,10 +754,12 @@ int do_coarse_mass(cubep3m_b200_ctx* ctx, float mass_p) {
   CK(cudaGetLastError());
   return 0;
 }
+int do_coarse_force_slab(cubep3m_b200_ctx* ctx);
 int do_coarse_force(cubep3m_b200_ctx* ctx) {
   // coarse_force.f90:18-90 with the cube<->slab repack + distributed FFT of fft_coarse.f90 replaced by: all-gather the ranks' rho_c
   // cubes over NVLink, solve the WHOLE (Nx,Ny,Nz) coarse mesh on every GPU (<= 0.5 GB even for 8 x 512^3 particles), and gather
   // this rank's cube plus its one-cell halo from the periodic result (which is what coarse_force_buffer.f90:23-63 exchanges).
+  if (ctx->coarse_mode == 1) return do_coarse_force_slab(ctx);
   const Dims& d = ctx->d;
   const int Nx = d.Nc[0], Ny = d.Nc[1], Nz = d.Nc[2], nc = d.nc_node;
   const long long nrc = (long long)nc * nc * nc;
@@ -697,6 +790,62 @@ int do_coarse_force(cubep3m_b200_ctx* ctx) {
     LAUNCH(ctx, KC_COARSE_MISC, coarse::extract_force_kernel, grid_for(nfc, coarse::TPB), coarse::TPB, 0, ctx->creal, Nx, Ny, Nz, nc, d.coord[0], d.coord[1],
            d.coord[2], ctx->force_c, comp);
   }
+  ctx->fft_class_base = 0;
+  LAUNCH(ctx, KC_COARSE_MISC, coarse::force_max_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->force_c, nc, &ctx->dcnt->c_force_max_bits);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// coarse_force.f90:18-90 on the slab decomposition (coarse_slab.cuh): everything is enqueued on ctx->stream, nothing synchronises the host
+int do_coarse_force_slab(cubep3m_b200_ctx* ctx) {
+  const Dims& d = ctx->d;
+  const int W = d.world, me = ctx->cfg.rank, Nx = d.Nc[0], Ny = d.Nc[1], Nz = d.Nc[2], nc = d.nc_node, hc = Nx / 2 + 1, zs = ctx->cs_zs, ys = ctx->cs_ys;
+  const long long nrc = (long long)nc * nc * nc;
+  const int ep = (int)++ctx->cs_epoch;
+  const cslab::Peers& P = ctx->cs_peers;
+  const int* mail = reinterpret_cast<const int*>(ctx->cs_xchg + ctx->cs_off_mail);
+  const long long tmo = 20000000000LL;
+  auto sig = [&](int ph) { LAUNCH(ctx, KC_COARSE_MISC, cslab::signal_kernel, 1, 32, 0, P, (long long)ctx->cs_off_mail, W, me, ph, ep); };
+  auto wait = [&](int ph) { LAUNCH(ctx, KC_COARSE_XCHG, cslab::wait_kernel, 1, 32, 0, mail, W, ph, ep, &ctx->dcnt->xchg_timeout, tmo); };
+  float* slab = ctx->cs_xchg + ctx->cs_off_slab;
+  float2* T = reinterpret_cast<float2*>(ctx->cs_xchg + ctx->cs_off_T);
+  float2* G = reinterpret_cast<float2*>(ctx->cs_G);
+  ctx->fft_class_base = KC_COARSE_FFT;
+  // 1. pack_slab (fftw3ds.f90:4-54)
+  LAUNCH(ctx, KC_COARSE_XCHG, cslab::scatter_cube_kernel, grid_for(nrc, cslab::TPB), cslab::TPB, 0, ctx->rho_c, P, (long long)ctx->cs_off_slab, nc, zs, Nx, Ny, d.coord[0],
+         d.coord[1], d.coord[2], &ctx->dcnt->sum_rho_c);
+  sig(cslab::PH_CUBE); wait(cslab::PH_CUBE);
+  // 2. slab: r2c along x, forward y
+  if (int st = fftk::launch_x_r2c(ctx, KC_COARSE_FFT, Nx, slab, Ny * zs, ctx->tw_c[0])) return st;
+  float2* cs = reinterpret_cast<float2*>(slab);
+  if (int st = fftk::launch_strided(ctx, KC_COARSE_FFT, Ny, false, cs, cs, hc, (long long)hc, (long long)Ny * hc, 0, zs, nullptr, 0, 0, 0, Ny - 1, ctx->tw_c[1])) return st;
+  // 3. transpose to y-pencils
+  const dim3 tgrid((unsigned)std::max(1, std::min(64, (ys * hc + cslab::TPB - 1) / cslab::TPB)), (unsigned)(W * zs));
+  LAUNCH(ctx, KC_COARSE_XCHG, cslab::transpose_kernel<true>, tgrid, cslab::TPB, 0, cs, P, (long long)ctx->cs_off_T, W, me, zs, ys, Ny, hc);
+  sig(cslab::PH_FWD); wait(cslab::PH_FWD);
+  // 4. forward z on the pencils; per component: x i*kern_c fused into the inverse z pass; 5. transpose back
+  if (int st = fftk::launch_strided(ctx, KC_COARSE_FFT, Nz, false, T, T, hc, (long long)ys * hc, (long long)hc, 0, ys, nullptr, 0, 0, 0, Nz - 1, ctx->tw_c[2])) return st;
+  const long long krow = (long long)Nz * ys * hc;
+  for (int comp = 0; comp < 3; ++comp) {                                            // coarse_force.f90:37-90
+    if (int st = fftk::launch_strided(ctx, KC_COARSE_FFT, Nz, true, T, G, hc, (long long)ys * hc, (long long)hc, 0, ys, ctx->cs_kern_rows + comp * krow, (long long)ys * hc,
+                                      (long long)hc, 0, Nz - 1, ctx->tw_c[2])) return st;
+    LAUNCH(ctx, KC_COARSE_XCHG, cslab::transpose_kernel<false>, tgrid, cslab::TPB, 0, G, P, (long long)ctx->cs_off_back[comp], W, me, zs, ys, Ny, hc);
+    sig(cslab::PH_BWD0 + comp);
+  }
+  // 6. slab: inverse y, c2r along x, 1/(Nx Ny Nz)  (fftw3ds.f90:161)
+  const float scale = 1.0f / (((float)Nx * (float)Ny) * (float)Nz);
+  for (int comp = 0; comp < 3; ++comp) {
+    wait(cslab::PH_BWD0 + comp);
+    float2* b = reinterpret_cast<float2*>(ctx->cs_xchg + ctx->cs_off_back[comp]);
+    if (int st = fftk::launch_strided(ctx, KC_COARSE_FFT, Ny, true, b, b, hc, (long long)hc, (long long)Ny * hc, 0, zs, nullptr, 0, 0, 0, Ny - 1, ctx->tw_c[1])) return st;
+    if (int st = fftk::launch_x_c2r(ctx, KC_COARSE_FFT, Nx, b, ctx->cs_real3 + (size_t)comp * zs * Ny * Nx, 0, Nx, 0, Ny, 0, zs, Ny, (long long)Nx, (long long)Ny, scale,
+                                    ctx->tw_c[0])) return st;
+  }
+  // 7. unpack_slab (fftw3ds.f90:56-101) + coarse_force_buffer.f90:23-63
+  const int fc = nc + 2;
+  LAUNCH(ctx, KC_COARSE_XCHG, cslab::scatter_halo_kernel, dim3((unsigned)std::min(16, (fc * fc + cslab::TPB - 1) / cslab::TPB), (unsigned)(W * fc)), cslab::TPB, 0, ctx->cs_real3, P,
+         (long long)ctx->cs_off_force, me, nc, zs, Nx, Ny, Nz, d.Dg[0], d.Dg[1]);
+  sig(cslab::PH_HALO); wait(cslab::PH_HALO);
   ctx->fft_class_base = 0;
   LAUNCH(ctx, KC_COARSE_MISC, coarse::force_max_kernel, grid_for(nrc, coarse::TPB), coarse::TPB, 0, ctx->force_c, nc, &ctx->dcnt->c_force_max_bits);
   CK(cudaGetLastError());
@@ -766,6 +915,7 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
   auto F = [](void* p) { if (p) cudaFree(p); };
   for (int i = 0; i < 2; ++i) { F(ctx->xv[i]); F(ctx->pid[i]); F(ctx->sendbuf[i]); F(ctx->sendpid[i]); F(ctx->recvbuf_own[i]); F(ctx->recvpid_own[i]); }
   for (void* q : ctx->ipc_opened) cudaIpcCloseMemHandle(q);
+  cs_free(ctx);
   if (ctx->mailbox) cudaFree(ctx->mailbox);
   if (ctx->hbox) cudaFreeHost(ctx->hbox);
 #ifdef CUBEP3M_WITH_NCCL
@@ -797,7 +947,7 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   if (int st = derive(*cfg, d)) return st;
   if (d.world > 1 && (!nccl_unique_id || world_size != d.world)) return CUBEP3M_B200_EINVAL;
   if (cfg->tile_split > 1) return CUBEP3M_B200_EINVAL;   // superseded by nodes_dim_xyz (block split of a non-cubic box)
-  if ((!kern_f || !kern_c) && (!fine_table || !coarse_table)) return CUBEP3M_B200_EINVAL;
+  if ((!kern_f && !fine_table) || (!kern_c && !coarse_table)) return CUBEP3M_B200_EINVAL;
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (ndev < 1 || cfg->local_gpu >= ndev) return CUBEP3M_B200_ECUDA;
@@ -863,6 +1013,8 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   {
     const char* e = getenv("CUBEP3M_B200_PPEXT");       // "direct": the one-thread-per-target kernel (A/B measurements); default: tiled
     ctx->ppext_mode = (e && !strcmp(e, "direct")) ? 0 : 1;
+    const char* em = getenv("CUBEP3M_B200_PPEXT_MARGIN");
+    ctx->ppext_margin_max = !(em && atoi(em) == 0);
     if (cudaFuncSetAttribute(pp::ppext_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp::TB_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(pp::ppext_tiled_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp::TB_SMEM) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   }
@@ -887,12 +1039,16 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   const int Nx = d.Nc[0], Ny = d.Nc[1], Nz = d.Nc[2];
   const size_t ncs = (size_t)(Nx / 2 + 1) * Ny * Nz;
   const size_t nrc = (size_t)d.nc_node * d.nc_node * d.nc_node;
-  TRY(dmalloc(&ctx->kern_c, 3 * ncs));
   TRY(dmalloc(&ctx->rho_c, nrc));
-  TRY(dmalloc(&ctx->slab, (size_t)(Nx + 2) * Ny * Nz));
-  TRY(dmalloc(&ctx->slab_g, (size_t)(Nx + 2) * Ny * Nz));
-  TRY(dmalloc(&ctx->creal, (size_t)(Nx + 2) * Ny * Nz));
-  TRY(dmalloc(&ctx->force_c, (size_t)3 * (d.nc_node + 2) * (d.nc_node + 2) * (d.nc_node + 2)));
+  {
+    // coarse solve: one rank keeps the whole mesh on its GPU; several ranks use the slab decomposition over peer memory (coarse_slab.cuh).
+    // CUBEP3M_B200_COARSE=slab forces the slab pipeline on one rank too (tests), =replicated the all-gather + replicated solve (A/B, and
+    // the automatic fallback when the peers' memory cannot be mapped).
+    const char* e = getenv("CUBEP3M_B200_COARSE");
+    const bool want_slab = e ? !strcmp(e, "slab") : d.world > 1;
+    ctx->coarse_mode = (want_slab && cs_supported(d)) ? 1 : 0;
+  }
+  if (ctx->coarse_mode == 1) TRY(cs_alloc(ctx));
   for (int a = 0; a < 3; ++a) {
     for (int b2 = 0; b2 < a; ++b2) if (d.Nc[b2] == d.Nc[a]) ctx->tw_c[a] = ctx->tw_c[b2];
     if (!ctx->tw_c[a]) TRY(fftk::make_twiddles(d.Nc[a], &ctx->tw_c[a]));
@@ -901,7 +1057,6 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   TRY(dmalloc(&ctx->cntbuf, (size_t)8));
   if (d.world > 1) {
 #ifdef CUBEP3M_WITH_NCCL
-    TRY(dmalloc(&ctx->gather, nrc * d.world));
     for (int i = 0; i < 2; ++i) {
       TRY(dmalloc(&ctx->recvbuf_own[i], (size_t)d.max_buf));
       if (cfg->pid) TRY(dmalloc(&ctx->recvpid_own[i], (size_t)d.max_buf / 6 + 1));
@@ -910,6 +1065,15 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
     memcpy(&id, nccl_unique_id, sizeof(id));
     if (ncclCommInitRank(&ctx->comm, d.world, id, cfg->rank) != ncclSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ENCCL; }
     if (int st = p2p_init(ctx)) { cubep3m_b200_finalize(ctx); return st; }
+    if (ctx->coarse_mode == 1) {
+      bool ok = false;
+      if (int st = cs_map_peers(ctx, &ok)) { cubep3m_b200_finalize(ctx); return st; }
+      if (!ok) {
+        if (cfg->rank == 0) fprintf(stderr, "cubep3m_b200: peer memory unavailable for the slab-decomposed coarse solve, using the all-gathered replicated solve\n");
+        cs_free(ctx);
+        ctx->coarse_mode = 0;
+      }
+    }
 #else
     cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ENCCL;
 #endif
@@ -920,10 +1084,33 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   memset(ctx->hcnt, 0, sizeof(DevCounters));
   if (kern_f) TRY(upload_interleaved(ctx->kern_f, kern_f, (size_t)ctx->kf_stride, 0, (size_t)d.hc * d.n * d.n, (size_t)d.hc, (size_t)ctx->kf_pitch));
   else TRY(build_kern_f(ctx));
-  // a host kern_c is this rank's slab kern_c(3,hc,nc_dim,nc_slab) (cubep3m.fh:56): it is the whole mesh only when there is one rank;
-  // with more ranks the library rebuilds the global table itself (every rank needs all of it for the replicated solve)
+  // Coarse Green's function. The whole-mesh solve keeps the global table [comp][z][y][kx]; the slab solve keeps only this rank's rows of it
+  // (the global table and the FFT workspace that builds it are init-time temporaries then).
+  TRY(dmalloc(&ctx->kern_c, 3 * ncs));
+  TRY(dmalloc(&ctx->slab, (size_t)(Nx + 2) * Ny * Nz));
+  if (ctx->coarse_mode == 0) {
+    TRY(dmalloc(&ctx->slab_g, (size_t)(Nx + 2) * Ny * Nz));
+    TRY(dmalloc(&ctx->creal, (size_t)(Nx + 2) * Ny * Nz));
+    TRY(dmalloc(&ctx->force_c, (size_t)3 * (d.nc_node + 2) * (d.nc_node + 2) * (d.nc_node + 2)));
+    if (d.world > 1) TRY(dmalloc(&ctx->gather, nrc * d.world));
+  }
   if (kern_c && d.world == 1) TRY(upload_interleaved(ctx->kern_c, kern_c, ncs, 0, ncs));
-  else { if (!coarse_table) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_EINVAL; } TRY(build_kern_c(ctx)); }
+  else if (kern_c && d.nc_slab > 0) {
+    // the driver's kern_c(3,hc,nc_dim,nc_slab) is this rank's z-slab (cubep3m.fh:56; slabs are rank-major in z): all-gather the slabs per component
+#ifdef CUBEP3M_WITH_NCCL
+    const size_t per = (size_t)(Nx / 2 + 1) * Ny * d.nc_slab;
+    TRY(upload_interleaved(ctx->kern_c, kern_c, ncs, per * cfg->rank, per));
+    for (int comp = 0; comp < 3; ++comp)
+      if (ncclAllGather(ctx->kern_c + comp * ncs + per * cfg->rank, ctx->kern_c + comp * ncs, per, ncclFloat, ctx->comm, ctx->stream) != ncclSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ENCCL; }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
+#endif
+  } else { if (!coarse_table) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_EINVAL; } TRY(build_kern_c(ctx)); }
+  if (ctx->coarse_mode == 1) {
+    LAUNCH(ctx, KC_MISC, cslab::extract_rows_kernel, grid_for((long long)3 * Nz * ctx->cs_ys * (Nx / 2 + 1), cslab::TPB), cslab::TPB, 0, ctx->kern_c, ctx->cs_kern_rows, Nz, Ny,
+           Nx / 2 + 1, ctx->cs_ys, cfg->rank * ctx->cs_ys);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
+    if (d.world > 1) { cudaFree(ctx->kern_c); cudaFree(ctx->slab); ctx->kern_c = nullptr; ctx->slab = nullptr; }   // one rank keeps them for the debug getters / cic_power
+  }
 #undef TRY
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   *out = ctx;
@@ -1048,7 +1235,9 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   if (int st = fetch_counters(ctx)) return st;
   const DevCounters hc = *ctx->hcnt;
   ctx->ppext_fallback = hc.n_ppext_fallback;
+  ctx->pairs_ppint = (long long)hc.pairs_ppint; ctx->pairs_ppext = (long long)hc.pairs_ppext;
   if (int st = overflow_status(&hc)) return st;
+  if (hc.xchg_timeout) { fprintf(stderr, "cubep3m_b200: coarse-mesh exchange timed out waiting for a peer\n"); return CUBEP3M_B200_ENCCL; }
   // coarse_velocity (coarse_mesh.f90:106) rides on delete_particles' compaction (particle_mesh_threaded.f90:720)
   const float kick2[2] = {a_mid, dt};
   if (int st = do_delete(ctx, c.coarse_vel_update ? kick2 : nullptr)) return st;
@@ -1116,6 +1305,12 @@ int cubep3m_b200_debug_ppext_blocks(cubep3m_b200_ctx* ctx, int32_t* blocks, int3
   if (fallback) *fallback = ctx->ppext_fallback;
   return 0;
 }
+int cubep3m_b200_debug_pair_counts(cubep3m_b200_ctx* ctx, int64_t* ppint, int64_t* ppext) {
+  if (!ctx) return CUBEP3M_B200_EINVAL;
+  if (ppint) *ppint = ctx->pairs_ppint;
+  if (ppext) *ppext = ctx->pairs_ppext;
+  return 0;
+}
 int cubep3m_b200_num_kernel_classes(void) { return KC_COUNT; }
 const char* cubep3m_b200_kernel_class_name(int k) { return (k >= 0 && k < KC_COUNT) ? kKernelClassNames[k] : ""; }
 int cubep3m_b200_get_kernel_times(cubep3m_b200_ctx* ctx, float* ms, int64_t* launches) {
@@ -1161,6 +1356,7 @@ int cubep3m_b200_debug_kern_c(cubep3m_b200_ctx* ctx, float* kern_c) {
   CK(cudaSetDevice(ctx->device));
   // reference layout kern_c(3,hc,nc_dim,nc_slab): this rank's z-slab for the reference's cubic grids, else the whole table
   const Dims& d = ctx->d;
+  if (!ctx->kern_c) return CUBEP3M_B200_ENOTREADY;   // slab-decomposed multi-rank runs keep only the rank's pencil rows of the table
   const size_t plane = (size_t)(d.Nc[0] / 2 + 1) * d.Nc[1] * d.Nc[2];
   if (d.nc_slab > 0) { const size_t per = (size_t)(d.Nc[0] / 2 + 1) * d.Nc[1] * d.nc_slab; return download_interleaved(kern_c, ctx->kern_c, plane, per * ctx->cfg.rank, per); }
   return download_interleaved(kern_c, ctx->kern_c, plane, 0, plane);
@@ -1219,7 +1415,7 @@ int cubep3m_b200_debug_fft3d(cubep3m_b200_ctx* ctx, int32_t n, float* data, int3
   const Dims& d = ctx->d;
   float *buf, *scratch; fftk::Mesh3 g;
   if (n == d.n) { buf = ctx->tile_rho; scratch = ctx->tile_g; g = fine_mesh(ctx); }
-  else if (n == d.Nc[0] && n == d.Nc[1] && n == d.Nc[2]) { buf = ctx->slab; scratch = ctx->creal; g = coarse_mesh3(ctx); }
+  else if (n == d.Nc[0] && n == d.Nc[1] && n == d.Nc[2] && ctx->slab && ctx->creal) { buf = ctx->slab; scratch = ctx->creal; g = coarse_mesh3(ctx); }
   else return CUBEP3M_B200_EINVAL;
   const size_t bytes = sizeof(float) * (size_t)(n + 2) * n * n;
   CK(cudaMemcpyAsync(buf, data, bytes, cudaMemcpyHostToDevice, ctx->stream));

@@ -39,10 +39,12 @@ __global__ void __launch_bounds__(TPB) ppint_kernel(float* __restrict__ xv, cons
   const int nwarps = gridDim.x * (TPB / 32);
   const int n_list = min(*n_list_ptr, list_cap);
   float fmax = 0.f;
+  unsigned long long npair = 0;            // ordered pairs evaluated (bench.py: pairs/s and the FP32 fraction of this stage)
   for (int w = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); w < n_list; w += nwarps) {
     const int k = list[w];
     const int s0 = fstart[k], s1 = fstart[k + 1];
     if (s1 - s0 > max_llf) { if (lane == 0) atomicOr(&cnt->overflow, 4); continue; }   // 'exceeded max_llf' :280-283
+    if (lane == 0) npair += (unsigned long long)(s1 - s0) * (unsigned long long)(s1 - s0 - 1);
     for (int ib = s0; ib < s1; ib += 32) {
       const int i = ib + lane;
       const bool vi = i < s1;
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(TPB) ppint_kernel(float* __restrict__ xv, cons
   }
   fmax = warp_max(fmax);
   if (lane == 0 && fmax > 0.f) atomic_max_float_nonneg(&cnt->pp_force_max_bits, fmax);
+  if (lane == 0 && npair) atomicAdd(&cnt->pairs_ppint, npair);
 }
 
 // PP_EXT, one THREAD per target particle of the cell-sorted array (ghosts and non-physical cells are skipped). At the mean density
@@ -83,7 +86,8 @@ __global__ void __launch_bounds__(TPB) ppint_kernel(float* __restrict__ xv, cons
 // Neighbouring lanes hold neighbouring particles, so their range lookups and source loads hit the same L1 lines.
 // The same-cell pairs belong to PPINT (:496-523 excludes the cell itself): the centre row is walked as [gx-pr,gx-1] and [gx+1,gx+pr].
 // one contiguous range of sources
-__device__ __forceinline__ void ppext_sources(const float* __restrict__ xv, int s, int e, const float3 pi, const PPParams& P, float3& acc) {
+__device__ __forceinline__ void ppext_sources(const float* __restrict__ xv, int s, int e, const float3 pi, const PPParams& P, float3& acc, unsigned* npair = nullptr) {
+  if (npair) *npair += (unsigned)max(e - s, 0);
 #pragma unroll 1
   for (int j = s; j < e; ++j) {
     const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * j;
@@ -98,7 +102,7 @@ constexpr int EXT_MAXR = 2;    // largest pp_range (cubepm.par:92 uses 2)
 // force on the target particle i (a physical-cell particle at position pi, fine cell (gx,gy,gz) of the hoc range) from every particle of the
 // cells within pr, looked up in the global fine-cell table
 __device__ __forceinline__ float3 ppext_direct(const float* __restrict__ xv, const int* __restrict__ fstart, int H, int pr, const float3 pi, int gx, int gy,
-                                               int gz, const PPParams& P) {
+                                               int gz, const PPParams& P, unsigned* npair) {
   float3 acc = make_float3(0.f, 0.f, 0.f);
   // x cells gx-pr..gx+pr lie in coarse cells ca (fine cells fa0..fa1) and, if the window straddles a coarse boundary, cb (0..fb1)
   const int xa = gx - pr, xb = gx + pr;
@@ -125,8 +129,8 @@ __device__ __forceinline__ float3 ppext_direct(const float* __restrict__ xv, con
 #pragma unroll
     for (int q = 0; q < 2 * EXT_MAXR + 1; ++q) {
       if (dz == 0 && q == EXT_MAXR) continue;       // the centre row is handled below (own cell excluded)
-      ppext_sources(xv, rs[q][0], re[q][0], pi, P, acc);
-      ppext_sources(xv, rs[q][1], re[q][1], pi, P, acc);
+      ppext_sources(xv, rs[q][0], re[q][0], pi, P, acc, npair);
+      ppext_sources(xv, rs[q][1], re[q][1], pi, P, acc, npair);
     }
   }
   {   // centre row: cells [gx-pr, gx-1] and [gx+1, gx+pr]; the pairs inside the own cell belong to PPINT (:496-523)
@@ -139,7 +143,7 @@ __device__ __forceinline__ float3 ppext_direct(const float* __restrict__ xv, con
       for (int cc = c0; cc <= c1; ++cc) {
         const int f0 = (cc == c0) ? (x0 & 3) : 0, f1 = (cc == c1) ? (x1 & 3) : 3;
         const long long k0 = rowkey + (long long)cc * 64;
-        ppext_sources(xv, fstart[k0 + f0], fstart[k0 + f1 + 1], pi, P, acc);
+        ppext_sources(xv, fstart[k0 + f0], fstart[k0 + f1 + 1], pi, P, acc, npair);
       }
     }
   }
@@ -161,6 +165,7 @@ __global__ void __launch_bounds__(EXT_TPB) ppext_kernel(float* __restrict__ xv, 
                                                         int nc_node, int pr, PPParams P, DevCounters* __restrict__ cnt) {
   const int i = blockIdx.x * EXT_TPB + threadIdx.x;
   float fm = 0.f;
+  unsigned npair = 0;
   if (i < np_all) {
     float2* p = reinterpret_cast<float2*>(xv) + 3LL * i;
     const float2 a = p[0];
@@ -168,7 +173,74 @@ __global__ void __launch_bounds__(EXT_TPB) ppext_kernel(float* __restrict__ xv, 
     const int gx = (int)floorf(a.x) + b, gy = (int)floorf(a.y) + b, gz = (int)floorf(z) + b;   // as part::make_key
     const int lo = nc_buf * 4, hi = (nc_buf + nc_node) * 4;
     if (gx >= lo && gx < hi && gy >= lo && gy < hi && gz >= lo && gz < hi)                        // kick only particles of the physical cells (:576-590)
-      fm = ppext_apply(p, ppext_direct(xv, fstart, H, pr, make_float3(a.x, a.y, z), gx, gy, gz, P), P);
+      fm = ppext_apply(p, ppext_direct(xv, fstart, H, pr, make_float3(a.x, a.y, z), gx, gy, gz, P, &npair), P);
+  }
+  fm = warp_max(fm);
+  if ((threadIdx.x & 31) == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_ext_force_max_bits, fm);
+  const int np_w = warp_sum_i((int)npair);
+  if ((threadIdx.x & 31) == 0 && np_w) atomicAdd(&cnt->pairs_ppext, (unsigned long long)np_w);
+}
+
+// ---- pp_ext_force_max of the MARGIN particles (particle_mesh_threaded.f90:617).
+// The reference evaluates PP_EXT per tile over the tile's physical fine cells plus pp_range cells around them (:397-402) and takes the
+// maximum of |pp_ext_force_accum| over EVERY particle of that region (:617), not only over the kicked (physical) ones. A particle in the
+// margin of a tile has, in that tile, only the partial sum over the partner cells that lie inside the tile's region — and on a near-uniform
+// particle load such a one-sided sum is larger than any complete sum, so it is what sets dt_pp_ext_acc (:692). The kicks never see these
+// sums; this kernel recomputes them for the limiter only: one thread per particle of the cell-sorted array, up to 7 (tile, margin) roles
+// per particle, partner cells clipped to the tile's region. Cell pairs whose two cells both lie in the tile's upper z margin are never
+// visited by the reference's half stencil ("we never loop towards smaller z", k = 1..nf_physical_tile_dim+pp_range at :496) and are skipped.
+__global__ void __launch_bounds__(EXT_TPB) ppext_margin_max_kernel(const float* __restrict__ xv, const int* __restrict__ fstart, int np_all, int H, int b, int m, int T,
+                                                                   int pr, PPParams P, DevCounters* __restrict__ cnt) {
+  const int i = blockIdx.x * EXT_TPB + threadIdx.x;
+  float fm = 0.f;
+  if (i < np_all) {
+    const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * i;
+    const float2 a = p[0];
+    const float z = p[1].x;
+    const float3 pi = make_float3(a.x, a.y, z);
+    const int g[3] = {(int)floorf(a.x) + b, (int)floorf(a.y) + b, (int)floorf(z) + b};     // fine cell in the hoc-range frame (part::make_key)
+    int tl[3], th[3];
+    bool any_margin = false;
+    for (int ax = 0; ax < 3; ++ax) {
+      const int q = g[ax] - b;                                  // fine cell in the node frame, [-nf_buf, mT + nf_buf)
+      auto fdiv = [&](int v) { return v >= 0 ? v / m : -((-v + m - 1) / m); };
+      tl[ax] = max(0, fdiv(q - pr)); th[ax] = min(T - 1, fdiv(q + pr));
+      any_margin |= (tl[ax] <= th[ax]) && (tl[ax] != th[ax] || q < tl[ax] * m || q >= (tl[ax] + 1) * m);
+    }
+    if (any_margin && tl[0] <= th[0] && tl[1] <= th[1] && tl[2] <= th[2]) {
+      for (int tz = tl[2]; tz <= th[2]; ++tz)
+        for (int ty = tl[1]; ty <= th[1]; ++ty)
+          for (int tx = tl[0]; tx <= th[0]; ++tx) {
+            const int t3[3] = {tx, ty, tz};
+            int lo[3], hi[3];                                   // the tile's region in the hoc-range frame (inclusive)
+            bool interior = true;
+            for (int ax = 0; ax < 3; ++ax) {
+              lo[ax] = t3[ax] * m - pr + b; hi[ax] = (t3[ax] + 1) * m + pr - 1 + b;
+              interior &= (g[ax] >= lo[ax] + pr && g[ax] <= hi[ax] - pr);
+            }
+            if (interior) continue;                             // physical particle of this tile: its complete sum comes from the kick kernels
+            const int ztop = (tz + 1) * m + b;                  // first cell of the upper z margin
+            float3 acc = make_float3(0.f, 0.f, 0.f);
+            const int x0 = max(g[0] - pr, lo[0]), x1 = min(g[0] + pr, hi[0]);
+            for (int nz = max(g[2] - pr, lo[2]); nz <= min(g[2] + pr, hi[2]); ++nz) {
+              if (g[2] >= ztop && nz >= ztop) continue;
+              for (int ny = max(g[1] - pr, lo[1]); ny <= min(g[1] + pr, hi[1]); ++ny) {
+                const long long rowkey = ((long long)((nz >> 2) * H + (ny >> 2)) * H) * 64 + (((nz & 3) << 4) | ((ny & 3) << 2));
+                const bool centre = nz == g[2] && ny == g[1];
+                for (int side = 0; side < (centre ? 2 : 1); ++side) {
+                  const int xa = centre ? (side ? g[0] + 1 : x0) : x0, xb = centre ? (side ? x1 : g[0] - 1) : x1;
+                  if (xa > xb) continue;
+                  for (int cc = xa >> 2; cc <= (xb >> 2); ++cc) {
+                    const int f0 = (cc == (xa >> 2)) ? (xa & 3) : 0, f1 = (cc == (xb >> 2)) ? (xb & 3) : 3;
+                    const long long k0 = rowkey + (long long)cc * 64;
+                    ppext_sources(xv, fstart[k0 + f0], fstart[k0 + f1 + 1], pi, P, acc);
+                  }
+                }
+              }
+            }
+            fm = fmaxf(fm, sqrtf(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z));
+          }
+    }
   }
   fm = warp_max(fm);
   if ((threadIdx.x & 31) == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_ext_force_max_bits, fm);
@@ -310,6 +382,7 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
   for (int w = 0; w < TB_NT / 32; ++w) total += wsum[w];
   __syncthreads();
   float fm = 0.f;
+  int npair = 0;                                     // ordered pairs evaluated by this thread (bench.py)
   const int plo = 4 * nc_buf, phi = 4 * phys_hi;
   if (total > TB_CAP) {
     if (tid == 0) ovf_list[atomicAdd(n_fallback, 1)] = blockIdx.x;     // walked by ppext_blocklist_kernel
@@ -364,6 +437,7 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
             constexpr int W = 2 * PRT + 1;
             const int q = qz * W + qy, off = 4 * (((qz - PRT) * TB_RY + (qy - PRT)) * TB_RX);
             const int n = lds_i32(a_own + off + 4 * (PRT + 1)) - lds_i32(a_own + off - 4 * PRT) - (q == (W * W - 1) / 2 ? own_e - own_s : 0);
+            npair += n;
             rows |= (n > 0 ? 1u : 0u) << q;
           }
       } else {
@@ -371,6 +445,7 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
         for (int qz = 0, q = 0; qz < w; ++qz, rb += (TB_RY - w) * TB_RX)
           for (int qy = 0; qy < w; ++qy, ++q, rb += TB_RX) {
             const int n = tab[rb + pr + 1] - tab[rb - pr] - (q == qc ? own_e - own_s : 0);
+            npair += n;
             rows |= (n > 0 ? 1u : 0u) << q;
           }
       }
@@ -395,6 +470,8 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
   }
   fm = warp_max(fm);
   if (lane == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_ext_force_max_bits, fm);
+  npair = warp_sum_i(npair);
+  if (lane == 0 && npair) atomicAdd(&cnt->pairs_ppext, (unsigned long long)npair);
 }
 
 // direct walk for the targets of the blocks the tiled kernel could not hold (same block decode)
@@ -404,6 +481,7 @@ __global__ void __launch_bounds__(TB_NT) ppext_blocklist_kernel(float* __restric
   const int n = *n_list, tid = threadIdx.x;
   const int phys_hi = nc_buf + nc_node;
   float fm = 0.f;
+  unsigned npair = 0;
   for (int k = blockIdx.x; k < n; k += gridDim.x) {
     const int blk = list[k];
     const int bx = blk % nbx, by = (blk / nbx) % nby, bz = blk / (nbx * nby);
@@ -418,12 +496,14 @@ __global__ void __launch_bounds__(TB_NT) ppext_blocklist_kernel(float* __restric
         const float2 a = p[0];
         const float z = p[1].x;
         const int gx = (int)floorf(a.x) + b, gy = (int)floorf(a.y) + b, gz = (int)floorf(z) + b;
-        fm = fmaxf(fm, ppext_apply(p, ppext_direct(xv, fstart, H, pr, make_float3(a.x, a.y, z), gx, gy, gz, P), P));
+        fm = fmaxf(fm, ppext_apply(p, ppext_direct(xv, fstart, H, pr, make_float3(a.x, a.y, z), gx, gy, gz, P, &npair), P));
       }
     }
   }
   fm = warp_max(fm);
   if ((tid & 31) == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_ext_force_max_bits, fm);
+  const unsigned long long np_w = (unsigned long long)__reduce_add_sync(0xffffffffu, npair);
+  if ((tid & 31) == 0 && np_w) atomicAdd(&cnt->pairs_ppext, np_w);
 }
 
 }  // namespace pp

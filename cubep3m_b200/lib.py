@@ -26,7 +26,7 @@ SYMBOLS = ["cubep3m_b200_version", "cubep3m_b200_strerror", "cubep3m_b200_defaul
            "cubep3m_b200_move_grid_back", "cubep3m_b200_debug_cell_counts", "cubep3m_b200_debug_tile_counts",
            "cubep3m_b200_debug_sorted_particles", "cubep3m_b200_debug_kern_f", "cubep3m_b200_debug_kern_c",
            "cubep3m_b200_debug_rho_c", "cubep3m_b200_debug_force_c", "cubep3m_b200_debug_fine_tile",
-           "cubep3m_b200_debug_fft3d", "cubep3m_b200_debug_ppext_blocks", "cubep3m_b200_launch_count", "cubep3m_b200_set_profiling", "cubep3m_b200_set_tile_streams",
+           "cubep3m_b200_debug_fft3d", "cubep3m_b200_debug_ppext_blocks", "cubep3m_b200_debug_pair_counts", "cubep3m_b200_launch_count", "cubep3m_b200_set_profiling", "cubep3m_b200_set_tile_streams",
            "cubep3m_b200_num_kernel_classes", "cubep3m_b200_kernel_class_name", "cubep3m_b200_get_kernel_times",
            "cubep3m_b200_cic_power", "cubep3m_b200_clock_init",
            "cubep3m_b200_expansion", "cubep3m_b200_timestep"]
@@ -78,6 +78,7 @@ def load_library():
     L.cubep3m_b200_debug_force_c.argtypes = [C.c_void_p, _fp]
     L.cubep3m_b200_debug_fine_tile.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]
     L.cubep3m_b200_debug_fft3d.argtypes = [C.c_void_p, C.c_int32, _fp, C.c_int32]
+    L.cubep3m_b200_debug_pair_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.cubep3m_b200_launch_count.argtypes = [C.c_void_p]
     L.cubep3m_b200_launch_count.restype = C.c_int64
     L.cubep3m_b200_set_profiling.argtypes = [C.c_void_p, C.c_int]
@@ -202,6 +203,12 @@ class ParticleMesh:
         nb, nf = C.c_int32(), C.c_int32()
         _chk(self.lib.cubep3m_b200_debug_ppext_blocks(self.h, C.byref(nb), C.byref(nf)))
         return nb.value, nf.value
+
+    def pair_counts(self):
+        """(PPINT, PP_EXT) ordered pair interactions evaluated in the last particle_mesh call."""
+        a, b = C.c_int64(), C.c_int64()
+        _chk(self.lib.cubep3m_b200_debug_pair_counts(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def sorted_particles(self):
         n = C.c_int32()

@@ -174,6 +174,9 @@ int cubep3m_b200_debug_fft3d(cubep3m_b200_ctx* ctx, int32_t n, float* data, int3
 /* PP_EXT of the last particle_mesh call (particle_mesh_threaded.f90:378-624): target blocks launched by the tiled shared-memory kernel and
  * how many of them exceeded the shared-memory source capacity and were walked through the global cell table instead */
 int cubep3m_b200_debug_ppext_blocks(cubep3m_b200_ctx* ctx, int32_t* blocks, int32_t* fallback);
+/* ordered particle-pair interactions evaluated by PPINT (:324-361) and PP_EXT (:496-590) in the last particle_mesh call: every unordered pair
+ * the reference visits once is evaluated twice here (once per partner), so these are 2 x the reference's pair counts */
+int cubep3m_b200_debug_pair_counts(cubep3m_b200_ctx* ctx, int64_t* ppint, int64_t* ppext);
 /* number of kernels this context launched so far (bench.py's gpu_launches) */
 int64_t cubep3m_b200_launch_count(cubep3m_b200_ctx* ctx);
 /* Per-kernel-class device time of the last particle_mesh call: when profiling is on every launch is bracketed by

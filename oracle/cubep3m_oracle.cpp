@@ -418,7 +418,7 @@ struct TileScratch {
   std::vector<float> rho_f, cmplx_rho_f, force_f;
   std::vector<int> llf;            // llf(max_llf,4,4,4) grown on demand
   std::vector<float> pp_force_accum;
-  std::vector<int> hoc_fine, ll_fine;
+  std::vector<int> hoc_fine, ll_fine, tile_pp;
   std::vector<float> pp_ext_force_accum;
 };
 
@@ -630,18 +630,23 @@ void fine_tile(World& w, RankState& r, int cur_tile, float a_mid, float dt, floa
     const int pr = p.c.pp_range;
     const int fd = m + 2 * pr;
     S.hoc_fine.assign((size_t)fd * fd * fd, 0);                        // :393
-    if ((int)S.ll_fine.size() < r.np_local) S.ll_fine.resize(r.np_local);
     int fl[3], fh[3];
     for (int d = 0; d < 3; ++d) { fl[d] = tile[d] * m + 1 - pr; fh[d] = (tile[d] + 1) * m + pr; }   // :397-402
     auto HF = [&](int i, int j, int k) -> int& { return S.hoc_fine[(size_t)(i - 1) + (size_t)fd * ((j - 1) + (size_t)fd * (k - 1))]; };
+    // The reference keeps ll_fine(max_np) and pp_ext_force_accum(3,max_np) per thread and clears / scans all of them for every tile
+    // (:393, :491, :617). Same scan over all np_local particles (:410-438), same chain order, same sums and maximum here, but the per-thread
+    // arrays are indexed by the particle's position in the tile's own list (S.tile_pp), so that a 512^3 box does not need 2.4 GB per thread.
+    S.tile_pp.clear();
+    S.ll_fine.clear();
     for (int pp = 1; pp <= r.np_local; ++pp) {                         // :410-438
       const float* q = &r.xv[(size_t)6 * (pp - 1)];
       int i = ifloor(q[0]) + 1, j = ifloor(q[1]) + 1, k = ifloor(q[2]) + 1;
       if (i < fl[0] || i > fh[0] || j < fl[1] || j > fh[1] || k < fl[2] || k > fh[2]) continue;
       int& h = HF(i - fl[0] + 1, j - fl[1] + 1, k - fl[2] + 1);
-      S.ll_fine[pp - 1] = h; h = pp;
+      S.tile_pp.push_back(pp);
+      S.ll_fine.push_back(h); h = (int)S.tile_pp.size();               // 1-based index into the tile's list
     }
-    S.pp_ext_force_accum.assign((size_t)3 * r.np_local, 0.f);          // :491
+    S.pp_ext_force_accum.assign((size_t)3 * S.tile_pp.size(), 0.f);    // :491
     const float cut = (float)p.c.nf_cutoff;
     if (pr != 0) {
       for (int k = 1; k <= m + pr; ++k)                                // :496
@@ -660,10 +665,10 @@ void fine_tile(World& w, RankState& r, int cur_tile, float a_mid, float dt, floa
                   int pp2h = HF(ip, jp, kp);
                   if (pp2h == 0) continue;
                   const bool phys2 = (pr < ip && ip <= m + pr && pr < jp && jp <= m + pr && pr < kp && kp <= m + pr);  // :584-586
-                  for (int pp1 = pp1h; pp1 != 0; pp1 = S.ll_fine[pp1 - 1])
-                    for (int pp2 = pp2h; pp2 != 0; pp2 = S.ll_fine[pp2 - 1]) {
-                      float* q1 = &r.xv[(size_t)6 * (pp1 - 1)];
-                      float* q2 = &r.xv[(size_t)6 * (pp2 - 1)];
+                  for (int l1 = pp1h; l1 != 0; l1 = S.ll_fine[l1 - 1])
+                    for (int l2 = pp2h; l2 != 0; l2 = S.ll_fine[l2 - 1]) {
+                      float* q1 = &r.xv[(size_t)6 * (S.tile_pp[l1 - 1] - 1)];
+                      float* q2 = &r.xv[(size_t)6 * (S.tile_pp[l2 - 1] - 1)];
                       float sep[3] = {q1[0] - q2[0], q1[1] - q2[1], q1[2] - q2[2]};
                       float rmag = std::sqrt((sep[0] * sep[0] + sep[1] * sep[1]) + sep[2] * sep[2]);
                       if (rmag > p.c.rsoft) {                          // :558-564
@@ -677,8 +682,8 @@ void fine_tile(World& w, RankState& r, int cur_tile, float a_mid, float dt, floa
                         for (int d = 0; d < 3; ++d) {
                           float force_pp = mass_p * (sep[d] / rb3);
                           if (!far) force_pp = force_pp * poly;
-                          S.pp_ext_force_accum[(size_t)3 * (pp1 - 1) + d] -= force_pp;
-                          S.pp_ext_force_accum[(size_t)3 * (pp2 - 1) + d] += force_pp;
+                          S.pp_ext_force_accum[(size_t)3 * (l1 - 1) + d] -= force_pp;
+                          S.pp_ext_force_accum[(size_t)3 * (l2 - 1) + d] += force_pp;
                           if (p.c.pp_ext_force_flag) {
                             if (phys1) q1[3 + d] = q1[3 + d] - ((force_pp * a_mid) * G) * dt;
                             if (phys2) q2[3 + d] = q2[3 + d] + ((force_pp * a_mid) * G) * dt;
@@ -691,9 +696,9 @@ void fine_tile(World& w, RankState& r, int cur_tile, float a_mid, float dt, floa
             }
           }
     }
-    float mx = 0.f;                                                    // :617
-    for (int pp = 0; pp < r.np_local; ++pp) {
-      const float* f = &S.pp_ext_force_accum[(size_t)3 * pp];
+    float mx = 0.f;                                                    // :617 (every other particle's accumulator is zero)
+    for (size_t l = 0; l < S.tile_pp.size(); ++l) {
+      const float* f = &S.pp_ext_force_accum[(size_t)3 * l];
       float mag = std::sqrt((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]);
       if (mag > mx) mx = mag;
     }
@@ -889,7 +894,13 @@ int particle_mesh(World& w, float dt, float dt_old, float a_mid, float mass_p, c
     std::vector<double> td(nthreads * 5, 0.0);
     // PP_EXT kicks ghost-free but reads/writes velocities of particles in neighbouring tiles' margins
     // only through "phys" guards, so tiles are independent exactly as in the reference's !$omp do (:84-85).
-#pragma omp parallel
+    // fewer tiles than threads (tiles_node_dim = 1 or 2): the idle threads go to the batches of each tile's FFT passes (fft_ref.h)
+    const int team = std::max(1, std::min(nthreads, p.tiles_node));
+#ifdef _OPENMP
+    omp_set_max_active_levels(2);
+    oracle::g_threads = nthreads;
+#endif
+#pragma omp parallel num_threads(team)
     {
       int tid = 0;
 #ifdef _OPENMP

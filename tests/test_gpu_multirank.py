@@ -30,8 +30,14 @@ def _worker(rank, world, grid, nf_tile, uid, tmp, lrck):
     pm.close()
 
 
-@pytest.mark.parametrize("case", ["native"])
-def test_multi_gpu_step_matches_oracle(built, tmp_path, case):
+@pytest.mark.parametrize("case", ["native", "nccl_pass_replicated_coarse"])
+def test_multi_gpu_step_matches_oracle(built, tmp_path, case, monkeypatch):
+    """native: particle_pass packed into the neighbour's memory + slab-decomposed coarse solve over peer memory (coarse_slab.cuh).
+    nccl_pass_replicated_coarse: the fallbacks — ncclSend/Recv particle_pass inside the step (CUBEP3M_B200_P2P=0) and the all-gathered
+    replicated coarse solve (CUBEP3M_B200_COARSE=replicated)."""
+    if case != "native":
+        monkeypatch.setenv("CUBEP3M_B200_P2P", "0")
+        monkeypatch.setenv("CUBEP3M_B200_COARSE", "replicated")
     import torch
     import torch.multiprocessing as mp
     from cubep3m_b200.lib import get_unique_id
@@ -74,5 +80,7 @@ def test_multi_gpu_step_matches_oracle(built, tmp_path, case):
                 assert np.sqrt(np.mean(rel ** 2)) < 1e-4, (r, np.sqrt(np.mean(rel ** 2)))
             assert sc[3] == pytest.approx(oo.dt_f_acc, rel=1e-3) and sc[6] == pytest.approx(oo.dt_c_acc, rel=1e-3)
             assert sc[4] == pytest.approx(oo.dt_pp_acc, rel=1e-2)
+            if step == 0:
+                assert sc[5] == pytest.approx(oo.dt_pp_ext_acc, rel=2e-4), "dt_pp_ext_acc incl. margin particles (particle_mesh_threaded.f90:617,692)"
             assert sc[7] == pytest.approx(oo.sum_rho_f, rel=1e-9) and sc[8] == pytest.approx(oo.sum_rho_c, rel=1e-6)
     o.close()

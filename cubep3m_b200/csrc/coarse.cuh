@@ -46,6 +46,52 @@ __global__ void __launch_bounds__(TPB) cic_mass_kernel(const float* __restrict__
   }
 }
 
+// The same deposit, staged in shared memory: the particles of one coarse x-row (cy, cz) only reach the 3 x 3 rho_c rows (cy-1..cy+1, cz-1..cz+1)
+// (x = xv/4 - 0.5 puts i1 in {c-1, c} for a particle of coarse cell c), so the CTA accumulates them in a 9-row shared-memory window with
+// shared-memory atomics and flushes each row once with coalesced global atomics: 9*nc_node global atomics per CTA instead of 8 per particle
+// (8x fewer at the mean density of 8 particles per coarse cell, and contention-free however strongly the box clusters).
+__global__ void __launch_bounds__(TPB) cic_mass_smem_kernel(const float* __restrict__ xv, const int* __restrict__ fstart, float* __restrict__ rho_c,
+                                                            int H, int nc_buf, int nc_node, float mass_p, int coarse_ngp) {
+  extern __shared__ float win[];                       // [3 z][3 y][W], W = nc_node + 4: x cells -1 .. nc_node + 2
+  const int W = nc_node + 4;
+  const int rows = nc_node + 2;
+  const int ry = blockIdx.x % rows, rz = blockIdx.x / rows;     // hoc cells 0 .. nc_node + 1
+  const int cy = nc_buf - 1 + ry, cz = nc_buf - 1 + rz, cx0 = nc_buf - 1;
+  const long long k0 = ((long long)(cz * H + cy) * H + cx0) * 64;
+  const int s0 = fstart[k0], s1 = fstart[k0 + (long long)rows * 64];
+  if (s1 == s0) return;
+  for (int t = threadIdx.x; t < 9 * W; t += TPB) win[t] = 0.f;
+  __syncthreads();
+  for (int i = s0 + threadIdx.x; i < s1; i += TPB) {
+    const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * i;
+    const float2 a = p[0];
+    const float z = p[1].x;
+    int ix, iy, iz; float dx1, dx2, dy1, dy2, dz1, dz2;
+    cic_setup(a.x, coarse_ngp, ix, dx1, dx2);
+    cic_setup(a.y, coarse_ngp, iy, dy1, dy2);
+    cic_setup(z, coarse_ngp, iz, dz1, dz2);
+    dx1 = mass_p * dx1; dx2 = mass_p * dx2;
+    // window-local indices: y, z relative to (ry - 1, rz - 1) (1-based cells), x relative to cell -1
+    const int ly = iy - (ry - 1), lz = iz - (rz - 1), lx = ix + 1;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float w = (((c & 1) ? dx2 : dx1) * (((c >> 1) & 1) ? dy2 : dy1)) * ((c >> 2) ? dz2 : dz1);
+      atomicAdd(&win[((lz + (c >> 2)) * 3 + (ly + ((c >> 1) & 1))) * W + lx + (c & 1)], w);
+    }
+  }
+  __syncthreads();
+  // flush: window row (wz, wy) is rho_c row (jy, jz) = (ry - 1 + wy, rz - 1 + wz), kept if inside 1..nc_node (coarse_cic_mass_buffer.f90:59-113)
+  for (int r = 0; r < 9; ++r) {
+    const int jy = ry - 1 + r % 3, jz = rz - 1 + r / 3;
+    if (jy < 1 || jy > nc_node || jz < 1 || jz > nc_node) continue;
+    float* out = rho_c + ((long long)(jz - 1) * nc_node + (jy - 1)) * nc_node;
+    for (int x = threadIdx.x; x < nc_node; x += TPB) {
+      const float v = win[r * W + x + 2];                // cell jx = x + 1 sits at window index jx + 1
+      if (v != 0.f) atomicAdd(&out[x], v);
+    }
+  }
+}
+
 // copy one rank's cube into the padded global FFT array (Nx+2, Ny, Nz) at offset (ox,oy,oz) — the pack_slab of
 // fft_coarse.f90:4-54 for a replicated global mesh — and (for the rank's own cube) the DIAG sum of coarse_mesh.f90:31-43
 __global__ void __launch_bounds__(TPB) cube_to_slab_kernel(const float* __restrict__ rho_c, float* __restrict__ slab, int nc_node, int Nx, int Ny,

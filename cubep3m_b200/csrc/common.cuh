@@ -85,6 +85,7 @@ struct DevCounters {
   int np_phys;           // after delete_particles
   int n_cand;            // particles within half an ulp below a fine-cell boundary (see fine::ngp_fixup_kernel)
   int n_blist;           // particles near a y or z face, listed by the first particle_pass kernel
+  int n_margin_roles;    // (particle, tile) margin roles listed for the PP_EXT limiter (pp::ppext_margin_list_kernel)
   int xchg_timeout;      // a coarse-mesh exchange wait (coarse_slab.cuh) gave up on a peer
   int n_ppext_fallback;  // PP_EXT blocks whose source region exceeded the shared-memory capacity (walked directly instead)
   double sum_rho_f;
@@ -149,6 +150,7 @@ struct cubep3m_b200_ctx {
   int ppext_mode = 1;          // 1: tiled shared-memory kernel (pp::ppext_tiled_kernel), 0: direct one-thread-per-target kernel (CUBEP3M_B200_PPEXT=direct)
   int* ppext_ovf = nullptr;    // ids of the PP_EXT target blocks that exceeded the tiled kernel's shared-memory capacity
   bool ppext_margin_max = true; // also evaluate the margin particles' partial sums for pp_ext_force_max (particle_mesh_threaded.f90:617); CUBEP3M_B200_PPEXT_MARGIN=0 skips it
+  int2* margin_roles = nullptr; int margin_cap = 0;   // (particle index, tile) list of the PP_EXT margin roles
   int ppext_blocks = 0, ppext_fallback = 0;
   long long pairs_ppint = 0, pairs_ppext = 0;   // of the last step   // of the last step (debug getter)
   bool hist_clean = false;     // fcur (the fine-cell histogram) is all zeros

@@ -509,8 +509,14 @@ inline bool supported(int n) {
   return false;
 }
 
+// cudaFuncSetAttribute is per DEVICE: a process that opens contexts on several GPUs (cfg.local_gpu) must opt in on each of them
+// (ADVICE r1). The flags are only written from the thread that owns the handle (the library is not re-entrant per handle);
+// the cached occupancy numbers further down are the same on every B200 and therefore stay process-wide.
 template <int N> int set_smem_attr() {
-  static bool done = false;
+  static bool done_dev[64] = {false};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  bool& done = done_dev[dev & 63];
   if (done) return 0;
   const int bytes = (int)smem_bytes(N);
   CK(cudaFuncSetAttribute(fft_x_r2c<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));

@@ -736,9 +736,14 @@ int do_pp_ext(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
              ctx->d.b, ctx->d.nc_buf, ctx->d.nc_node, ctx->cfg.pp_range, P, ctx->dcnt);
     }
     // :617 takes the maximum over the margin particles' partial sums as well (limiter only, no kick)
-    if (ctx->np_all > 0 && ctx->ppext_margin_max)
-      LAUNCH(ctx, KC_PPEXT_MARGIN, pp::ppext_margin_max_kernel, (ctx->np_all + pp::EXT_TPB - 1) / pp::EXT_TPB, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->np_all,
-             ctx->d.H, ctx->d.b, ctx->d.m, ctx->d.T, ctx->cfg.pp_range, P, ctx->dcnt);
+    if (ctx->np_all > 0 && ctx->ppext_margin_max) {
+      const pp::MarginGeom G{ctx->d.H, ctx->d.b, ctx->d.m, ctx->d.T, ctx->cfg.pp_range};
+      CK(cudaMemsetAsync(&ctx->dcnt->n_margin_roles, 0, sizeof(int), ctx->stream));
+      LAUNCH(ctx, KC_PPEXT_MARGIN, pp::ppext_margin_list_kernel, (ctx->np_all + pp::EXT_TPB - 1) / pp::EXT_TPB, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->np_all, G, ctx->margin_roles,
+             ctx->margin_cap, &ctx->dcnt->n_margin_roles);
+      LAUNCH(ctx, KC_PPEXT_MARGIN, pp::ppext_margin_roles_kernel, NUM_SMS * 16, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->np_all, G, ctx->margin_roles, ctx->margin_cap,
+             &ctx->dcnt->n_margin_roles, P, ctx->dcnt);
+    }
   }
   CK(cudaGetLastError());
   return 0;
@@ -749,8 +754,14 @@ int do_coarse_mass(cubep3m_b200_ctx* ctx, float mass_p) {
   const Dims& d = ctx->d;
   const size_t nrc = (size_t)d.nc_node * d.nc_node * d.nc_node;
   CK(cudaMemsetAsync(ctx->rho_c, 0, nrc * sizeof(float), ctx->stream));
-  LAUNCH(ctx, KC_CIC_MASS, coarse::cic_mass_kernel, (d.nc_node + 2) * (d.nc_node + 2), coarse::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->rho_c, d.H, d.nc_buf,
-         d.nc_node, mass_p, ctx->cfg.coarse_ngp);
+  const size_t win = (size_t)9 * (d.nc_node + 4) * sizeof(float);
+  static const bool plain = [] { const char* e = getenv("CUBEP3M_B200_CICMASS"); return e && !strcmp(e, "global"); }();   // A/B knob: one global atomic per contribution
+  if (!plain && win <= 48 * 1024)
+    LAUNCH(ctx, KC_CIC_MASS, coarse::cic_mass_smem_kernel, (d.nc_node + 2) * (d.nc_node + 2), coarse::TPB, win, ctx->xv[ctx->cur], ctx->fstart, ctx->rho_c, d.H, d.nc_buf,
+           d.nc_node, mass_p, ctx->cfg.coarse_ngp);
+  else
+    LAUNCH(ctx, KC_CIC_MASS, coarse::cic_mass_kernel, (d.nc_node + 2) * (d.nc_node + 2), coarse::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->rho_c, d.H, d.nc_buf,
+           d.nc_node, mass_p, ctx->cfg.coarse_ngp);
   CK(cudaGetLastError());
   return 0;
 }
@@ -930,7 +941,7 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->stream_coarse) cudaStreamDestroy(ctx->stream_coarse);
-  F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->creal); F(ctx->gather); F(ctx->force_c); F(ctx->redbuf); F(ctx->cntbuf); F(ctx->dcnt); F(ctx->ppext_ovf);
+  F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->creal); F(ctx->gather); F(ctx->force_c); F(ctx->redbuf); F(ctx->cntbuf); F(ctx->dcnt); F(ctx->ppext_ovf); F(ctx->margin_roles);
   for (int a = 0; a < 3; ++a) { bool dup = false; for (int b2 = 0; b2 < a; ++b2) dup |= (ctx->tw_c[b2] == ctx->tw_c[a]); if (!dup) F(ctx->tw_c[a]); }
   if (ctx->hcnt) cudaFreeHost(ctx->hcnt);
   if (ctx->ev_ok) for (auto& e : ctx->ev) cudaEventDestroy(e);
@@ -990,6 +1001,8 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   if (cfg->pp_ext) {
     const int nc = ctx->d.nc_node;
     TRY(dmalloc(&ctx->ppext_ovf, (size_t)((nc + pp::TB_X - 1) / pp::TB_X) * ((nc + pp::TB_Y - 1) / pp::TB_Y) * ((nc + pp::TB_Z - 1) / pp::TB_Z)));
+    ctx->margin_cap = d.max_np / 8 + 4096;
+    TRY(dmalloc(&ctx->margin_roles, (size_t)ctx->margin_cap));
   }
   const size_t rowoff_n = (size_t)d.nc_node * d.nc_node + 16 + d.tiles_node;
   TRY(dmalloc(&ctx->rowoff, rowoff_n));

@@ -10,7 +10,8 @@ REF_TAGS = {"drift": "pos updt", "link": "linklist", "pass": "par pass", "coarse
             "coarse_force": "cm force", "coarse_vel": "cm   vel", "delete": "del part"}
 
 ERRORS = {0: "ok", 1: "bad configuration", 2: "CUDA failure", 3: "not enough buffer space in pass",
-          4: "exceeded max_np in pass", 5: "exceeded max_llf", 6: "NCCL failure", 7: "call order violated"}
+          4: "exceeded max_np in pass", 5: "exceeded max_llf", 6: "NCCL failure", 7: "call order violated",
+          8: "internal work list overflow"}
 
 
 class Config(C.Structure):
@@ -21,7 +22,7 @@ class Config(C.Structure):
                [(n, C.c_int32) for n in
                 ("ngp", "ppint", "pp_ext", "coarse_ngp", "pid", "lrckcorr", "move_grid_back",
                  "ngp_fmesh_force", "pp_force_flag", "pp_ext_force_flag", "coarse_vel_update",
-                 "rank", "local_gpu", "tile_split", "tile_split_rank")] + \
+                 "rank", "local_gpu")] + \
                [("nodes_dim_xyz", C.c_int32 * 3)]
 
     # derived sizes, cubepm.par:190-208
@@ -72,7 +73,7 @@ def default_config(**kw) -> Config:
     c.eps = 1.0e-3
     c.ngp, c.ppint, c.pp_ext, c.coarse_ngp, c.pid, c.lrckcorr, c.move_grid_back = 1, 1, 0, 0, 0, 1, 0
     c.ngp_fmesh_force = c.pp_force_flag = c.pp_ext_force_flag = c.coarse_vel_update = 1
-    c.rank, c.local_gpu, c.tile_split, c.tile_split_rank = 0, 0, 1, 0
+    c.rank, c.local_gpu = 0, 0
     for k, v in kw.items():
         if not hasattr(c, k):
             raise AttributeError(k)

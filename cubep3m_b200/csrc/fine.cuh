@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(TPB) cic_fine_kick_kernel(float* __restrict__ 
 constexpr int DELTA_CAP = 2048;   // moves per tile (expected: a few tens)
 __global__ void __launch_bounds__(TPB) build_tile_deltas_kernel(const float* __restrict__ cand, const int* __restrict__ n_cand_ptr, int cand_cap, int n, int b,
                                                                 int m, int T, float mass_p, int2* __restrict__ deltas, int* __restrict__ ndelta,
-                                                                double* __restrict__ sum_phys) {
+                                                                double* __restrict__ sum_phys, int* __restrict__ overflow) {
   const int nc = min(*n_cand_ptr, cand_cap);
   for (int i = blockIdx.x * TPB + threadIdx.x; i < nc; i += gridDim.x * TPB) {
     const float p[3] = {cand[3 * i], cand[3 * i + 1], cand[3 * i + 2]};
@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(TPB) build_tile_deltas_kernel(const float* __r
           if (!ok || !diff) continue;
           const int tile = (tz * T + ty) * T + tx;
           const int slot = atomicAdd(&ndelta[tile], 1);
-          if (slot < DELTA_CAP) deltas[(long long)tile * DELTA_CAP + slot] = make_int2((k[2] * n + k[1]) * n + k[0], (r[2] * n + r[1]) * n + r[0]);
+          if (slot >= DELTA_CAP) { atomicOr(overflow, 8); continue; }   // never silently truncated: the step returns ECAPACITY
+          deltas[(long long)tile * DELTA_CAP + slot] = make_int2((k[2] * n + k[1]) * n + k[0], (r[2] * n + r[1]) * n + r[0]);
           const bool pk = k[0] >= b && k[0] < n - b && k[1] >= b && k[1] < n - b && k[2] >= b && k[2] < n - b;
           const bool pr = r[0] >= b && r[0] < n - b && r[1] >= b && r[1] < n - b && r[2] >= b && r[2] < n - b;
           if (pk != pr) atomicAdd(sum_phys, pr ? (double)mass_p : -(double)mass_p);

@@ -410,6 +410,7 @@ int overflow_status(const DevCounters* h) {
   if (h->overflow & 1) return CUBEP3M_B200_EPASSBUF;
   if (h->overflow & 2) return CUBEP3M_B200_EMAXNP;
   if (h->overflow & 4) return CUBEP3M_B200_EMAXLLF;
+  if (h->overflow & 8) return CUBEP3M_B200_ECAPACITY;
   return 0;
 }
 
@@ -591,9 +592,13 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
   }
   if (np > 0)
     LAUNCH(ctx, KC_SCATTER, part::scatter_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->fcur, ctx->fstart,
-           ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1]);
+           ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1], d.max_np);
   CK(cudaGetLastError());
   if (int st = fetch_counters(ctx)) return st;
+  if (ctx->hcnt->overflow & (4 | 8)) {      // a wrapped cell counter leaves the histogram dirty: clear it before the next sort
+    ctx->hist_clean = false;
+    return overflow_status(ctx->hcnt);
+  }
   ctx->hist_clean = true;
   ctx->cur ^= 1;
   ctx->np_all = np - ctx->hcnt->np_deleted;
@@ -665,7 +670,7 @@ int do_fine(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p, float* m
   if (ctx->cfg.ngp) LAUNCH(ctx, KC_DENSITY, fine::tile_counts_kernel, d.tiles_node, fine::TPB, 0, ctx->fstart, d.H, d.nc_buf, d.nc_tile, d.T, ctx->tile_counts);
   if (ctx->cfg.ngp && ctx->hcnt->n_cand > 0)
     LAUNCH(ctx, KC_DENSITY, fine::build_tile_deltas_kernel, std::min(NUM_SMS, (std::min(ctx->hcnt->n_cand, ctx->cand_cap) + fine::TPB - 1) / fine::TPB), fine::TPB,
-           0, ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, d.n, d.b, d.m, d.T, mass_p, ctx->deltas, ctx->ndelta, &ctx->dcnt->sum_rho_f);
+           0, ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, d.n, d.b, d.m, d.T, mass_p, ctx->deltas, ctx->ndelta, &ctx->dcnt->sum_rho_f, &ctx->dcnt->overflow);
   const int S = std::min(ctx->tile_streams, d.tiles_node);
   const size_t fstride = (size_t)d.fdim * d.fdim * d.fdim;
   if (S > 1) {
@@ -889,6 +894,7 @@ const char* cubep3m_b200_strerror(int st) {
     case CUBEP3M_B200_EMAXLLF: return "exceeded max_llf";
     case CUBEP3M_B200_ENCCL: return "NCCL failure";
     case CUBEP3M_B200_ENOTREADY: return "call order violated";
+    case CUBEP3M_B200_ECAPACITY: return "internal work list overflow";
   }
   return "unknown";
 }
@@ -903,7 +909,7 @@ void cubep3m_b200_default_config(cubep3m_b200_config* c) {
   c->eps = 1.0e-3f;
   c->ngp = 1; c->ppint = 1; c->pp_ext = 0; c->coarse_ngp = 0; c->pid = 0; c->lrckcorr = 1; c->move_grid_back = 0;
   c->ngp_fmesh_force = c->pp_force_flag = c->pp_ext_force_flag = c->coarse_vel_update = 1;
-  c->rank = 0; c->local_gpu = 0; c->tile_split = 1; c->tile_split_rank = 0;
+  c->rank = 0; c->local_gpu = 0;
   c->nodes_dim_xyz[0] = c->nodes_dim_xyz[1] = c->nodes_dim_xyz[2] = 0;
 }
 
@@ -957,8 +963,9 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   Dims d;
   if (int st = derive(*cfg, d)) return st;
   if (d.world > 1 && (!nccl_unique_id || world_size != d.world)) return CUBEP3M_B200_EINVAL;
-  if (cfg->tile_split > 1) return CUBEP3M_B200_EINVAL;   // superseded by nodes_dim_xyz (block split of a non-cubic box)
   if ((!kern_f && !fine_table) || (!kern_c && !coarse_table)) return CUBEP3M_B200_EINVAL;
+  if (cfg->move_grid_back) return CUBEP3M_B200_EINVAL;   // the in-step shift of particle_mesh_threaded.f90:714-716 is not supported (out of scope); the
+                                                         // driver-level call (cubepm.f90:179) is cubep3m_b200_move_grid_back
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (ndev < 1 || cfg->local_gpu >= ndev) return CUBEP3M_B200_ECUDA;
@@ -1174,6 +1181,7 @@ int cubep3m_b200_link_list(cubep3m_b200_ctx* ctx, int32_t* np_deleted) {
   if (!ctx) return CUBEP3M_B200_EINVAL;
   CK(cudaSetDevice(ctx->device));
   ctx->np_all = ctx->np_local; ctx->passed = false;
+  CK(cudaMemsetAsync(&ctx->dcnt->overflow, 0, sizeof(int), ctx->stream));
   return do_sort(ctx, np_deleted);
 }
 
@@ -1183,6 +1191,7 @@ int cubep3m_b200_particle_pass(cubep3m_b200_ctx* ctx, int32_t* np_with_ghosts) {
   if (ctx->passed) return CUBEP3M_B200_ENOTREADY;
   int bufmax = 0;
   ctx->np_all = ctx->np_local;
+  CK(cudaMemsetAsync(&ctx->dcnt->overflow, 0, sizeof(int), ctx->stream));
   if (int st = do_pass(ctx, &bufmax)) return st;
   if (int st = do_sort(ctx, nullptr)) return st;
   if (np_with_ghosts) *np_with_ghosts = ctx->np_all;
@@ -1192,6 +1201,7 @@ int cubep3m_b200_particle_pass(cubep3m_b200_ctx* ctx, int32_t* np_with_ghosts) {
 int cubep3m_b200_delete_particles(cubep3m_b200_ctx* ctx, int32_t* np_local) {
   if (!ctx) return CUBEP3M_B200_EINVAL;
   CK(cudaSetDevice(ctx->device));
+  CK(cudaMemsetAsync(&ctx->dcnt->overflow, 0, sizeof(int), ctx->stream));
   if (!ctx->sorted) { if (int st = do_sort(ctx, nullptr)) return st; }
   if (int st = do_delete(ctx)) return st;
   if (np_local) *np_local = ctx->np_local;
@@ -1225,6 +1235,10 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   if (int st = do_sort(ctx, &ndel)) return st;                                            // :61 link_list as a cell sort
   const int np_ghost = ctx->np_all;
   CK(cudaEventRecord(ev[3], ctx->stream));
+  // INVARIANT of the overlapped streams below (coarse stream, two fine tiles in flight, PP after the tiles): kernels on other streams or CTAs
+  // may READ a record's position words while a kick kernel stores the record's (z, vx) float2. The stored z is the value that was loaded
+  // (bit-identical) and an aligned 8-byte store is not torn, so every reader sees the one valid position; velocities are only read by the
+  // kernel that updates them. tests/test_gpu_parity_sizes.py::test_stream_overlap_does_not_change_positions pins this.
   // The coarse-mesh density and force solve only need the sorted positions: run them on their own stream, concurrently with
   // the fine-tile loop (the reference cannot: rho_f/rho_c and force_f/force_c are EQUIVALENCEd, cubep3m.fh:134-135).
   CK(cudaStreamWaitEvent(ctx->stream_coarse, ev[3], 0));

@@ -208,9 +208,12 @@ __global__ void __launch_bounds__(TPB) key_hist_kernel(const float* __restrict__
     const unsigned old = atomicAdd(&hist[k >> 1], 1u << sh);
     if (((old >> sh) & 0xffffu) >= 0xfffeu) atomicOr(&cnt->overflow, 4);
     const float th = 3.0517578125e-05f;   // 2^-15 >= half an ulp of any |x + offset| < 1024
-    if (ceilf(a.x) - a.x <= th || ceilf(a.y) - a.y <= th || ceilf(z) - z <= th) {
+    // exact integers are not candidates: x + offset is exact for them, so both binnings agree
+    const float ux = ceilf(a.x) - a.x, uy = ceilf(a.y) - a.y, uz = ceilf(z) - z;
+    if ((ux > 0.f && ux <= th) || (uy > 0.f && uy <= th) || (uz > 0.f && uz <= th)) {
       const int slot = atomicAdd(&cnt->n_cand, 1);
       if (slot < cand_cap) { cand[3 * slot] = a.x; cand[3 * slot + 1] = a.y; cand[3 * slot + 2] = z; }
+      else atomicOr(&cnt->overflow, 8);     // never silently truncated: the step returns ECAPACITY
     }
   } else {
     atomicAdd(&cnt->np_deleted, 1);   // 'PARTICLE DELETED' link_list.f90:32
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(TPB) scan_apply_kernel(const unsigned int* __r
 
 __global__ void __launch_bounds__(TPB) scatter_kernel(const float* __restrict__ xv_in, const int64_t* __restrict__ pid_in,
                                                       const unsigned int* __restrict__ key, int np, unsigned int* __restrict__ hist,
-                                                      const int* __restrict__ fstart, float* __restrict__ xv_out, int64_t* __restrict__ pid_out) {
+                                                      const int* __restrict__ fstart, float* __restrict__ xv_out, int64_t* __restrict__ pid_out, int np_cap) {
   const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
   if (i >= np) return;
   const unsigned int k = key[i];
@@ -408,6 +411,7 @@ __global__ void __launch_bounds__(TPB) scatter_kernel(const float* __restrict__ 
   // after the scatter and needs no memset before the next step's key_hist_kernel
   const unsigned sh = (k & 1u) << 4;
   const int dst = fstart[k] + (int)((atomicSub(&hist[k >> 1], 1u << sh) >> sh) & 0xffffu) - 1;
+  if ((unsigned)dst >= (unsigned)np_cap) return;   // only reachable after a 16-bit cell counter overflowed (flagged by key_hist_kernel, the step fails with EMAXLLF)
   store_xv(xv_out, dst, a, b, c);
   if (pid_in) pid_out[dst] = pid_in[i];
 }

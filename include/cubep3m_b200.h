@@ -26,6 +26,7 @@ extern "C" {
 #define CUBEP3M_B200_EMAXLLF         5  /* 'exceeded max_llf'                  particle_mesh_threaded.f90:280   */
 #define CUBEP3M_B200_ENCCL           6  /* NCCL failure (replaces an MPI error)                                */
 #define CUBEP3M_B200_ENOTREADY       7  /* call order violated (e.g. particle_mesh before upload)              */
+#define CUBEP3M_B200_ECAPACITY       8  /* an internal work list overflowed (boundary candidates / per-tile moves); nothing is truncated silently */
 
 /*
  * Compile-time `parameter`s of the reference turned into runtime values
@@ -43,7 +44,7 @@ typedef struct cubep3m_b200_config {
   int32_t pp_range;         /* cubepm.par:92                                           */
   int32_t max_np;           /* cubepm.par:170-172; 0 => computed from density_buffer   */
   int32_t max_buf;          /* cubepm.par:175 (floats); 0 => 2.2*max_np                */
-  int32_t max_llf;          /* cubepm.par:183                                          */
+  int32_t max_llf;          /* cubepm.par:183; the library also stops (EMAXLLF) at 65534 particles in ONE fine cell (16-bit cell histogram) */
   float   density_buffer;   /* parameters: density_buffer                              */
   float   rsoft;            /* cubepm.par:76                                           */
   float   pp_bias;          /* cubepm.par:80                                           */
@@ -65,8 +66,6 @@ typedef struct cubep3m_b200_config {
   /* topology (mpi_initialization.f90:42-76): rank = x + D*y + D*D*z, cart_coords(1)=z   */
   int32_t rank;
   int32_t local_gpu;        /* CUDA device ordinal for this rank                       */
-  int32_t tile_split;       /* >1: the T^3 tiles of ONE node are split over this many GPUs (2/4-GPU mode) */
-  int32_t tile_split_rank;  /* which part this process owns                            */
   /* Rank grid (Dx,Dy,Dz) of cubic nodes; all zero => nodes_dim^3 (the reference's only option, mpi_initialization.f90:55-64).
    * 2- and 4-GPU runs use (2,1,1) / (2,2,1): the tiles of one (non-cubic) box split block-wise over the GPUs.
    * rank = x + Dx*(y + Dy*z), as the reference's row-major mpi_cart_create with cart_coords(1) = z.                       */

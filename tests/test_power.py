@@ -80,3 +80,56 @@ def test_device_cic_power_matches_host_twin(built):
         assert rel.max() < 2e-4, (ngp, rel.max())
         assert np.allclose(sg, sh, rtol=5e-3, atol=1e-12)
     pm.close()
+
+
+@pytest.mark.gpu
+def test_pk_config0_z100_to_z10(built):
+    """BASELINE configs[0] as the reference runs it: 128^3 particles, 256^3 fine mesh, tiles_node_dim = 2 (nf_tile = 176), PM only, dist_init-style
+    Zel'dovich ICs at z = 100 evolved to the z = 10 checkpoint by the driver twin (timestep.f90 chooses dt: ~230 steps of da/a <= 1 %, the last
+    one cut to land on a_checkpoint, timestep.f90:128-137) — on the GPU path and on the CPU oracle, each with its own clock fed by its own
+    limiters, same shake offsets. Gate (north_star): cic_power at the final checkpoint within 0.1 % per bin."""
+    from cubep3m_b200.lib import ParticleMesh, clock_init, timestep, absorb_limiters
+    from oracle import Oracle
+    cfg = default_config(nf_tile=176, tiles_node_dim=2, ppint=0, pp_ext=0)
+    box, z_i, z_f = 200.0, 100.0, 10.0
+    xv = ic.zeldovich_ics(cfg.nf_physical_dim, box=box, z_i=z_i, seed=12345)
+    nc = cfg.nf_physical_dim
+    mass_p = float(np.float32(nc) ** 3 / np.float32(len(xv)))
+    pm, o = ParticleMesh(cfg), Oracle(cfg)
+    pm.upload_particles(xv); o.set_particles(xv)
+    a_t = float(np.float32(1.0) / np.float32(1.0 + z_f))
+    ca, cb = clock_init(z_i, ppint=0, a_target=a_t), clock_init(z_i, ppint=0, a_target=a_t)
+    rng = np.random.default_rng(777)
+    shake = np.zeros(3, np.float32)
+    steps = 0
+    while not (ca.checkpoint_step and cb.checkpoint_step):
+        assert steps < 400, "the clocks never reached the checkpoint"
+        assert ca.checkpoint_step == cb.checkpoint_step, "the two sides fell out of step"
+        timestep(ca); timestep(cb)
+        off = ((rng.random(3, dtype=np.float32) - np.float32(0.5)) * np.float32(16.0) - shake).astype(np.float32)
+        shake = shake + off
+        og = pm.particle_mesh(ca.dt, ca.dt_old, ca.a_mid, mass_p, off)
+        oo = o.particle_mesh(cb.dt, cb.dt_old, cb.a_mid, mass_p, off)
+        absorb_limiters(ca, og); absorb_limiters(cb, oo)
+        assert og.np_total == oo.np_total == len(xv)
+        steps += 1
+    assert steps > 150 and ca.nts == cb.nts
+    assert ca.a == pytest.approx(a_t, rel=1e-5) and cb.a == pytest.approx(a_t, rel=1e-5)
+    # checkpoint: half drift to the end of the step (cubepm.f90:175-176), positions minus the shake offset (checkpoint.f90:92)
+    off = ((rng.random(3, dtype=np.float32) - np.float32(0.5)) * np.float32(16.0) - shake).astype(np.float32)
+    shake = shake + off
+    pm.update_position(ca.dt, 0.0, off); o.update_position(cb.dt, 0.0, off)
+    kd, dd, _ = pm.cic_power(box, shake=shake)                       # device cic_power of the resident particles
+    g, r = pm.download_particles(), o.get_particles()
+    pm.close(); o.close()
+    undo = lambda p: np.mod(p[:, :3] - shake, np.float32(nc))
+    kg, dg, _ = power.power_spectrum(undo(g), nc, box)
+    kr, dr, _ = power.power_spectrum(undo(r), nc, box)
+    rel = np.abs(dg - dr) / np.maximum(np.abs(dr), 1e-30)
+    assert rel.max() < 1e-3, (steps, float(rel.max()), int(rel.argmax()))
+    reld = np.abs(dd - dr) / np.maximum(np.abs(dr), 1e-30)
+    assert reld.max() < 1e-3, ("device cic_power", float(reld.max()))
+    # growth sanity: linear growth from z = 100 to z = 10 is (101/11)^2 = 84 in power on large scales (Omega_m ~ 1 at these redshifts)
+    k0, d0, _ = power.power_spectrum(xv[:, :3], nc, box)
+    big = slice(2, 10)
+    assert 60 < np.median(dr[big] / d0[big]) < 110, np.median(dr[big] / d0[big])

@@ -114,7 +114,8 @@ def test_pk_config0_z100_to_z10(built):
         assert og.np_total == oo.np_total == len(xv)
         steps += 1
     assert steps > 150 and ca.nts == cb.nts
-    assert ca.a == pytest.approx(a_t, rel=1e-5) and cb.a == pytest.approx(a_t, rel=1e-5)
+    # the last step is cut linearly in dt (timestep.f90:131-133), which lands a within ~2e-5 of a_checkpoint, not on it
+    assert ca.a == pytest.approx(a_t, rel=1e-4) and cb.a == pytest.approx(ca.a, rel=2e-6)
     # checkpoint: half drift to the end of the step (cubepm.f90:175-176), positions minus the shake offset (checkpoint.f90:92)
     off = ((rng.random(3, dtype=np.float32) - np.float32(0.5)) * np.float32(16.0) - shake).astype(np.float32)
     shake = shake + off

@@ -40,6 +40,7 @@ WORKLOADS = {
     "c2": (304, 4, 1, 1, 200.0, 100.0, "BASELINE configs[2]: 512^3 particles, 1024^3 fine mesh, PPINT + PP_EXT, nodes_dim=1, tiles_node_dim=4 (nf_tile=304); ICs = 2x2x2 periodic replication of the 256^3-particle box"),
     "c0": (176, 2, 0, 0, 200.0, 100.0, "BASELINE configs[0]: 128^3 particles, 256^3 fine mesh, PM only, tiles_node_dim=2 (nf_tile=176)"),
     "c1c": (560, 1, 1, 0, 200.0, 100.0, "BASELINE configs[1] variant: 256^3 particles, 512^3 fine mesh, PPINT on, tiles_node_dim=1 (nf_tile=560)"),
+    "c1x": (304, 2, 1, 1, 200.0, 100.0, "BASELINE configs[1] box (256^3 particles, 512^3 fine mesh, nf_tile=304) with PPINT + PP_EXT on: one octant of configs[2], used for the clustered-input PP measurement"),
     "c0x": (176, 2, 1, 1, 200.0, 100.0, "profiling aid: BASELINE configs[0] box (128^3 particles, 256^3 fine mesh) with PPINT + PP_EXT on"),
     "tiny": (112, 2, 1, 0, 50.0, 20.0, "dev smoke: 64^3 particles, 128^3 fine mesh"),
 }
@@ -87,7 +88,7 @@ def algorithmic_bytes(cfg, np_local, np_all):
         "cic_mass": 12.0 * np_all * ((cfg.nc_node + 2) / cfg.H) ** 3 + 4.0 * cfg.nc_node ** 3,   # §8(d): 12 B per deposited particle (+ rho_c written once)
         "cic_kick": 48.0 * np_local,                    # fused coarse kick + compaction: 24 B record read + 24 B written
         "compact": None,
-        "coarse_fft": None, "coarse_misc": None, "coarse_xchg": None, "ppint": None, "ppext": None, "ppext_margin": None, "misc": None,
+        "coarse_fft": None, "coarse_misc": None, "coarse_xchg": None, "ppint": None, "ppext": None, "ppext_dense": None, "ppext_margin": None, "misc": None,
         "_NF": NF, "_A": A,
     }
 
@@ -286,6 +287,20 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    evolve = None
+    if args.evolve_to_z is not None:
+        # clustered input: the box is evolved on the GPU from the ICs to redshift z with the driver twin choosing dt, so that PPINT /
+        # PP_EXT are measured on halos instead of the z_i near-lattice; the timed steps that follow continue the same run
+        a_stop = 1.0 / (1.0 + args.evolve_to_z)
+        t_ev = time.perf_counter()
+        n_ev = 0
+        while clk.a < a_stop and n_ev < args.evolve_max_steps:
+            o_ev = one_step()
+            n_ev += 1
+            if rank == 0 and n_ev % 100 == 0:
+                print(f"[evolve] step {n_ev} a={clk.a:.4f} z={1 / clk.a - 1:.2f} dt={clk.dt:.4f} step_ms={o_ev.stage_ms[12]:.2f} pp_ext_ms={o_ev.stage_ms[7]:.2f} "
+                      f"limiters f={o_ev.dt_f_acc:.3f} pp={o_ev.dt_pp_acc:.3f} ppx={o_ev.dt_pp_ext_acc:.3f} c={o_ev.dt_c_acc:.3f}", file=sys.stderr, flush=True)
+        evolve = {"to_z": 1.0 / clk.a - 1.0, "steps": n_ev, "seconds": time.perf_counter() - t_ev}
     for _ in range(args.warmup):
         one_step()
     # ---- timed region A: K steps, resident mode, no per-launch instrumentation -> `value`
@@ -363,6 +378,9 @@ def run_ours(args):
                 e["algorithmic_MB_per_launch"] = ab[k] / 1e6
                 e["achieved_GBs"] = ab[k] / (per * 1e-3) / 1e9
                 e["frac_of_hbm_peak"] = e["achieved_GBs"] / peak
+            if k == "ppext" and "ppext_dense" in class_ms:
+                ms = ms + class_ms["ppext_dense"][0]     # the pair count covers the sparse (tiled) and the dense (cell-pair) kernels together
+                e["ms_per_step_incl_dense"] = ms / args.steps
             if k in pair_counts and pair_counts[k] > 0:
                 # FP32-pipe stages: 20 flop per ordered pair interaction evaluated against the measured FFMA peak
                 fpk, fsrc = fp32_peak()
@@ -413,7 +431,8 @@ def run_ours(args):
                        "timing": "host clock around K steps between barrier+synchronize, max over ranks (CUDA-event sum in device_ms_per_step); working set (particles 0.4 GB + cell table 1.4 GB) exceeds the 126 MB L2",
                        "ics": f"Zel'dovich LCDM (EH no-wiggle), z_i={z_i}, box={box} Mpc/h per node, numpy seed 12345 (same box on every rank), generated in {t_ic:.1f}s",
                        "rank_grid": list(grid), "parallelism": f"{world} rank(s), one cubic node of {cfg.tiles_node} tiles per GPU; particle_pass packed straight into the neighbour's memory over NVLink (NCCL send/recv fallback), all-gathered replicated coarse solve",
-                       "mode": "resident (particles stay in HBM between steps)", "fine_tiles_in_flight": min(tile_streams, cfg.tiles_node)},
+                       "mode": "resident (particles stay in HBM between steps)", "fine_tiles_in_flight": min(tile_streams, cfg.tiles_node),
+                       "evolved": evolve, "ppext_blocks_tiled_fallback": list(pm.ppext_blocks())},
             "device_ms_per_step": dev_step,
             "e2e": {"value": total_particles / (e2e_ms * 1e-3), "unit": "particles/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(npart) * 24, "d2h_bytes_per_step": int(npart) * 24, "steps": e2e_steps,
@@ -442,6 +461,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--evolve-to-z", type=float, default=None, help="evolve the box on the GPU to this redshift before measuring (clustered input for the PP stages)")
+    ap.add_argument("--evolve-max-steps", type=int, default=4000)
     ap.add_argument("--no-profile", action="store_true", help="do not bracket launches with events in the timed region (overhead check)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -28,12 +28,12 @@
 enum KernelClass {
   KC_DRIFT = 0, KC_PASS_PACK, KC_PASS_UNPACK, KC_KEY_HIST, KC_SCAN, KC_SCATTER, KC_DENSITY,
   KC_FFT_X_R2C, KC_FFT_FWD_STRIDED, KC_FFT_INV_Z_MUL, KC_FFT_INV_Y, KC_FFT_X_C2R, KC_FORCE_MAX, KC_NGP_KICK,
-  KC_PPINT, KC_PPEXT, KC_PPEXT_MARGIN, KC_CIC_MASS, KC_COARSE_FFT, KC_COARSE_MISC, KC_COARSE_XCHG, KC_CIC_KICK, KC_COMPACT, KC_MISC, KC_COUNT
+  KC_PPINT, KC_PPEXT, KC_PPEXT_DENSE, KC_PPEXT_MARGIN, KC_CIC_MASS, KC_COARSE_FFT, KC_COARSE_MISC, KC_COARSE_XCHG, KC_CIC_KICK, KC_COMPACT, KC_MISC, KC_COUNT
 };
 static const char* const kKernelClassNames[KC_COUNT] = {
   "drift", "pass_pack", "pass_unpack", "key_hist", "scan", "scatter", "ngp_density",
   "fft_x_r2c", "fft_fwd_strided", "fft_inv_z_mul", "fft_inv_y", "fft_x_c2r", "force_max", "ngp_kick",
-  "ppint", "ppext", "ppext_margin", "cic_mass", "coarse_fft", "coarse_misc", "coarse_xchg", "cic_kick", "compact", "misc"};
+  "ppint", "ppext", "ppext_dense", "ppext_margin", "cic_mass", "coarse_fft", "coarse_misc", "coarse_xchg", "cic_kick", "compact", "misc"};
 
 constexpr int PROF_MAX = 8192;   // profiled launches per step
 
@@ -85,6 +85,8 @@ struct DevCounters {
   int np_phys;           // after delete_particles
   int n_cand;            // particles within half an ulp below a fine-cell boundary (see fine::ngp_fixup_kernel)
   int n_blist;           // particles near a y or z face, listed by the first particle_pass kernel
+  int n_ppext_items;     // (fine cell, 32-target chunk) items of the dense PP_EXT blocks (pp::ppext_items_kernel)
+  int ppext_ticket;      // work ticket of pp::ppext_cell_kernel (must follow n_ppext_items: both are cleared together)
   int n_margin_roles;    // (particle, tile) margin roles listed for the PP_EXT limiter (pp::ppext_margin_list_kernel)
   int xchg_timeout;      // a coarse-mesh exchange wait (coarse_slab.cuh) gave up on a peer
   int n_ppext_fallback;  // PP_EXT blocks whose source region exceeded the shared-memory capacity (walked directly instead)
@@ -150,6 +152,7 @@ struct cubep3m_b200_ctx {
   int ppext_mode = 1;          // 1: tiled shared-memory kernel (pp::ppext_tiled_kernel), 0: direct one-thread-per-target kernel (CUBEP3M_B200_PPEXT=direct)
   int* ppext_ovf = nullptr;    // ids of the PP_EXT target blocks that exceeded the tiled kernel's shared-memory capacity
   bool ppext_margin_max = true; // also evaluate the margin particles' partial sums for pp_ext_force_max (particle_mesh_threaded.f90:617); CUBEP3M_B200_PPEXT_MARGIN=0 skips it
+  int2* ppext_items = nullptr; int ppext_item_cap = 0; bool ppext_cell_mode = true;   // dense-block PP_EXT work items
   int2* margin_roles = nullptr; int margin_cap = 0;   // (particle index, tile) list of the PP_EXT margin roles
   int ppext_blocks = 0, ppext_fallback = 0;
   long long pairs_ppint = 0, pairs_ppext = 0;   // of the last step   // of the last step (debug getter)

@@ -734,8 +734,17 @@ int do_pp_ext(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
       else
         LAUNCH(ctx, KC_PPEXT, pp::ppext_tiled_kernel<-1>, ctx->ppext_blocks, pp::TB_NT, pp::TB_SMEM, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->d.b, ctx->d.nc_buf, nc, nbx, nby,
                ctx->cfg.pp_range, P, ctx->dcnt, &ctx->dcnt->n_ppext_fallback, ctx->ppext_ovf);
-      LAUNCH(ctx, KC_PPEXT, pp::ppext_blocklist_kernel, std::min(ctx->ppext_blocks, NUM_SMS * 8), pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->d.b, ctx->d.nc_buf, nc,
-             nbx, nby, ctx->cfg.pp_range, P, ctx->dcnt, &ctx->dcnt->n_ppext_fallback, ctx->ppext_ovf);
+      // dense blocks (overflow list): (cell, chunk) items -> one warp per item; the direct walk only if the item list overflowed
+      const int icap = ctx->ppext_cell_mode ? ctx->ppext_item_cap : 0;
+      CK(cudaMemsetAsync(&ctx->dcnt->n_ppext_items, 0, 2 * sizeof(int), ctx->stream));
+      if (icap > 0) {
+        LAUNCH(ctx, KC_PPEXT, pp::ppext_items_kernel, std::min(ctx->ppext_blocks, NUM_SMS * 8), pp::TB_NT, 0, ctx->fstart, ctx->d.H, ctx->d.nc_buf, nc, nbx, nby,
+               &ctx->dcnt->n_ppext_fallback, ctx->ppext_ovf, ctx->ppext_items, icap, &ctx->dcnt->n_ppext_items);
+        LAUNCH(ctx, KC_PPEXT_DENSE, pp::ppext_cell_kernel, NUM_SMS * 8, pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->cfg.pp_range, P, ctx->dcnt, ctx->ppext_items, icap,
+               &ctx->dcnt->n_ppext_items, &ctx->dcnt->ppext_ticket);
+      }
+      LAUNCH(ctx, KC_PPEXT_DENSE, pp::ppext_blocklist_kernel, std::min(ctx->ppext_blocks, NUM_SMS * 8), pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->d.b, ctx->d.nc_buf, nc,
+             nbx, nby, ctx->cfg.pp_range, P, ctx->dcnt, &ctx->dcnt->n_ppext_fallback, ctx->ppext_ovf, &ctx->dcnt->n_ppext_items, icap);
     } else if (ctx->np_all > 0) {
       LAUNCH(ctx, KC_PPEXT, pp::ppext_kernel, (ctx->np_all + pp::EXT_TPB - 1) / pp::EXT_TPB, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->np_all, ctx->d.H,
              ctx->d.b, ctx->d.nc_buf, ctx->d.nc_node, ctx->cfg.pp_range, P, ctx->dcnt);
@@ -947,7 +956,7 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->stream_coarse) cudaStreamDestroy(ctx->stream_coarse);
-  F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->creal); F(ctx->gather); F(ctx->force_c); F(ctx->redbuf); F(ctx->cntbuf); F(ctx->dcnt); F(ctx->ppext_ovf); F(ctx->margin_roles);
+  F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->creal); F(ctx->gather); F(ctx->force_c); F(ctx->redbuf); F(ctx->cntbuf); F(ctx->dcnt); F(ctx->ppext_ovf); F(ctx->margin_roles); F(ctx->ppext_items);
   for (int a = 0; a < 3; ++a) { bool dup = false; for (int b2 = 0; b2 < a; ++b2) dup |= (ctx->tw_c[b2] == ctx->tw_c[a]); if (!dup) F(ctx->tw_c[a]); }
   if (ctx->hcnt) cudaFreeHost(ctx->hcnt);
   if (ctx->ev_ok) for (auto& e : ctx->ev) cudaEventDestroy(e);
@@ -1008,6 +1017,9 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   if (cfg->pp_ext) {
     const int nc = ctx->d.nc_node;
     TRY(dmalloc(&ctx->ppext_ovf, (size_t)((nc + pp::TB_X - 1) / pp::TB_X) * ((nc + pp::TB_Y - 1) / pp::TB_Y) * ((nc + pp::TB_Z - 1) / pp::TB_Z)));
+    ctx->ppext_item_cap = d.max_np / 8 + 4096;
+    TRY(dmalloc(&ctx->ppext_items, (size_t)ctx->ppext_item_cap));
+    { const char* e = getenv("CUBEP3M_B200_PPEXT_DENSE"); ctx->ppext_cell_mode = !(e && !strcmp(e, "direct")); }   // A/B: "direct" = the one-thread-per-target walk
     ctx->margin_cap = d.max_np / 8 + 4096;
     TRY(dmalloc(&ctx->margin_roles, (size_t)ctx->margin_cap));
   }

@@ -2,4 +2,4 @@
 
 This package is the thin Python harness: ctypes binding of the CUDA library, the kernel tables, the
 synthetic IC generator and the P(k) twin.  The product is cubep3m_b200/csrc (CUDA + C ABI)."""
-from .abi import Config, StepOut, Clock, default_config, copy_config, max_np, ST_NAMES  # noqa: F401
+from .abi import Config, StepOut, Clock, CheckpointHeader, checkpoint_name, default_config, copy_config, max_np, ST_NAMES  # noqa: F401

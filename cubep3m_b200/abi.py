@@ -113,6 +113,18 @@ class Clock(C.Structure):
                [(n, C.c_int32) for n in ("nts", "ppint", "pp_ext", "cosmo", "checkpoint_step")]
 
 
+class CheckpointHeader(C.Structure):
+    """checkpoint.f90:72-78 (the file holds dt_pp_acc only with -DPPINT)."""
+    _fields_ = [("np_local", C.c_int32), ("a", C.c_float), ("t", C.c_float), ("tau", C.c_float), ("nts", C.c_int32),
+                ("dt_f_acc", C.c_float), ("dt_pp_acc", C.c_float), ("dt_c_acc", C.c_float),
+                ("cur_checkpoint", C.c_int32), ("cur_projection", C.c_int32), ("cur_halofind", C.c_int32), ("mass_p", C.c_float)]
+
+
+def checkpoint_name(z, rank, kind="xv"):
+    """checkpoint.f90:31-46: write(z_s,'(f7.3)') z; adjustl; <z>xv<rank>.dat / <z>PID<rank>.dat"""
+    return f"{z:7.3f}".strip() + kind + f"{rank:d}" + ".dat"
+
+
 def max_np(c: Config) -> int:
     """cubepm.par:170-172."""
     if c.max_np > 0:

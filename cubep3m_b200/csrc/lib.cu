@@ -10,6 +10,7 @@
 #include "coarse.cuh"
 #include "coarse_slab.cuh"
 #include "power.cuh"
+#include "distinit.cuh"
 
 namespace {
 
@@ -1523,6 +1524,180 @@ int cubep3m_b200_cic_power(cubep3m_b200_ctx* ctx, const float shake_offset[3], d
     delta2_out[sh - 1] = 4.0 * M_PI * keff * keff * keff * Pm;
     if (sigma_out) sigma_out[sh - 1] = 4.0 * M_PI * keff * keff * keff * sqrt(var / std::max(W[sh] - 1.0, 1.0));
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------- dist_init on the device (utils/dist_init/dist_init_dm.f90)
+extern "C" int cubep3m_b200_dist_init(cubep3m_b200_ctx* ctx, int32_t nc, int32_t reps, float box, float vfactor, uint64_t seed, const float* k_table,
+                                      const float* delta2_table, int32_t n_table, const float* noise, int32_t* np_local) {
+  if (!ctx || !k_table || !delta2_table || n_table < 2 || reps < 1 || nc < 4 || nc % 2) return CUBEP3M_B200_EINVAL;
+  const Dims& d = ctx->d;
+  if (d.world != 1 || nc * reps != d.mT || !fftk::supported(nc)) return CUBEP3M_B200_EINVAL;   // one rank; the box (times its replication) is the node
+  const long long np = (long long)(nc / 2) * (nc / 2) * (nc / 2) * reps * reps * reps;
+  if (np > d.max_np) return CUBEP3M_B200_EMAXNP;
+  CK(cudaSetDevice(ctx->device));
+  const size_t nreal = (size_t)(nc + 2) * nc * nc;
+  float *mesh = nullptr, *phi = nullptr, *tab = nullptr; float2* tw = nullptr;
+  auto cleanup = [&]() { if (mesh) cudaFree(mesh); if (phi) cudaFree(phi); if (tab) cudaFree(tab); if (tw) cudaFree(tw); };
+#define DCK(x) do { if ((x) != cudaSuccess) { cleanup(); return CUBEP3M_B200_ECUDA; } } while (0)
+  DCK(cudaMalloc((void**)&mesh, nreal * sizeof(float)));
+  DCK(cudaMalloc((void**)&phi, nreal * sizeof(float)));
+  DCK(cudaMalloc((void**)&tab, (size_t)2 * n_table * sizeof(float)));
+  if (fftk::make_twiddles(nc, &tw)) { cleanup(); return CUBEP3M_B200_ECUDA; }
+  DCK(cudaMemcpyAsync(tab, k_table, n_table * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  DCK(cudaMemcpyAsync(tab + n_table, delta2_table, n_table * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  if (noise) DCK(cudaMemcpy2DAsync(mesh, (size_t)(nc + 2) * sizeof(float), noise, (size_t)nc * sizeof(float), (size_t)nc * sizeof(float), (size_t)nc * nc, cudaMemcpyHostToDevice, ctx->stream));
+  else LAUNCH(ctx, KC_MISC, distinit::noise_kernel, NUM_SMS * 8, distinit::TPB, 0, mesh, nc, (unsigned long long)seed);      // :535-667
+  const fftk::Mesh3 g{nc, nc, nc, tw, tw, tw};
+  if (int st = fftk::forward3d(ctx, g, mesh)) { cleanup(); return st; }                                                        // :653
+  LAUNCH(ctx, KC_MISC, distinit::phi_k_kernel, NUM_SMS * 8, distinit::TPB, 0, reinterpret_cast<float2*>(mesh), nc, box, tab, tab + n_table, n_table);   // :685-712, :814-832
+  const int lo[3] = {0, 0, 0}, cnt[3] = {nc, nc, nc};
+  const float scale = 1.0f / (((float)nc * (float)nc) * (float)nc);
+  if (int st = fftk::backward3d(ctx, g, mesh, mesh, nullptr, phi, lo, cnt, nc, nc, scale)) { cleanup(); return st; }           // :958-969
+  LAUNCH(ctx, KC_MISC, distinit::particles_kernel, NUM_SMS * 8, distinit::TPB, 0, phi, nc, reps, vfactor, ctx->xv[ctx->cur]); // :1011-1036
+  DCK(cudaStreamSynchronize(ctx->stream));
+  DCK(cudaGetLastError());
+#undef DCK
+  cleanup();
+  ctx->np_local = (int)np; ctx->np_all = (int)np; ctx->sorted = false; ctx->passed = false;
+  if (np_local) *np_local = (int32_t)np;
+  return 0;
+}
+
+// ---------------------------------------------------------------- checkpoint.f90:72-95 / particle_initialization.f90:88-189
+namespace {
+size_t ckpt_header_bytes(const cubep3m_b200_ctx* ctx) { return ctx->cfg.ppint ? 48 : 44; }
+void ckpt_pack_header(const cubep3m_b200_ctx* ctx, const cubep3m_b200_checkpoint_header& h, unsigned char* out) {
+  unsigned char* p = out;
+  auto put = [&](const void* v) { memcpy(p, v, 4); p += 4; };
+  put(&h.np_local); put(&h.a); put(&h.t); put(&h.tau); put(&h.nts); put(&h.dt_f_acc);
+  if (ctx->cfg.ppint) put(&h.dt_pp_acc);
+  put(&h.dt_c_acc); put(&h.cur_checkpoint); put(&h.cur_projection); put(&h.cur_halofind); put(&h.mass_p);
+}
+void ckpt_unpack_header(const cubep3m_b200_ctx* ctx, const unsigned char* in, cubep3m_b200_checkpoint_header* h) {
+  const unsigned char* p = in;
+  auto get = [&](void* v) { memcpy(v, p, 4); p += 4; };
+  memset(h, 0, sizeof(*h));
+  get(&h->np_local); get(&h->a); get(&h->t); get(&h->tau); get(&h->nts); get(&h->dt_f_acc);
+  if (ctx->cfg.ppint) get(&h->dt_pp_acc);
+  get(&h->dt_c_acc); get(&h->cur_checkpoint); get(&h->cur_projection); get(&h->cur_halofind); get(&h->mass_p);
+}
+constexpr long long CKPT_BLOCK = (32LL * 1024 * 1024) / 24;   // particles per block: the reference's blocksize (checkpoint.f90:51, particle_initialization.f90:128)
+}  // namespace
+
+extern "C" int cubep3m_b200_write_checkpoint(cubep3m_b200_ctx* ctx, const char* path_xv, const char* path_pid, const cubep3m_b200_checkpoint_header* hdr,
+                                             const float shake_offset[3]) {
+  if (!ctx || !path_xv || !hdr) return CUBEP3M_B200_EINVAL;
+  if (ctx->passed) return CUBEP3M_B200_ENOTREADY;            // ghosts must be gone (the driver checkpoints between steps)
+  CK(cudaSetDevice(ctx->device));
+  const long long np = ctx->np_local;
+  cubep3m_b200_checkpoint_header h = *hdr;
+  h.np_local = (int32_t)np;
+  unsigned char hb[48];
+  ckpt_pack_header(ctx, h, hb);
+  const float zero[3] = {0.f, 0.f, 0.f};
+  const float* so = shake_offset ? shake_offset : zero;
+  FILE* f = fopen(path_xv, "wb");
+  if (!f) { fprintf(stderr, "cubep3m_b200: error opening checkpoint file for write: %s\n", path_xv); return CUBEP3M_B200_EINVAL; }   // checkpoint.f90:60-64
+  int status = 0;
+  float* dstage[2] = {nullptr, nullptr};
+  float* hstage[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  const long long blk = std::min<long long>(CKPT_BLOCK, std::max<long long>(np, 1));
+  for (int q = 0; q < 2 && !status; ++q)
+    if (cudaMalloc((void**)&dstage[q], blk * 24) != cudaSuccess || cudaMallocHost((void**)&hstage[q], blk * 24) != cudaSuccess ||
+        cudaEventCreateWithFlags(&done[q], cudaEventDisableTiming) != cudaSuccess) status = CUBEP3M_B200_ECUDA;
+  if (!status && fwrite(hb, 1, ckpt_header_bytes(ctx), f) != ckpt_header_bytes(ctx)) status = CUBEP3M_B200_EINVAL;
+  // double-buffered: block k+1 is packed and copied while block k is written to the file
+  const long long nblk = (np + blk - 1) / blk;
+  auto issue = [&](long long k) {
+    const int q = (int)(k & 1);
+    const long long first = k * blk;
+    const int cnt = (int)std::min(blk, np - first);
+    LAUNCH(ctx, KC_MISC, part::checkpoint_pack_kernel, (cnt + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], first, cnt, so[0], so[1], so[2], dstage[q]);
+    cudaMemcpyAsync(hstage[q], dstage[q], (size_t)cnt * 24, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaEventRecord(done[q], ctx->stream);
+  };
+  if (!status && nblk > 0) issue(0);
+  for (long long k = 0; k < nblk && !status; ++k) {
+    const int q = (int)(k & 1);
+    if (cudaEventSynchronize(done[q]) != cudaSuccess) { status = CUBEP3M_B200_ECUDA; break; }
+    if (k + 1 < nblk) issue(k + 1);
+    const size_t cnt = (size_t)std::min(blk, np - k * blk);
+    if (fwrite(hstage[q], 24, cnt, f) != cnt) status = CUBEP3M_B200_EINVAL;
+  }
+  if (fclose(f) != 0 && !status) status = CUBEP3M_B200_EINVAL;
+  if (!status && path_pid && ctx->cfg.pid) {                   // checkpoint.f90:99-135
+    FILE* g = fopen(path_pid, "wb");
+    if (!g) status = CUBEP3M_B200_EINVAL;
+    else {
+      if (fwrite(hb, 1, ckpt_header_bytes(ctx), g) != ckpt_header_bytes(ctx)) status = CUBEP3M_B200_EINVAL;
+      int64_t* hp = reinterpret_cast<int64_t*>(hstage[0]);
+      const long long pblk = blk * 3;                          // ids per staging buffer
+      for (long long first = 0; first < np && !status; first += pblk) {
+        const size_t cnt = (size_t)std::min(pblk, np - first);
+        if (cudaMemcpyAsync(hp, ctx->pid[ctx->cur] + first, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { status = CUBEP3M_B200_ECUDA; break; }
+        if (fwrite(hp, 8, cnt, g) != cnt) status = CUBEP3M_B200_EINVAL;
+      }
+      if (fclose(g) != 0 && !status) status = CUBEP3M_B200_EINVAL;
+    }
+  }
+  cudaStreamSynchronize(ctx->stream);
+  for (int q = 0; q < 2; ++q) { if (dstage[q]) cudaFree(dstage[q]); if (hstage[q]) cudaFreeHost(hstage[q]); if (done[q]) cudaEventDestroy(done[q]); }
+  if (cudaGetLastError() != cudaSuccess && !status) status = CUBEP3M_B200_ECUDA;
+  return status;
+}
+
+extern "C" int cubep3m_b200_read_checkpoint(cubep3m_b200_ctx* ctx, const char* path_xv, const char* path_pid, cubep3m_b200_checkpoint_header* hdr) {
+  if (!ctx || !path_xv || !hdr) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  FILE* f = fopen(path_xv, "rb");
+  if (!f) { fprintf(stderr, "cubep3m_b200: error opening checkpoint: %s\n", path_xv); return CUBEP3M_B200_EINVAL; }     // particle_initialization.f90:106-110
+  unsigned char hb[48];
+  if (fread(hb, 1, ckpt_header_bytes(ctx), f) != ckpt_header_bytes(ctx)) { fclose(f); return CUBEP3M_B200_EINVAL; }
+  ckpt_unpack_header(ctx, hb, hdr);
+  const long long np = hdr->np_local;
+  if (np < 0 || np > ctx->d.max_np) { fclose(f); fprintf(stderr, "cubep3m_b200: too many particles to store\n"); return CUBEP3M_B200_EMAXNP; }   // :122-126
+  int status = 0;
+  float* hstage[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  const long long blk = std::min<long long>(CKPT_BLOCK, std::max<long long>(np, 1));
+  for (int q = 0; q < 2 && !status; ++q)
+    if (cudaMallocHost((void**)&hstage[q], blk * 24) != cudaSuccess || cudaEventCreateWithFlags(&done[q], cudaEventDisableTiming) != cudaSuccess) status = CUBEP3M_B200_ECUDA;
+  const long long nblk = (np + blk - 1) / blk;
+  for (long long k = 0; k < nblk && !status; ++k) {
+    const int q = (int)(k & 1);
+    if (k >= 2 && cudaEventSynchronize(done[q]) != cudaSuccess) { status = CUBEP3M_B200_ECUDA; break; }   // the copy that last used this buffer has finished
+    const size_t cnt = (size_t)std::min(blk, np - k * blk);
+    if (fread(hstage[q], 24, cnt, f) != cnt) { status = CUBEP3M_B200_EINVAL; break; }
+    if (cudaMemcpyAsync(ctx->xv[ctx->cur] + (size_t)6 * k * blk, hstage[q], cnt * 24, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { status = CUBEP3M_B200_ECUDA; break; }
+    cudaEventRecord(done[q], ctx->stream);
+  }
+  fclose(f);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !status) status = CUBEP3M_B200_ECUDA;
+  if (!status && path_pid && ctx->cfg.pid) {                   // particle_initialization.f90:146-189
+    FILE* g = fopen(path_pid, "rb");
+    if (!g) status = CUBEP3M_B200_EINVAL;
+    else {
+      unsigned char hb2[48];
+      cubep3m_b200_checkpoint_header h2;
+      if (fread(hb2, 1, ckpt_header_bytes(ctx), g) != ckpt_header_bytes(ctx)) status = CUBEP3M_B200_EINVAL;
+      else { ckpt_unpack_header(ctx, hb2, &h2); if (h2.np_local != hdr->np_local) status = CUBEP3M_B200_EINVAL; }
+      int64_t* hp = reinterpret_cast<int64_t*>(hstage[0]);
+      const long long pblk = blk * 3;
+      for (long long first = 0; first < np && !status; first += pblk) {
+        const size_t cnt = (size_t)std::min(pblk, np - first);
+        if (fread(hp, 8, cnt, g) != cnt) { status = CUBEP3M_B200_EINVAL; break; }
+        if (cudaMemcpyAsync(ctx->pid[ctx->cur] + first, hp, cnt * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) status = CUBEP3M_B200_ECUDA;
+      }
+      fclose(g);
+    }
+  }
+  for (int q = 0; q < 2; ++q) { if (hstage[q]) cudaFreeHost(hstage[q]); if (done[q]) cudaEventDestroy(done[q]); }
+  if (status) return status;
+  ctx->np_local = (int)np; ctx->np_all = (int)np; ctx->sorted = false; ctx->passed = false;
   return 0;
 }
 

@@ -44,6 +44,17 @@ __global__ void __launch_bounds__(TPB) shift_kernel(float* __restrict__ xv, int 
   p[0] = a; p[1] = b;
 }
 
+// checkpoint.f90:92: write(12) xv(1:3,j) - shake_offset, xv(4:6,j)  — a block of records staged for the writer
+__global__ void __launch_bounds__(TPB) checkpoint_pack_kernel(const float* __restrict__ xv, long long first, int count, float sx, float sy, float sz,
+                                                              float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i >= count) return;
+  float2 a, b, c;
+  load_xv(xv, first + i, a, b, c);
+  a.x = __fsub_rn(a.x, sx); a.y = __fsub_rn(a.y, sy); b.x = __fsub_rn(b.x, sz);
+  store_xv(out, i, a, b, c);
+}
+
 // link_list.f90:26-31: a particle is chained iff floor(x/4)+1 lies in [hoc_nc_l, hoc_nc_h] on all axes,
 // i.e. -nf_buf <= x < mT + nf_buf.
 __device__ __forceinline__ bool in_hoc_range(float x, float y, float z, float lo, float hi) {

@@ -9,7 +9,7 @@ import os
 import subprocess
 import numpy as np
 
-from .abi import Config, StepOut, Clock, ERRORS, max_np
+from .abi import Config, StepOut, Clock, CheckpointHeader, ERRORS, max_np
 from . import tables
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -28,7 +28,7 @@ SYMBOLS = ["cubep3m_b200_version", "cubep3m_b200_strerror", "cubep3m_b200_defaul
            "cubep3m_b200_debug_rho_c", "cubep3m_b200_debug_force_c", "cubep3m_b200_debug_fine_tile",
            "cubep3m_b200_debug_fft3d", "cubep3m_b200_debug_ppext_blocks", "cubep3m_b200_debug_pair_counts", "cubep3m_b200_launch_count", "cubep3m_b200_set_profiling", "cubep3m_b200_set_tile_streams",
            "cubep3m_b200_num_kernel_classes", "cubep3m_b200_kernel_class_name", "cubep3m_b200_get_kernel_times",
-           "cubep3m_b200_cic_power", "cubep3m_b200_clock_init",
+           "cubep3m_b200_cic_power", "cubep3m_b200_dist_init", "cubep3m_b200_write_checkpoint", "cubep3m_b200_read_checkpoint", "cubep3m_b200_clock_init",
            "cubep3m_b200_expansion", "cubep3m_b200_timestep"]
 
 
@@ -85,6 +85,9 @@ def load_library():
     L.cubep3m_b200_set_tile_streams.argtypes = [C.c_void_p, C.c_int]
     L.cubep3m_b200_cic_power.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_double, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          C.POINTER(C.c_double), C.c_int32]
+    L.cubep3m_b200_dist_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_uint64, _fp, _fp, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]
+    L.cubep3m_b200_write_checkpoint.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(CheckpointHeader), C.POINTER(C.c_float)]
+    L.cubep3m_b200_read_checkpoint.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(CheckpointHeader)]
     L.cubep3m_b200_kernel_class_name.restype = C.c_char_p
     L.cubep3m_b200_kernel_class_name.argtypes = [C.c_int]
     L.cubep3m_b200_get_kernel_times.argtypes = [C.c_void_p, _fp, C.c_void_p]
@@ -260,6 +263,31 @@ class ParticleMesh:
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
         _chk(self.lib.cubep3m_b200_cic_power(self.h, off, C.c_double(box), 1 if ngp_binning else 0, dp(k), dp(d2), dp(sg), n))
         return k, d2, sg
+
+    def dist_init(self, nc, box, z_i, reps=1, seed=12345, noise=None, om=0.24, ol=0.76, table=None):
+        """Device twin of utils/dist_init (dist_init_dm.f90): Zel'dovich ICs generated in place; returns np_local. `table` = (k, Delta^2) at the
+        initial epoch; default: the Eisenstein-Hu no-wiggle spectrum of cubep3m_b200/ic.py (the reference reads a CAMB table)."""
+        from . import ic
+        a = 1.0 / (1.0 + z_i)
+        if table is None:
+            k = np.logspace(-4, 2, 2048)
+            table = (k, ic.delta2(k, a, om, ol))
+        kt = np.ascontiguousarray(table[0], np.float32); dt = np.ascontiguousarray(table[1], np.float32)
+        nz = None if noise is None else np.ascontiguousarray(noise, np.float32)
+        n = C.c_int32()
+        _chk(self.lib.cubep3m_b200_dist_init(self.h, int(nc), int(reps), float(box), float(ic.vfactor(a, om, ol)), int(seed), kt, dt, len(kt), _ptr(nz), C.byref(n)))
+        return n.value
+
+    def write_checkpoint(self, path_xv, hdr: CheckpointHeader, shake=(0.0, 0.0, 0.0), path_pid=None):
+        """checkpoint.f90:72-95: header + (x - shake_offset, v) records of the resident particles (+ the PID file with -DPID_FLAG)."""
+        off = (C.c_float * 3)(*[float(v) for v in shake])
+        _chk(self.lib.cubep3m_b200_write_checkpoint(self.h, os.fsencode(path_xv), None if path_pid is None else os.fsencode(path_pid), C.byref(hdr), off))
+
+    def read_checkpoint(self, path_xv, path_pid=None) -> CheckpointHeader:
+        """particle_initialization.f90:88-189 (restart_ic): fills the device copy from the checkpoint, returns the header."""
+        hdr = CheckpointHeader()
+        _chk(self.lib.cubep3m_b200_read_checkpoint(self.h, os.fsencode(path_xv), None if path_pid is None else os.fsencode(path_pid), C.byref(hdr)))
+        return hdr
 
     def set_profiling(self, on=True):
         _chk(self.lib.cubep3m_b200_set_profiling(self.h, 1 if on else 0))

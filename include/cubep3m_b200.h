@@ -199,6 +199,40 @@ int cubep3m_b200_cic_power(cubep3m_b200_ctx* ctx, const float shake_offset[3], d
                            double* k, double* delta2, double* sigma, int32_t nshells);
 
 /*
+ * dist_init on the device (utils/dist_init/dist_init_dm.f90:448-1046, single rank): Zel'dovich initial conditions generated straight into the
+ * resident particle array, in dist_init's file order. nc = mesh cells per dimension of the generated box (nc/2 particles per dimension), reps >= 1
+ * replicates the periodic box reps^3 times (nc * reps must equal the node's nf_physical_dim; nc must be a transform length the library supports).
+ * (k_table, delta2_table)[n_table]: the dimensionless power spectrum Delta^2(k) at the initial scale factor, k in h/Mpc ascending — what
+ * dist_init builds from batch/camb_WMAP5_transfer_z0.dat, sigma_8 and Dgrow (:448-531); interpolated log-log as `power` does (:1270-1299).
+ * vfactor = a^2 H(a) (:1324-1337). noise: optional host white-noise field nc^3 (z slowest); NULL draws it on the device (Philox4x32-10, Box-Muller
+ * as :617-629). The short-range kernel correction (:850-903) is not applied.
+ */
+int cubep3m_b200_dist_init(cubep3m_b200_ctx* ctx, int32_t nc, int32_t reps, float box, float vfactor, uint64_t seed, const float* k_table,
+                           const float* delta2_table, int32_t n_table, const float* noise, int32_t* np_local);
+
+/*
+ * Checkpoint files in the reference's -DBINARY stream format (checkpoint.f90:72-95 writer, particle_initialization.f90:88-189 reader):
+ *   <z>xv<rank>.dat  = header, then np_local records of 6 float32 (x - shake_offset, v)      (checkpoint.f90:92)
+ *   <z>PID<rank>.dat = the same header, then np_local int64 ids                                (-DPID_FLAG)
+ * header = np_local, a, t, tau, nts, dt_f_acc, [dt_pp_acc only with -DPPINT], dt_c_acc, cur_checkpoint, cur_projection, cur_halofind, mass_p
+ * (4-byte fields, 48 bytes with PPINT, 44 without: the library follows cfg.ppint). The writer streams the RESIDENT particles from the device in
+ * 32 MB blocks (the reference's blocksize) with the shake offset subtracted on the fly, so resident mode never round-trips xv through the driver;
+ * the reader fills the device copy (np_local comes from the file) and returns the header. File names are the caller's (the shim builds them as
+ * checkpoint.f90:31-46 does). path_pid may be NULL.
+ */
+typedef struct cubep3m_b200_checkpoint_header {
+  int32_t np_local;
+  float   a, t, tau;
+  int32_t nts;
+  float   dt_f_acc, dt_pp_acc, dt_c_acc;
+  int32_t cur_checkpoint, cur_projection, cur_halofind;
+  float   mass_p;
+} cubep3m_b200_checkpoint_header;
+int cubep3m_b200_write_checkpoint(cubep3m_b200_ctx* ctx, const char* path_xv, const char* path_pid, const cubep3m_b200_checkpoint_header* hdr,
+                                  const float shake_offset[3]);
+int cubep3m_b200_read_checkpoint(cubep3m_b200_ctx* ctx, const char* path_xv, const char* path_pid, cubep3m_b200_checkpoint_header* hdr);
+
+/*
  * Driver twin (host C++): restatement of timestep / expansion (timestep.f90:2-293) so the harness can
  * run multi-step parity without the Fortran driver. Not needed when the Fortran driver is present.
  */

@@ -167,6 +167,31 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE the pinned host buffers are allocated,
+    so that the e2e leg's H2D / D2H copies of every rank stay on the GPU's own NUMA node (round 1: eight ranks staged through one node and the
+    e2e weak-scaling efficiency at 8 GPUs was 0.33). Returns a note for the JSON line; a no-op when sysfs has nothing to say."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        path = f"/sys/bus/pci/devices/{bdf}/local_cpulist"
+        txt = open(path).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, allowed)
+            return f"rank bound to the {len(allowed)} CPUs local to GPU {bdf}"
+        return f"GPU {bdf}: all allowed CPUs are local ({txt})"
+    except Exception as e:      # noqa: BLE001
+        return f"no NUMA binding ({type(e).__name__})"
+
+
 def oracle_run(cfg, xv, z_i, steps, warmup, budget_s=None):
     """Times the CPU oracle (all host threads) on full particle_mesh steps of the given workload; with budget_s the number of timed steps
     is cut so that the run stays inside the budget (at least one)."""
@@ -238,6 +263,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -430,13 +456,13 @@ def run_ours(args):
             "config": {"workload": desc, "particles_per_gpu": int(npart), "particles_with_ghosts": int(np_all),
                        "timing": "host clock around K steps between barrier+synchronize, max over ranks (CUDA-event sum in device_ms_per_step); working set (particles 0.4 GB + cell table 1.4 GB) exceeds the 126 MB L2",
                        "ics": f"Zel'dovich LCDM (EH no-wiggle), z_i={z_i}, box={box} Mpc/h per node, numpy seed 12345 (same box on every rank), generated in {t_ic:.1f}s",
-                       "rank_grid": list(grid), "parallelism": f"{world} rank(s), one cubic node of {cfg.tiles_node} tiles per GPU; particle_pass packed straight into the neighbour's memory over NVLink (NCCL send/recv fallback), all-gathered replicated coarse solve",
+                       "rank_grid": list(grid), "parallelism": f"{world} rank(s), one cubic node of {cfg.tiles_node} tiles per GPU; particle_pass packed straight into the neighbour's memory over NVLink (NCCL send/recv fallback); coarse mesh " + ("on the one GPU" if world == 1 else "slab-decomposed, pencil transposes and cube/halo scatters stored straight into the peers' memory (all-gather + replicated solve as fallback)"),
                        "mode": "resident (particles stay in HBM between steps)", "fine_tiles_in_flight": min(tile_streams, cfg.tiles_node),
                        "evolved": evolve, "ppext_blocks_tiled_fallback": list(pm.ppext_blocks())},
             "device_ms_per_step": dev_step,
             "e2e": {"value": total_particles / (e2e_ms * 1e-3), "unit": "particles/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(npart) * 24, "d2h_bytes_per_step": int(npart) * 24, "steps": e2e_steps,
-                    "mode": "strict drop-in: pinned host xv -> H2D, particle_mesh, D2H every step (cubepm.f90:143 semantics)"},
+                    "mode": "strict drop-in: pinned host xv -> H2D, particle_mesh, D2H every step (cubepm.f90:143 semantics)", "host_numa": numa_note},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stages": stages,
             "stage_ms_last_step": {k: round(v, 3) for k, v in last.stages().items()},

@@ -290,6 +290,8 @@ def run_ours(args):
     host = torch.empty((max_np(cfg), 6), dtype=torch.float32).pin_memory().numpy()
     host[:npart] = xv
     pm.upload_particles(host[:npart])
+    if world > 1:
+        dist.barrier()          # pinning the host buffers takes seconds and varies per rank: start the first step together
     clk = clock_init(z_i, ppint=cfg.ppint, pp_ext=cfg.pp_ext)
     rng = np.random.default_rng(777)
     shake = np.zeros(3, np.float32)

@@ -468,7 +468,7 @@ int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max, const float* drift = nullptr
       ctx->hbox[0] = ctx->hbox[1] = ctx->hbox[2] = 0;
       CK(cudaMemsetAsync(ctx->cntbuf, 0, 4 * sizeof(int), ctx->stream));
       LAUNCH(ctx, KC_PASS_PACK, part::pass_publish_kernel, 1, 32, 0, ctx->dcnt, ctx->peer_box[axis][0], ctx->peer_box[axis][1], (int)ctx->p2p_epoch);
-      LAUNCH(ctx, KC_PASS_UNPACK, part::pass_wait_kernel, 1, 32, 0, ctx->mailbox + axis * 4, (int)ctx->p2p_epoch, ctx->cntbuf, 10000000000LL);
+      LAUNCH(ctx, KC_PASS_UNPACK, part::pass_wait_kernel, 1, 32, 0, ctx->mailbox + axis * 4, (int)ctx->p2p_epoch, ctx->cntbuf, 60000000000LL);   // ~30 s: ranks may enter a step seconds apart
       CK(cudaMemcpyAsync(ctx->hbox, ctx->cntbuf, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (int st = fetch_counters(ctx)) return st;
@@ -830,7 +830,7 @@ int do_coarse_force_slab(cubep3m_b200_ctx* ctx) {
   const int ep = (int)++ctx->cs_epoch;
   const cslab::Peers& P = ctx->cs_peers;
   const int* mail = reinterpret_cast<const int*>(ctx->cs_xchg + ctx->cs_off_mail);
-  const long long tmo = 20000000000LL;
+  const long long tmo = 60000000000LL;                 // ~30 s of spinning before a wait gives up (ranks may enter a step seconds apart)
   auto sig = [&](int ph) { LAUNCH(ctx, KC_COARSE_MISC, cslab::signal_kernel, 1, 32, 0, P, (long long)ctx->cs_off_mail, W, me, ph, ep); };
   auto wait = [&](int ph) { LAUNCH(ctx, KC_COARSE_XCHG, cslab::wait_kernel, 1, 32, 0, mail, W, ph, ep, &ctx->dcnt->xchg_timeout, tmo); };
   float* slab = ctx->cs_xchg + ctx->cs_off_slab;

@@ -1138,6 +1138,10 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
 #endif
   } else { if (!coarse_table) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_EINVAL; } TRY(build_kern_c(ctx)); }
+  // cudaMemcpy / cudaMemset above run on the legacy default stream, which the library's non-blocking streams do not wait for, and a pageable
+  // host-to-device cudaMemcpy may return before its last DMA has landed: settle the device before any of the library's streams reads the tables
+  // (an intermittent garbage row table of the slab solve — extracted right below from kern_c — was the symptom)
+  if (cudaDeviceSynchronize() != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   if (ctx->coarse_mode == 1) {
     LAUNCH(ctx, KC_MISC, cslab::extract_rows_kernel, grid_for((long long)3 * Nz * ctx->cs_ys * (Nx / 2 + 1), cslab::TPB), cslab::TPB, 0, ctx->kern_c, ctx->cs_kern_rows, Nz, Ny,
            Nx / 2 + 1, ctx->cs_ys, cfg->rank * ctx->cs_ys);
@@ -1145,7 +1149,7 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
     if (d.world > 1) { cudaFree(ctx->kern_c); cudaFree(ctx->slab); ctx->kern_c = nullptr; ctx->slab = nullptr; }   // one rank keeps them for the debug getters / cic_power
   }
 #undef TRY
-  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
+  if (cudaDeviceSynchronize() != cudaSuccess) { cubep3m_b200_finalize(ctx); return CUBEP3M_B200_ECUDA; }
   *out = ctx;
   return 0;
 }

@@ -181,135 +181,6 @@ __global__ void __launch_bounds__(EXT_TPB) ppext_kernel(float* __restrict__ xv, 
   if ((threadIdx.x & 31) == 0 && np_w) atomicAdd(&cnt->pairs_ppext, (unsigned long long)np_w);
 }
 
-// ---- pp_ext_force_max of the MARGIN particles (particle_mesh_threaded.f90:617).
-// The reference evaluates PP_EXT per tile over the tile's physical fine cells plus pp_range cells around them (:397-402) and takes the
-// maximum of |pp_ext_force_accum| over EVERY particle of that region (:617), not only over the kicked (physical) ones. A particle in the
-// margin of a tile has, in that tile, only the partial sum over the partner cells that lie inside the tile's region — and on a near-uniform
-// particle load such a one-sided sum is larger than any complete sum, so it is what sets dt_pp_ext_acc (:692). The kicks never see these
-// sums; they are recomputed here for the limiter only. A (particle, tile) pair with the particle in the tile's margin is a ROLE (up to 7 per
-// particle, ~5 % of the particles have one): ppext_margin_list_kernel compacts the roles (one thread per particle, warp-aggregated append),
-// ppext_margin_roles_kernel evaluates one role per thread with all lanes busy (a thread-per-particle version left 95 % of the lanes idle
-// next to a lane walking 25 neighbour rows: 8.7 ms at 512^3 particles). Cell pairs whose two cells both lie in the tile's upper z margin
-// are never visited by the reference's half stencil ("we never loop towards smaller z", k = 1..nf_physical_tile_dim+pp_range at :496).
-struct MarginGeom { int H, b, m, T, pr; };
-
-// tiles whose region [t*m - pr, (t+1)*m + pr) holds node-frame fine cell q: [tl, th] (empty if tl > th)
-__device__ __forceinline__ void margin_tiles(int q, const MarginGeom& G, int& tl, int& th) {
-  auto fdiv = [&](int v) { return v >= 0 ? v / G.m : -((-v + G.m - 1) / G.m); };
-  tl = max(0, fdiv(q - G.pr)); th = min(G.T - 1, fdiv(q + G.pr));
-}
-// bit (dz*4 + dy*2 + dx) of the result = tile (tl + d) is a ROLE of the particle in hoc-frame fine cell g (in the region, not in the interior)
-__device__ __forceinline__ unsigned margin_roles(const int g[3], const MarginGeom& G, int tl[3]) {
-  int th[3];
-  for (int ax = 0; ax < 3; ++ax) { margin_tiles(g[ax] - G.b, G, tl[ax], th[ax]); if (tl[ax] > th[ax]) return 0u; }
-  unsigned mask = 0;
-  for (int dz = 0; dz <= th[2] - tl[2]; ++dz)
-    for (int dy = 0; dy <= th[1] - tl[1]; ++dy)
-      for (int dx = 0; dx <= th[0] - tl[0]; ++dx) {
-        const int t3[3] = {tl[0] + dx, tl[1] + dy, tl[2] + dz};
-        bool interior = true;
-        for (int ax = 0; ax < 3; ++ax) interior &= (g[ax] - G.b >= t3[ax] * G.m && g[ax] - G.b < (t3[ax] + 1) * G.m);
-        if (!interior) mask |= 1u << (dz * 4 + dy * 2 + dx);
-      }
-  return mask;
-}
-// |partial sum| of the particle at pi (hoc-frame fine cell g) over the partner cells inside the region of tile t3
-__device__ __forceinline__ float margin_role_sum(const float* __restrict__ xv, const int* __restrict__ fstart, const float3 pi, const int g[3], const int t3[3],
-                                                 const MarginGeom& G, const PPParams& P) {
-  const int pr = G.pr, H = G.H;
-  int lo[3], hi[3];                                   // the tile's region in the hoc-range frame (inclusive)
-  for (int ax = 0; ax < 3; ++ax) { lo[ax] = t3[ax] * G.m - pr + G.b; hi[ax] = (t3[ax] + 1) * G.m + pr - 1 + G.b; }
-  const int ztop = (t3[2] + 1) * G.m + G.b;           // first cell of the upper z margin
-  float3 acc = make_float3(0.f, 0.f, 0.f);
-  const int x0 = max(g[0] - pr, lo[0]), x1 = min(g[0] + pr, hi[0]);
-#pragma unroll 1
-  for (int nz = max(g[2] - pr, lo[2]); nz <= min(g[2] + pr, hi[2]); ++nz) {
-    if (g[2] >= ztop && nz >= ztop) continue;
-#pragma unroll 1
-    for (int ny = max(g[1] - pr, lo[1]); ny <= min(g[1] + pr, hi[1]); ++ny) {
-      const int rowkey = (((nz >> 2) * H + (ny >> 2)) * H) * 64 + (((nz & 3) << 4) | ((ny & 3) << 2));
-      const bool centre = nz == g[2] && ny == g[1];
-      for (int side = 0; side < (centre ? 2 : 1); ++side) {
-        const int xa = centre ? (side ? g[0] + 1 : x0) : x0, xb = centre ? (side ? x1 : g[0] - 1) : x1;
-        if (xa > xb) continue;
-        const int ca = xa >> 2, cb = xb >> 2;
-        // at most two coarse cells (the window is <= 5 cells wide): both ranges looked up before either is walked
-        const int ka = rowkey + ca * 64, kb = rowkey + cb * 64;
-        const int sa = fstart[ka + (xa & 3)], ea = fstart[ka + (ca == cb ? (xb & 3) : 3) + 1];
-        int sb = 0, eb = 0;
-        if (cb != ca) { sb = fstart[kb]; eb = fstart[kb + (xb & 3) + 1]; }
-        ppext_sources(xv, sa, ea, pi, P, acc);
-        ppext_sources(xv, sb, eb, pi, P, acc);
-      }
-    }
-  }
-  return sqrtf(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z);
-}
-
-__global__ void __launch_bounds__(EXT_TPB) ppext_margin_list_kernel(const float* __restrict__ xv, int np_all, MarginGeom G, int2* __restrict__ roles, int cap,
-                                                                    int* __restrict__ n_roles) {
-  const int i = blockIdx.x * EXT_TPB + threadIdx.x;
-  unsigned mask = 0;
-  int tl[3] = {0, 0, 0};
-  if (i < np_all) {
-    const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * i;
-    const float2 a = p[0];
-    const int g[3] = {(int)floorf(a.x) + G.b, (int)floorf(a.y) + G.b, (int)floorf(p[1].x) + G.b};     // fine cell in the hoc-range frame (part::make_key)
-    mask = margin_roles(g, G, tl);
-  }
-  const int n = __popc(mask), lane = threadIdx.x & 31;
-  int inc = n;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-  const int total = __shfl_sync(0xffffffffu, inc, 31);
-  if (total == 0) return;
-  int base = 0;
-  if (lane == 31) base = atomicAdd(n_roles, total);
-  base = __shfl_sync(0xffffffffu, base, 31) + inc - n;
-  while (mask) {
-    const int bit = __ffs(mask) - 1;
-    mask &= mask - 1;
-    if (base < cap) roles[base] = make_int2(i, ((tl[2] + (bit >> 2)) * G.T + (tl[1] + ((bit >> 1) & 1))) * G.T + (tl[0] + (bit & 1)));
-    ++base;
-  }
-}
-// one role per thread (persistent grid). If the list overflowed (n_roles > cap: only with extreme clustering on the tile faces) the list is
-// ignored and every particle evaluates its own roles, which is slow but complete.
-__global__ void __launch_bounds__(EXT_TPB) ppext_margin_roles_kernel(const float* __restrict__ xv, const int* __restrict__ fstart, int np_all, MarginGeom G,
-                                                                     const int2* __restrict__ roles, int cap, const int* __restrict__ n_roles, PPParams P,
-                                                                     DevCounters* __restrict__ cnt) {
-  const int n = *n_roles;
-  float fm = 0.f;
-  if (n <= cap) {
-    for (int r = blockIdx.x * EXT_TPB + threadIdx.x; r < n; r += gridDim.x * EXT_TPB) {
-      const int2 role = roles[r];
-      const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * role.x;
-      const float2 a = p[0];
-      const float z = p[1].x;
-      const int g[3] = {(int)floorf(a.x) + G.b, (int)floorf(a.y) + G.b, (int)floorf(z) + G.b};
-      const int t3[3] = {role.y % G.T, (role.y / G.T) % G.T, role.y / (G.T * G.T)};
-      fm = fmaxf(fm, margin_role_sum(xv, fstart, make_float3(a.x, a.y, z), g, t3, G, P));
-    }
-  } else {
-    for (int i = blockIdx.x * EXT_TPB + threadIdx.x; i < np_all; i += gridDim.x * EXT_TPB) {
-      const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * i;
-      const float2 a = p[0];
-      const float z = p[1].x;
-      const int g[3] = {(int)floorf(a.x) + G.b, (int)floorf(a.y) + G.b, (int)floorf(z) + G.b};
-      int tl[3];
-      unsigned mask = margin_roles(g, G, tl);
-      while (mask) {
-        const int bit = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int t3[3] = {tl[0] + (bit & 1), tl[1] + ((bit >> 1) & 1), tl[2] + (bit >> 2)};
-        fm = fmaxf(fm, margin_role_sum(xv, fstart, make_float3(a.x, a.y, z), g, t3, G, P));
-      }
-    }
-  }
-  fm = warp_max(fm);
-  if ((threadIdx.x & 31) == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_ext_force_max_bits, fm);
-}
-
 // ---------------------------------------------------------------------------------------------------------------------------------
 // PP_EXT, tiled: one CTA per block of TB_X x TB_Y x TB_Z coarse cells (the targets) and the TB_HALO fine cells around it (the sources).
 // The direct kernel above spends its time on table look-ups (up to 100 global fstart reads per target: the 4^3 fine cells of a coarse
@@ -350,19 +221,169 @@ __device__ __forceinline__ float4 lds_f4(unsigned a) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
   return v;
 }
-__device__ __forceinline__ void pair_force_fast(const float3 pi, const float4 pj, const PPParams& P, float inv_cut, float3& acc) {
+// The PP_EXT pair weight (particle_mesh_threaded.f90:558-564), algebraically folded. With rb = r pp_bias and u = rb / nf_cutoff the reference's
+//   w = mass_p / rb^3 * (1 - 7/4 u^3 + 3/4 u^5)        (always this branch: r <= 3 sqrt(3) < nf_cutoff + sqrt(3) at pp_range <= 2)
+// is  w = c1 / r^3 + c4 r^2 - c5  with c1 = mass_p / pp_bias^3, c5 = 7/4 mass_p / nf_cutoff^3, c4 = 3/4 mass_p pp_bias^2 / nf_cutoff^5
+// (mass_p / rb^3 * u^3 is the constant mass_p / nf_cutoff^3): one MUFU.RSQ, 2 FMUL, 2 FFMA instead of a square root, two reciprocals and the
+// polynomial — 16 instead of 28 instructions per pair, in kernels that are bound by instruction issue. The soft-core test r > rsoft is r^2 > rsoft^2.
+// No cancellation anywhere in the range (c1 / r^3 >= 20 c5 at r = 5.2). Differences to the reference's evaluation order are ~1e-6 relative.
+struct PairConst { float c1, c4, c5, rs2; };
+__device__ __forceinline__ PairConst make_pair_const(const PPParams& P) {
+  PairConst K;
+  const float ic = 1.0f / P.cutoff, ib = 1.0f / P.pp_bias;
+  K.c1 = P.mass_p * ib * ib * ib;
+  K.c5 = 1.75f * P.mass_p * ic * ic * ic;
+  K.c4 = 0.75f * P.mass_p * P.pp_bias * P.pp_bias * ic * ic * ic * ic * ic;
+  K.rs2 = P.rsoft * P.rsoft;
+  return K;
+}
+__device__ __forceinline__ void pair_force_fast(const float3 pi, const float4 pj, const PairConst& K, float3& acc) {
   const float sx = pi.x - pj.x, sy = pi.y - pj.y, sz = pi.z - pj.z;
   const float r2 = sx * sx + sy * sy + sz * sz;
-  const float r = r2 * rsqrt_ftz(r2);              // one MUFU.RSQ (2 ulp); r2 = 0 gives NaN, which fails the test below like r = 0 does
-  if (r > P.rsoft) {
-    const float rb = r * P.pp_bias;
-    float w = P.mass_p * rcp_ftz(rb * rb * rb);    // one MUFU.RCP (1 ulp); rb^3 > rsoft^3 is far from the denormal range
-    if (!(r > P.cutoff + 1.7320508f)) {
-      const float u = rb * inv_cut, u2 = u * u, u3 = u2 * u;
-      w *= (1.0f - 1.75f * u3 + 0.75f * u3 * u2);
-    }
-    acc.x -= sx * w; acc.y -= sy * w; acc.z -= sz * w;
+  const float ir = rsqrt_ftz(r2);                    // r2 = 0 gives +inf, which the select below discards
+  const float ir3 = ir * ir * ir;
+  float w = fmaf(K.c1, ir3, fmaf(K.c4, r2, -K.c5));
+  w = r2 > K.rs2 ? w : 0.0f;
+  acc.x = fmaf(-sx, w, acc.x); acc.y = fmaf(-sy, w, acc.y); acc.z = fmaf(-sz, w, acc.z);
+}
+
+__device__ __forceinline__ void ppext_sources_fast(const float* __restrict__ xv, int s, int e, const float3 pi, const PairConst& K, float3& acc) {
+#pragma unroll 1
+  for (int j = s; j < e; ++j) {
+    const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * j;
+    const float2 a = p[0];
+    pair_force_fast(pi, make_float4(a.x, a.y, p[1].x, 0.f), K, acc);
   }
+}
+
+// ---- pp_ext_force_max of the MARGIN particles (particle_mesh_threaded.f90:617).
+// The reference evaluates PP_EXT per tile over the tile's physical fine cells plus pp_range cells around them (:397-402) and takes the
+// maximum of |pp_ext_force_accum| over EVERY particle of that region (:617), not only over the kicked (physical) ones. A particle in the
+// margin of a tile has, in that tile, only the partial sum over the partner cells that lie inside the tile's region — and on a near-uniform
+// particle load such a one-sided sum is larger than any complete sum, so it is what sets dt_pp_ext_acc (:692). The kicks never see these
+// sums; they are recomputed here for the limiter only. A (particle, tile) pair with the particle in the tile's margin is a ROLE (up to 7 per
+// particle, ~5 % of the particles have one): ppext_margin_list_kernel compacts the roles (one thread per particle, warp-aggregated append),
+// ppext_margin_roles_kernel evaluates one role per thread with all lanes busy (a thread-per-particle version left 95 % of the lanes idle
+// next to a lane walking 25 neighbour rows: 8.7 ms at 512^3 particles). Cell pairs whose two cells both lie in the tile's upper z margin
+// are never visited by the reference's half stencil ("we never loop towards smaller z", k = 1..nf_physical_tile_dim+pp_range at :496).
+struct MarginGeom { int H, b, m, T, pr; };
+
+// tiles whose region [t*m - pr, (t+1)*m + pr) holds node-frame fine cell q: [tl, th] (empty if tl > th)
+__device__ __forceinline__ void margin_tiles(int q, const MarginGeom& G, int& tl, int& th) {
+  auto fdiv = [&](int v) { return v >= 0 ? v / G.m : -((-v + G.m - 1) / G.m); };
+  tl = max(0, fdiv(q - G.pr)); th = min(G.T - 1, fdiv(q + G.pr));
+}
+// bit (dz*4 + dy*2 + dx) of the result = tile (tl + d) is a ROLE of the particle in hoc-frame fine cell g (in the region, not in the interior)
+__device__ __forceinline__ unsigned margin_roles(const int g[3], const MarginGeom& G, int tl[3]) {
+  int th[3];
+  for (int ax = 0; ax < 3; ++ax) { margin_tiles(g[ax] - G.b, G, tl[ax], th[ax]); if (tl[ax] > th[ax]) return 0u; }
+  unsigned mask = 0;
+  for (int dz = 0; dz <= th[2] - tl[2]; ++dz)
+    for (int dy = 0; dy <= th[1] - tl[1]; ++dy)
+      for (int dx = 0; dx <= th[0] - tl[0]; ++dx) {
+        const int t3[3] = {tl[0] + dx, tl[1] + dy, tl[2] + dz};
+        bool interior = true;
+        for (int ax = 0; ax < 3; ++ax) interior &= (g[ax] - G.b >= t3[ax] * G.m && g[ax] - G.b < (t3[ax] + 1) * G.m);
+        if (!interior) mask |= 1u << (dz * 4 + dy * 2 + dx);
+      }
+  return mask;
+}
+// |partial sum| of the particle at pi (hoc-frame fine cell g) over the partner cells inside the region of tile t3
+__device__ __forceinline__ float margin_role_sum(const float* __restrict__ xv, const int* __restrict__ fstart, const float3 pi, const int g[3], const int t3[3],
+                                                 const MarginGeom& G, const PairConst& KC) {
+  const int pr = G.pr, H = G.H;
+  int lo[3], hi[3];                                   // the tile's region in the hoc-range frame (inclusive)
+  for (int ax = 0; ax < 3; ++ax) { lo[ax] = t3[ax] * G.m - pr + G.b; hi[ax] = (t3[ax] + 1) * G.m + pr - 1 + G.b; }
+  const int ztop = (t3[2] + 1) * G.m + G.b;           // first cell of the upper z margin
+  float3 acc = make_float3(0.f, 0.f, 0.f);
+  const int x0 = max(g[0] - pr, lo[0]), x1 = min(g[0] + pr, hi[0]);
+#pragma unroll 1
+  for (int nz = max(g[2] - pr, lo[2]); nz <= min(g[2] + pr, hi[2]); ++nz) {
+    if (g[2] >= ztop && nz >= ztop) continue;
+#pragma unroll 1
+    for (int ny = max(g[1] - pr, lo[1]); ny <= min(g[1] + pr, hi[1]); ++ny) {
+      const int rowkey = (((nz >> 2) * H + (ny >> 2)) * H) * 64 + (((nz & 3) << 4) | ((ny & 3) << 2));
+      const bool centre = nz == g[2] && ny == g[1];
+      for (int side = 0; side < (centre ? 2 : 1); ++side) {
+        const int xa = centre ? (side ? g[0] + 1 : x0) : x0, xb = centre ? (side ? x1 : g[0] - 1) : x1;
+        if (xa > xb) continue;
+        const int ca = xa >> 2, cb = xb >> 2;
+        // at most two coarse cells (the window is <= 5 cells wide): both ranges looked up before either is walked
+        const int ka = rowkey + ca * 64, kb = rowkey + cb * 64;
+        const int sa = fstart[ka + (xa & 3)], ea = fstart[ka + (ca == cb ? (xb & 3) : 3) + 1];
+        int sb = 0, eb = 0;
+        if (cb != ca) { sb = fstart[kb]; eb = fstart[kb + (xb & 3) + 1]; }
+        ppext_sources_fast(xv, sa, ea, pi, KC, acc);
+        ppext_sources_fast(xv, sb, eb, pi, KC, acc);
+      }
+    }
+  }
+  return sqrtf(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z);
+}
+
+__global__ void __launch_bounds__(EXT_TPB) ppext_margin_list_kernel(const float* __restrict__ xv, int np_all, MarginGeom G, int2* __restrict__ roles, int cap,
+                                                                    int* __restrict__ n_roles) {
+  const int i = blockIdx.x * EXT_TPB + threadIdx.x;
+  unsigned mask = 0;
+  int tl[3] = {0, 0, 0};
+  if (i < np_all) {
+    const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * i;
+    const float2 a = p[0];
+    const int g[3] = {(int)floorf(a.x) + G.b, (int)floorf(a.y) + G.b, (int)floorf(p[1].x) + G.b};     // fine cell in the hoc-range frame (part::make_key)
+    mask = margin_roles(g, G, tl);
+  }
+  const int n = __popc(mask), lane = threadIdx.x & 31;
+  int inc = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+  const int total = __shfl_sync(0xffffffffu, inc, 31);
+  if (total == 0) return;
+  int base = 0;
+  if (lane == 31) base = atomicAdd(n_roles, total);
+  base = __shfl_sync(0xffffffffu, base, 31) + inc - n;
+  while (mask) {
+    const int bit = __ffs(mask) - 1;
+    mask &= mask - 1;
+    if (base < cap) roles[base] = make_int2(i, ((tl[2] + (bit >> 2)) * G.T + (tl[1] + ((bit >> 1) & 1))) * G.T + (tl[0] + (bit & 1)));
+    ++base;
+  }
+}
+// one role per thread (persistent grid). If the list overflowed (n_roles > cap: only with extreme clustering on the tile faces) the list is
+// ignored and every particle evaluates its own roles, which is slow but complete.
+__global__ void __launch_bounds__(EXT_TPB) ppext_margin_roles_kernel(const float* __restrict__ xv, const int* __restrict__ fstart, int np_all, MarginGeom G,
+                                                                     const int2* __restrict__ roles, int cap, const int* __restrict__ n_roles, PPParams P,
+                                                                     DevCounters* __restrict__ cnt) {
+  const int n = *n_roles;
+  const PairConst KC = make_pair_const(P);
+  float fm = 0.f;
+  if (n <= cap) {
+    for (int r = blockIdx.x * EXT_TPB + threadIdx.x; r < n; r += gridDim.x * EXT_TPB) {
+      const int2 role = roles[r];
+      const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * role.x;
+      const float2 a = p[0];
+      const float z = p[1].x;
+      const int g[3] = {(int)floorf(a.x) + G.b, (int)floorf(a.y) + G.b, (int)floorf(z) + G.b};
+      const int t3[3] = {role.y % G.T, (role.y / G.T) % G.T, role.y / (G.T * G.T)};
+      fm = fmaxf(fm, margin_role_sum(xv, fstart, make_float3(a.x, a.y, z), g, t3, G, KC));
+    }
+  } else {
+    for (int i = blockIdx.x * EXT_TPB + threadIdx.x; i < np_all; i += gridDim.x * EXT_TPB) {
+      const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * i;
+      const float2 a = p[0];
+      const float z = p[1].x;
+      const int g[3] = {(int)floorf(a.x) + G.b, (int)floorf(a.y) + G.b, (int)floorf(z) + G.b};
+      int tl[3];
+      unsigned mask = margin_roles(g, G, tl);
+      while (mask) {
+        const int bit = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int t3[3] = {tl[0] + (bit & 1), tl[1] + ((bit >> 1) & 1), tl[2] + (bit >> 2)};
+        fm = fmaxf(fm, margin_role_sum(xv, fstart, make_float3(a.x, a.y, z), g, t3, G, KC));
+      }
+    }
+  }
+  fm = warp_max(fm);
+  if ((threadIdx.x & 31) == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_ext_force_max_bits, fm);
 }
 
 // PRT: compile-time pp_range (2 = cubepm.par:92, every loop of the walk unrolls and the row decode folds to constants) or -1 = run-time pr_rt
@@ -478,7 +499,7 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
     __syncthreads();
     // ---- 5. walk
     const int nt = trow_pre[TB_NTROW];
-    const float inv_cut = 1.0f / P.cutoff;
+    const PairConst KC = make_pair_const(P);
     for (int t = tid; t < nt; t += TB_NT) {
       int r = 0;
 #pragma unroll
@@ -526,7 +547,7 @@ __global__ void __launch_bounds__(TB_NT) ppext_tiled_kernel(float* __restrict__ 
           s = lds_i32(a_rb - 4 * pr); e = lds_i32(a_rb + 4 * (pr + 1));
           if (s == own_s) s = own_e;
         }
-        pair_force_fast(pi, lds_f4(a_src + 16u * (unsigned)s), P, inv_cut, acc);
+        pair_force_fast(pi, lds_f4(a_src + 16u * (unsigned)s), KC, acc);
         ++s;
       }
       fm = fmaxf(fm, ppext_apply(reinterpret_cast<float2*>(xv) + 3LL * __float_as_int(me.w), acc, P));
@@ -612,7 +633,7 @@ __global__ void __launch_bounds__(TB_NT) ppext_cell_kernel(float* __restrict__ x
   if (n > cap) return;                                  // list overflow: ppext_blocklist_kernel does the work
   const int lane = threadIdx.x & 31;
   const float2* xv2 = reinterpret_cast<const float2*>(xv);
-  const float inv_cut = 1.0f / P.cutoff;
+  const PairConst KC = make_pair_const(P);
   float fm = 0.f;
   unsigned long long npair = 0;
   for (;;) {
@@ -664,7 +685,7 @@ __global__ void __launch_bounds__(TB_NT) ppext_cell_kernel(float* __restrict__ x
           const float2* q = xv2 + 3LL * j;
           const float2 a = q[0];
           const float z = q[1].x;
-          pair_force_fast(pi, make_float4(a.x, a.y, z, 0.f), P, inv_cut, acc);
+          pair_force_fast(pi, make_float4(a.x, a.y, z, 0.f), KC, acc);
         }
       }
     }

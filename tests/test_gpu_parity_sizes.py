@@ -147,6 +147,8 @@ def test_coarse_slab_pipeline_on_one_rank(built, monkeypatch):
     fa, fb = res["replicated"][0], res["slab"][0]
     assert np.abs(fa - fb).max() <= 2e-6 * np.abs(fa).max()
     assert np.array_equal(res["replicated"][1][:, :3], res["slab"][1][:, :3])
+    dv = np.abs(res["replicated"][1][:, 3:] - res["slab"][1][:, 3:]).max()
+    assert dv <= 1e-5 * np.abs(res["replicated"][1][:, 3:]).max(), ("velocities after the step, slab vs whole-mesh solve", dv)
     assert res["slab"][2].dt_c_acc == pytest.approx(res["replicated"][2].dt_c_acc, rel=1e-5)
     assert res["slab"][2].sum_rho_c == pytest.approx(res["replicated"][2].sum_rho_c, rel=1e-9)
     monkeypatch.setenv("CUBEP3M_B200_COARSE", "slab")

@@ -120,6 +120,8 @@ struct cubep3m_b200_ctx {
   bool sorted = false;   // xv[cur] is cell-sorted and fstart is valid
   bool passed = false;
   unsigned int* key = nullptr;
+  int* blist = nullptr;       // particles near a y / z face, listed by the first pack kernel of particle_pass
+  bool keys_fused = false;    // the pass kernels of this step already produced key[] and the histogram (do_sort skips key_hist_kernel)
   int* fstart = nullptr; // exclusive scan of fine-cell counts, NF+1 entries
   unsigned int* fcur = nullptr;   // fine-cell histogram, two 16-bit counters per word (NF/2 words); counts itself back to zero in the scatter
   int* blocksum = nullptr;

@@ -438,7 +438,21 @@ int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max, const float* drift = nullptr
   int np = ctx->np_all;
   const int np_first = np;                          // particles present before the first exchange
   int nlist = 0;
-  int* blist = reinterpret_cast<int*>(ctx->key);    // the sort's key array is free until do_sort
+  int* blist = ctx->blist;
+  const Dims& dd = ctx->d;
+  // CUBEP3M_B200_FUSE_KEYS=1: key + histogram ride on the pack / unpack kernels (do_sort then skips key_hist_kernel). Measured at 512^3: pass 1.8 -> 5.0 ms
+  // against 1.4 ms saved — the table atomic's DRAM round trip lands in front of the pack kernel's warp-synchronous slot allocation and the kernel turns
+  // latency-bound; the stand-alone key_hist_kernel (load -> atomic -> exit) runs at the DRAM limit. Off by default.
+  static const bool fuse_env = [] { const char* e = getenv("CUBEP3M_B200_FUSE_KEYS"); return e && atoi(e) == 1; }();
+  const bool fuse_keys = fuse_env && in_step && drift != nullptr;
+  part::KeyArgs KA{lo, hi, dd.b, dd.H, fuse_keys ? ctx->key : nullptr, ctx->fcur, ctx->cand, ctx->cand_cap};
+  if (fuse_keys) {
+    if (!ctx->hist_clean) CK(cudaMemsetAsync(ctx->fcur, 0, sizeof(unsigned int) * (dd.NF / 2), ctx->stream));
+    ctx->hist_clean = false;
+    CK(cudaMemsetAsync(&ctx->dcnt->np_deleted, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(&ctx->dcnt->n_cand, 0, sizeof(int), ctx->stream));
+  }
+  ctx->keys_fused = fuse_keys;
   *np_buf_max = 0;
   CK(cudaMemsetAsync(&ctx->dcnt->n_blist, 0, sizeof(int), ctx->stream));
   for (int axis = 0; axis < 3; ++axis) {
@@ -455,8 +469,9 @@ int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max, const float* drift = nullptr
       const long long nvis = axis == 0 ? np : (long long)nlist + (np - np_first);
       const int grid = (int)((nvis + part::TPB - 1) / part::TPB);
 #define PACK_ARGS ctx->xv[ctx->cur], ctx->pid[ctx->cur], np, axis, lo, hi, cut_hi, cut_lo, dst_plus, dst_minus, ctx->sendpid[0], ctx->sendpid[1], cap_axis, \
-                  ctx->dcnt, dr[0], dr[1], dr[2], dr[3], blist, nlist, np_first
-      if (axis == 0 && drift) LAUNCH(ctx, KC_PASS_PACK, (part::pass_pack_kernel<true, false>), grid, part::TPB, 0, PACK_ARGS);
+                  ctx->dcnt, dr[0], dr[1], dr[2], dr[3], blist, nlist, np_first, KA
+      if (axis == 0 && drift && fuse_keys) LAUNCH(ctx, KC_PASS_PACK, (part::pass_pack_kernel<true, false, true>), grid, part::TPB, 0, PACK_ARGS);
+      else if (axis == 0 && drift) LAUNCH(ctx, KC_PASS_PACK, (part::pass_pack_kernel<true, false>), grid, part::TPB, 0, PACK_ARGS);
       else if (axis == 0) LAUNCH(ctx, KC_PASS_PACK, (part::pass_pack_kernel<false, false>), grid, part::TPB, 0, PACK_ARGS);
       else if (grid > 0) LAUNCH(ctx, KC_PASS_PACK, (part::pass_pack_kernel<false, true>), grid, part::TPB, 0, PACK_ARGS);
 #undef PACK_ARGS
@@ -489,7 +504,7 @@ int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max, const float* drift = nullptr
     const int nr = r_plus + r_minus;
     if (nr > 0)
       LAUNCH(ctx, KC_PASS_UNPACK, part::pass_unpack_kernel, (nr + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], np, axis,
-             ctx->recvbuf[0], r_plus, ctx->recvbuf[1], r_minus, ctx->recvpid[0], ctx->recvpid[1], fmT, rnf, ctx->cfg.eps, hi_clamp);
+             ctx->recvbuf[0], r_plus, ctx->recvbuf[1], r_minus, ctx->recvpid[0], ctx->recvpid[1], fmT, rnf, ctx->cfg.eps, hi_clamp, KA, ctx->dcnt);
     CK(cudaGetLastError());
     np += nr;
   }
@@ -573,13 +588,18 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
   const Dims& d = ctx->d;
   const int np = ctx->np_all;
   const float lo = -(float)d.b, hi = (float)d.mT + (float)d.b;
-  if (!ctx->hist_clean) CK(cudaMemsetAsync(ctx->fcur, 0, sizeof(unsigned int) * (d.NF / 2), ctx->stream));   // two 16-bit counters per word   // otherwise the last scatter left it zeroed
-  ctx->hist_clean = false;
-  CK(cudaMemsetAsync(&ctx->dcnt->np_deleted, 0, sizeof(int), ctx->stream));
   CK(cudaMemsetAsync(&ctx->dcnt->n_multi, 0, 2 * sizeof(int), ctx->stream));
-  CK(cudaMemsetAsync(&ctx->dcnt->n_cand, 0, sizeof(int), ctx->stream));
-  if (np > 0)
-    LAUNCH(ctx, KC_KEY_HIST, part::key_hist_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], np, lo, hi, d.b, d.H, ctx->key, ctx->fcur, ctx->cand, ctx->cand_cap, ctx->dcnt);
+  if (!ctx->keys_fused) {
+    if (!ctx->hist_clean) CK(cudaMemsetAsync(ctx->fcur, 0, sizeof(unsigned int) * (d.NF / 2), ctx->stream));   // two 16-bit counters per word; otherwise the last scatter left it zeroed
+    ctx->hist_clean = false;
+    CK(cudaMemsetAsync(&ctx->dcnt->np_deleted, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(&ctx->dcnt->n_cand, 0, sizeof(int), ctx->stream));
+    if (np > 0) {
+      part::KeyArgs KA{lo, hi, d.b, d.H, ctx->key, ctx->fcur, ctx->cand, ctx->cand_cap};
+      LAUNCH(ctx, KC_KEY_HIST, part::key_hist_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], np, KA, ctx->dcnt);
+    }
+  }
+  ctx->keys_fused = false;
   const int nb = (int)((d.NF + part::SCAN_BLOCK - 1) / part::SCAN_BLOCK);
   if (ctx->scan_onepass) {
     CK(cudaMemsetAsync(ctx->scan_status, 0, sizeof(unsigned long long) * ((size_t)nb + 1), ctx->stream));
@@ -750,16 +770,25 @@ int do_pp_ext(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
       LAUNCH(ctx, KC_PPEXT, pp::ppext_kernel, (ctx->np_all + pp::EXT_TPB - 1) / pp::EXT_TPB, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->np_all, ctx->d.H,
              ctx->d.b, ctx->d.nc_buf, ctx->d.nc_node, ctx->cfg.pp_range, P, ctx->dcnt);
     }
-    // :617 takes the maximum over the margin particles' partial sums as well (limiter only, no kick)
-    if (ctx->np_all > 0 && ctx->ppext_margin_max) {
-      const pp::MarginGeom G{ctx->d.H, ctx->d.b, ctx->d.m, ctx->d.T, ctx->cfg.pp_range};
-      CK(cudaMemsetAsync(&ctx->dcnt->n_margin_roles, 0, sizeof(int), ctx->stream));
-      LAUNCH(ctx, KC_PPEXT_MARGIN, pp::ppext_margin_list_kernel, (ctx->np_all + pp::EXT_TPB - 1) / pp::EXT_TPB, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->np_all, G, ctx->margin_roles,
-             ctx->margin_cap, &ctx->dcnt->n_margin_roles);
-      LAUNCH(ctx, KC_PPEXT_MARGIN, pp::ppext_margin_roles_kernel, NUM_SMS * 16, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->np_all, G, ctx->margin_roles, ctx->margin_cap,
-             &ctx->dcnt->n_margin_roles, P, ctx->dcnt);
-    }
   }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// :617 takes the maximum over the margin particles' partial sums as well (limiter only, no kick). Needs only the sorted positions and the cell
+// table: particle_mesh runs it on the coarse stream behind the coarse solve, where it fills the SM slots the bandwidth-bound fine-tile kernels
+// leave free instead of adding 2.6 ms (512^3) behind the PP_EXT kick kernels.
+int do_pp_ext_margin(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
+  if (!(ctx->cfg.pp_ext && ctx->cfg.pp_range > 0 && ctx->np_all > 0 && ctx->ppext_margin_max)) return 0;
+  pp::PPParams P;
+  P.mass_p = mass_p; P.rsoft = ctx->cfg.rsoft; P.pp_bias = ctx->cfg.pp_bias; P.a_mid = a_mid; P.G = ctx->cfg.G; P.dt = dt;
+  P.cutoff = (float)ctx->cfg.nf_cutoff; P.apply = 0;
+  const pp::MarginGeom G{ctx->d.H, ctx->d.b, ctx->d.m, ctx->d.T, ctx->cfg.pp_range};
+  CK(cudaMemsetAsync(&ctx->dcnt->n_margin_roles, 0, sizeof(int), ctx->stream));
+  LAUNCH(ctx, KC_PPEXT_MARGIN, pp::ppext_margin_list_kernel, (ctx->np_all + pp::EXT_TPB - 1) / pp::EXT_TPB, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->np_all, G, ctx->margin_roles,
+         ctx->margin_cap, &ctx->dcnt->n_margin_roles);
+  LAUNCH(ctx, KC_PPEXT_MARGIN, pp::ppext_margin_roles_kernel, NUM_SMS * 16, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->np_all, G, ctx->margin_roles, ctx->margin_cap,
+         &ctx->dcnt->n_margin_roles, P, ctx->dcnt);
   CK(cudaGetLastError());
   return 0;
 }
@@ -948,7 +977,7 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
 #ifdef CUBEP3M_WITH_NCCL
   if (ctx->comm) ncclCommDestroy(ctx->comm);
 #endif
-  F(ctx->cand); F(ctx->deltas); F(ctx->ndelta); F(ctx->tile_counts); F(ctx->key); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->scan_status); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
+  F(ctx->cand); F(ctx->deltas); F(ctx->ndelta); F(ctx->tile_counts); F(ctx->key); F(ctx->blist); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->scan_status); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
   F(ctx->kern_f); F(ctx->tile_rho); F(ctx->tile_g); F(ctx->force_f[0]); 
   for (int q = 1; q < cubep3m_b200_ctx::MAX_TILE_STREAMS; ++q) {
     F(ctx->tile_rho_s[q]); F(ctx->tile_g_s[q]); F(ctx->force_f_s[q]);
@@ -996,6 +1025,7 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
     if (cfg->pid) TRY(dmalloc(&ctx->sendpid[i], (size_t)d.max_buf / 6 + 1));
   }
   TRY(dmalloc(&ctx->key, (size_t)d.max_np));
+  TRY(dmalloc(&ctx->blist, (size_t)d.max_np));
   ctx->cand_cap = std::max(4096, d.max_np / 64);
   TRY(dmalloc(&ctx->cand, (size_t)3 * ctx->cand_cap));
   TRY(dmalloc(&ctx->deltas, (size_t)d.tiles_node * fine::DELTA_CAP));
@@ -1197,7 +1227,7 @@ int cubep3m_b200_move_grid_back(cubep3m_b200_ctx* ctx, const float s[3]) {
 int cubep3m_b200_link_list(cubep3m_b200_ctx* ctx, int32_t* np_deleted) {
   if (!ctx) return CUBEP3M_B200_EINVAL;
   CK(cudaSetDevice(ctx->device));
-  ctx->np_all = ctx->np_local; ctx->passed = false;
+  ctx->np_all = ctx->np_local; ctx->passed = false; ctx->keys_fused = false;
   CK(cudaMemsetAsync(&ctx->dcnt->overflow, 0, sizeof(int), ctx->stream));
   return do_sort(ctx, np_deleted);
 }
@@ -1219,7 +1249,7 @@ int cubep3m_b200_delete_particles(cubep3m_b200_ctx* ctx, int32_t* np_local) {
   if (!ctx) return CUBEP3M_B200_EINVAL;
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemsetAsync(&ctx->dcnt->overflow, 0, sizeof(int), ctx->stream));
-  if (!ctx->sorted) { if (int st = do_sort(ctx, nullptr)) return st; }
+  if (!ctx->sorted) { ctx->keys_fused = false; if (int st = do_sort(ctx, nullptr)) return st; }
   if (int st = do_delete(ctx)) return st;
   if (np_local) *np_local = ctx->np_local;
   return 0;
@@ -1265,15 +1295,28 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   CK(cudaEventRecord(ev[7], ctx->stream));
   if (!cst) cst = do_coarse_force(ctx);                                                   // coarse_mesh.f90:84-100
   CK(cudaEventRecord(ev[8], ctx->stream));
+  CK(cudaEventRecord(ev[13], ctx->stream));
   ctx->stream = ctx->stream_main;
   if (cst) return cst;
   if (int st = do_fine(ctx, a_mid, dt, mass_p, nullptr, nullptr)) return st;              // :84-368 (mesh part)
   CK(cudaEventRecord(ev[4], ctx->stream));
   if (int st = do_pp(ctx, a_mid, dt, mass_p)) return st;                                  // :274-361
   CK(cudaEventRecord(ev[5], ctx->stream));
+  // the limiter part of PP_EXT (:617) only reads positions: with CUBEP3M_B200_MARGIN=overlap it runs on the (by now idle) coarse stream next to the
+  // PP_EXT kick kernels instead of behind them. (Running it next to the fine tiles cost more than it hid: fine_fft 33.1 -> 37.9 ms at 512^3.)
+  static const bool margin_overlap = [] { const char* e = getenv("CUBEP3M_B200_MARGIN"); return e && !strcmp(e, "overlap"); }();
+  if (margin_overlap) {
+    CK(cudaStreamWaitEvent(ctx->stream_coarse, ev[5], 0));
+    ctx->stream = ctx->stream_coarse;
+    const int mst = do_pp_ext_margin(ctx, a_mid, dt, mass_p);
+    CK(cudaEventRecord(ev[13], ctx->stream));
+    ctx->stream = ctx->stream_main;
+    if (mst) return mst;
+  }
   if (int st = do_pp_ext(ctx, a_mid, dt, mass_p)) return st;                              // :378-624
+  if (!margin_overlap) { if (int st = do_pp_ext_margin(ctx, a_mid, dt, mass_p)) return st; }
   CK(cudaEventRecord(ev[11], ctx->stream));
-  CK(cudaStreamWaitEvent(ctx->stream, ev[8], 0));                                         // join the coarse stream
+  CK(cudaStreamWaitEvent(ctx->stream, ev[13], 0));                                        // join the coarse stream
   CK(cudaEventRecord(ev[12], ctx->stream));
   CK(cudaEventRecord(ev[9], ctx->stream));
   if (int st = fetch_counters(ctx)) return st;

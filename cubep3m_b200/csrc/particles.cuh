@@ -61,6 +61,45 @@ __device__ __forceinline__ bool in_hoc_range(float x, float y, float z, float lo
   return x >= lo && x < hi && y >= lo && y < hi && z >= lo && z < hi;
 }
 
+// ---- cell keys.  Fine cell of a particle in the extended node frame: g = floor(x) + nf_buf in [0, mT + 2 nf_buf);
+// coarse cell (0-based inside the hoc range) = g >> 2 == floor(x/4)+1 - hoc_nc_l  (link_list.f90:26-28);
+// key = ((cz*H + cy)*H + cx)*64 + (fz*16 + fy*4 + fx): x-rows of coarse cells are contiguous, and so are the
+// 64 fine cells of one coarse cell (the llf(.,4,4,4) binning of particle_mesh_threaded.f90:276-284).
+__device__ __forceinline__ unsigned int make_key(float x, float y, float z, int b, int H) {
+  const int gx = (int)floorf(x) + b, gy = (int)floorf(y) + b, gz = (int)floorf(z) + b;
+  const unsigned int cx = gx >> 2, cy = gy >> 2, cz = gz >> 2;
+  return ((cz * H + cy) * H + cx) * 64u + (unsigned)(((gz & 3) << 4) | ((gy & 3) << 2) | (gx & 3));
+}
+
+// key + histogram + boundary-candidate list for ONE particle at (x, y, z) (link_list.f90:26-47 as a counting sort): shared by key_hist_kernel and by the
+// particle_pass kernels, which already hold every record in registers inside particle_mesh (the stand-alone pass over all records is saved).
+// Lists the particles that sit within 2^-15 below an integer coordinate on any axis: only for those can the reference's tile-local cell
+// floor(fl(x + offset)) (particle_mesh_threaded.f90:139-143) differ from floor(x)+offset.
+// The histogram holds two 16-bit counters per 32-bit word (cell k -> word k>>1, half k&1): the table is the largest array the sort touches
+// (H^3*64 cells, ~8 per particle) and every atomic on it is a DRAM sector read-modify-write, so halving its footprint halves that traffic.
+// A fine cell with >= 65535 particles raises the 'exceeded max_llf' flag (max_llf = 100000 in cubepm.par:183 is the same kind of bound).
+struct KeyArgs { float lo, hi; int b, H; unsigned int* key; unsigned int* hist; float* cand; int cand_cap; };
+__device__ __forceinline__ void key_one(const KeyArgs& A, long long i, float x, float y, float z, DevCounters* __restrict__ cnt) {
+  unsigned int k = KEY_DEAD;
+  if (in_hoc_range(x, y, z, A.lo, A.hi)) {
+    k = make_key(x, y, z, A.b, A.H);
+    const unsigned sh = (k & 1u) << 4;
+    const unsigned old = atomicAdd(&A.hist[k >> 1], 1u << sh);
+    if (((old >> sh) & 0xffffu) >= 0xfffeu) atomicOr(&cnt->overflow, 4);
+    const float th = 3.0517578125e-05f;   // 2^-15 >= half an ulp of any |x + offset| < 1024
+    // exact integers are not candidates: x + offset is exact for them, so both binnings agree
+    const float ux = ceilf(x) - x, uy = ceilf(y) - y, uz = ceilf(z) - z;
+    if ((ux > 0.f && ux <= th) || (uy > 0.f && uy <= th) || (uz > 0.f && uz <= th)) {
+      const int slot = atomicAdd(&cnt->n_cand, 1);
+      if (slot < A.cand_cap) { A.cand[3 * slot] = x; A.cand[3 * slot + 1] = y; A.cand[3 * slot + 2] = z; }
+      else atomicOr(&cnt->overflow, 8);     // never silently truncated: the step returns ECAPACITY
+    }
+  } else {
+    atomicAdd(&cnt->np_deleted, 1);   // 'PARTICLE DELETED' link_list.f90:32
+  }
+  A.key[i] = k;
+}
+
 // particle_pass.f90:73-94 (+ pass) and :173-192 (- pass) for one axis: every chained particle with
 // x >= mT - nf_buf goes to the + neighbour, every one with x < nf_buf to the - neighbour.
 // Both directions read the same pre-axis particle list (the reference relinks only after both).
@@ -69,13 +108,14 @@ __device__ __forceinline__ bool in_hoc_range(float x, float y, float z, float lo
 // The first axis' kernel (LIST = false) scans all np particles and also lists (blist) the chained ones that lie within nf_buf of a y or z
 // face: only those, plus the ghosts received so far (indices >= np_first), can be sent along the later axes, whose kernels (LIST = true) then
 // visit nlist + (np - np_first) records instead of all np.
-template <bool DRIFT, bool LIST>
+// KEYS (first axis only): also the sort's key + histogram for every visited record (key_one).
+template <bool DRIFT, bool LIST, bool KEYS = false>
 __global__ void __launch_bounds__(TPB) pass_pack_kernel(float* __restrict__ xv, const int64_t* __restrict__ pid, int np, int axis,
                                                         float lo, float hi, float cut_hi, float cut_lo,
                                                         float* __restrict__ send_plus, float* __restrict__ send_minus,
                                                         int64_t* __restrict__ pid_plus, int64_t* __restrict__ pid_minus,
                                                         int cap, DevCounters* __restrict__ cnt, float hdt, float ox, float oy, float oz,
-                                                        int* __restrict__ blist, int nlist, int np_first) {
+                                                        int* __restrict__ blist, int nlist, int np_first, KeyArgs KA) {
   const long long t = (long long)blockIdx.x * TPB + threadIdx.x;
   long long i = t;
   bool act = t < np;
@@ -94,6 +134,7 @@ __global__ void __launch_bounds__(TPB) pass_pack_kernel(float* __restrict__ xv, 
       float2* p = reinterpret_cast<float2*>(xv) + 3 * i;
       p[0] = a; p[1] = b;
     }
+    if (KEYS) key_one(KA, i, a.x, a.y, b.x, cnt);
     bool face = false;
     if (in_hoc_range(a.x, a.y, b.x, lo, hi)) {
       const float q = axis == 0 ? a.x : (axis == 1 ? a.y : b.x);
@@ -171,7 +212,7 @@ __global__ void __launch_bounds__(TPB) pass_unpack_kernel(float* __restrict__ xv
                                                           const float* __restrict__ recv_plus, int n_plus,
                                                           const float* __restrict__ recv_minus, int n_minus,
                                                           const int64_t* __restrict__ rpid_plus, const int64_t* __restrict__ rpid_minus,
-                                                          float fmT, float rnf_buf, float eps, float hi_clamp) {
+                                                          float fmT, float rnf_buf, float eps, float hi_clamp, KeyArgs KA, DevCounters* __restrict__ cnt) {
   const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
   if (i >= n_plus + n_minus) return;
   float2 a, b, c;
@@ -186,50 +227,16 @@ __global__ void __launch_bounds__(TPB) pass_unpack_kernel(float* __restrict__ xv
   }
   if (axis == 0) a.x = q; else if (axis == 1) a.y = q; else b.x = q;
   store_xv(xv, (long long)np0 + i, a, b, c);
+  if (KA.key) key_one(KA, (long long)np0 + i, a.x, a.y, b.x, cnt);   // inside particle_mesh: the ghost's sort key, while its record is in registers
   if (pid) pid[np0 + i] = plus ? rpid_plus[i] : rpid_minus[i - n_plus];
 }
 
-// ---- cell keys.  Fine cell of a particle in the extended node frame: g = floor(x) + nf_buf in [0, mT + 2 nf_buf);
-// coarse cell (0-based inside the hoc range) = g >> 2 == floor(x/4)+1 - hoc_nc_l  (link_list.f90:26-28);
-// key = ((cz*H + cy)*H + cx)*64 + (fz*16 + fy*4 + fx): x-rows of coarse cells are contiguous, and so are the
-// 64 fine cells of one coarse cell (the llf(.,4,4,4) binning of particle_mesh_threaded.f90:276-284).
-__device__ __forceinline__ unsigned int make_key(float x, float y, float z, int b, int H) {
-  const int gx = (int)floorf(x) + b, gy = (int)floorf(y) + b, gz = (int)floorf(z) + b;
-  const unsigned int cx = gx >> 2, cy = gy >> 2, cz = gz >> 2;
-  return ((cz * H + cy) * H + cx) * 64u + (unsigned)(((gz & 3) << 4) | ((gy & 3) << 2) | (gx & 3));
-}
-
-// Also lists the particles that sit within 2^-15 below an integer coordinate on any axis: only for those can the
-// reference's tile-local cell floor(fl(x + offset)) (particle_mesh_threaded.f90:139-143) differ from floor(x)+offset.
-// The histogram holds two 16-bit counters per 32-bit word (cell k -> word k>>1, half k&1): the table is the largest array the sort touches
-// (H^3*64 cells, ~8 per particle) and every atomic on it is a DRAM sector read-modify-write, so halving its footprint halves that traffic.
-// A fine cell with >= 65535 particles raises the 'exceeded max_llf' flag (max_llf = 100000 in cubepm.par:183 is the same kind of bound).
-__global__ void __launch_bounds__(TPB) key_hist_kernel(const float* __restrict__ xv, int np, float lo, float hi, int b, int H,
-                                                       unsigned int* __restrict__ key, unsigned int* __restrict__ hist, float* __restrict__ cand, int cand_cap,
-                                                       DevCounters* __restrict__ cnt) {
+__global__ void __launch_bounds__(TPB) key_hist_kernel(const float* __restrict__ xv, int np, KeyArgs A, DevCounters* __restrict__ cnt) {
   const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
   if (i >= np) return;
   const float2* p = reinterpret_cast<const float2*>(xv) + 3 * i;
   const float2 a = p[0];
-  const float z = p[1].x;
-  unsigned int k = KEY_DEAD;
-  if (in_hoc_range(a.x, a.y, z, lo, hi)) {
-    k = make_key(a.x, a.y, z, b, H);
-    const unsigned sh = (k & 1u) << 4;
-    const unsigned old = atomicAdd(&hist[k >> 1], 1u << sh);
-    if (((old >> sh) & 0xffffu) >= 0xfffeu) atomicOr(&cnt->overflow, 4);
-    const float th = 3.0517578125e-05f;   // 2^-15 >= half an ulp of any |x + offset| < 1024
-    // exact integers are not candidates: x + offset is exact for them, so both binnings agree
-    const float ux = ceilf(a.x) - a.x, uy = ceilf(a.y) - a.y, uz = ceilf(z) - z;
-    if ((ux > 0.f && ux <= th) || (uy > 0.f && uy <= th) || (uz > 0.f && uz <= th)) {
-      const int slot = atomicAdd(&cnt->n_cand, 1);
-      if (slot < cand_cap) { cand[3 * slot] = a.x; cand[3 * slot + 1] = a.y; cand[3 * slot + 2] = z; }
-      else atomicOr(&cnt->overflow, 8);     // never silently truncated: the step returns ECAPACITY
-    }
-  } else {
-    atomicAdd(&cnt->np_deleted, 1);   // 'PARTICLE DELETED' link_list.f90:32
-  }
-  key[i] = k;
+  key_one(A, i, a.x, a.y, p[1].x, cnt);
 }
 
 // ---- exclusive scan over NF fine-cell counts: block reduce -> scan of block sums -> block scan.

@@ -87,6 +87,8 @@ struct DevCounters {
   int n_blist;           // particles near a y or z face, listed by the first particle_pass kernel
   int n_ppext_items;     // (fine cell, 32-target chunk) items of the dense PP_EXT blocks (pp::ppext_items_kernel)
   int ppext_ticket;      // work ticket of pp::ppext_cell_kernel (must follow n_ppext_items: both are cleared together)
+  int n_ppint_items;     // (fine cell, chunk) items of PPINT (pp::ppint_items_kernel) and their work ticket (cleared together)
+  int ppint_ticket;
   int n_margin_roles;    // (particle, tile) margin roles listed for the PP_EXT limiter (pp::ppext_margin_list_kernel)
   int xchg_timeout;      // a coarse-mesh exchange wait (coarse_slab.cuh) gave up on a peer
   int n_ppext_fallback;  // PP_EXT blocks whose source region exceeded the shared-memory capacity (walked directly instead)
@@ -155,6 +157,7 @@ struct cubep3m_b200_ctx {
   int* ppext_ovf = nullptr;    // ids of the PP_EXT target blocks that exceeded the tiled kernel's shared-memory capacity
   bool ppext_margin_max = true; // also evaluate the margin particles' partial sums for pp_ext_force_max (particle_mesh_threaded.f90:617); CUBEP3M_B200_PPEXT_MARGIN=0 skips it
   int2* ppext_items = nullptr; int ppext_item_cap = 0; bool ppext_cell_mode = true;   // dense-block PP_EXT work items
+  int2* ppint_items = nullptr; int ppint_item_cap = 0;
   int2* margin_roles = nullptr; int margin_cap = 0;   // (particle index, tile) list of the PP_EXT margin roles
   int ppext_blocks = 0, ppext_fallback = 0;
   long long pairs_ppint = 0, pairs_ppext = 0;   // of the last step   // of the last step (debug getter)

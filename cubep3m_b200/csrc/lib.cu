@@ -731,9 +731,19 @@ int do_pp(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
   if (ctx->cfg.ppint && ctx->cfg.ngp) {      // the llf binning of particle_mesh_threaded.f90:274-285 only exists inside #ifdef NGP
     P.apply = ctx->cfg.pp_force_flag;
     const int n_multi = std::min(ctx->hcnt->n_multi, ctx->list_cap);
-    if (n_multi > 0)
+    if (n_multi > 0) {
+      // (cell, 32-target chunk) items, one warp each; the one-warp-per-cell kernel only if the item list overflowed (decided on the device)
+      const int icap = ctx->ppext_cell_mode ? ctx->ppint_item_cap : 0;
+      CK(cudaMemsetAsync(&ctx->dcnt->n_ppint_items, 0, 2 * sizeof(int), ctx->stream));
+      if (icap > 0) {
+        LAUNCH(ctx, KC_PPINT, pp::ppint_items_kernel, std::min((n_multi + pp::TB_NT - 1) / pp::TB_NT, NUM_SMS * 8), pp::TB_NT, 0, ctx->fstart, ctx->multi_list, &ctx->dcnt->n_multi,
+               ctx->list_cap, ctx->cfg.max_llf, ctx->ppint_items, icap, &ctx->dcnt->n_ppint_items, ctx->dcnt);
+        LAUNCH(ctx, KC_PPINT, pp::ppint_cell_kernel, NUM_SMS * 8, pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, P, ctx->dcnt, ctx->ppint_items, icap, &ctx->dcnt->n_ppint_items,
+               &ctx->dcnt->ppint_ticket);
+      }
       LAUNCH(ctx, KC_PPINT, pp::ppint_kernel, std::min((n_multi + 3) / 4, NUM_SMS * 16), pp::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->multi_list,
-             &ctx->dcnt->n_multi, ctx->list_cap, P, ctx->cfg.max_llf, ctx->dcnt);
+             &ctx->dcnt->n_multi, ctx->list_cap, P, ctx->cfg.max_llf, ctx->dcnt, &ctx->dcnt->n_ppint_items, icap);
+    }
   }
   CK(cudaGetLastError());
   return 0;
@@ -986,7 +996,7 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->stream_coarse) cudaStreamDestroy(ctx->stream_coarse);
-  F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->creal); F(ctx->gather); F(ctx->force_c); F(ctx->redbuf); F(ctx->cntbuf); F(ctx->dcnt); F(ctx->ppext_ovf); F(ctx->margin_roles); F(ctx->ppext_items);
+  F(ctx->tw_f); F(ctx->kern_c); F(ctx->rho_c); F(ctx->slab); F(ctx->slab_g); F(ctx->creal); F(ctx->gather); F(ctx->force_c); F(ctx->redbuf); F(ctx->cntbuf); F(ctx->dcnt); F(ctx->ppext_ovf); F(ctx->margin_roles); F(ctx->ppext_items); F(ctx->ppint_items);
   for (int a = 0; a < 3; ++a) { bool dup = false; for (int b2 = 0; b2 < a; ++b2) dup |= (ctx->tw_c[b2] == ctx->tw_c[a]); if (!dup) F(ctx->tw_c[a]); }
   if (ctx->hcnt) cudaFreeHost(ctx->hcnt);
   if (ctx->ev_ok) for (auto& e : ctx->ev) cudaEventDestroy(e);
@@ -1043,14 +1053,19 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
     const char* e = getenv("CUBEP3M_B200_SCAN");
     ctx->scan_onepass = e && !strcmp(e, "1pass");
   }
+  { const char* e = getenv("CUBEP3M_B200_PPEXT_DENSE"); ctx->ppext_cell_mode = !(e && !strcmp(e, "direct")); }   // A/B: "direct" = round 1's per-target / per-cell kernels
   ctx->list_cap = d.max_np / 2 + 1024;
-  if (cfg->ppint) TRY(dmalloc(&ctx->multi_list, (size_t)ctx->list_cap));
+  if (cfg->ppint) {
+    TRY(dmalloc(&ctx->multi_list, (size_t)ctx->list_cap));
+    ctx->ppint_item_cap = d.max_np / 4 + 4096;
+    TRY(dmalloc(&ctx->ppint_items, (size_t)ctx->ppint_item_cap));
+  }
   if (cfg->pp_ext) {
     const int nc = ctx->d.nc_node;
     TRY(dmalloc(&ctx->ppext_ovf, (size_t)((nc + pp::TB_X - 1) / pp::TB_X) * ((nc + pp::TB_Y - 1) / pp::TB_Y) * ((nc + pp::TB_Z - 1) / pp::TB_Z)));
     ctx->ppext_item_cap = d.max_np / 8 + 4096;
     TRY(dmalloc(&ctx->ppext_items, (size_t)ctx->ppext_item_cap));
-    { const char* e = getenv("CUBEP3M_B200_PPEXT_DENSE"); ctx->ppext_cell_mode = !(e && !strcmp(e, "direct")); }   // A/B: "direct" = the one-thread-per-target walk
+
     ctx->margin_cap = d.max_np / 8 + 4096;
     TRY(dmalloc(&ctx->margin_roles, (size_t)ctx->margin_cap));
   }

@@ -34,7 +34,8 @@ __device__ __forceinline__ void pair_force(const float3 pi, const float3 pj, con
 // one warp per fine cell with >= 2 particles
 __global__ void __launch_bounds__(TPB) ppint_kernel(float* __restrict__ xv, const int* __restrict__ fstart, const int* __restrict__ list,
                                                     const int* __restrict__ n_list_ptr, int list_cap, PPParams P, int max_llf,
-                                                    DevCounters* __restrict__ cnt) {
+                                                    DevCounters* __restrict__ cnt, const int* __restrict__ n_items, int item_cap) {
+  if (item_cap > 0 && *n_items <= item_cap) return;    // the (cell, chunk) items were listed in full: ppint_cell_kernel does the work
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * (TPB / 32);
   const int n_list = min(*n_list_ptr, list_cap);
@@ -321,6 +322,7 @@ __device__ __forceinline__ float margin_role_sum(const float* __restrict__ xv, c
   return sqrtf(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z);
 }
 
+// (A one-thread-per-face-adjacent-coarse-cell listing was tried: no gain on the lattice, 3.6x slower on a clustered box, where one thread walks a halo core.)
 __global__ void __launch_bounds__(EXT_TPB) ppext_margin_list_kernel(const float* __restrict__ xv, int np_all, MarginGeom G, int2* __restrict__ roles, int cap,
                                                                     int* __restrict__ n_roles) {
   const int i = blockIdx.x * EXT_TPB + threadIdx.x;
@@ -698,6 +700,73 @@ __global__ void __launch_bounds__(TB_NT) ppext_cell_kernel(float* __restrict__ x
   fm = warp_max(fm);
   if (lane == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_ext_force_max_bits, fm);
   if (lane == 0 && npair) atomicAdd(&cnt->pairs_ppext, npair);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// PPINT as (fine cell, 32-target chunk) items, the same lane mapping as ppext_cell_kernel with the cell's own range as the only source range
+// (self-pair excluded). One warp per CELL (ppint_kernel) leaves a halo core of a few thousand particles to a single warp: 19 ms for 3.8e8 pairs on the
+// clustered profile box, 20 G pairs/s.
+__global__ void __launch_bounds__(TB_NT) ppint_items_kernel(const int* __restrict__ fstart, const int* __restrict__ list, const int* __restrict__ n_list_ptr, int list_cap,
+                                                            int max_llf, int2* __restrict__ items, int cap, int* __restrict__ n_items, DevCounters* __restrict__ cnt) {
+  const int n_list = min(*n_list_ptr, list_cap);
+  for (int w = blockIdx.x * TB_NT + threadIdx.x; w < n_list; w += gridDim.x * TB_NT) {
+    const int k = list[w];
+    const int c = fstart[k + 1] - fstart[k];
+    if (c > max_llf) { atomicOr(&cnt->overflow, 4); continue; }   // 'exceeded max_llf' :280-283
+    const int nch = (c + 31) >> 5;
+    const int base = atomicAdd(n_items, nch);
+    for (int q = 0; q < nch; ++q) if (base + q < cap) items[base + q] = make_int2(k, q);
+  }
+}
+
+__global__ void __launch_bounds__(TB_NT) ppint_cell_kernel(float* __restrict__ xv, const int* __restrict__ fstart, PPParams P, DevCounters* __restrict__ cnt,
+                                                           const int2* __restrict__ items, int cap, const int* __restrict__ n_items, int* __restrict__ ticket) {
+  const int n = *n_items;
+  if (n > cap) return;                                  // list overflow: ppint_kernel does the work
+  const int lane = threadIdx.x & 31;
+  const float2* xv2 = reinterpret_cast<const float2*>(xv);
+  const PairConst KC = make_pair_const(P);
+  float fm = 0.f;
+  unsigned long long npair = 0;
+  for (;;) {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(ticket, 1);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= n) break;
+    const int2 item = items[it];
+    const int s = fstart[item.x], e = fstart[item.x + 1];
+    const int t0 = s + 32 * item.y, nt = min(e, t0 + 32) - t0;
+    int T = 1;
+    while (T < nt) T <<= 1;
+    const int sf = 32 / T, slot = lane & (T - 1), slice = lane / T;
+    const bool live = slot < nt;
+    const int me = t0 + slot;
+    float3 pi = make_float3(0.f, 0.f, 0.f);
+    if (live) { const float2* p = xv2 + 3LL * me; const float2 a = p[0]; pi = make_float3(a.x, a.y, p[1].x); }
+    float3 acc = make_float3(0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int j = s + slice; j < e; j += sf) {
+      const float2* q = xv2 + 3LL * j;
+      const float2 a = q[0];
+      const float z = q[1].x;
+      // w = mass_p / (r pp_bias)^3 for r > rsoft (:344); the pair of a particle with itself has r = 0 and drops out with the soft core
+      const float sx = pi.x - a.x, sy = pi.y - a.y, sz = pi.z - z;
+      const float r2 = sx * sx + sy * sy + sz * sz;
+      const float ir = rsqrt_ftz(r2);
+      float w = KC.c1 * (ir * ir * ir);
+      w = (r2 > KC.rs2 && j != me) ? w : 0.0f;
+      acc.x = fmaf(-sx, w, acc.x); acc.y = fmaf(-sy, w, acc.y); acc.z = fmaf(-sz, w, acc.z);
+    }
+    for (int o = T; o < 32; o <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o); acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+    }
+    if (live && slice == 0) fm = fmaxf(fm, ppext_apply(reinterpret_cast<float2*>(xv) + 3LL * me, acc, P));     // :349-358
+    if (lane == 0) npair += (unsigned long long)(e - s - 1) * (unsigned long long)nt;
+  }
+  fm = warp_max(fm);
+  if (lane == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_force_max_bits, fm);
+  if (lane == 0 && npair) atomicAdd(&cnt->pairs_ppint, npair);
 }
 
 }  // namespace pp

@@ -87,7 +87,7 @@ struct DevCounters {
   int n_blist;           // particles near a y or z face, listed by the first particle_pass kernel
   int n_ppext_items;     // (fine cell, 32-target chunk) items of the dense PP_EXT blocks (pp::ppext_items_kernel)
   int ppext_ticket;      // work ticket of pp::ppext_cell_kernel (must follow n_ppext_items: both are cleared together)
-  int n_ppint_items;     // (fine cell, chunk) items of PPINT (pp::ppint_items_kernel) and their work ticket (cleared together)
+  int n_ppint_items[2];  // (fine cell, chunk) items of PPINT (pp::ppint_items_kernel): heavy (front of the list), light (back); and the heavy items' work ticket (cleared together)
   int ppint_ticket;
   int n_margin_roles;    // (particle, tile) margin roles listed for the PP_EXT limiter (pp::ppext_margin_list_kernel)
   int xchg_timeout;      // a coarse-mesh exchange wait (coarse_slab.cuh) gave up on a peer

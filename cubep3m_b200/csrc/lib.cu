@@ -734,15 +734,15 @@ int do_pp(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
     if (n_multi > 0) {
       // (cell, 32-target chunk) items, one warp each; the one-warp-per-cell kernel only if the item list overflowed (decided on the device)
       const int icap = ctx->ppext_cell_mode ? ctx->ppint_item_cap : 0;
-      CK(cudaMemsetAsync(&ctx->dcnt->n_ppint_items, 0, 2 * sizeof(int), ctx->stream));
+      CK(cudaMemsetAsync(&ctx->dcnt->n_ppint_items[0], 0, 3 * sizeof(int), ctx->stream));
       if (icap > 0) {
         LAUNCH(ctx, KC_PPINT, pp::ppint_items_kernel, std::min((n_multi + pp::TB_NT - 1) / pp::TB_NT, NUM_SMS * 8), pp::TB_NT, 0, ctx->fstart, ctx->multi_list, &ctx->dcnt->n_multi,
-               ctx->list_cap, ctx->cfg.max_llf, ctx->ppint_items, icap, &ctx->dcnt->n_ppint_items, ctx->dcnt);
-        LAUNCH(ctx, KC_PPINT, pp::ppint_cell_kernel, NUM_SMS * 8, pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, P, ctx->dcnt, ctx->ppint_items, icap, &ctx->dcnt->n_ppint_items,
+               ctx->list_cap, ctx->cfg.max_llf, ctx->ppint_items, icap, ctx->dcnt->n_ppint_items, ctx->dcnt);
+        LAUNCH(ctx, KC_PPINT, pp::ppint_cell_kernel, NUM_SMS * 16, pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, P, ctx->dcnt, ctx->ppint_items, icap, ctx->dcnt->n_ppint_items,
                &ctx->dcnt->ppint_ticket);
       }
       LAUNCH(ctx, KC_PPINT, pp::ppint_kernel, std::min((n_multi + 3) / 4, NUM_SMS * 16), pp::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->multi_list,
-             &ctx->dcnt->n_multi, ctx->list_cap, P, ctx->cfg.max_llf, ctx->dcnt, &ctx->dcnt->n_ppint_items, icap);
+             &ctx->dcnt->n_multi, ctx->list_cap, P, ctx->cfg.max_llf, ctx->dcnt, ctx->dcnt->n_ppint_items, icap);
     }
   }
   CK(cudaGetLastError());
@@ -771,7 +771,7 @@ int do_pp_ext(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
       if (icap > 0) {
         LAUNCH(ctx, KC_PPEXT, pp::ppext_items_kernel, std::min(ctx->ppext_blocks, NUM_SMS * 8), pp::TB_NT, 0, ctx->fstart, ctx->d.H, ctx->d.nc_buf, nc, nbx, nby,
                &ctx->dcnt->n_ppext_fallback, ctx->ppext_ovf, ctx->ppext_items, icap, &ctx->dcnt->n_ppext_items);
-        LAUNCH(ctx, KC_PPEXT_DENSE, pp::ppext_cell_kernel, NUM_SMS * 8, pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->cfg.pp_range, P, ctx->dcnt, ctx->ppext_items, icap,
+        LAUNCH(ctx, KC_PPEXT_DENSE, pp::ppext_cell_kernel, NUM_SMS * 16, pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->cfg.pp_range, P, ctx->dcnt, ctx->ppext_items, icap,
                &ctx->dcnt->n_ppext_items, &ctx->dcnt->ppext_ticket);
       }
       LAUNCH(ctx, KC_PPEXT_DENSE, pp::ppext_blocklist_kernel, std::min(ctx->ppext_blocks, NUM_SMS * 8), pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->d.b, ctx->d.nc_buf, nc,

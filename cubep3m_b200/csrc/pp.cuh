@@ -35,7 +35,7 @@ __device__ __forceinline__ void pair_force(const float3 pi, const float3 pj, con
 __global__ void __launch_bounds__(TPB) ppint_kernel(float* __restrict__ xv, const int* __restrict__ fstart, const int* __restrict__ list,
                                                     const int* __restrict__ n_list_ptr, int list_cap, PPParams P, int max_llf,
                                                     DevCounters* __restrict__ cnt, const int* __restrict__ n_items, int item_cap) {
-  if (item_cap > 0 && *n_items <= item_cap) return;    // the (cell, chunk) items were listed in full: ppint_cell_kernel does the work
+  if (item_cap > 0 && n_items[0] + n_items[1] <= item_cap) return;    // the (cell, chunk) items were listed in full: ppint_cell_kernel does the work
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * (TPB / 32);
   const int n_list = min(*n_list_ptr, list_cap);
@@ -638,11 +638,14 @@ __global__ void __launch_bounds__(TB_NT) ppext_cell_kernel(float* __restrict__ x
   const PairConst KC = make_pair_const(P);
   float fm = 0.f;
   unsigned long long npair = 0;
+  // dynamic distribution (item costs span three orders of magnitude: a static round-robin deal was 15 % slower on the clustered boxes); the ticket of the
+  // NEXT item is drawn before the current one is processed, so its L2 round trip is off the critical path
+  int nxt = 0;
+  if (lane == 0) nxt = atomicAdd(ticket, 1);
   for (;;) {
-    int it = 0;
-    if (lane == 0) it = atomicAdd(ticket, 1);
-    it = __shfl_sync(0xffffffffu, it, 0);
+    const int it = __shfl_sync(0xffffffffu, nxt, 0);
     if (it >= n) break;
+    if (lane == 0) nxt = atomicAdd(ticket, 1);
     const int2 item = items[it];
     const int key = item.x;
     const int f = key & 63, cc = key >> 6;
@@ -682,8 +685,19 @@ __global__ void __launch_bounds__(TB_NT) ppext_cell_kernel(float* __restrict__ x
       for (int h = 0; h < 2; ++h) {
         const int s = __shfl_sync(0xffffffffu, h ? sb : sa, r), e = __shfl_sync(0xffffffffu, h ? eb : ea, r);
         nsrc += max(e - s, 0);
-#pragma unroll 2
-        for (int j = s + slice; j < e; j += sf) {
+        // four sources per trip, all eight loads issued before the first pair is evaluated (the sources come from L2: the loop is bound by load
+        // latency, not by the 16-instruction pair body, unless several loads are in flight per lane)
+        int j = s + slice;
+#pragma unroll 1
+        for (; j + 3 * sf < e; j += 4 * sf) {
+          float2 a[4]; float z[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { const float2* q = xv2 + 3LL * (j + u * sf); a[u] = q[0]; z[u] = q[1].x; }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) pair_force_fast(pi, make_float4(a[u].x, a[u].y, z[u], 0.f), KC, acc);
+        }
+#pragma unroll 1
+        for (; j < e; j += sf) {
           const float2* q = xv2 + 3LL * j;
           const float2 a = q[0];
           const float z = q[1].x;
@@ -707,6 +721,9 @@ __global__ void __launch_bounds__(TB_NT) ppext_cell_kernel(float* __restrict__ x
 // PPINT as (fine cell, 32-target chunk) items, the same lane mapping as ppext_cell_kernel with the cell's own range as the only source range
 // (self-pair excluded). One warp per CELL (ppint_kernel) leaves a halo core of a few thousand particles to a single warp: 19 ms for 3.8e8 pairs on the
 // clustered profile box, 20 G pairs/s.
+// items: chunks of cells with more than PPINT_HEAVY particles fill the list from the front (n_items[0], drawn by ticket: their costs vary by orders of
+// magnitude), all others from the back (n_items[1], dealt round-robin: there are millions of them and a ticket per 2-particle cell is pure latency)
+constexpr int PPINT_HEAVY = 64;
 __global__ void __launch_bounds__(TB_NT) ppint_items_kernel(const int* __restrict__ fstart, const int* __restrict__ list, const int* __restrict__ n_list_ptr, int list_cap,
                                                             int max_llf, int2* __restrict__ items, int cap, int* __restrict__ n_items, DevCounters* __restrict__ cnt) {
   const int n_list = min(*n_list_ptr, list_cap);
@@ -715,26 +732,26 @@ __global__ void __launch_bounds__(TB_NT) ppint_items_kernel(const int* __restric
     const int c = fstart[k + 1] - fstart[k];
     if (c > max_llf) { atomicOr(&cnt->overflow, 4); continue; }   // 'exceeded max_llf' :280-283
     const int nch = (c + 31) >> 5;
-    const int base = atomicAdd(n_items, nch);
-    for (int q = 0; q < nch; ++q) if (base + q < cap) items[base + q] = make_int2(k, q);
+    if (c > PPINT_HEAVY) {
+      const int base = atomicAdd(&n_items[0], nch);
+      for (int q = 0; q < nch; ++q) if (base + q < cap) items[base + q] = make_int2(k, q);
+    } else {
+      const int base = atomicAdd(&n_items[1], nch);
+      for (int q = 0; q < nch; ++q) if (base + q < cap) items[cap - 1 - (base + q)] = make_int2(k, q);
+    }
   }
 }
 
 __global__ void __launch_bounds__(TB_NT) ppint_cell_kernel(float* __restrict__ xv, const int* __restrict__ fstart, PPParams P, DevCounters* __restrict__ cnt,
                                                            const int2* __restrict__ items, int cap, const int* __restrict__ n_items, int* __restrict__ ticket) {
-  const int n = *n_items;
-  if (n > cap) return;                                  // list overflow: ppint_kernel does the work
+  const int nh = n_items[0], nl = n_items[1];
+  if (nh + nl > cap) return;                            // list overflow: ppint_kernel does the work
   const int lane = threadIdx.x & 31;
   const float2* xv2 = reinterpret_cast<const float2*>(xv);
   const PairConst KC = make_pair_const(P);
   float fm = 0.f;
   unsigned long long npair = 0;
-  for (;;) {
-    int it = 0;
-    if (lane == 0) it = atomicAdd(ticket, 1);
-    it = __shfl_sync(0xffffffffu, it, 0);
-    if (it >= n) break;
-    const int2 item = items[it];
+  auto run_item = [&](const int2 item) {
     const int s = fstart[item.x], e = fstart[item.x + 1];
     const int t0 = s + 32 * item.y, nt = min(e, t0 + 32) - t0;
     int T = 1;
@@ -763,7 +780,19 @@ __global__ void __launch_bounds__(TB_NT) ppint_cell_kernel(float* __restrict__ x
     }
     if (live && slice == 0) fm = fmaxf(fm, ppext_apply(reinterpret_cast<float2*>(xv) + 3LL * me, acc, P));     // :349-358
     if (lane == 0) npair += (unsigned long long)(e - s - 1) * (unsigned long long)nt;
+  };
+  // heavy items: dynamic, the next ticket always one draw ahead (see ppext_cell_kernel)
+  int nxt = 0;
+  if (lane == 0) nxt = atomicAdd(ticket, 1);
+  for (;;) {
+    const int it = __shfl_sync(0xffffffffu, nxt, 0);
+    if (it >= nh) break;
+    if (lane == 0) nxt = atomicAdd(ticket, 1);
+    run_item(items[it]);
   }
+  // light items: round-robin over the warps of the grid
+  const int nwarps = gridDim.x * (TB_NT / 32);
+  for (int it = blockIdx.x * (TB_NT / 32) + (threadIdx.x >> 5); it < nl; it += nwarps) run_item(items[cap - 1 - it]);
   fm = warp_max(fm);
   if (lane == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_force_max_bits, fm);
   if (lane == 0 && npair) atomicAdd(&cnt->pairs_ppint, npair);

@@ -12,6 +12,7 @@
 // Buffers are AoS float2 [N][PITCH]: PITCH = 16 for the strided passes, 17 for the contiguous-axis passes whose transposing accesses
 // run lanes along the sequence (stride 17 float2 = 34 words: conflict-free per half-warp for 64-bit accesses).
 #pragma once
+#include <type_traits>
 #include "fft_smem.cuh"
 
 namespace fftk {

@@ -520,13 +520,15 @@ template <int N> int set_smem_attr() {
   if (done) return 0;
   const int bytes = (int)smem_bytes(N);
   CK(cudaFuncSetAttribute(fft_x_r2c<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CK(cudaFuncSetAttribute(fft_x_r2c_ngp<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CK(cudaFuncSetAttribute(fft_x_c2r<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CK(cudaFuncSetAttribute(fft_x_c2r3<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CK(cudaFuncSetAttribute((fft_strided<N, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CK(cudaFuncSetAttribute((fft_strided<N, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CK(cudaFuncSetAttribute((fft_strided<N, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CK(cudaFuncSetAttribute(fft_z_sandwich<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_sandwich(N)));
+  CK(cudaFuncSetAttribute(fft_x_c2r3<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));      // also the fine-CIC path of the two-stage sizes (odd row pitch)
+  if constexpr (!Plan2<N>::ok) {      // the first-generation strided / fused kernels only exist for the sizes the two-stage plan cannot do (16, 512, 560)
+    CK(cudaFuncSetAttribute(fft_x_r2c_ngp<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute((fft_strided<N, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute((fft_strided<N, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute((fft_strided<N, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(fft_z_sandwich<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_sandwich(N)));
+  }
   if constexpr (Plan2<N>::ok) {
     const int b2 = (int)smem_bytes2(N, 2, LX);
     CK(cudaFuncSetAttribute((fft_strided2<N, false, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, b2));
@@ -566,10 +568,11 @@ template <int N> int launch_x_r2c_ngp_t(cubep3m_b200_ctx* ctx, int kc, float2* d
     LAUNCH(ctx, kc, fft_x_r2c_ngp2<N>, dim3(N * N / (2 * LX)), dim3(Plan2<N>::NT), (int)smem_bytes2(N, 1, XP), data, cp, g.fstart, g.H, g.b, g.ox, g.oy, g.oz, g.mass_p,
            g.deltas, g.ndelta, g.delta_cap, g.sum_phys, tw);
     return 0;
+  } else {
+    LAUNCH(ctx, kc, fft_x_r2c_ngp<N>, dim3(N * N / (2 * LX)), dim3(NT), (int)smem_bytes(N), data, cp, g.fstart, g.H, g.b, g.ox, g.oy, g.oz, g.mass_p, g.deltas,
+           g.ndelta, g.delta_cap, g.sum_phys, tw);
+    return 0;
   }
-  LAUNCH(ctx, kc, fft_x_r2c_ngp<N>, dim3(N * N / (2 * LX)), dim3(NT), (int)smem_bytes(N), data, cp, g.fstart, g.H, g.b, g.ox, g.oy, g.oz, g.mass_p, g.deltas,
-         g.ndelta, g.delta_cap, g.sum_phys, tw);
-  return 0;
 }
 template <int N> int launch_strided_t(cubep3m_b200_ctx* ctx, int kc, bool inv, const float2* in, float2* out, int hc, long long estride,
                                       long long ostride, int outer0, int nouter, const float* kern, long long kes, long long kos, int elo,
@@ -592,6 +595,15 @@ template <int N> int launch_strided_t(cubep3m_b200_ctx* ctx, int kc, bool inv, c
     // 32-bit element offsets (loads) and 32-bit BYTE offsets (stage-B stores) inside the kernel: the largest offset touched must stay below 2^29 elements
     const long long span = (long long)(nbatch - 1) * bstride + (long long)(outer0 + nouter) * ostride + (long long)N * estride + hc;
     const long long kspan = kern ? (long long)(outer0 + nouter) * kos + (long long)N * kes + hc : 0;
+    if constexpr (N == 32 || N == 64) {
+      // arrays beyond 4 GB (bigfft.cuh: the four-step passes of cic_power's 1024^3 / 2048^3 meshes): forward, no multiply, 64-bit offsets
+      if (span >= (1LL << 29) && !inv && !kern && total2 < (1LL << 31)) {
+        static bool attr64 = false;
+        if (!attr64) { CK(cudaFuncSetAttribute((fft_strided2<N, false, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, sm2)); attr64 = true; }
+        LAUNCH(ctx, kc, (fft_strided2<N, false, false, false, true>), grid2(occ2[0]), blk, sm2, in, out, hc, estride, ostride, outer0, nouter, nbatch, nullptr, 0, 0, elo, ehi, tw, bstride);
+        return 0;
+      }
+    }
     if (span >= (1LL << 29) || kspan >= (1LL << 31) || total2 >= (1LL << 31)) return CUBEP3M_B200_EINVAL;
     const int es = (int)estride, os = (int)ostride, bs = (int)bstride, ke = (int)kes, ko = (int)kos;
     if (!inv && a16) LAUNCH(ctx, kc, (fft_strided2<N, false, false, true>), grid2(occ2[0]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, nullptr, 0, 0, elo, ehi, tw, bs);
@@ -600,7 +612,7 @@ template <int N> int launch_strided_t(cubep3m_b200_ctx* ctx, int kc, bool inv, c
     else if (a16) LAUNCH(ctx, kc, (fft_strided2<N, true, false, true>), grid2(occ2[2]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, nullptr, 0, 0, elo, ehi, tw, bs);
     else LAUNCH(ctx, kc, (fft_strided2<N, true, false, false>), grid2(occ2[2]), blk, sm2, in, out, hc, es, os, outer0, nouter, nbatch, nullptr, 0, 0, elo, ehi, tw, bs);
     return 0;
-  }
+  } else {
   const int sm = (int)smem_bytes_aos(N, 2);
   static int occ[3] = {0, 0, 0};    // resident CTAs per SM of the three instantiations
   if (!occ[0]) {
@@ -614,6 +626,7 @@ template <int N> int launch_strided_t(cubep3m_b200_ctx* ctx, int kc, bool inv, c
   else if (kern) LAUNCH(ctx, kc, (fft_strided<N, true, true>), grid(occ[1]), dim3(NT), sm, in, out, hc, estride, ostride, outer0, nouter, nbatch, kern, kes, kos, elo, ehi, tw, bstride);
   else LAUNCH(ctx, kc, (fft_strided<N, true, false>), grid(occ[2]), dim3(NT), sm, in, out, hc, estride, ostride, outer0, nouter, nbatch, nullptr, 0LL, 0LL, elo, ehi, tw, bstride);
   return 0;
+  }
 }
 template <int N> int launch_sandwich_t(cubep3m_b200_ctx* ctx, int kc, const float2* spec, float2* g, long long gstride, int hc, int cp, int ny, const float* kern,
                                        long long kstride, int kp, int elo, int ehi, const float2* tw) {
@@ -629,13 +642,14 @@ template <int N> int launch_sandwich_t(cubep3m_b200_ctx* ctx, int kc, const floa
     if (a16) LAUNCH(ctx, kc, (fft_z_sandwich2<N, true>), grd, dim3(Plan2<N>::NT), sm2, spec, g, (int)gstride, hc, cp, ny, kern, kstride, kp, elo, ehi, tw);
     else LAUNCH(ctx, kc, (fft_z_sandwich2<N, false>), grd, dim3(Plan2<N>::NT), sm2, spec, g, (int)gstride, hc, cp, ny, kern, kstride, kp, elo, ehi, tw);
     return 0;
-  }
+  } else {
   static int occ = 0;
   if (!occ) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fft_z_sandwich<N>, NT, (int)smem_bytes_sandwich(N)));
   const long long total = (long long)((hc + LX - 1) / LX) * ny;
   LAUNCH(ctx, kc, fft_z_sandwich<N>, dim3((unsigned)std::min<long long>(total, (long long)NUM_SMS * std::max(occ, 1))), dim3(NT), (int)smem_bytes_sandwich(N), spec,
          g, gstride, hc, cp, ny, kern, kstride, kp, elo, ehi, tw);
   return 0;
+  }
 }
 template <int N> int launch_x_c2r_t(cubep3m_b200_ctx* ctx, int kc, const float2* in, float* out, int lo_x, int cnt_x, int lo_y, int cnt_y, int lo_z,
                                     int cnt_z, int ny_src, long long opx, long long opy, float scale, const float2* tw, int nbatch, long long ibs,
@@ -685,6 +699,7 @@ template <int N> int launch_x_c2r3_t(cubep3m_b200_ctx* ctx, int kc, const float2
            scale, fmax_bits, tw);
     return 0;
   }
+  // first-generation kernel: the three-factor sizes, and the fine-CIC path of every size (its in-place r2c layout has an odd row pitch n/2+1)
   LAUNCH(ctx, kc, fft_x_c2r3<N>, dim3((unsigned)((nrows + 2 * LX - 1) / (2 * LX))), dim3(NT), (int)smem_bytes(N), in, cp, out, lo, cnt, ibs, obs, scale, fmax_bits, tw);
   return 0;
 }

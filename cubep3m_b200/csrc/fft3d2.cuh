@@ -43,7 +43,7 @@ template <int N> __device__ __forceinline__ unsigned crop_mask(int j, int elo, i
 // A16 = false: thread (j, col) copies element col of rows j, j+ES, ... with 8-byte cp.async (any pitch); columns beyond hc are zero-filled.
 // A16 = true : the block starts on a 128-byte boundary and the pitch is even (padded spectra): 8 threads copy one row with 16-byte cp.async,
 //              half as many copies; columns beyond hc are read from the (zero) padding.
-template <int N, int NTH, bool A16> __device__ __forceinline__ void stage_block(const float2* __restrict__ blk, int estride, bool ok, unsigned sbuf,
+template <int N, int NTH, bool A16, typename ES = int> __device__ __forceinline__ void stage_block(const float2* __restrict__ blk, ES estride, bool ok, unsigned sbuf,
                                                                                 float2* __restrict__ gbuf) {
   if constexpr (A16) {
     constexpr int RPP = NTH / 8;                   // rows per pass
@@ -74,10 +74,15 @@ template <int N, int NTH, bool A16> __device__ __forceinline__ void stage_block(
 
 // ---------------------------------------------------------------------------------------------- strided pass
 // element e of column c of item (bx, outer, bz): in[bz*bstride + (outer + outer0)*ostride + bx*16 + e*estride + c]   (all offsets < 2^31)
-template <int N, bool INV, bool MUL, bool A16>
-__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_strided2(const float2* __restrict__ in, float2* __restrict__ out, int hc, int estride, int ostride,
+// W64: 64-bit element offsets for arrays beyond 4 GB (the 1024^3 / 2048^3-slab spectra of cic_power, bigfft.cuh); the 32-bit form is the hot path.
+template <int N, bool INV, bool MUL, bool A16, bool W64 = false>
+__global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_strided2(const float2* __restrict__ in, float2* __restrict__ out, int hc,
+                                                                typename std::conditional<W64, long long, int>::type estride,
+                                                                typename std::conditional<W64, long long, int>::type ostride,
                                                                 int outer0, int nouter, int nbatch, const float* __restrict__ kern, int kes, int kos,
-                                                                int elo, int ehi, const float2* __restrict__ tw_g, int bstride) {
+                                                                int elo, int ehi, const float2* __restrict__ tw_g,
+                                                                typename std::conditional<W64, long long, int>::type bstride) {
+  using off_t = typename std::conditional<W64, long long, int>::type;
   using P = Plan2<N>;
   constexpr int NT2 = P::NT, R0 = P::R0, R1 = P::R1;
   extern __shared__ __align__(16) unsigned char raw[];
@@ -90,16 +95,17 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_strided2(const float2* __
   const int total = (int)nbx * nouter * nbatch;
   const unsigned mask = crop_mask<N>(j, elo, ehi);
   const unsigned s0 = smem_u32(buf0), s1 = smem_u32(buf1);
-  const int joff = j * estride + col;
-  auto decode = [&](int item, int& off, int& koff, bool& ok) {      // off: offset of the block's first element (column 0, element 0)
+  const off_t joff = (off_t)j * estride + col;
+  auto decode = [&](int item, off_t& off, int& koff, bool& ok) {      // off: offset of the block's first element (column 0, element 0)
     const unsigned bx = (unsigned)item % nbx, t = (unsigned)item / nbx;
     const unsigned o = t % (unsigned)nouter, bz = t / (unsigned)nouter;
     const int kx = (int)bx * LX;
-    off = (int)bz * bstride + ((int)o + outer0) * ostride + kx;
+    off = (off_t)bz * bstride + (off_t)((int)o + outer0) * ostride + kx;
     koff = ((int)o + outer0) * kos + kx + col;
     ok = kx + col < hc;
   };
-  int item = blockIdx.x, off = 0, koff = 0;
+  int item = blockIdx.x, koff = 0;
+  off_t off = 0;
   bool ok = false;
   int p = 0;
   if (item < total) {
@@ -110,7 +116,8 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_strided2(const float2* __
   while (item < total) {
     float2* buf = p ? buf1 : buf0;
     const int next = item + gridDim.x;
-    int noff = 0, nkoff = 0;
+    off_t noff = 0;
+    int nkoff = 0;
     bool nok = false;
     cp_async_wait_all();
     __syncthreads();                               // item landed; every thread is done with the other buffer
@@ -137,12 +144,18 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_strided2(const float2* __
     __syncthreads();
     if (threadIdx.x < P::NB) {
       // 32-bit byte offsets from the array base: one IMAD per store instead of a 64-bit address chain rebuilt for every output
-      const unsigned ob = (unsigned)(off + joff) * 8u, stepb = (unsigned)(R0 * estride) * 8u;
-      char* obase = reinterpret_cast<char*>(out);
       const unsigned m = ok ? mask : 0u;
-      stageB<N, INV, LX>(buf, tw, j, col, [&](int r, float2 val) {
-        if (m & (1u << r)) *reinterpret_cast<float2*>(obase + (ob + (unsigned)r * stepb)) = val;
-      });
+      if constexpr (W64) {
+        float2* op = out + (off + joff);
+        const long long step = (long long)R0 * estride;
+        stageB<N, INV, LX>(buf, tw, j, col, [&](int r, float2 val) { if (m & (1u << r)) op[(long long)r * step] = val; });
+      } else {
+        const unsigned ob = (unsigned)(off + joff) * 8u, stepb = (unsigned)(R0 * estride) * 8u;
+        char* obase = reinterpret_cast<char*>(out);
+        stageB<N, INV, LX>(buf, tw, j, col, [&](int r, float2 val) {
+          if (m & (1u << r)) *reinterpret_cast<float2*>(obase + (ob + (unsigned)r * stepb)) = val;
+        });
+      }
     }
     item = next; off = noff; koff = nkoff; ok = nok;
     p ^= 1;

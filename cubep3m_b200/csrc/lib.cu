@@ -11,6 +11,7 @@
 #include "coarse_slab.cuh"
 #include "power.cuh"
 #include "distinit.cuh"
+#include "bigfft.cuh"
 
 namespace {
 
@@ -348,16 +349,19 @@ int cs_alloc(cubep3m_b200_ctx* ctx) {
   ctx->cs_peers.base[ctx->cfg.rank] = ctx->cs_xchg;
   return 0;
 }
-// maps every other rank's exchange allocation (cudaIpc handles all-gathered over NCCL); ok = false if any rank could not
-int cs_map_peers(cubep3m_b200_ctx* ctx, bool* ok_out) {
+// maps every other rank's copy of an exchange allocation (cudaIpc handles all-gathered over NCCL) into P->base[]; ok = false if any rank could not.
+// Collective: every rank must call it with its own allocation.
+int map_peers(cubep3m_b200_ctx* ctx, float* mine_ptr, PeerTable* P, std::vector<void*>* opened, bool* ok_out) {
   *ok_out = true;
+  for (int r = 0; r < 8; ++r) P->base[r] = nullptr;
+  P->base[ctx->cfg.rank] = mine_ptr;
   if (ctx->d.world == 1) return 0;
 #ifdef CUBEP3M_WITH_NCCL
   const Dims& d = ctx->d;
   struct Handle { cudaIpcMemHandle_t h; int ok; int pad[3]; };
   Handle mine;
   memset(&mine, 0, sizeof(mine));
-  mine.ok = cudaIpcGetMemHandle(&mine.h, ctx->cs_xchg) == cudaSuccess;
+  mine.ok = cudaIpcGetMemHandle(&mine.h, mine_ptr) == cudaSuccess;
   cudaGetLastError();
   Handle* dall = nullptr;
   CK(cudaMalloc((void**)&dall, sizeof(Handle) * d.world));
@@ -373,9 +377,9 @@ int cs_map_peers(cubep3m_b200_ctx* ctx, bool* ok_out) {
     if (r == ctx->cfg.rank) continue;
     void* p = nullptr;
     ok = cudaIpcOpenMemHandle(&p, all[r].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-    if (p) ctx->cs_ipc_opened.push_back(p);
+    if (p) opened->push_back(p);
     if (!ok) { cudaGetLastError(); break; }
-    ctx->cs_peers.base[r] = (float*)p;
+    P->base[r] = (float*)p;
   }
   int* dflag = ctx->cntbuf;
   const int mine_ok = ok ? 1 : 0;
@@ -389,6 +393,17 @@ int cs_map_peers(cubep3m_b200_ctx* ctx, bool* ok_out) {
 #else
   *ok_out = false;
   return 0;
+#endif
+}
+int cs_map_peers(cubep3m_b200_ctx* ctx, bool* ok_out) { return map_peers(ctx, ctx->cs_xchg, &ctx->cs_peers, &ctx->cs_ipc_opened, ok_out); }
+// a stream-ordered barrier over all ranks (a one-int all-reduce)
+int rank_barrier(cubep3m_b200_ctx* ctx) {
+  if (ctx->d.world == 1) return 0;
+#ifdef CUBEP3M_WITH_NCCL
+  NCK(ncclAllReduce(ctx->cntbuf + 4, ctx->cntbuf + 4, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream));
+  return 0;
+#else
+  return CUBEP3M_B200_ENCCL;
 #endif
 }
 void cs_free(cubep3m_b200_ctx* ctx) {
@@ -1534,17 +1549,135 @@ int cubep3m_b200_debug_fft3d(cubep3m_b200_ctx* ctx, int32_t n, float* data, int3
 }
 int64_t cubep3m_b200_launch_count(cubep3m_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+// ---------------------------------------------------------------- cic_power over z-slabs / y-pencils (several ranks, or meshes beyond one CTA's transform length)
+namespace {
+void power_shells(const std::vector<double>& sums, int stride, int nc, double box, int ngp_binning, double* k_out, double* delta2_out, double* sigma_out) {
+  const double* P = sums.data(); const double* P2 = P + stride; const double* W = P2 + stride; const double* K = W + stride;
+  for (int sh = 1; sh <= nc / 2; ++sh) {                      // cic_power.f90:1649-1660
+    const double Wn = std::max(W[sh], 1e-300), kavg = K[sh] / Wn, Pm = P[sh] / Wn;
+    const double var = std::max(P2[sh] / Wn - Pm * Pm, 0.0);
+    const double keff = ngp_binning ? kavg : kavg - 1.0;
+    k_out[sh - 1] = 2.0 * M_PI * kavg / box;
+    delta2_out[sh - 1] = 4.0 * M_PI * keff * keff * keff * Pm;
+    if (sigma_out) sigma_out[sh - 1] = 4.0 * M_PI * keff * keff * keff * sqrt(var / std::max(W[sh] - 1.0, 1.0));
+  }
+}
+
+// The reference's layout (cic_power.f90:840-954: cube -> slab, distributed r2c, shell sums reduced over the ranks) with the library's means: the CIC deposit
+// adds straight into the owners' z-slabs over NVLink (power::cic_density_dist_kernel), x and y passes run on the slab, one transpose stores into the
+// peers' y-pencils (cslab::transpose_kernel), the z pass and the shell binning run on the pencils, the shell sums are all-reduced. `big`: the axis
+// length needs the four-step passes of bigfft.cuh (1024, 2048); the y / z frequencies then stay digit-transposed and the binning kernel maps them.
+int cic_power_slabs(cubep3m_b200_ctx* ctx, const float shake_offset[3], double box, int ngp_binning, double* k_out, double* delta2_out, double* sigma_out, int nc,
+                    bool big) {
+  const Dims& d = ctx->d;
+  const int W = d.world, me = ctx->cfg.rank, zs = nc / W, ys = nc / W, hc = nc / 2 + 1;
+  const size_t slab_f = ((size_t)(nc + 2) * nc * zs + 63) / 64 * 64;       // floats: a z-slab (nc+2, nc, zs) = a y-pencil block (hc, ys, nc) complex
+  const int nb = nc / 2 + 2, stride = nb + 2;
+  float *xchg = nullptr, *outb = nullptr; double *dsinc = nullptr, *dsums = nullptr; float2* tw = nullptr;
+  fftk::BigTwiddles BT;
+  PeerTable P;
+  std::vector<void*> opened;
+  int status = 0;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(ctx->stream);
+    for (void* q : opened) cudaIpcCloseMemHandle(q);
+    if (xchg) cudaFree(xchg); if (outb) cudaFree(outb); if (dsinc) cudaFree(dsinc); if (dsums) cudaFree(dsums); if (tw) cudaFree(tw);
+    fftk::big_free(BT);
+  };
+#define PCK(x) do { if ((x) != cudaSuccess) { cleanup(); return CUBEP3M_B200_ECUDA; } } while (0)
+#define PST(x) do { status = (x); if (status) { cleanup(); return status; } } while (0)
+  PCK(cudaMalloc((void**)&xchg, 2 * slab_f * sizeof(float)));               // [slab A | pencils T]: what the peers store into
+  if (big) PCK(cudaMalloc((void**)&outb, slab_f * sizeof(float)));
+  PCK(cudaMalloc((void**)&dsinc, nc * sizeof(double)));
+  PCK(cudaMalloc((void**)&dsums, 4 * stride * sizeof(double)));
+  if (big) PST(fftk::big_init(nc, BT)); else PST(fftk::make_twiddles(nc, &tw));
+  bool ok = true;
+  PST(map_peers(ctx, xchg, &P, &opened, &ok));
+  if (!ok) { cleanup(); return CUBEP3M_B200_ENCCL; }
+  // global particle count -> particle mass (nc / np)^3 of cic_power.f90
+  double np_tot = (double)ctx->np_local;
+  if (W > 1) {
+#ifdef CUBEP3M_WITH_NCCL
+    double* dn = reinterpret_cast<double*>(ctx->redbuf + 16);
+    PCK(cudaMemcpyAsync(dn, &np_tot, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (ncclAllReduce(dn, dn, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream) != ncclSuccess) { cleanup(); return CUBEP3M_B200_ENCCL; }
+    PCK(cudaMemcpyAsync(&np_tot, dn, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PCK(cudaStreamSynchronize(ctx->stream));
+#endif
+  }
+  const float mp = (float)(((double)nc * nc * nc) / np_tot);
+  float* A = xchg;
+  float2* T = reinterpret_cast<float2*>(xchg + slab_f);
+  PCK(cudaMemsetAsync(A, 0, slab_f * sizeof(float), ctx->stream));
+  PCK(cudaMemsetAsync(dsums, 0, 4 * stride * sizeof(double), ctx->stream));
+  std::vector<double> sinc4(nc);
+  for (int i = 0; i < nc; ++i) {
+    const int k = i < nc / 2 ? i : i - nc;
+    const double x = M_PI * (double)k / (double)nc, sc = (k == 0) ? 1.0 : sin(x) / x;
+    sinc4[i] = sc * sc * sc * sc;
+  }
+  PCK(cudaMemcpyAsync(dsinc, sinc4.data(), nc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  PST(rank_barrier(ctx));                                                    // every slab is zeroed before the first remote contribution arrives
+  const float zero[3] = {0.f, 0.f, 0.f};
+  const float* so = shake_offset ? shake_offset : zero;
+  LAUNCH(ctx, KC_MISC, power::cic_density_dist_kernel, (ctx->np_local + power::TPB - 1) / power::TPB, power::TPB, 0, ctx->xv[ctx->cur], ctx->np_local, nc,
+         (float)(d.coord[0] * d.mT), (float)(d.coord[1] * d.mT), (float)(d.coord[2] * d.mT), so[0], so[1], so[2], mp, P, 0LL, zs);
+  PST(rank_barrier(ctx));                                                    // all contributions to this rank's slab have landed
+  float2* S = reinterpret_cast<float2*>(A);
+  if (big) {
+    PST(fftk::big_forward_x(ctx, KC_MISC, BT, A, reinterpret_cast<float2*>(outb), (long long)nc * zs));
+    S = reinterpret_cast<float2*>(outb);
+    PST(fftk::big_forward_strided(ctx, KC_MISC, BT, S, hc, (long long)hc, (long long)nc * hc, zs));
+  } else {
+    PST(fftk::launch_x_r2c(ctx, KC_MISC, nc, A, nc * zs, tw));
+    PST(fftk::launch_strided(ctx, KC_MISC, nc, false, S, S, hc, (long long)hc, (long long)nc * hc, 0, zs, nullptr, 0, 0, 0, nc - 1, tw));
+  }
+  {
+    const dim3 tgrid((unsigned)std::max(1, std::min(64, (ys * hc + cslab::TPB - 1) / cslab::TPB)), (unsigned)(W * zs));
+    LAUNCH(ctx, KC_MISC, cslab::transpose_kernel<true>, tgrid, cslab::TPB, 0, S, P, (long long)slab_f, W, me, zs, ys, nc, hc);
+  }
+  PST(rank_barrier(ctx));                                                    // this rank's pencils are complete
+  if (big) PST(fftk::big_forward_strided(ctx, KC_MISC, BT, T, hc, (long long)ys * hc, (long long)hc, ys));
+  else PST(fftk::launch_strided(ctx, KC_MISC, nc, false, T, T, hc, (long long)ys * hc, (long long)hc, 0, ys, nullptr, 0, 0, 0, nc - 1, tw));
+  PCK(cudaFuncSetAttribute(power::shell_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * stride * sizeof(double))));
+  LAUNCH(ctx, KC_MISC, power::shell_bin_kernel, NUM_SMS * 4, power::TPB, 4 * stride * sizeof(double), T, nc, ys, me * ys, big ? fftk::BIG_N1 : 0, big ? nc / fftk::BIG_N1 : 0,
+         dsinc, ngp_binning, nb, dsums);
+  if (W > 1) {
+#ifdef CUBEP3M_WITH_NCCL
+    if (ncclAllReduce(dsums, dsums, (size_t)4 * stride, ncclDouble, ncclSum, ctx->comm, ctx->stream) != ncclSuccess) { cleanup(); return CUBEP3M_B200_ENCCL; }
+#endif
+  }
+  std::vector<double> sums(4 * stride);
+  PCK(cudaMemcpyAsync(sums.data(), dsums, sums.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PCK(cudaStreamSynchronize(ctx->stream));
+  PCK(cudaGetLastError());
+  PST(rank_barrier(ctx));                                                    // nobody unmaps a buffer a peer may still be reading
+  PCK(cudaStreamSynchronize(ctx->stream));
+#undef PCK
+#undef PST
+  cleanup();
+  power_shells(sums, stride, nc, box, ngp_binning, k_out, delta2_out, sigma_out);
+  return 0;
+}
+}  // namespace
+
 // ---------------------------------------------------------------- cic_power on the device (utils/cic_power/cic_power.f90)
 int cubep3m_b200_cic_power(cubep3m_b200_ctx* ctx, const float shake_offset[3], double box, int32_t ngp_binning, double* k_out, double* delta2_out,
                            double* sigma_out, int32_t nshells) {
   if (!ctx || !k_out || !delta2_out) return CUBEP3M_B200_EINVAL;
   const Dims& d = ctx->d;
-  if (d.world != 1) return CUBEP3M_B200_EINVAL;             // the mesh lives on one GPU; the distributed transform is listed under "next"
-  const int nc = d.mT;                                        // nf_physical_dim
-  if (!fftk::supported(nc) || nshells != nc / 2) return CUBEP3M_B200_EINVAL;
+  if (d.world > 1 && !(d.Dg[0] == d.Dg[1] && d.Dg[1] == d.Dg[2])) return CUBEP3M_B200_EINVAL;   // a cubic box only (the reference's nodes_dim^3)
+  const int nc = d.mT * d.Dg[0];                              // nf_physical_dim
+  const char* pmode = getenv("CUBEP3M_B200_POWER");             // "slab": the slab / pencil pipeline on one rank; "big": also the four-step transforms (tests)
+  const bool force_big = pmode && !strcmp(pmode, "big") && fftk::big_supported(nc);
+  const bool direct = fftk::supported(nc) && !force_big, big = !direct && fftk::big_supported(nc);
+  if ((!direct && !big) || nshells != nc / 2 || nc % d.world) return CUBEP3M_B200_EINVAL;
   CK(cudaSetDevice(ctx->device));
   const int np = ctx->np_local;
   if (np <= 0 || ctx->passed) return CUBEP3M_B200_ENOTREADY;   // needs the physical particles only (after delete_particles / upload)
+  {
+    if (d.world > 1 || big || (pmode && !strcmp(pmode, "slab"))) return cic_power_slabs(ctx, shake_offset, box, ngp_binning, k_out, delta2_out, sigma_out, nc, big);
+  }
   const size_t nreal = (size_t)(nc + 2) * nc * nc;
   const int nb = nc / 2 + 2, stride = nb + 2;
   float* rho = nullptr; float2* tw = nullptr; double *dsinc = nullptr, *dsums = nullptr;
@@ -1570,7 +1703,7 @@ int cubep3m_b200_cic_power(cubep3m_b200_ctx* ctx, const float shake_offset[3], d
   const fftk::Mesh3 g{nc, nc, nc, tw, tw, tw};
   if (int st = fftk::forward3d(ctx, g, rho)) { cleanup(); return st; }
   PCK(cudaFuncSetAttribute(power::shell_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * stride * sizeof(double))));
-  LAUNCH(ctx, KC_MISC, power::shell_bin_kernel, NUM_SMS * 4, power::TPB, 4 * stride * sizeof(double), reinterpret_cast<const float2*>(rho), nc, dsinc, ngp_binning, nb, dsums);
+  LAUNCH(ctx, KC_MISC, power::shell_bin_kernel, NUM_SMS * 4, power::TPB, 4 * stride * sizeof(double), reinterpret_cast<const float2*>(rho), nc, nc, 0, 0, 0, dsinc, ngp_binning, nb, dsums);
   std::vector<double> sums(4 * stride);
   PCK(cudaMemcpyAsync(sums.data(), dsums, sums.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   PCK(cudaStreamSynchronize(ctx->stream));

@@ -257,7 +257,7 @@ class ParticleMesh:
     def cic_power(self, box, shake=(0.0, 0.0, 0.0), ngp_binning=True):
         """Device twin of utils/cic_power (cic_power.f90:840-954): returns (k [h/Mpc], Delta^2, sigma) for shells 1..nc/2 of the resident
         physical particles after subtracting the accumulated shake offset (checkpoint.f90:92)."""
-        n = self.cfg.nf_physical_dim // 2
+        n = self.cfg.mT * self.cfg.grid[0] // 2
         k, d2, sg = (np.empty(n, np.float64) for _ in range(3))
         off = (C.c_float * 3)(*[float(v) for v in shake])
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))

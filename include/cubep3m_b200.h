@@ -190,7 +190,10 @@ int cubep3m_b200_get_kernel_times(cubep3m_b200_ctx* ctx, float* ms, int64_t* lau
 
 /*
  * cic_power on the device (utils/cic_power/cic_power.f90:840-954 driver, :1496-1539 CIC deposit, :1583-1615 mode weights and shells,
- * :1649-1660 output columns): power spectrum of the resident physical particles on the global nf_physical_dim^3 mesh, single rank.
+ * :1649-1660 output columns): power spectrum of the resident physical particles on the global nf_physical_dim^3 mesh. One rank with a mesh the
+ * library transforms directly (<= 560): everything on the one GPU. Several ranks (cubic rank grid; collective call, every rank gets the result) or
+ * meshes of 1024 / 2048 cells: z-slabs / y-pencils as the reference's cube -> slab -> distributed r2c (:840-954), the deposit added straight into the
+ * owners' slabs over NVLink, the transpose stored into the peers' pencils, shell sums all-reduced; 1024 and 2048 go through four-step passes.
  * shake_offset is subtracted first, as checkpoint.f90:92 does before the particles reach cic_power. nshells must be nf_physical_dim/2;
  * k [h/Mpc], Delta^2(k) and its standard error (may be NULL) are written for shells 1..nshells. ngp_binning = 1 is the build
  * COMPILE_cic_power.csh:20 uses (w1 = 1, w2 = 0), 0 the CIC shell weights.

@@ -134,3 +134,107 @@ def test_pk_config0_z100_to_z10(built):
     k0, d0, _ = power.power_spectrum(xv[:, :3], nc, box)
     big = slice(2, 10)
     assert 60 < np.median(dr[big] / d0[big]) < 110, np.median(dr[big] / d0[big])
+
+
+@pytest.mark.gpu
+def test_cic_power_slab_and_four_step_paths_match_direct(built, monkeypatch):
+    """cubep3m_b200_cic_power three ways on the same 512^3 mesh (256^3 particles): everything-on-one-GPU direct transform (default), the z-slab / y-pencil
+    pipeline of the multi-rank path with W = 1 (CUBEP3M_B200_POWER=slab), and that pipeline with the four-step transforms of bigfft.cuh that 1024 / 2048
+    meshes need (=big; 512 = 16*16*2 on x, 32*16 on y and z, frequencies left digit-transposed). Same fp32 data, different summation orders: 2e-5."""
+    from cubep3m_b200.lib import ParticleMesh
+    cfg = default_config(nf_tile=304, tiles_node_dim=2, pp_ext=0)
+    nc, box = cfg.nf_physical_dim, 200.0
+    xv = ic.zeldovich_ics(nc, box=box, z_i=20.0, seed=3)
+    shake = np.array([1.25, -3.5, 0.5], np.float32)
+    xv[:, :3] = np.mod(xv[:, :3] + shake, np.float32(nc))
+    res = {}
+    for mode in ("direct", "slab", "big"):
+        monkeypatch.setenv("CUBEP3M_B200_POWER", mode)
+        pm = ParticleMesh(cfg)
+        pm.upload_particles(xv)
+        res[mode] = {ngp: pm.cic_power(box, shake=shake, ngp_binning=ngp) for ngp in (True, False)}
+        pm.close()
+    for mode in ("slab", "big"):
+        for ngp in (True, False):
+            k0, d0, s0 = res["direct"][ngp]
+            k1, d1, s1 = res[mode][ngp]
+            assert np.allclose(k0, k1, rtol=1e-12), mode
+            rel = np.abs(d1 - d0) / np.maximum(np.abs(d0), 1e-30)
+            assert rel.max() < 2e-5, (mode, ngp, float(rel.max()), int(rel.argmax()))
+            assert np.allclose(s0, s1, rtol=1e-3, atol=1e-12), mode
+
+
+def _expected_power_of_2x_replicated_box(small_pos, nb_small, box_big):
+    """Shell-averaged Delta^2 (NGP shells, cic_power.f90:1583-1660) of the 2x2x2 periodic replication of a box, from the small box alone:
+    delta_big(2k') = delta_small(k') mode by mode (same CIC cells, 8 replicas over 8x the volume), every mode with an odd component vanishes; the mode counts and
+    mean |k| of the big mesh are enumerated exactly, plane by plane."""
+    from cubep3m_b200.power import cic_density
+    try:
+        from scipy import fft as sfft
+        kw = {"workers": -1}
+    except Exception:
+        sfft, kw = np.fft, {}
+    nc = 2 * nb_small
+    rho = cic_density(small_pos, nb_small)
+    dk = sfft.rfftn(rho - 1.0, **kw) / float(nb_small) ** 3
+    n2 = nc // 2
+    P = np.zeros(n2 + 3); Wn = np.zeros(n2 + 3); K = np.zeros(n2 + 3)
+    sinc = lambda kk, n: np.where(kk == 0, 1.0, np.sin(np.pi * kk / n) / np.where(kk == 0, 1.0, np.pi * kk / n))
+    kx_s = np.arange(nb_small // 2 + 1, dtype=np.float64)[None, :]
+    fs = np.fft.fftfreq(nb_small, 1.0 / nb_small)
+    ky_s = fs[:, None]
+    # In the big mesh the small box's Nyquist index -nb/2 (fftfreq convention) sits at k = -nb = index nb of a 2nb mesh, i.e. frequency +nb/2 * 2 ... as
+    # a SIGNED big-mesh frequency 2k' = -nb which is not the big mesh's Nyquist, so no folding happens: k = 2k' is used as is for every k'.
+    for iz, kz in enumerate(fs):
+        kr = 2.0 * np.sqrt(kx_s ** 2 + ky_s ** 2 + kz ** 2)
+        pw = (dk[iz].real ** 2 + dk[iz].imag ** 2) / (sinc(kx_s, nb_small) * sinc(ky_s, nb_small) * sinc(np.float64(kz), nb_small)) ** 4
+        keep = ~((kx_s == 0) & ~((ky_s > 0) | ((ky_s == 0) & (kz > 0)))) & (kr > 0)
+        k1 = np.ceil(kr).astype(np.int64)
+        sel = keep & (k1 <= n2 + 1)
+        np.add.at(P, k1[sel], pw[sel])
+    kx_b = np.arange(nc // 2 + 1, dtype=np.float64)[None, :]
+    ky_b = np.fft.fftfreq(nc, 1.0 / nc)[:, None]
+    for kz in np.fft.fftfreq(nc, 1.0 / nc):
+        kr = np.sqrt(kx_b ** 2 + ky_b ** 2 + kz ** 2)
+        keep = ~((kx_b == 0) & ~((ky_b > 0) | ((ky_b == 0) & (kz > 0)))) & (kr > 0)
+        k1 = np.ceil(kr).astype(np.int64)
+        sel = keep & (k1 <= n2 + 1)
+        np.add.at(Wn, k1[sel], 1.0); np.add.at(K, k1[sel], kr[sel])
+    sh = np.arange(1, n2 + 1)
+    kavg = K[sh] / Wn[sh]
+    return 2 * np.pi * kavg / box_big, 4 * np.pi * kavg ** 3 * P[sh] / Wn[sh]
+
+
+def test_replicated_box_expectation_matches_host_twin():
+    """The expectation used by the 1024^3 GPU test, checked here on the CPU at 32 -> 64 cells against the host twin run on the replicated particles."""
+    nb = 32
+    small = ic.zeldovich_ics(nb, box=50.0, z_i=5.0, seed=9)
+    small[:, :3] = np.mod(small[:, :3], np.float32(nb))
+    big = ic.tile_box(small, nb, 2)
+    k, d2, _ = power.power_spectrum(big[:, :3], 2 * nb, 100.0)
+    ke, de = _expected_power_of_2x_replicated_box(small[:, :3], nb, 100.0)
+    assert np.allclose(k, ke, rtol=1e-9)
+    good = de > 1e-12 * de.max()
+    assert np.abs(d2[good] - de[good]).max() <= 1e-6 * de.max() and np.allclose(d2[good], de[good], rtol=1e-4)
+
+
+@pytest.mark.gpu
+def test_cic_power_1024_mesh_against_replicated_512(built):
+    """BASELINE configs[2]'s mesh (1024^3, a 4.3 GB half spectrum: four-step passes with 64-bit offsets). The particles are a 2x2x2 periodic replication of a
+    512-cell box, for which the answer is known from the small box alone (_expected_power_of_2x_replicated_box, float64 on the host); gate 2e-4 (fp32 mesh)."""
+    from cubep3m_b200.lib import ParticleMesh
+    cfg = default_config(nf_tile=304, tiles_node_dim=4, ppint=0, pp_ext=0, max_np=40_000_000)
+    nc, box, nb_small = cfg.nf_physical_dim, 400.0, 512
+    assert nc == 1024
+    small = ic.zeldovich_ics(nb_small, box=200.0, z_i=10.0, seed=5)[::8].copy()          # 2.1 M particles of a 512-cell box
+    small[:, :3] = np.mod(small[:, :3], np.float32(nb_small))
+    xv = ic.tile_box(small, nb_small, 2)
+    pm = ParticleMesh(cfg)
+    pm.upload_particles(xv)
+    k, d2, _ = pm.cic_power(box, ngp_binning=True)
+    pm.close()
+    ke, want = _expected_power_of_2x_replicated_box(small[:, :3], nb_small, box)
+    assert np.allclose(k, ke, rtol=1e-9)
+    good = want > 1e-12 * want.max()
+    rel = np.abs(d2[good] - want[good]) / want[good]
+    assert rel.max() < 2e-4, (float(rel.max()), int(np.argmax(rel)))

@@ -382,6 +382,19 @@ def run_ours(args):
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
 
+    # ---- the acceptance metric on the benchmark box itself: cic_power of the resident particles on the global nf_physical_dim^3 mesh (1024^3 at N = 1,
+    # 2048^3 over 8 GPUs: z-slabs / y-pencils, four-step transforms). Collective over the ranks; needs a cubic rank grid (N = 1 or 8). Not part of `value`.
+    power_info = None
+    if grid[0] == grid[1] == grid[2]:
+        try:
+            barrier()
+            t0 = time.perf_counter()
+            pk, pd2, _ = pm.cic_power(box * grid[0], shake=shake)
+            barrier()
+            power_info = {"mesh": int(cfg.mT * grid[0]), "ms": (time.perf_counter() - t0) * 1e3, "k_first": float(pk[0]), "delta2_first5": [float(v) for v in pd2[:5]],
+                          "delta2_nyquist": float(pd2[-1]), "finite": bool(np.isfinite(pd2).all())}
+        except Exception as e:      # noqa: BLE001 - the bench line must survive
+            power_info = {"error": f"{type(e).__name__}: {e}"}
     if world > 1:
         t = torch.tensor([ms_step, e2e_ms, dev_step], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -467,6 +480,7 @@ def run_ours(args):
                     "mode": "strict drop-in: pinned host xv -> H2D, particle_mesh, D2H every step (cubepm.f90:143 semantics)", "host_numa": numa_note},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stages": stages,
+            "cic_power": power_info,
             "stage_ms_last_step": {k: round(v, 3) for k, v in last.stages().items()},
             "limiters_last_step": {"dt_f_acc": last.dt_f_acc, "dt_pp_acc": last.dt_pp_acc, "dt_c_acc": last.dt_c_acc,
                                    "sum_rho_f": last.sum_rho_f, "sum_rho_c": last.sum_rho_c, "a": clk.a, "nts": clk.nts},

@@ -156,7 +156,7 @@ struct cubep3m_b200_ctx {
   int ppext_mode = 1;          // 1: tiled shared-memory kernel (pp::ppext_tiled_kernel), 0: direct one-thread-per-target kernel (CUBEP3M_B200_PPEXT=direct)
   int* ppext_ovf = nullptr;    // ids of the PP_EXT target blocks that exceeded the tiled kernel's shared-memory capacity
   bool ppext_margin_max = true; // also evaluate the margin particles' partial sums for pp_ext_force_max (particle_mesh_threaded.f90:617); CUBEP3M_B200_PPEXT_MARGIN=0 skips it
-  int2* ppext_items = nullptr; int ppext_item_cap = 0; bool ppext_cell_mode = true;   // dense-block PP_EXT work items
+  int2* ppext_items = nullptr; int ppext_item_cap = 0; bool ppext_cell_mode = true, ppext_dense_tma = false;   // dense-block PP_EXT work items
   int2* ppint_items = nullptr; int ppint_item_cap = 0;
   int2* margin_roles = nullptr; int margin_cap = 0;   // (particle index, tile) list of the PP_EXT margin roles
   int ppext_blocks = 0, ppext_fallback = 0;

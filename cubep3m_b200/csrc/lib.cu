@@ -786,8 +786,12 @@ int do_pp_ext(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p) {
       if (icap > 0) {
         LAUNCH(ctx, KC_PPEXT, pp::ppext_items_kernel, std::min(ctx->ppext_blocks, NUM_SMS * 8), pp::TB_NT, 0, ctx->fstart, ctx->d.H, ctx->d.nc_buf, nc, nbx, nby,
                &ctx->dcnt->n_ppext_fallback, ctx->ppext_ovf, ctx->ppext_items, icap, &ctx->dcnt->n_ppext_items);
-        LAUNCH(ctx, KC_PPEXT_DENSE, pp::ppext_cell_kernel, NUM_SMS * 16, pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->cfg.pp_range, P, ctx->dcnt, ctx->ppext_items, icap,
-               &ctx->dcnt->n_ppext_items, &ctx->dcnt->ppext_ticket);
+        if (ctx->ppext_dense_tma)
+          LAUNCH(ctx, KC_PPEXT_DENSE, pp::ppext_cell_tma_kernel, NUM_SMS * 8, pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->cfg.pp_range, P, ctx->dcnt, ctx->ppext_items,
+                 icap, &ctx->dcnt->n_ppext_items, &ctx->dcnt->ppext_ticket);
+        else
+          LAUNCH(ctx, KC_PPEXT_DENSE, pp::ppext_cell_kernel, NUM_SMS * 16, pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->cfg.pp_range, P, ctx->dcnt, ctx->ppext_items, icap,
+                 &ctx->dcnt->n_ppext_items, &ctx->dcnt->ppext_ticket);
       }
       LAUNCH(ctx, KC_PPEXT_DENSE, pp::ppext_blocklist_kernel, std::min(ctx->ppext_blocks, NUM_SMS * 8), pp::TB_NT, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->d.H, ctx->d.b, ctx->d.nc_buf, nc,
              nbx, nby, ctx->cfg.pp_range, P, ctx->dcnt, &ctx->dcnt->n_ppext_fallback, ctx->ppext_ovf, &ctx->dcnt->n_ppext_items, icap);
@@ -1044,7 +1048,7 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   ctx->ev_ok = true;
   TRY(fftk::init_constants());
   for (int i = 0; i < 2; ++i) {
-    TRY(dmalloc(&ctx->xv[i], (size_t)6 * d.max_np));
+    TRY(dmalloc(&ctx->xv[i], (size_t)6 * d.max_np + 64));   // + slack: bulk copies of the PP kernels round their last chunk up to 16 bytes
     if (cfg->pid) TRY(dmalloc(&ctx->pid[i], (size_t)d.max_np));
     TRY(dmalloc(&ctx->sendbuf[i], (size_t)d.max_buf));
     if (cfg->pid) TRY(dmalloc(&ctx->sendpid[i], (size_t)d.max_buf / 6 + 1));
@@ -1068,7 +1072,11 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
     const char* e = getenv("CUBEP3M_B200_SCAN");
     ctx->scan_onepass = e && !strcmp(e, "1pass");
   }
-  { const char* e = getenv("CUBEP3M_B200_PPEXT_DENSE"); ctx->ppext_cell_mode = !(e && !strcmp(e, "direct")); }   // A/B: "direct" = round 1's per-target / per-cell kernels
+  {   // A/B: "direct" = round 1's per-target / per-cell kernels, "tma" = the cell kernel with bulk-copy staging of the long source ranges
+    const char* e = getenv("CUBEP3M_B200_PPEXT_DENSE");
+    ctx->ppext_cell_mode = !(e && !strcmp(e, "direct"));
+    ctx->ppext_dense_tma = e && !strcmp(e, "tma");
+  }
   ctx->list_cap = d.max_np / 2 + 1024;
   if (cfg->ppint) {
     TRY(dmalloc(&ctx->multi_list, (size_t)ctx->list_cap));

@@ -717,6 +717,158 @@ __global__ void __launch_bounds__(TB_NT) ppext_cell_kernel(float* __restrict__ x
 }
 
 
+// ---- the same kernel with TMA staging (CUBEP3M_B200_PPEXT_DENSE=tma).
+// Source staging: ranges of at least CT_MIN records (the clumps, where the pairs are) are streamed through a per-warp shared-memory ring by the TMA engine —
+// cp.async.bulk of up to CT_CH 24-byte records per chunk, completion on an mbarrier, the next chunk in flight while the current one is evaluated — so the
+// pair loop reads its sources with two LDS instead of two L2 loads (ncu on the clustered profile box before: long-scoreboard 51 % of the stalls with the
+// FMA pipe at 40 %). Records start 8-byte aligned (24 j), bulk copies need 16: an odd first record is fetched from 8 bytes earlier. Short ranges (the sparse
+// cells around a clump) keep the direct loads, four in flight per lane.
+// MEASURED (B200): no gain — z = 2 evolved box: dense blocks 1.78 ms with direct loads, 2.60 ms staged (2.75 with a two-slot ring); clump-dominated profile
+// box: 4.3 vs 4.3 ms. The direct version already keeps 4 x 32 records in flight per warp out of L2 (96 % L2 hit rate), the staged one pays two warp barriers,
+// an mbarrier wait and 25 KB of shared memory per CTA for every 64 records. Kept as an A/B knob; ppext_cell_kernel (direct loads) is the default.
+constexpr int CT_CH = 64, CT_MIN = 24, CT_BUF = CT_CH * 24 + 16, CT_NS = 4;   // ring: CT_NS slots per warp, up to CT_NS chunks (256 records) in flight
+__global__ void __launch_bounds__(TB_NT) ppext_cell_tma_kernel(float* __restrict__ xv, const int* __restrict__ fstart, int H, int pr, PPParams P, DevCounters* __restrict__ cnt,
+                                                               const int2* __restrict__ items, int cap, const int* __restrict__ n_items, int* __restrict__ ticket) {
+  __shared__ __align__(16) unsigned char ring[TB_NT / 32][CT_NS][CT_BUF];
+  __shared__ __align__(8) unsigned long long bars[TB_NT / 32][CT_NS];
+  __shared__ int meta[TB_NT / 32][CT_NS][2];            // (first record is odd, records) of the chunk in each slot
+  const int n = *n_items;
+  if (n > cap) return;                                  // list overflow: ppext_blocklist_kernel does the work
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float2* xv2 = reinterpret_cast<const float2*>(xv);
+  const PairConst KC = make_pair_const(P);
+  const unsigned bar_base = fftk::smem_u32(&bars[warp][0]), buf_base = fftk::smem_u32(&ring[warp][0][0]);
+  if (lane == 0) { for (int q = 0; q < CT_NS; ++q) fftk::mbar_init(bar_base + 8u * q, 1); fftk::mbar_fence_init(); }
+  __syncwarp();
+  unsigned phase = 0;                                   // bit q: mbarrier phase parity of ring slot q (uniform over the warp)
+  float fm = 0.f;
+  unsigned long long npair = 0;
+  // dynamic distribution (item costs span three orders of magnitude: a static round-robin deal was 15 % slower on the clustered boxes); the ticket of the
+  // NEXT item is drawn before the current one is processed, so its L2 round trip is off the critical path
+  int nxt = 0;
+  if (lane == 0) nxt = atomicAdd(ticket, 1);
+  for (;;) {
+    const int it = __shfl_sync(0xffffffffu, nxt, 0);
+    if (it >= n) break;
+    if (lane == 0) nxt = atomicAdd(ticket, 1);
+    const int2 item = items[it];
+    const int key = item.x;
+    const int f = key & 63, cc = key >> 6;
+    const int cx = cc % H, cy = (cc / H) % H, cz = cc / (H * H);
+    const int gx = 4 * cx + (f & 3), gy = 4 * cy + ((f >> 2) & 3), gz = 4 * cz + (f >> 4);
+    const int t0 = fstart[key] + 32 * item.y, t1 = min(fstart[key + 1], t0 + 32);
+    const int nt = t1 - t0;
+    // ---- source ranges: lane r < 25 owns neighbour row r (dz = r/5 - 2, dy = r%5 - 2 for pr = 2; generally w = 2 pr + 1); the centre row's lane holds
+    //      the cells left of the own cell, lane 25..: the cells right of it. Each row is at most two ranges (two coarse cells).
+    const int w = 2 * pr + 1, nrow = w * w, qc = (nrow - 1) >> 1;
+    int sa = 0, ea = 0, sb = 0, eb = 0;
+    if (lane <= nrow) {
+      const int r = lane < nrow ? lane : qc;
+      const int nz = gz + r / w - pr, ny = gy + r % w - pr;
+      int xa = gx - pr, xb = gx + pr;
+      if (r == qc) { if (lane < nrow) xb = gx - 1; else xa = gx + 1; }
+      if (xa <= xb) {
+        const int rowkey = (((nz >> 2) * H + (ny >> 2)) * H) * 64 + (((nz & 3) << 4) | ((ny & 3) << 2));
+        const int ca = xa >> 2, cb = xb >> 2;
+        const int ka = rowkey + ca * 64, kb = rowkey + cb * 64;
+        sa = fstart[ka + (xa & 3)]; ea = fstart[ka + (ca == cb ? (xb & 3) : 3) + 1];
+        if (cb != ca) { sb = fstart[kb]; eb = fstart[kb + (xb & 3) + 1]; }
+      }
+    }
+    // ---- lanes = (target slot, source slice)
+    int T = 1;
+    while (T < nt) T <<= 1;
+    const int sf = 32 / T, slot = lane & (T - 1), slice = lane / T;
+    const bool live = slot < nt;
+    float3 pi = make_float3(0.f, 0.f, 0.f);
+    if (live) { const float2* p = xv2 + 3LL * (t0 + slot); const float2 a = p[0]; pi = make_float3(a.x, a.y, p[1].x); }
+    float3 acc = make_float3(0.f, 0.f, 0.f);
+    int nsrc = 0;
+    const int nrange = 2 * (nrow + 1);
+    // ---- short ranges: direct loads
+#pragma unroll 1
+    for (int rr = 0; rr < nrange; ++rr) {
+      const int s = __shfl_sync(0xffffffffu, (rr & 1) ? sb : sa, rr >> 1), e = __shfl_sync(0xffffffffu, (rr & 1) ? eb : ea, rr >> 1);
+      const int len = e - s;
+      nsrc += max(len, 0);
+      if (len <= 0 || len >= CT_MIN) continue;
+      int j = s + slice;
+#pragma unroll 1
+      for (; j + 3 * sf < e; j += 4 * sf) {
+        float2 a[4]; float z[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const float2* q = xv2 + 3LL * (j + u * sf); a[u] = q[0]; z[u] = q[1].x; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pair_force_fast(pi, make_float4(a[u].x, a[u].y, z[u], 0.f), KC, acc);
+      }
+#pragma unroll 1
+      for (; j < e; j += sf) {
+        const float2* q = xv2 + 3LL * j;
+        const float2 a = q[0];
+        pair_force_fast(pi, make_float4(a.x, a.y, q[1].x, 0.f), KC, acc);
+      }
+    }
+    // ---- long ranges: chunks of <= CT_CH records through the shared-memory ring
+    {
+      int rr = 0, cs = 0, ce = 0;                       // chunk iterator, uniform over the warp
+      auto next_chunk = [&](int& j0, int& cntc) -> bool {
+        while (cs >= ce) {
+          if (rr >= nrange) return false;
+          const int s = __shfl_sync(0xffffffffu, (rr & 1) ? sb : sa, rr >> 1), e = __shfl_sync(0xffffffffu, (rr & 1) ? eb : ea, rr >> 1);
+          ++rr;
+          if (e - s >= CT_MIN) { cs = s; ce = e; }
+        }
+        j0 = cs; cntc = min(CT_CH, ce - cs); cs += cntc;
+        return true;
+      };
+      int issued = 0, consumed = 0;
+      auto top_up = [&]() {
+        while (issued - consumed < CT_NS) {
+          int j0, cntc;
+          if (!next_chunk(j0, cntc)) break;
+          const int q = issued % CT_NS;
+          if (lane == 0) {
+            const unsigned odd = (unsigned)(j0 & 1);
+            const unsigned bytes = (24u * (unsigned)cntc + 8u * odd + 15u) & ~15u;
+            meta[warp][q][0] = (int)odd; meta[warp][q][1] = cntc;
+            fftk::fence_proxy_async();                // the warp's generic reads of this slot are ordered before the async-proxy writes
+            fftk::mbar_expect_tx(bar_base + 8u * q, bytes);
+            fftk::bulk_g2s(buf_base + (unsigned)(CT_BUF * q), reinterpret_cast<const char*>(xv) + 24LL * j0 - 8 * (int)odd, bytes, bar_base + 8u * q);
+          }
+          ++issued;
+        }
+      };
+      top_up();
+      while (consumed < issued) {
+        const int q = consumed % CT_NS;
+        __syncwarp();                                   // lane 0's meta[] entry is visible
+        fftk::mbar_wait(bar_base + 8u * q, (phase >> q) & 1u);
+        phase ^= 1u << q;
+        const int c0 = meta[warp][q][1];
+        const unsigned base = buf_base + (unsigned)(CT_BUF * q) + 8u * (unsigned)meta[warp][q][0];
+#pragma unroll 2
+        for (int jj = slice; jj < c0; jj += sf) {
+          float x, y, z;
+          const unsigned ad = base + 24u * (unsigned)jj;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%3];\n\tld.shared.f32 %2, [%3+8];" : "=f"(x), "=f"(y), "=f"(z) : "r"(ad) : "memory");
+          pair_force_fast(pi, make_float4(x, y, z, 0.f), KC, acc);
+        }
+        ++consumed;
+        __syncwarp();                                   // every lane is done with slot q before it is refilled
+        top_up();
+      }
+    }
+    for (int o = T; o < 32; o <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o); acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+    }
+    if (live && slice == 0) fm = fmaxf(fm, ppext_apply(reinterpret_cast<float2*>(xv) + 3LL * (t0 + slot), acc, P));
+    if (lane == 0) npair += (unsigned long long)nsrc * (unsigned long long)nt;
+  }
+  fm = warp_max(fm);
+  if (lane == 0 && fm > 0.f) atomic_max_float_nonneg(&cnt->pp_ext_force_max_bits, fm);
+  if (lane == 0 && npair) atomicAdd(&cnt->pairs_ppext, npair);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------------
 // PPINT as (fine cell, 32-target chunk) items, the same lane mapping as ppext_cell_kernel with the cell's own range as the only source range
 // (self-pair excluded). One warp per CELL (ppint_kernel) leaves a halo core of a few thousand particles to a single warp: 19 ms for 3.8e8 pairs on the

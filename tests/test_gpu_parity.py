@@ -287,8 +287,10 @@ def test_pp_ext_tiled_capacity_fallback_and_direct_agree(built, monkeypatch):
     r = sort_records(o.get_particles())
     o.close()
     res = {}
-    for mode in ("tiled", "direct"):
-        monkeypatch.setenv("CUBEP3M_B200_PPEXT", mode)
+    for mode in ("tiled", "direct", "tiled_dense_tma", "tiled_dense_walk"):
+        monkeypatch.setenv("CUBEP3M_B200_PPEXT", "direct" if mode == "direct" else "tiled")
+        # dense (over-capacity) blocks: cell-pair warp kernel (default), its TMA-staged variant, round 1's per-target walk
+        monkeypatch.setenv("CUBEP3M_B200_PPEXT_DENSE", {"tiled_dense_tma": "tma", "tiled_dense_walk": "direct"}.get(mode, "cell"))
         pm = ParticleMesh(cfg)
         pm.upload_particles(xv)
         og = pm.particle_mesh(*args)

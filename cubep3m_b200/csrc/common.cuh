@@ -158,7 +158,8 @@ struct cubep3m_b200_ctx {
   bool ppext_margin_max = true; // also evaluate the margin particles' partial sums for pp_ext_force_max (particle_mesh_threaded.f90:617); CUBEP3M_B200_PPEXT_MARGIN=0 skips it
   int2* ppext_items = nullptr; int ppext_item_cap = 0; bool ppext_cell_mode = true, ppext_dense_tma = false;   // dense-block PP_EXT work items
   int2* ppint_items = nullptr; int ppint_item_cap = 0;
-  int2* margin_roles = nullptr; int margin_cap = 0;   // (particle index, tile) list of the PP_EXT margin roles
+  int2* margin_roles = nullptr; int margin_cap = 0;
+  bool want_roles = false, roles_listed = false;      // particle_mesh asks the scatter to list the margin roles; the limiter kernel then skips its own listing   // (particle index, tile) list of the PP_EXT margin roles
   int ppext_blocks = 0, ppext_fallback = 0;
   long long pairs_ppint = 0, pairs_ppext = 0;   // of the last step   // of the last step (debug getter)
   bool hist_clean = false;     // fcur (the fine-cell histogram) is all zeros

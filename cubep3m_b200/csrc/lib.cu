@@ -626,9 +626,21 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
     LAUNCH(ctx, KC_SCAN, part::scan_apply_kernel<false>, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->multi_list,
            ctx->occ_list, ctx->list_cap, ctx->cfg.ppint ? 1 : 0, 0, ctx->dcnt, nullptr, nb);
   }
-  if (np > 0)
-    LAUNCH(ctx, KC_SCATTER, part::scatter_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->fcur, ctx->fstart,
-           ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1], d.max_np);
+  // inside particle_mesh with PP_EXT on, the scatter also lists the margin roles for the PP_EXT limiter (do_pp_ext_margin)
+  const bool roles = ctx->want_roles && ctx->cfg.pp_ext && ctx->cfg.pp_range > 0 && ctx->ppext_margin_max && ctx->margin_roles;
+  ctx->roles_listed = false;
+  if (np > 0) {
+    const part::MarginGeom G{d.H, d.b, d.m, d.T, ctx->cfg.pp_range};
+    if (roles) {
+      CK(cudaMemsetAsync(&ctx->dcnt->n_margin_roles, 0, sizeof(int), ctx->stream));
+      LAUNCH(ctx, KC_SCATTER, part::scatter_kernel<true>, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->fcur, ctx->fstart,
+             ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1], d.max_np, G, ctx->margin_roles, ctx->margin_cap, &ctx->dcnt->n_margin_roles);
+      ctx->roles_listed = true;
+    } else {
+      LAUNCH(ctx, KC_SCATTER, part::scatter_kernel<false>, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->fcur, ctx->fstart,
+             ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1], d.max_np, G, nullptr, 0, nullptr);
+    }
+  }
   CK(cudaGetLastError());
   if (int st = fetch_counters(ctx)) return st;
   if (ctx->hcnt->overflow & (4 | 8)) {      // a wrapped cell counter leaves the histogram dirty: clear it before the next sort
@@ -813,9 +825,11 @@ int do_pp_ext_margin(cubep3m_b200_ctx* ctx, float a_mid, float dt, float mass_p)
   P.mass_p = mass_p; P.rsoft = ctx->cfg.rsoft; P.pp_bias = ctx->cfg.pp_bias; P.a_mid = a_mid; P.G = ctx->cfg.G; P.dt = dt;
   P.cutoff = (float)ctx->cfg.nf_cutoff; P.apply = 0;
   const pp::MarginGeom G{ctx->d.H, ctx->d.b, ctx->d.m, ctx->d.T, ctx->cfg.pp_range};
-  CK(cudaMemsetAsync(&ctx->dcnt->n_margin_roles, 0, sizeof(int), ctx->stream));
-  LAUNCH(ctx, KC_PPEXT_MARGIN, pp::ppext_margin_list_kernel, (ctx->np_all + pp::EXT_TPB - 1) / pp::EXT_TPB, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->np_all, G, ctx->margin_roles,
-         ctx->margin_cap, &ctx->dcnt->n_margin_roles);
+  if (!ctx->roles_listed) {       // normally the scatter of this step's cell sort has listed the roles already
+    CK(cudaMemsetAsync(&ctx->dcnt->n_margin_roles, 0, sizeof(int), ctx->stream));
+    LAUNCH(ctx, KC_PPEXT_MARGIN, pp::ppext_margin_list_kernel, (ctx->np_all + pp::EXT_TPB - 1) / pp::EXT_TPB, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->np_all, G, ctx->margin_roles,
+           ctx->margin_cap, &ctx->dcnt->n_margin_roles);
+  }
   LAUNCH(ctx, KC_PPEXT_MARGIN, pp::ppext_margin_roles_kernel, NUM_SMS * 16, pp::EXT_TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->np_all, G, ctx->margin_roles, ctx->margin_cap,
          &ctx->dcnt->n_margin_roles, P, ctx->dcnt);
   CK(cudaGetLastError());
@@ -1317,7 +1331,13 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   if (ctx->np_local > 0) { if (int st = do_pass(ctx, &bufmax, drift4, true)) return st; }
   else { if (int st = do_drift(ctx, dt, dt_old, off3)) return st; if (int st = do_pass(ctx, &bufmax, nullptr, true)) return st; }
   CK(cudaEventRecord(ev[2], ctx->stream));
-  if (int st = do_sort(ctx, &ndel)) return st;                                            // :61 link_list as a cell sort
+  // CUBEP3M_B200_ROLES=scatter: the scatter lists the PP_EXT margin roles itself (it knows every particle's cell and sorted index) instead of a separate
+  // listing kernel. Measured at 512^3: listing kernel -1.26 ms, scatter +1.94 ms (the role arithmetic lengthens a DRAM-latency-bound kernel). Off.
+  static const bool roles_in_scatter = [] { const char* e = getenv("CUBEP3M_B200_ROLES"); return e && !strcmp(e, "scatter"); }();
+  ctx->want_roles = roles_in_scatter;
+  const int sort_st = do_sort(ctx, &ndel);                                                // :61 link_list as a cell sort
+  ctx->want_roles = false;
+  if (sort_st) return sort_st;
   const int np_ghost = ctx->np_all;
   CK(cudaEventRecord(ev[3], ctx->stream));
   // INVARIANT of the overlapped streams below (coarse stream, two fine tiles in flight, PP after the tiles): kernels on other streams or CTAs

@@ -423,22 +423,80 @@ __global__ void __launch_bounds__(TPB) scan_apply_kernel(const unsigned int* __r
   }
 }
 
+// ---- PP_EXT margin roles (particle_mesh_threaded.f90:617; pp.cuh: ppext_margin_roles_kernel evaluates them). A (particle, tile) pair with the particle inside
+// the tile's region [t*m - pr, (t+1)*m + pr) but outside the tile itself is a ROLE (up to 7 per particle, ~5 % of the particles have one).
+struct MarginGeom { int H, b, m, T, pr; };
+
+// tiles whose region [t*m - pr, (t+1)*m + pr) holds node-frame fine cell q: [tl, th] (empty if tl > th)
+__device__ __forceinline__ void margin_tiles(int q, const MarginGeom& G, int& tl, int& th) {
+  auto fdiv = [&](int v) { return v >= 0 ? v / G.m : -((-v + G.m - 1) / G.m); };
+  tl = max(0, fdiv(q - G.pr)); th = min(G.T - 1, fdiv(q + G.pr));
+}
+// bit (dz*4 + dy*2 + dx) of the result = tile (tl + d) is a ROLE of the particle in hoc-frame fine cell g (in the region, not in the interior)
+__device__ __forceinline__ unsigned margin_roles(const int g[3], const MarginGeom& G, int tl[3]) {
+  int th[3];
+  for (int ax = 0; ax < 3; ++ax) { margin_tiles(g[ax] - G.b, G, tl[ax], th[ax]); if (tl[ax] > th[ax]) return 0u; }
+  unsigned mask = 0;
+  for (int dz = 0; dz <= th[2] - tl[2]; ++dz)
+    for (int dy = 0; dy <= th[1] - tl[1]; ++dy)
+      for (int dx = 0; dx <= th[0] - tl[0]; ++dx) {
+        const int t3[3] = {tl[0] + dx, tl[1] + dy, tl[2] + dz};
+        bool interior = true;
+        for (int ax = 0; ax < 3; ++ax) interior &= (g[ax] - G.b >= t3[ax] * G.m && g[ax] - G.b < (t3[ax] + 1) * G.m);
+        if (!interior) mask |= 1u << (dz * 4 + dy * 2 + dx);
+      }
+  return mask;
+}
+
+// ROLES: the scatter already knows every particle's fine cell (its key) and its place in the sorted array, so it also appends the particle's margin roles
+// (sorted index, tile) to the list the PP_EXT limiter works from — a separate listing kernel re-read all records (1.26 ms at 512^3).
+template <bool ROLES>
 __global__ void __launch_bounds__(TPB) scatter_kernel(const float* __restrict__ xv_in, const int64_t* __restrict__ pid_in,
                                                       const unsigned int* __restrict__ key, int np, unsigned int* __restrict__ hist,
-                                                      const int* __restrict__ fstart, float* __restrict__ xv_out, int64_t* __restrict__ pid_out, int np_cap) {
+                                                      const int* __restrict__ fstart, float* __restrict__ xv_out, int64_t* __restrict__ pid_out, int np_cap,
+                                                      MarginGeom G, int2* __restrict__ roles, int role_cap, int* __restrict__ n_roles) {
   const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
-  if (i >= np) return;
-  const unsigned int k = key[i];
-  if (k == KEY_DEAD) return;
-  float2 a, b, c;
-  load_xv(xv_in, i, a, b, c);
-  // slot = cell start + (remaining count - 1): every particle decrements its cell once, so the histogram is back to all zeros
-  // after the scatter and needs no memset before the next step's key_hist_kernel
-  const unsigned sh = (k & 1u) << 4;
-  const int dst = fstart[k] + (int)((atomicSub(&hist[k >> 1], 1u << sh) >> sh) & 0xffffu) - 1;
-  if ((unsigned)dst >= (unsigned)np_cap) return;   // only reachable after a 16-bit cell counter overflowed (flagged by key_hist_kernel, the step fails with EMAXLLF)
-  store_xv(xv_out, dst, a, b, c);
-  if (pid_in) pid_out[dst] = pid_in[i];
+  unsigned int k = KEY_DEAD;
+  if (i < np) k = key[i];
+  int dst = -1;
+  if (k != KEY_DEAD) {
+    float2 a, b, c;
+    load_xv(xv_in, i, a, b, c);
+    // slot = cell start + (remaining count - 1): every particle decrements its cell once, so the histogram is back to all zeros
+    // after the scatter and needs no memset before the next step's key_hist_kernel
+    const unsigned sh = (k & 1u) << 4;
+    dst = fstart[k] + (int)((atomicSub(&hist[k >> 1], 1u << sh) >> sh) & 0xffffu) - 1;
+    if ((unsigned)dst >= (unsigned)np_cap) dst = -1;   // only reachable after a 16-bit cell counter overflowed (flagged by key_hist_kernel, the step fails with EMAXLLF)
+    else {
+      store_xv(xv_out, dst, a, b, c);
+      if (pid_in) pid_out[dst] = pid_in[i];
+    }
+  }
+  if (ROLES) {
+    unsigned mask = 0;
+    int tl[3] = {0, 0, 0};
+    if (dst >= 0) {
+      const unsigned cc = k >> 6, f = k & 63u;
+      const int H = G.H;
+      const int g[3] = {(int)(4 * (cc % H) + (f & 3u)), (int)(4 * ((cc / H) % H) + ((f >> 2) & 3u)), (int)(4 * (cc / (H * H)) + (f >> 4))};
+      mask = margin_roles(g, G, tl);
+    }
+    const int n = __popc(mask), lane = threadIdx.x & 31;
+    int inc = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(n_roles, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + inc - n;
+    while (mask) {
+      const int bit = __ffs(mask) - 1;
+      mask &= mask - 1;
+      if (base < role_cap) roles[base] = make_int2(dst, ((tl[2] + (bit >> 2)) * G.T + (tl[1] + ((bit >> 1) & 1))) * G.T + (tl[0] + (bit & 1)));
+      ++base;
+    }
+  }
 }
 
 // ---- delete_particles.f90:14-50: keep particles with 0 <= x,y,z < mT, i.e. exactly those chained in coarse cells

@@ -267,28 +267,10 @@ __device__ __forceinline__ void ppext_sources_fast(const float* __restrict__ xv,
 // ppext_margin_roles_kernel evaluates one role per thread with all lanes busy (a thread-per-particle version left 95 % of the lanes idle
 // next to a lane walking 25 neighbour rows: 8.7 ms at 512^3 particles). Cell pairs whose two cells both lie in the tile's upper z margin
 // are never visited by the reference's half stencil ("we never loop towards smaller z", k = 1..nf_physical_tile_dim+pp_range at :496).
-struct MarginGeom { int H, b, m, T, pr; };
+using part::MarginGeom;
+using part::margin_tiles;
+using part::margin_roles;
 
-// tiles whose region [t*m - pr, (t+1)*m + pr) holds node-frame fine cell q: [tl, th] (empty if tl > th)
-__device__ __forceinline__ void margin_tiles(int q, const MarginGeom& G, int& tl, int& th) {
-  auto fdiv = [&](int v) { return v >= 0 ? v / G.m : -((-v + G.m - 1) / G.m); };
-  tl = max(0, fdiv(q - G.pr)); th = min(G.T - 1, fdiv(q + G.pr));
-}
-// bit (dz*4 + dy*2 + dx) of the result = tile (tl + d) is a ROLE of the particle in hoc-frame fine cell g (in the region, not in the interior)
-__device__ __forceinline__ unsigned margin_roles(const int g[3], const MarginGeom& G, int tl[3]) {
-  int th[3];
-  for (int ax = 0; ax < 3; ++ax) { margin_tiles(g[ax] - G.b, G, tl[ax], th[ax]); if (tl[ax] > th[ax]) return 0u; }
-  unsigned mask = 0;
-  for (int dz = 0; dz <= th[2] - tl[2]; ++dz)
-    for (int dy = 0; dy <= th[1] - tl[1]; ++dy)
-      for (int dx = 0; dx <= th[0] - tl[0]; ++dx) {
-        const int t3[3] = {tl[0] + dx, tl[1] + dy, tl[2] + dz};
-        bool interior = true;
-        for (int ax = 0; ax < 3; ++ax) interior &= (g[ax] - G.b >= t3[ax] * G.m && g[ax] - G.b < (t3[ax] + 1) * G.m);
-        if (!interior) mask |= 1u << (dz * 4 + dy * 2 + dx);
-      }
-  return mask;
-}
 // |partial sum| of the particle at pi (hoc-frame fine cell g) over the partner cells inside the region of tile t3
 __device__ __forceinline__ float margin_role_sum(const float* __restrict__ xv, const int* __restrict__ fstart, const float3 pi, const int g[3], const int t3[3],
                                                  const MarginGeom& G, const PairConst& KC) {

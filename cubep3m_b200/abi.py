@@ -113,6 +113,9 @@ class Clock(C.Structure):
                [(n, C.c_int32) for n in ("nts", "ppint", "pp_ext", "cosmo", "checkpoint_step")]
 
 
+PEAK_DTYPE = [("i", "<i4"), ("j", "<i4"), ("k", "<i4"), ("tile", "<i4"), ("den", "<f4"), ("x", "<f4"), ("y", "<f4"), ("z", "<f4")]   # cubep3m_b200_peak
+
+
 class CheckpointHeader(C.Structure):
     """checkpoint.f90:72-78 (the file holds dt_pp_acc only with -DPPINT)."""
     _fields_ = [("np_local", C.c_int32), ("a", C.c_float), ("t", C.c_float), ("tau", C.c_float), ("nts", C.c_int32),

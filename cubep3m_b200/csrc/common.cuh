@@ -112,6 +112,7 @@ struct cubep3m_b200_ctx {
   float class_ms[KC_COUNT] = {0};        // of the last profiled step
   long long class_n[KC_COUNT] = {0};
   int fft_class_base = 0;                // KC_COARSE_FFT while the coarse solve runs, else 0
+  cubep3m_b200_clock* dclock = nullptr;  // device copy of the driver clock (cubep3m_b200_timestep_device)
   int world = 1;
   // particles (AoS 24-byte records as the reference's xv(6,:)), double buffered
   float* xv[2] = {nullptr, nullptr};

@@ -538,6 +538,7 @@ template <int N> int set_smem_attr() {
     CK(cudaFuncSetAttribute((fft_strided2<N, true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b2));
     CK(cudaFuncSetAttribute((fft_z_sandwich2<N, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_sandwich2(N)));
     CK(cudaFuncSetAttribute((fft_z_sandwich2<N, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_sandwich2(N)));
+    CK(cudaFuncSetAttribute(fft_z_sandwich3<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sand3<N>::smem));
     CK(cudaFuncSetAttribute(fft_x_r2c_ngp2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes2(N, 1, XP)));
     CK(cudaFuncSetAttribute(fft_x_c2r3_v2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_c2r3_v2(N)));
     CK(cudaFuncSetAttribute(fft_x_c2r3_v3<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2R3<N>::smem));
@@ -639,6 +640,15 @@ template <int N> int launch_sandwich_t(cubep3m_b200_ctx* ctx, int kc, const floa
     if (kp % 16 != 0 || 3 * gstride >= (1LL << 29)) return CUBEP3M_B200_EINVAL;   // stage-B stores use 32-bit byte offsets from g
     const dim3 grd((unsigned)std::min<long long>(total2, (long long)NUM_SMS * std::max(occ2, 1)));
     const bool a16 = cp % 2 == 0 && cp >= (hc + LX - 1) / LX * LX && ((uintptr_t)spec & 15) == 0;
+    static const bool use_v3 = [] { const char* e = getenv("CUBEP3M_B200_SANDWICH"); return e && !strcmp(e, "v3"); }();   // A/B knob: 8-column items (measured: 144 vs 141 us per tile at n = 304, so off)
+    if (a16 && use_v3) {
+      static int occ3 = 0;
+      if (!occ3) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, fft_z_sandwich3<N>, Sand3<N>::NT, (int)Sand3<N>::smem));
+      const long long total3 = (long long)((hc + Sand3<N>::CW - 1) / Sand3<N>::CW) * ny;
+      LAUNCH(ctx, kc, fft_z_sandwich3<N>, dim3((unsigned)std::min<long long>(total3, (long long)NUM_SMS * std::max(occ3, 1))), dim3(Sand3<N>::NT), (int)Sand3<N>::smem, spec, g,
+             (int)gstride, hc, cp, ny, kern, kstride, kp, elo, ehi, tw);
+      return 0;
+    }
     if (a16) LAUNCH(ctx, kc, (fft_z_sandwich2<N, true>), grd, dim3(Plan2<N>::NT), sm2, spec, g, (int)gstride, hc, cp, ny, kern, kstride, kp, elo, ehi, tw);
     else LAUNCH(ctx, kc, (fft_z_sandwich2<N, false>), grd, dim3(Plan2<N>::NT), sm2, spec, g, (int)gstride, hc, cp, ny, kern, kstride, kp, elo, ehi, tw);
     return 0;

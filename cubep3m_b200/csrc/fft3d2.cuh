@@ -268,6 +268,157 @@ __global__ void __launch_bounds__(Plan2<N>::NT, 2) fft_z_sandwich2(const float2*
 }
 constexpr size_t smem_bytes_sandwich2(int n) { return (size_t)2 * n * LX * sizeof(float2) + (size_t)n * LX * sizeof(float) + (size_t)n * sizeof(float2); }
 
+// ---------------------------------------------------------------------------------------------- fused z pass, 8-column items
+// Same pipeline as fft_z_sandwich2 on items of 8 columns (64-byte rows): 160-thread CTAs, FOUR per SM instead of two 320-thread ones — the same
+// warps and registers per SM, but four independent barrier domains whose phases interleave (what the row-major c2r pass gained from its 8-column
+// items), and half the tail of the persistent grid in time. Two layouts per buffer: X = natural order [N][8] (what the copies deliver and what
+// stage A gathers from, x[j + r R1]: consecutive j are consecutive rows, conflict-free), Y = stage A's output y[j R0 + r] with every group of R0
+// rows skewed by one row ((R0 + 1) * 8 float2 per group): a half-warp's two j then fall into different halves of a 128-byte bank line, and stage B
+// reads y[j + r R0] as consecutive rows again. Because X and Y differ, the forward transform runs A: L(X) -> W(Y), B: W(Y) -> L(X) (one barrier
+// fewer than in place), components 0 and 1 run A: L(X) -> W(Y), B: W(Y) -> global, component 2 runs A: L(X) -> registers -> L(Y), B: L(Y) -> global
+// while W receives the next item.
+template <int N> struct Sand3 {
+  using P = Plan2<N>;
+  static constexpr int CW = 8;
+  static constexpr int R0 = P::R0, R1 = P::R1;
+  static constexpr int NT = ((CW * P::RMAX + 31) / 32) * 32;      // 160 for N = 304
+  static constexpr int NA = CW * R1, NB = CW * R0;
+  static constexpr int YP = (R0 + 1) * CW;                        // float2 per skewed group of R0 rows
+  static constexpr int BUF = R1 * YP;                             // float2 per buffer (>= N * CW)
+  static constexpr int CPS = 4;                                   // CTAs per SM
+  static constexpr size_t smem = (size_t)2 * BUF * sizeof(float2) + (size_t)N * CW * sizeof(float) + (size_t)N * sizeof(float2);
+};
+
+template <int N>
+__global__ void __launch_bounds__(Sand3<N>::NT, Sand3<N>::CPS) fft_z_sandwich3(const float2* __restrict__ spec, float2* __restrict__ g, int gstride, int hc, int cp, int ny,
+                                                                                const float* __restrict__ kern, long long kstride, int kp, int elo, int ehi,
+                                                                                const float2* __restrict__ tw_g) {
+  using S = Sand3<N>;
+  constexpr int NT3 = S::NT, R0 = S::R0, R1 = S::R1, CW = S::CW, YP = S::YP;
+  extern __shared__ __align__(16) unsigned char raw[];
+  float2* L = reinterpret_cast<float2*>(raw);
+  float2* W = L + S::BUF;
+  float* K = reinterpret_cast<float*>(W + S::BUF);
+  float2* tw = reinterpret_cast<float2*>(K + N * CW);
+  for (int t = threadIdx.x; t < N; t += NT3) tw[t] = tw_g[t];
+  const int col = threadIdx.x % CW, j = threadIdx.x / CW;
+  const unsigned nbx = (hc + CW - 1) / CW;
+  const int total = (int)nbx * ny;
+  const int estride = ny * cp;
+  const long long kes = (long long)ny * kp;         // z stride of the Green's function table
+  const unsigned mask = crop_mask<N>(j, elo, ehi);
+  const int joff = j * estride + col;
+  unsigned sL = smem_u32(L), sW = smem_u32(W);
+  const unsigned sK = smem_u32(K);
+  const bool actA = threadIdx.x < S::NA, actB = threadIdx.x < S::NB;
+  auto decode = [&](int item, int& off, int& kb, bool& ok) {
+    const unsigned bx = (unsigned)item % nbx, y = (unsigned)item / nbx;
+    off = (int)y * cp + (int)bx * CW;
+    kb = (int)y * kp + (int)bx * CW;
+    ok = (int)bx * CW + col < hc;
+  };
+  auto issueS = [&](int off, unsigned sdst) {        // N rows of 8 float2 = 4 x 16 bytes each, natural (X) order
+    constexpr int RPP = NT3 / 4;
+    const int row = threadIdx.x >> 2, q = threadIdx.x & 3;
+    const float2* src = spec + off + (long long)row * estride + q * 2;
+    const unsigned sd = sdst + (row * CW + q * 2) * 8;
+#pragma unroll
+    for (int it = 0; it < (N + RPP - 1) / RPP; ++it) {
+      if (row + it * RPP < N) cp_async16(sd + it * RPP * CW * 8, src);
+      src += (long long)RPP * estride;
+    }
+  };
+  auto issueK = [&](int comp, int kb) {             // N rows of 8 floats = 2 x 16 bytes each
+    const float* src = kern + comp * kstride + kb;
+#pragma unroll
+    for (int it = 0; it < (2 * N + NT3 - 1) / NT3; ++it) {
+      const int t = threadIdx.x + it * NT3;
+      if (t < 2 * N) cp_async16(sK + t * 16, src + (long long)(t >> 1) * kes + (t & 1) * 4);
+    }
+    cp_async_commit();
+  };
+  auto loadA = [&](const float2* __restrict__ X, float2 (&v)[R0]) {       // x[j + r R1]
+    const float2* p = X + j * CW + col;
+#pragma unroll
+    for (int r = 0; r < R0; ++r) v[r] = p[r * R1 * CW];
+  };
+  auto storeA = [&](float2* __restrict__ Y, const float2 (&v)[R0]) {      // y[j R0 + r]
+    float2* q = Y + j * YP + col;
+#pragma unroll
+    for (int r = 0; r < R0; ++r) q[r * CW] = v[r];
+  };
+  // stage B on the Y layout: y[j + r R0] -> twiddle -> radix R1 -> emit(r, X[j + r R0])
+  auto runB = [&](const float2* __restrict__ Y, auto inv_tag, auto emit) {
+    constexpr bool INV = decltype(inv_tag)::value;
+    float2 u[R1];
+    const float2* p = Y + j * CW + col;
+#pragma unroll
+    for (int r = 0; r < R1; ++r) u[r] = p[r * YP];
+    const float2* t0 = tw + j;
+#pragma unroll
+    for (int r = 1; r < R1; ++r) u[r] = twmul<INV>(u[r], t0[(r - 1) * j]);
+    pradix_emit<R1, INV>(u, emit);
+  };
+  auto mulK = [&](float2 (&v)[R0]) {                 // i * kern_f (:188-189)
+    const float* kq = K + j * CW + col;
+#pragma unroll
+    for (int r = 0; r < R0; ++r) { const float kv = kq[r * R1 * CW]; v[r] = make_float2(-v[r].y * kv, v[r].x * kv); }
+  };
+  int item = blockIdx.x, off = 0, kb = 0;
+  bool ok = false;
+  if (item < total) {
+    decode(item, off, kb, ok);
+    issueS(off, sL);
+    issueK(0, kb);
+  }
+  const unsigned stepb = (unsigned)(R0 * estride) * 8u;
+  char* gbase = reinterpret_cast<char*>(g);
+  while (item < total) {
+    const int next = item + gridDim.x;
+    int noff = 0, nkb = 0;
+    bool nok = false;
+    if (next < total) decode(next, noff, nkb, nok);
+    const unsigned m = ok ? mask : 0u;
+    cp_async_wait_all();
+    __syncthreads();                                // spectrum block and kern_f(0) block landed; W free
+    float2 v[R0];
+    // ---- forward: A: L(X) -> W(Y), B: W(Y) -> L(X)
+    if (actA) { loadA(L, v); PRadix<R0, false>::run(v); storeA(W, v); }
+    __syncthreads();
+    if (actB) {
+      float2* sp = L + j * CW + col;
+      runB(W, std::false_type{}, [&](int r, float2 val) { sp[r * R0 * CW] = val; });
+    }
+    __syncthreads();
+    // ---- components 0 and 1: A: L(X) -> W(Y), B: W(Y) -> global
+#pragma unroll
+    for (int comp = 0; comp < 2; ++comp) {
+      if (actA) { loadA(L, v); mulK(v); PRadix<R0, true>::run(v); storeA(W, v); }
+      __syncthreads();                              // W complete; K consumed
+      issueK(comp + 1, kb);
+      if (actB) {
+        const unsigned ob = (unsigned)(comp * gstride + off + joff) * 8u;
+        runB(W, std::true_type{}, [&](int r, float2 val) { if (m & (1u << r)) *reinterpret_cast<float2*>(gbase + (ob + (unsigned)r * stepb)) = val; });
+      }
+      cp_async_wait_all();
+      __syncthreads();                              // next kern_f block landed; W free
+    }
+    if (next < total) { issueS(noff, sW); cp_async_commit(); }
+    // ---- component 2: A: L(X) -> registers -> L(Y), B: L(Y) -> global
+    if (actA) { loadA(L, v); mulK(v); PRadix<R0, true>::run(v); }
+    __syncthreads();                                // all gathers from L and K precede the scatter / the next kern_f block
+    if (next < total) issueK(0, nkb);
+    if (actA) storeA(L, v);
+    __syncthreads();
+    if (actB) {
+      const unsigned ob = (unsigned)(2 * gstride + off + joff) * 8u;
+      runB(L, std::true_type{}, [&](int r, float2 val) { if (m & (1u << r)) *reinterpret_cast<float2*>(gbase + (ob + (unsigned)r * stepb)) = val; });
+    }
+    { float2* t = L; L = W; W = t; const unsigned u = sL; sL = sW; sW = u; }
+    item = next; off = noff; kb = nkb; ok = nok;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- x pass forward + NGP density
 constexpr int XP = LX + 1;   // pitch (float2) of the contiguous-axis passes
 

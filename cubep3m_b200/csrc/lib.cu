@@ -12,6 +12,7 @@
 #include "power.cuh"
 #include "distinit.cuh"
 #include "bigfft.cuh"
+#include "halo.cuh"
 
 namespace {
 
@@ -962,6 +963,66 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime
 }  // namespace
 
 // =====================================================================================================
+
+// ---------------------------------------------------------------- driver twin: timestep.f90 (host and device)
+__host__ __device__ inline void expansion_core(float a0, float dt0, float omega_m, float omega_l, float wde, float* da1, float* da2) {
+  // timestep.f90:241-293: two half steps of a 3rd-order Taylor expansion, real(8) arithmetic from real(4) arguments
+  const float dt_x = dt0 / 2;
+  double a_x = a0;
+  for (int half = 0; half < 2; ++half) {
+    const double omHsq = 4.0 / 9.0;
+    const double a3rlm = pow(a_x, (double)(-3 * wde)) * omega_l / omega_m;
+    const double arkm = a_x * (1.0 - omega_m - omega_l) / omega_m;
+    const double adot = sqrt(omHsq * a_x * a_x * a_x * (1.0 + arkm + a3rlm));
+    const double addot = a_x * a_x * omHsq * (1.5 + 2.0 * arkm + 1.5 * (1.0 - wde) * a3rlm);
+    const double atdot = a_x * adot * omHsq * (3.0 + 6.0 * arkm + 1.5 * (2.0 - 3.0 * wde) * (1.0 - wde) * a3rlm);
+    const float da = (float)(adot * dt_x + (addot * (double)dt_x * dt_x) / 2.0 + (atdot * (double)dt_x * dt_x * dt_x) / 6.0);
+    if (half == 0) { *da1 = da; a_x = (double)(a0 + da); } else *da2 = da;
+  }
+}
+__host__ __device__ inline void timestep_core(cubep3m_b200_clock* c) {
+  // timestep.f90:20-196 (cosmo branch, dark matter only); dt_max = 1, ra_max = 0.01, dt_scale = 1 (cubepm.par:26-29)
+  const float dt_max = 1.0f, ra_max = 0.01f, dt_scale = 1.0f;
+  c->nts += 1;
+  if (c->nts != 1) c->dt_old = c->dt;
+  float da_1 = 0, da_2 = 0;
+  if (c->cosmo) {
+    float dt_e = dt_max;
+    int n = 0;
+    for (;;) {
+      n++;
+      expansion_core(c->a, dt_e, c->omega_m, c->omega_l, c->wde, &da_1, &da_2);
+      c->da = da_1 + da_2;
+      const float ra = c->da / (c->a + c->da);
+      if (ra > ra_max) dt_e = dt_e * (ra_max / ra); else break;
+      if (n > 10) break;
+    }
+    float dt = fminf(dt_e, fminf(c->dt_f_acc, c->dt_c_acc));
+    if (c->ppint) dt = fminf(dt, c->dt_pp_acc);
+    if (c->ppint && c->pp_ext) dt = fminf(dt, c->dt_pp_ext_acc);
+    dt = dt * dt_scale;
+    expansion_core(c->a, dt, c->omega_m, c->omega_l, c->wde, &da_1, &da_2);
+    c->da = da_1 + da_2;
+    c->checkpoint_step = 0;
+    if (c->a + c->da > c->a_target) {                 // timestep.f90:128-137
+      c->checkpoint_step = 1;
+      dt = dt * (c->a_target - c->a) / c->da;
+      expansion_core(c->a, dt, c->omega_m, c->omega_l, c->wde, &da_1, &da_2);
+    }
+    c->da = da_1 + da_2;
+    c->a_mid = c->a + (c->da / 2);
+    c->dt = dt;
+    c->tau += dt; c->t += dt; c->a += c->da;
+  } else {                                            // timestep.f90:198-221
+    c->a = 1.0f; c->a_mid = 1.0f; c->da = 0.f;
+    float dt = fminf(1.0f, fminf(c->dt_f_acc, c->dt_c_acc));
+    if (c->ppint) dt = fminf(dt, c->dt_pp_acc);
+    if (c->ppint && c->pp_ext) dt = fminf(dt, c->dt_pp_ext_acc);
+    c->dt = dt; c->t += dt;
+  }
+}
+__global__ void timestep_kernel(cubep3m_b200_clock* c) { if (threadIdx.x == 0 && blockIdx.x == 0) timestep_core(c); }
+
 extern "C" {
 
 const char* cubep3m_b200_version(void) { return "cubep3m_b200 0.1 (sm_100a, hand-written CUDA, no CPU fallback)"; }
@@ -1021,7 +1082,7 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
   if (ctx->comm) ncclCommDestroy(ctx->comm);
 #endif
   F(ctx->cand); F(ctx->deltas); F(ctx->ndelta); F(ctx->tile_counts); F(ctx->key); F(ctx->blist); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->scan_status); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
-  F(ctx->kern_f); F(ctx->tile_rho); F(ctx->tile_g); F(ctx->force_f[0]); 
+  F(ctx->dclock); F(ctx->kern_f); F(ctx->tile_rho); F(ctx->tile_g); F(ctx->force_f[0]); 
   for (int q = 1; q < cubep3m_b200_ctx::MAX_TILE_STREAMS; ++q) {
     F(ctx->tile_rho_s[q]); F(ctx->tile_g_s[q]); F(ctx->force_f_s[q]);
     if (ctx->stream_aux[q]) cudaStreamDestroy(ctx->stream_aux[q]);
@@ -1520,6 +1581,65 @@ int cubep3m_b200_debug_force_c(cubep3m_b200_ctx* ctx, float* force_c) {
   CK(cudaMemcpy(force_c, ctx->force_c, sizeof(float) * nfc, cudaMemcpyDeviceToHost));
   return 0;
 }
+// halofind.f90:564-672: density + maxima pass of find_halos over every tile of the node, in the reference's tile order (halofind.f90:48-54).
+// Valid in the state a halofind step is in (cubepm.f90:193-198: after link_list and particle_pass). Peaks come back tile by tile, inside a tile
+// by ascending density (the order indexedsort leaves them in, :676-679; ties in scan order).
+int cubep3m_b200_halofind_peaks(cubep3m_b200_ctx* ctx, float mass_p, float den_peak_cutoff, int32_t para_inter_hc, int32_t ngph, cubep3m_b200_peak* peaks,
+                                int32_t max_peaks, int32_t* n_peaks, double* cftmass) {
+  if (!ctx || !peaks || !n_peaks || max_peaks <= 0) return CUBEP3M_B200_EINVAL;
+  if (!ctx->sorted || !ctx->passed) return CUBEP3M_B200_ENOTREADY;
+  CK(cudaSetDevice(ctx->device));
+  static_assert(sizeof(halo::Peak) == sizeof(cubep3m_b200_peak), "peak record layout");
+  const Dims& d = ctx->d;
+  const int T = d.T, n = d.n;
+  int* scratch = ctx->rowoff + d.nc_node * d.nc_node + 4;
+  halo::Peak* dpk = nullptr;
+  double* dsum = nullptr;          // [0] deposit DIAG sum (unused), [1..2] cftmass, cftmass2
+  int* dn = nullptr;
+  CK(cudaMalloc(&dpk, sizeof(halo::Peak) * (size_t)max_peaks));
+  CK(cudaMalloc(&dsum, 3 * sizeof(double)));
+  CK(cudaMalloc(&dn, sizeof(int)));
+  CK(cudaMemsetAsync(dsum, 0, 3 * sizeof(double), ctx->stream));
+  CK(cudaMemsetAsync(dn, 0, sizeof(int), ctx->stream));
+  std::vector<int> tile_end(d.tiles_node, 0);
+  int status = 0;
+  for (int tile = 0; tile < d.tiles_node && !status; ++tile) {
+    const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;
+    if (!ngph) {
+      LAUNCH(ctx, KC_DENSITY, fine::cic_density_kernel, NUM_SMS * 16, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
+             dsum, scratch);
+    } else {
+      LAUNCH(ctx, KC_DENSITY, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p, dsum, scratch);
+      if (ctx->hcnt->n_cand > 0)
+        LAUNCH(ctx, KC_DENSITY, fine::ngp_fixup_kernel, NUM_SMS, fine::TPB, 0, ctx->cand, &ctx->dcnt->n_cand, ctx->cand_cap, ctx->tile_rho, n, d.b, d.m, tx, ty, tz,
+               mass_p, dsum);
+    }
+    const long long cells = (long long)d.m * d.m * d.m;
+    LAUNCH(ctx, KC_MISC, halo::peak_kernel, (unsigned)std::min<long long>((cells + halo::TPB - 1) / halo::TPB, (long long)NUM_SMS * 8), halo::TPB, 0, ctx->tile_rho, n, d.b, d.m,
+           den_peak_cutoff, para_inter_hc, tile, (float)(tx * d.m - d.b), (float)(ty * d.m - d.b), (float)(tz * d.m - d.b), dpk, max_peaks, dn, dsum + 1);
+    CK(cudaMemcpyAsync(&tile_end[tile], dn, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  double hs[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(hs, dsum, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int total = tile_end[d.tiles_node - 1];
+  if (total > max_peaks) status = CUBEP3M_B200_ECAPACITY;             // 'too many halos' (:626-629)
+  if (!status) {
+    std::vector<halo::Peak> h(total);
+    CK(cudaMemcpy(h.data(), dpk, sizeof(halo::Peak) * (size_t)total, cudaMemcpyDeviceToHost));
+    for (int tile = 0, s0 = 0; tile < d.tiles_node; ++tile) {
+      auto scan_key = [&](const halo::Peak& q) { return ((long long)q.k * n + q.j) * n + q.i; };
+      std::sort(h.begin() + s0, h.begin() + tile_end[tile], [&](const halo::Peak& a, const halo::Peak& b2) { return a.den != b2.den ? a.den < b2.den : scan_key(a) < scan_key(b2); });
+      s0 = tile_end[tile];
+    }
+    memcpy(peaks, h.data(), sizeof(halo::Peak) * (size_t)total);
+  }
+  *n_peaks = total;
+  if (cftmass) { cftmass[0] = hs[1]; cftmass[1] = hs[2]; }
+  cudaFree(dpk); cudaFree(dsum); cudaFree(dn);
+  return status;
+}
+
 int cubep3m_b200_debug_fine_tile(cubep3m_b200_ctx* ctx, int32_t tile, float mass_p, float* rho_f, float* force_f) {
   if (!ctx || !ctx->sorted || !ctx->passed) return CUBEP3M_B200_ENOTREADY;
   if (tile < 0 || tile >= ctx->d.tiles_node) return CUBEP3M_B200_EINVAL;
@@ -1925,21 +2045,7 @@ extern "C" int cubep3m_b200_read_checkpoint(cubep3m_b200_ctx* ctx, const char* p
 }
 
 // ---------------------------------------------------------------- driver twin (host): timestep.f90
-void cubep3m_b200_expansion(float a0, float dt0, float omega_m, float omega_l, float wde, float* da1, float* da2) {
-  // timestep.f90:241-293: two half steps of a 3rd-order Taylor expansion, real(8) arithmetic from real(4) arguments
-  const float dt_x = dt0 / 2;
-  double a_x = a0;
-  for (int half = 0; half < 2; ++half) {
-    const double omHsq = 4.0 / 9.0;
-    const double a3rlm = pow(a_x, (double)(-3 * wde)) * omega_l / omega_m;
-    const double arkm = a_x * (1.0 - omega_m - omega_l) / omega_m;
-    const double adot = sqrt(omHsq * a_x * a_x * a_x * (1.0 + arkm + a3rlm));
-    const double addot = a_x * a_x * omHsq * (1.5 + 2.0 * arkm + 1.5 * (1.0 - wde) * a3rlm);
-    const double atdot = a_x * adot * omHsq * (3.0 + 6.0 * arkm + 1.5 * (2.0 - 3.0 * wde) * (1.0 - wde) * a3rlm);
-    const float da = (float)(adot * dt_x + (addot * (double)dt_x * dt_x) / 2.0 + (atdot * (double)dt_x * dt_x * dt_x) / 6.0);
-    if (half == 0) { *da1 = da; a_x = (double)(a0 + da); } else *da2 = da;
-  }
-}
+void cubep3m_b200_expansion(float a0, float dt0, float omega_m, float omega_l, float wde, float* da1, float* da2) { expansion_core(a0, dt0, omega_m, omega_l, wde, da1, da2); }
 void cubep3m_b200_clock_init(cubep3m_b200_clock* c, float z_i, float omega_m, float omega_l) {
   memset(c, 0, sizeof(*c));
   c->a = 1.0f / (z_i + 1.0f);                        // cubepm.par:30, variable_initialization.f90:15-34
@@ -1948,46 +2054,19 @@ void cubep3m_b200_clock_init(cubep3m_b200_clock* c, float z_i, float omega_m, fl
   c->omega_m = omega_m; c->omega_l = omega_l; c->wde = -1.0f;
   c->a_target = 1.0f; c->cosmo = 1; c->ppint = 1;
 }
-void cubep3m_b200_timestep(cubep3m_b200_clock* c) {
-  // timestep.f90:20-196 (cosmo branch, dark matter only); dt_max = 1, ra_max = 0.01, dt_scale = 1 (cubepm.par:26-29)
-  const float dt_max = 1.0f, ra_max = 0.01f, dt_scale = 1.0f;
-  c->nts += 1;
-  if (c->nts != 1) c->dt_old = c->dt;
-  float da_1 = 0, da_2 = 0;
-  if (c->cosmo) {
-    float dt_e = dt_max;
-    int n = 0;
-    for (;;) {
-      n++;
-      cubep3m_b200_expansion(c->a, dt_e, c->omega_m, c->omega_l, c->wde, &da_1, &da_2);
-      c->da = da_1 + da_2;
-      const float ra = c->da / (c->a + c->da);
-      if (ra > ra_max) dt_e = dt_e * (ra_max / ra); else break;
-      if (n > 10) break;
-    }
-    float dt = std::min(dt_e, std::min(c->dt_f_acc, c->dt_c_acc));
-    if (c->ppint) dt = std::min(dt, c->dt_pp_acc);
-    if (c->ppint && c->pp_ext) dt = std::min(dt, c->dt_pp_ext_acc);
-    dt = dt * dt_scale;
-    cubep3m_b200_expansion(c->a, dt, c->omega_m, c->omega_l, c->wde, &da_1, &da_2);
-    c->da = da_1 + da_2;
-    c->checkpoint_step = 0;
-    if (c->a + c->da > c->a_target) {                 // timestep.f90:128-137
-      c->checkpoint_step = 1;
-      dt = dt * (c->a_target - c->a) / c->da;
-      cubep3m_b200_expansion(c->a, dt, c->omega_m, c->omega_l, c->wde, &da_1, &da_2);
-    }
-    c->da = da_1 + da_2;
-    c->a_mid = c->a + (c->da / 2);
-    c->dt = dt;
-    c->tau += dt; c->t += dt; c->a += c->da;
-  } else {                                            // timestep.f90:198-221
-    c->a = 1.0f; c->a_mid = 1.0f; c->da = 0.f;
-    float dt = std::min(1.0f, std::min(c->dt_f_acc, c->dt_c_acc));
-    if (c->ppint) dt = std::min(dt, c->dt_pp_acc);
-    if (c->ppint && c->pp_ext) dt = std::min(dt, c->dt_pp_ext_acc);
-    c->dt = dt; c->t += dt;
-  }
+void cubep3m_b200_timestep(cubep3m_b200_clock* c) { timestep_core(c); }
+
+// The same timestep on the device: the clock lives in device memory next to the step's counters, one thread runs timestep_core
+// (real(8) expansion, timestep.f90:241-293) after folding in the limiters the last particle_mesh left, and the host only reads the result back.
+int cubep3m_b200_timestep_device(cubep3m_b200_ctx* ctx, cubep3m_b200_clock* clock) {
+  if (!ctx || !clock) return CUBEP3M_B200_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->dclock) CK(cudaMalloc(&ctx->dclock, sizeof(cubep3m_b200_clock)));
+  CK(cudaMemcpyAsync(ctx->dclock, clock, sizeof(*clock), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(ctx, KC_MISC, timestep_kernel, 1, 32, 0, ctx->dclock);
+  CK(cudaMemcpyAsync(clock, ctx->dclock, sizeof(*clock), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 }  // extern "C"

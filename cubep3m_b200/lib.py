@@ -29,7 +29,7 @@ SYMBOLS = ["cubep3m_b200_version", "cubep3m_b200_strerror", "cubep3m_b200_defaul
            "cubep3m_b200_debug_fft3d", "cubep3m_b200_debug_ppext_blocks", "cubep3m_b200_debug_pair_counts", "cubep3m_b200_launch_count", "cubep3m_b200_set_profiling", "cubep3m_b200_set_tile_streams",
            "cubep3m_b200_num_kernel_classes", "cubep3m_b200_kernel_class_name", "cubep3m_b200_get_kernel_times",
            "cubep3m_b200_cic_power", "cubep3m_b200_dist_init", "cubep3m_b200_write_checkpoint", "cubep3m_b200_read_checkpoint", "cubep3m_b200_clock_init",
-           "cubep3m_b200_expansion", "cubep3m_b200_timestep"]
+           "cubep3m_b200_expansion", "cubep3m_b200_timestep", "cubep3m_b200_timestep_device", "cubep3m_b200_halofind_peaks"]
 
 
 def build_library(force=False, verbose=False):
@@ -94,6 +94,8 @@ def load_library():
     L.cubep3m_b200_clock_init.argtypes = [C.POINTER(Clock), C.c_float, C.c_float, C.c_float]
     L.cubep3m_b200_expansion.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.cubep3m_b200_timestep.argtypes = [C.POINTER(Clock)]
+    L.cubep3m_b200_timestep_device.argtypes = [C.c_void_p, C.POINTER(Clock)]
+    L.cubep3m_b200_halofind_peaks.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     _LIB = L
     return L
 
@@ -246,6 +248,21 @@ class ParticleMesh:
         frc = np.empty((f, f, f, 3), np.float32) if want_force else None
         _chk(self.lib.cubep3m_b200_debug_fine_tile(self.h, tile, mass_p, _ptr(rho), _ptr(frc)))
         return rho, frc
+
+    def halofind_peaks(self, mass_p, den_peak_cutoff=100.0, para_inter_hc=True, ngph=False, max_peaks=1 << 20):
+        """find_halos' density + maxima pass (halofind.f90:564-672) over every tile; call after link_list + particle_pass (cubepm.f90:193-198).
+        Returns (structured array of peaks, (cftmass, cftmass2))."""
+        from .abi import PEAK_DTYPE
+        pk = np.zeros(max_peaks, dtype=PEAK_DTYPE)
+        n = C.c_int32(0)
+        cft = (C.c_double * 2)()
+        _chk(self.lib.cubep3m_b200_halofind_peaks(self.h, mass_p, den_peak_cutoff, int(para_inter_hc), int(ngph), pk.ctypes.data, max_peaks, C.byref(n), cft))
+        return pk[:n.value].copy(), (cft[0], cft[1])
+
+    def timestep_device(self, c):
+        """timestep.f90 evaluated on the device (same state transition as timestep(c))."""
+        _chk(self.lib.cubep3m_b200_timestep_device(self.h, C.byref(c)))
+        return c
 
     def fft3d(self, a, inverse=False):
         n = a.shape[0]

@@ -249,6 +249,25 @@ typedef struct cubep3m_b200_clock {
 void cubep3m_b200_clock_init(cubep3m_b200_clock* c, float z_i, float omega_m, float omega_l);
 void cubep3m_b200_expansion(float a0, float dt0, float omega_m, float omega_l, float wde, float* da1, float* da2);
 void cubep3m_b200_timestep(cubep3m_b200_clock* c);
+/* The same timestep evaluated ON THE DEVICE: the clock is copied to device memory, one thread runs the identical
+ * real(8) expansion / limiter logic (timestep.f90:54-293), the result is read back. Same results as cubep3m_b200_timestep to the last
+ * bit of the float state except where the device's pow()/sqrt() differ from the host libm by an ulp of the real(8) intermediate. */
+int cubep3m_b200_timestep_device(cubep3m_b200_ctx* ctx, cubep3m_b200_clock* c);
+
+/*
+ * Halo finder, density + maxima pass: halofind.f90:564-672 (find_halos up to the peak sort), called per tile from halofind.f90:48-54 on a
+ * halofind step, i.e. after link_list and particle_pass (cubepm.f90:193-198; ENOTREADY otherwise). Per tile the fine density is deposited
+ * (ngph != 0: fine_ngp_mass as with -DNGPH, else fine_cic_mass, :597-616), every physical cell that is the maximum of its 3^3 neighbourhood
+ * and exceeds den_peak_cutoff (cubepm.par:124) becomes a peak (:620-632), its position refined by per-axis parabolic interpolation when
+ * para_inter_hc (cubepm.par:133, :634-655, para_inter :770-778). Output: i, j, k = ipeak (1-based tile-local cell), tile = 0-based tile index
+ * (x fastest), den = den_peak, x/y/z = peak_pos + offset (node-local fine-cell units, as halo_pos :723). Order: tile by tile, ascending density
+ * inside a tile (what indexedsort leaves, :676-679). cftmass[2] = sums of rho_f and rho_f**2 over the physical cells (:621-622).
+ * More than max_peaks maxima ('too many halos', :626-629) returns ECAPACITY with *n_peaks = the number found.
+ * The spherical-overdensity mass growth that follows in the reference (:683-745) consumes these peaks sequentially and stays with the driver.
+ */
+typedef struct cubep3m_b200_peak { int32_t i, j, k, tile; float den, x, y, z; } cubep3m_b200_peak;
+int cubep3m_b200_halofind_peaks(cubep3m_b200_ctx* ctx, float mass_p, float den_peak_cutoff, int32_t para_inter_hc, int32_t ngph,
+                                cubep3m_b200_peak* peaks, int32_t max_peaks, int32_t* n_peaks, double* cftmass);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,7 @@ def _lib():
         _LIB.oracle_set_debug_tile.argtypes = [C.c_void_p, C.c_int, C.c_int]
         _LIB.oracle_fine_tile.argtypes = [C.c_void_p, C.c_int, _fp, _fp]
         _LIB.oracle_fft3d.argtypes = [C.c_int, _fp, C.c_int]
+        _LIB.oracle_find_peaks.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         _LIB.oracle_set_num_threads.argtypes = [C.c_int]
     return _LIB
 
@@ -165,6 +166,15 @@ class Oracle:
     def set_debug_tile(self, tile, rank=0):
         """tile is 1-based cur_tile (particle_mesh_threaded.f90:85)."""
         self.lib.oracle_set_debug_tile(self.h, rank, tile)
+
+    def find_peaks(self, mass_p, den_peak_cutoff=100.0, para_inter_hc=True, ngph=False, rank=0, max_peaks=1 << 20):
+        """halofind.f90:564-672: peaks tile by tile in scan order (before the reference's sort), and (cftmass, cftmass2)."""
+        dt = [("i", "<i4"), ("j", "<i4"), ("k", "<i4"), ("tile", "<i4"), ("den", "<f4"), ("x", "<f4"), ("y", "<f4"), ("z", "<f4")]
+        pk = np.zeros(max_peaks, dtype=dt)
+        n = C.c_int(0)
+        cft = (C.c_double * 2)()
+        _chk(self.lib.oracle_find_peaks(self.h, rank, mass_p, den_peak_cutoff, int(para_inter_hc), int(ngph), pk.ctypes.data, max_peaks, C.byref(n), cft))
+        return pk[:n.value].copy(), (cft[0], cft[1])
 
     def fine_tile(self, rank=0):
         n, f = self.cfg.nf_tile, self.cfg.m + 3

@@ -959,6 +959,92 @@ int particle_mesh(World& w, float dt, float dt_old, float a_mid, float mass_p, c
 // -------------------------------------------------------------------------------------------------
 // C interface for ctypes (tests / bench cpu_baseline only)
 // -------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------- halofind.f90:564-672 (find_halos: density + maxima pass)
+struct OPeak { int i, j, k, tile; float den, x, y, z; };
+
+static float para_inter(const float x[3], const float fx[3]) {          // halofind.f90:770-778
+  return x[1] - 0.5f * (((x[1] - x[0]) * (x[1] - x[0])) * (fx[1] - fx[2]) - ((x[1] - x[2]) * (x[1] - x[2])) * (fx[1] - fx[0])) /
+                    ((x[1] - x[0]) * (fx[1] - fx[2]) - (x[1] - x[2]) * (fx[1] - fx[0]));
+}
+
+// peaks are appended tile by tile in the scan order of :620-627 (before the sort of :676-679); cft[0..1] += cftmass, cftmass2
+void find_peaks(World& w, RankState& r, float mass_p, float den_peak_cutoff, int para_inter_hc, int ngph, std::vector<OPeak>& out, double* cft) {
+  const Params& p = w.p;
+  const int n = p.n, n2 = n + 2, b = p.b, m = p.m, T = p.T;
+  std::vector<float> rho;
+  for (int cur = 1; cur <= p.tiles_node; ++cur) {                      // halofind.f90:48-54
+    int tile[3];
+    tile[2] = (cur - 1) / (T * T);
+    int j0 = cur - tile[2] * T * T;
+    tile[1] = (j0 - 1) / T;
+    j0 = j0 - tile[1] * T;
+    tile[0] = j0 - 1;
+    rho.assign((size_t)n2 * n * n, 0.f);                               // :591
+    auto RHO = [&](int i, int j, int k) -> float& { return rho[(size_t)(i - 1) + (size_t)n2 * ((j - 1) + (size_t)n * (k - 1))]; };
+    int cic_l[3], cic_h[3], off_i[3];
+    float offset[3];
+    for (int d = 0; d < 3; ++d) {
+      off_i[d] = tile[d] * m - b;                                      // :585
+      cic_l[d] = p.nc_tile * tile[d] + 2 - p.nc_buf;                   // :597
+      cic_h[d] = p.nc_tile * (tile[d] + 1) + p.nc_buf - 1;             // :598
+      offset[d] = (float)(-tile[d] * m + b);                           // fine_ngp_mass.f90:11 / fine_cic_mass.f90:13
+    }
+    for (int k = cic_l[2]; k <= cic_h[2]; ++k)                         // :602-616
+      for (int j = cic_l[1]; j <= cic_h[1]; ++j)
+        for (int i = cic_l[0]; i <= cic_h[0]; ++i) {
+          int pp = r.hoc[hidx(p, i, j, k)];
+          while (pp != 0) {
+            const float* q = &r.xv[(size_t)6 * (pp - 1)];
+            float x[3]; int i1[3];
+            for (int d = 0; d < 3; ++d) { x[d] = q[d] + offset[d]; i1[d] = ifloor(x[d]) + 1; }
+            if (ngph) {
+              RHO(i1[0], i1[1], i1[2]) = RHO(i1[0], i1[1], i1[2]) + mass_p;          // fine_ngp_mass.f90:19
+            } else {                                                                  // fine_cic_mass.f90:17-41
+              float dx1[3], dx2[3];
+              for (int d = 0; d < 3; ++d) { dx1[d] = (float)i1[d] - x[d]; dx2[d] = 1.f - dx1[d]; }
+              dx1[0] = mass_p * dx1[0]; dx2[0] = mass_p * dx2[0];
+              for (int cz = 0; cz < 2; ++cz)
+                for (int cy = 0; cy < 2; ++cy)
+                  for (int cx = 0; cx < 2; ++cx) {
+                    float wgt = ((cx ? dx2[0] : dx1[0]) * (cy ? dx2[1] : dx1[1])) * (cz ? dx2[2] : dx1[2]);
+                    float& c = RHO(i1[0] + cx, i1[1] + cy, i1[2] + cz);
+                    c = c + wgt;
+                  }
+            }
+            pp = r.ll[pp - 1];
+          }
+        }
+    for (int k = 1 + b; k <= b + m; ++k)                               // :620-672
+      for (int j = 1 + b; j <= b + m; ++j)
+        for (int i = 1 + b; i <= b + m; ++i) {
+          const float c = RHO(i, j, k);
+          cft[0] += (double)c;
+          cft[1] += (double)(c * c);
+          float denmax = c;
+          for (int kk = k - 1; kk <= k + 1; ++kk)
+            for (int jj = j - 1; jj <= j + 1; ++jj)
+              for (int ii = i - 1; ii <= i + 1; ++ii) denmax = std::max(denmax, RHO(ii, jj, kk));
+          if (denmax == c && denmax > den_peak_cutoff) {
+            OPeak q;
+            q.i = i; q.j = j; q.k = k; q.tile = cur - 1; q.den = denmax;
+            float pos[3];
+            if (para_inter_hc) {
+              const int c3[3] = {i, j, k};
+              for (int d = 0; d < 3; ++d) {
+                const float x[3] = {(float)(c3[d] - 1) - 0.5f, (float)c3[d] - 0.5f, (float)(c3[d] + 1) - 0.5f};
+                const float fx[3] = {RHO(i - (d == 0), j - (d == 1), k - (d == 2)), c, RHO(i + (d == 0), j + (d == 1), k + (d == 2))};
+                pos[d] = para_inter(x, fx);
+              }
+            } else {
+              pos[0] = (float)i - 0.5f; pos[1] = (float)j - 0.5f; pos[2] = (float)k - 0.5f;
+            }
+            q.x = pos[0] + (float)off_i[0]; q.y = pos[1] + (float)off_i[1]; q.z = pos[2] + (float)off_i[2];   // :723
+            out.push_back(q);
+          }
+        }
+  }
+}
+
 extern "C" {
 
 int oracle_create(const cubep3m_b200_config* cfg, const float* fine_table, const float* coarse_table, int build_kernels, void** out) {
@@ -1052,6 +1138,17 @@ int oracle_fine_tile(void* h, int rank, float* rho_f, float* force_f) {
   RankState& r = ((World*)h)->R[rank];
   if (r.dbg_rho_f.empty()) return CUBEP3M_B200_ENOTREADY;
   std::copy(r.dbg_rho_f.begin(), r.dbg_rho_f.end(), rho_f); std::copy(r.dbg_force_f.begin(), r.dbg_force_f.end(), force_f); return 0;
+}
+int oracle_find_peaks(void* h, int rank, float mass_p, float den_peak_cutoff, int para_inter_hc, int ngph, void* peaks, int max_peaks, int* n_peaks, double* cft) {
+  World* w = (World*)h;
+  std::vector<OPeak> v;
+  double c2[2] = {0.0, 0.0};
+  find_peaks(*w, w->R[rank], mass_p, den_peak_cutoff, para_inter_hc, ngph, v, c2);
+  *n_peaks = (int)v.size();
+  if (cft) { cft[0] = c2[0]; cft[1] = c2[1]; }
+  if ((int)v.size() > max_peaks) return 8;
+  memcpy(peaks, v.data(), v.size() * sizeof(OPeak));
+  return 0;
 }
 int oracle_fft3d(int n, float* data, int inverse) {
   oracle::Fft3dR2C f; f.init(n);

@@ -27,6 +27,10 @@ module cubep3m_b200
     integer(c_int32_t) :: rank, local_gpu
     integer(c_int32_t) :: nodes_dim_xyz(3)
   end type
+  type, bind(C) :: b200_peak               ! struct cubep3m_b200_peak: ipeak(1:3), 0-based tile, den_peak, peak_pos + offset
+    integer(c_int32_t) :: i, j, k, tile
+    real(c_float) :: den, x, y, z
+  end type
   type, bind(C) :: b200_step_out
     integer(c_int32_t) :: np_local, np_with_ghosts, np_deleted_ll, np_buf_max
     real(c_float)      :: dt_f_acc, dt_pp_acc, dt_pp_ext_acc, dt_c_acc
@@ -107,6 +111,16 @@ module cubep3m_b200
       real(c_double), value :: box
       integer(c_int32_t), value :: ngp_binning, nshells
       real(c_double), intent(out) :: k(*), d2(*), sig(*)
+    end function
+    !! find_halos' density + maxima pass on the device (halofind.f90:564-672)
+    integer(c_int) function b200_c_halofind_peaks(ctx, mass_p, den_cut, para, ngph, peaks, max_peaks, n_peaks, cft) bind(C, name='cubep3m_b200_halofind_peaks')
+      import
+      type(c_ptr), value :: ctx
+      real(c_float), value :: mass_p, den_cut
+      integer(c_int32_t), value :: para, ngph, max_peaks
+      type(b200_peak), intent(out) :: peaks(*)
+      integer(c_int32_t), intent(out) :: n_peaks
+      real(c_double), intent(out) :: cft(2)
     end function
   end interface
 contains
@@ -226,6 +240,25 @@ contains
     st = b200_c_delete_particles(b200_ctx, np_dl)
     call b200_check(st, 'delete_particles')
     np_local = np_dl
+  end subroutine
+  !! Replacement for the first half of find_halos (halofind.f90:564-679): fills ipeak / den_peak / peak_pos of one tile, sorted by density as
+  !! indexedsort leaves them, from the device pass over all tiles; the spherical-overdensity growth (:683-745) then runs unchanged on the host
+  !! against a rho_f the driver deposits itself, or is skipped when only the peak catalogue is wanted. Called once per halofind step after
+  !! link_list / particle_pass (cubepm.f90:193-198); tile_first(t) .. tile_first(t+1)-1 index the peaks of tile t (0-based).
+  subroutine b200_halofind_peaks(peaks, n_peaks, cft)
+    include 'cubepm.fh'
+    type(b200_peak), intent(out) :: peaks(max_maxima)
+    integer(4), intent(out) :: n_peaks
+    real(8), intent(out) :: cft(2)
+    integer(4) :: st, ngph, para
+    ngph = 0
+#ifdef NGPH
+    ngph = 1
+#endif
+    para = 0
+    if (para_inter_hc) para = 1
+    st = b200_c_halofind_peaks(b200_ctx, mass_p, den_peak_cutoff, para, ngph, peaks, max_maxima, n_peaks, cft)
+    call b200_check(st, 'halofind_peaks')   ! ECAPACITY = 'too many halos' (halofind.f90:626-629)
   end subroutine
 end module cubep3m_b200
 

@@ -395,6 +395,20 @@ def run_ours(args):
                           "delta2_nyquist": float(pd2[-1]), "finite": bool(np.isfinite(pd2).all())}
         except Exception as e:      # noqa: BLE001 - the bench line must survive
             power_info = {"error": f"{type(e).__name__}: {e}"}
+    # ---- the halo finder's density + maxima pass (halofind.f90:564-672) over the node's tiles, in the state a halofind step is in (cubepm.f90:193-198:
+    # link_list, particle_pass, halofind, delete_particles). One rank only (the bench line must not depend on it); not part of `value`.
+    halo_info = None
+    if world == 1:
+        try:
+            pm.link_list(); pm.particle_pass()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pks, cft = pm.halofind_peaks(mass_p, 100.0, True, False)
+            halo_info = {"ms": (time.perf_counter() - t0) * 1e3, "tiles": int(cfg.tiles_node_dim) ** 3, "n_peaks": int(len(pks)), "den_peak_cutoff": 100.0,
+                         "scheme": "CIC", "clumping_factor": float(cft[1] * float(cfg.mT) ** 3 / max(cft[0] ** 2, 1e-300))}
+            pm.delete_particles()
+        except Exception as e:      # noqa: BLE001 - the bench line must survive
+            halo_info = {"error": f"{type(e).__name__}: {e}"}
     if world > 1:
         t = torch.tensor([ms_step, e2e_ms, dev_step], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -481,6 +495,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stages": stages,
             "cic_power": power_info,
+            "halofind_peaks": halo_info,
             "stage_ms_last_step": {k: round(v, 3) for k, v in last.stages().items()},
             "limiters_last_step": {"dt_f_acc": last.dt_f_acc, "dt_pp_acc": last.dt_pp_acc, "dt_c_acc": last.dt_c_acc,
                                    "sum_rho_f": last.sum_rho_f, "sum_rho_c": last.sum_rho_c, "a": clk.a, "nts": clk.nts},

@@ -20,6 +20,12 @@ def _worker(rank, world, grid, nf_tile, uid, tmp, lrck):
     pm = ParticleMesh(cfg, nccl_id=uid, world_size=world)
     xv = np.load(os.path.join(tmp, f"in{rank}.npy"))
     pm.upload_particles(xv)
+    # a halofind step's sequence (cubepm.f90:193-198,228) on the initial particles: the peak pass sees the neighbours' ghosts
+    pm.link_list(); pm.particle_pass()
+    pk, cft = pm.halofind_peaks(8.0, 20.0, True, True)
+    np.save(os.path.join(tmp, f"peaks{rank}.npy"), pk)
+    np.save(os.path.join(tmp, f"cft{rank}.npy"), np.array(cft))
+    pm.delete_particles()
     outs = []
     for step in range(2):
         out = pm.particle_mesh(0.4, 0.2 * step + 0.1, 0.05, 8.0, (3.0, -1.5, 0.25))
@@ -62,6 +68,19 @@ def test_multi_gpu_step_matches_oracle(built, tmp_path, case, monkeypatch):
         o.set_particles(xv, rank=r)
     uid = get_unique_id()
     mp.spawn(_worker, args=(world, grid, nf_tile, uid, str(tmp_path), lrck), nprocs=world, join=True)
+    o.link_list(); o.particle_pass()
+    for r in range(world):
+        op, oc = o.find_peaks(8.0, 20.0, True, True, rank=r)
+        gp, gc = np.load(tmp_path / f"peaks{r}.npy"), np.load(tmp_path / f"cft{r}.npy")
+        key = lambda a: a[np.lexsort((a["i"], a["j"], a["k"], a["tile"]))]
+        gp, op = key(gp), key(op)
+        assert len(op) > 100 and len(gp) == len(op), (r, len(gp), len(op))
+        for f in ("tile", "i", "j", "k", "den"):
+            assert np.array_equal(gp[f], op[f]), (r, f)
+        for f in ("x", "y", "z"):
+            assert np.array_equal(gp[f], op[f], equal_nan=True), (r, f)
+        assert gc[0] == pytest.approx(oc[0], rel=1e-12) and gc[1] == pytest.approx(oc[1], rel=1e-12)
+    o.delete_particles()
     for step in range(2):
         oo = o.particle_mesh(0.4, 0.2 * step + 0.1, 0.05, 8.0, (3.0, -1.5, 0.25))
         for r in range(world):

@@ -22,7 +22,7 @@ def _worker(rank, world, grid, nf_tile, uid, tmp, lrck):
     pm.upload_particles(xv)
     # a halofind step's sequence (cubepm.f90:193-198,228) on the initial particles: the peak pass sees the neighbours' ghosts
     pm.link_list(); pm.particle_pass()
-    pk, cft = pm.halofind_peaks(8.0, 20.0, True, True)
+    pk, cft = pm.halofind_peaks(8.0, 4.0, True, True)
     np.save(os.path.join(tmp, f"peaks{rank}.npy"), pk)
     np.save(os.path.join(tmp, f"cft{rank}.npy"), np.array(cft))
     pm.delete_particles()
@@ -70,7 +70,7 @@ def test_multi_gpu_step_matches_oracle(built, tmp_path, case, monkeypatch):
     mp.spawn(_worker, args=(world, grid, nf_tile, uid, str(tmp_path), lrck), nprocs=world, join=True)
     o.link_list(); o.particle_pass()
     for r in range(world):
-        op, oc = o.find_peaks(8.0, 20.0, True, True, rank=r)
+        op, oc = o.find_peaks(8.0, 4.0, True, True, rank=r)
         gp, gc = np.load(tmp_path / f"peaks{r}.npy"), np.load(tmp_path / f"cft{r}.npy")
         key = lambda a: a[np.lexsort((a["i"], a["j"], a["k"], a["tile"]))]
         gp, op = key(gp), key(op)

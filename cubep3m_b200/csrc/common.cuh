@@ -123,6 +123,7 @@ struct cubep3m_b200_ctx {
   bool sorted = false;   // xv[cur] is cell-sorted and fstart is valid
   bool passed = false;
   unsigned int* key = nullptr;
+  unsigned short* rank = nullptr;   // rank of every particle inside its fine cell (the count its histogram atomic returned): scatter slot = fstart[key] + rank
   int* blist = nullptr;       // particles near a y / z face, listed by the first pack kernel of particle_pass
   bool keys_fused = false;    // the pass kernels of this step already produced key[] and the histogram (do_sort skips key_hist_kernel)
   int* fstart = nullptr; // exclusive scan of fine-cell counts, NF+1 entries
@@ -163,6 +164,7 @@ struct cubep3m_b200_ctx {
   bool want_roles = false, roles_listed = false;      // particle_mesh asks the scatter to list the margin roles; the limiter kernel then skips its own listing   // (particle index, tile) list of the PP_EXT margin roles
   int ppext_blocks = 0, ppext_fallback = 0;
   long long pairs_ppint = 0, pairs_ppext = 0;   // of the last step   // of the last step (debug getter)
+  bool hist_zero_in_scatter = false;  // CUBEP3M_B200_HISTZERO=scatter: the scatter stores zero into every occupied cell's histogram word instead of the clearing kernel under PP_EXT
   bool hist_clean = false;     // fcur (the fine-cell histogram) is all zeros
   cudaStream_t stream_main = nullptr, stream_aux[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};

@@ -461,7 +461,7 @@ int do_pass(cubep3m_b200_ctx* ctx, int* np_buf_max, const float* drift = nullptr
   // latency-bound; the stand-alone key_hist_kernel (load -> atomic -> exit) runs at the DRAM limit. Off by default.
   static const bool fuse_env = [] { const char* e = getenv("CUBEP3M_B200_FUSE_KEYS"); return e && atoi(e) == 1; }();
   const bool fuse_keys = fuse_env && in_step && drift != nullptr;
-  part::KeyArgs KA{lo, hi, dd.b, dd.H, fuse_keys ? ctx->key : nullptr, ctx->fcur, ctx->cand, ctx->cand_cap};
+  part::KeyArgs KA{lo, hi, dd.b, dd.H, fuse_keys ? ctx->key : nullptr, ctx->fcur, ctx->cand, ctx->cand_cap, ctx->rank};
   if (fuse_keys) {
     if (!ctx->hist_clean) CK(cudaMemsetAsync(ctx->fcur, 0, sizeof(unsigned int) * (dd.NF / 2), ctx->stream));
     ctx->hist_clean = false;
@@ -606,12 +606,12 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
   const float lo = -(float)d.b, hi = (float)d.mT + (float)d.b;
   CK(cudaMemsetAsync(&ctx->dcnt->n_multi, 0, 2 * sizeof(int), ctx->stream));
   if (!ctx->keys_fused) {
-    if (!ctx->hist_clean) CK(cudaMemsetAsync(ctx->fcur, 0, sizeof(unsigned int) * (d.NF / 2), ctx->stream));   // two 16-bit counters per word; otherwise the last scatter left it zeroed
+    if (!ctx->hist_clean) CK(cudaMemsetAsync(ctx->fcur, 0, sizeof(unsigned int) * (d.NF / 2), ctx->stream));   // two 16-bit counters per word; otherwise particle_mesh cleared it behind the last step's PP stage
     ctx->hist_clean = false;
     CK(cudaMemsetAsync(&ctx->dcnt->np_deleted, 0, sizeof(int), ctx->stream));
     CK(cudaMemsetAsync(&ctx->dcnt->n_cand, 0, sizeof(int), ctx->stream));
     if (np > 0) {
-      part::KeyArgs KA{lo, hi, d.b, d.H, ctx->key, ctx->fcur, ctx->cand, ctx->cand_cap};
+      part::KeyArgs KA{lo, hi, d.b, d.H, ctx->key, ctx->fcur, ctx->cand, ctx->cand_cap, ctx->rank};
       LAUNCH(ctx, KC_KEY_HIST, part::key_hist_kernel, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], np, KA, ctx->dcnt);
     }
   }
@@ -634,21 +634,20 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
     const part::MarginGeom G{d.H, d.b, d.m, d.T, ctx->cfg.pp_range};
     if (roles) {
       CK(cudaMemsetAsync(&ctx->dcnt->n_margin_roles, 0, sizeof(int), ctx->stream));
-      LAUNCH(ctx, KC_SCATTER, part::scatter_kernel<true>, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->fcur, ctx->fstart,
+      LAUNCH(ctx, KC_SCATTER, part::scatter_kernel<true>, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->rank, ctx->hist_zero_in_scatter ? ctx->fcur : nullptr, ctx->fstart,
              ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1], d.max_np, G, ctx->margin_roles, ctx->margin_cap, &ctx->dcnt->n_margin_roles);
       ctx->roles_listed = true;
     } else {
-      LAUNCH(ctx, KC_SCATTER, part::scatter_kernel<false>, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->fcur, ctx->fstart,
+      LAUNCH(ctx, KC_SCATTER, part::scatter_kernel<false>, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->rank, ctx->hist_zero_in_scatter ? ctx->fcur : nullptr, ctx->fstart,
              ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1], d.max_np, G, nullptr, 0, nullptr);
     }
   }
   CK(cudaGetLastError());
   if (int st = fetch_counters(ctx)) return st;
-  if (ctx->hcnt->overflow & (4 | 8)) {      // a wrapped cell counter leaves the histogram dirty: clear it before the next sort
-    ctx->hist_clean = false;
-    return overflow_status(ctx->hcnt);
-  }
-  ctx->hist_clean = true;
+  // the histogram stays as counted (the scatter no longer counts it down): the next sort clears it first, unless particle_mesh has meanwhile
+  // cleared it behind its PP stage (hist_clean)
+  if (ctx->hcnt->overflow & (4 | 8)) return overflow_status(ctx->hcnt);
+  if (ctx->hist_zero_in_scatter) ctx->hist_clean = true;      // every occupied cell's word was stored back to zero by the scatter
   ctx->cur ^= 1;
   ctx->np_all = np - ctx->hcnt->np_deleted;
   if (!ctx->passed) ctx->np_local = ctx->np_all;
@@ -1081,7 +1080,7 @@ int cubep3m_b200_finalize(cubep3m_b200_ctx* ctx) {
 #ifdef CUBEP3M_WITH_NCCL
   if (ctx->comm) ncclCommDestroy(ctx->comm);
 #endif
-  F(ctx->cand); F(ctx->deltas); F(ctx->ndelta); F(ctx->tile_counts); F(ctx->key); F(ctx->blist); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->scan_status); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
+  F(ctx->cand); F(ctx->deltas); F(ctx->ndelta); F(ctx->tile_counts); F(ctx->key); F(ctx->rank); F(ctx->blist); F(ctx->fstart); F(ctx->fcur); F(ctx->blocksum); F(ctx->scan_status); F(ctx->multi_list); F(ctx->occ_list); F(ctx->rowoff);
   F(ctx->dclock); F(ctx->kern_f); F(ctx->tile_rho); F(ctx->tile_g); F(ctx->force_f[0]); 
   for (int q = 1; q < cubep3m_b200_ctx::MAX_TILE_STREAMS; ++q) {
     F(ctx->tile_rho_s[q]); F(ctx->tile_g_s[q]); F(ctx->force_f_s[q]);
@@ -1129,6 +1128,7 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
     if (cfg->pid) TRY(dmalloc(&ctx->sendpid[i], (size_t)d.max_buf / 6 + 1));
   }
   TRY(dmalloc(&ctx->key, (size_t)d.max_np));
+  TRY(dmalloc(&ctx->rank, (size_t)d.max_np));
   TRY(dmalloc(&ctx->blist, (size_t)d.max_np));
   ctx->cand_cap = std::max(4096, d.max_np / 64);
   TRY(dmalloc(&ctx->cand, (size_t)3 * ctx->cand_cap));
@@ -1146,6 +1146,11 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
     // it saves, sets the pace. Kept as an option (bit-identical results, tests/test_gpu_parity.py::test_scan_variants_agree); default: three kernels.
     const char* e = getenv("CUBEP3M_B200_SCAN");
     ctx->scan_onepass = e && !strcmp(e, "1pass");
+  }
+  {   // A/B: how the sort's cell histogram returns to zero: one low-footprint clearing kernel under the PP_EXT kernels (default) or a plain store per
+      // particle in the scatter (CUBEP3M_B200_HISTZERO=scatter; measured: the partial-sector stores cost the scatter 1.5 ms at 512^3)
+    const char* e = getenv("CUBEP3M_B200_HISTZERO");
+    ctx->hist_zero_in_scatter = e && !strcmp(e, "scatter");
   }
   {   // A/B: "direct" = round 1's per-target / per-cell kernels, "tma" = the cell kernel with bulk-copy staging of the long source ranges
     const char* e = getenv("CUBEP3M_B200_PPEXT_DENSE");
@@ -1424,6 +1429,18 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   // the limiter part of PP_EXT (:617) only reads positions: with CUBEP3M_B200_MARGIN=overlap it runs on the (by now idle) coarse stream next to the
   // PP_EXT kick kernels instead of behind them. (Running it next to the fine tiles cost more than it hid: fine_fft 33.1 -> 37.9 ms at 512^3.)
   static const bool margin_overlap = [] { const char* e = getenv("CUBEP3M_B200_MARGIN"); return e && !strcmp(e, "overlap"); }();
+  {
+    // the sort's cell histogram is no longer needed (the scan was its last reader): clear it for the next step on the idle coarse stream, under the
+    // issue-bound PP_EXT kernels that leave the DRAM idle (2.5 GB at 512^3 particles; the main stream joins ev[13] below)
+    if (!ctx->hist_clean) {
+      CK(cudaStreamWaitEvent(ctx->stream_coarse, ev[5], 0));
+      ctx->stream = ctx->stream_coarse;
+      LAUNCH(ctx, KC_MISC, part::zero_words_kernel, NUM_SMS * 2, 32, 0, reinterpret_cast<uint4*>(ctx->fcur), (long long)(d.NF / 8));   // NF / 2 words, NF % 64 == 0
+      ctx->stream = ctx->stream_main;
+      CK(cudaEventRecord(ev[13], ctx->stream_coarse));
+      ctx->hist_clean = true;
+    }
+  }
   if (margin_overlap) {
     CK(cudaStreamWaitEvent(ctx->stream_coarse, ev[5], 0));
     ctx->stream = ctx->stream_coarse;

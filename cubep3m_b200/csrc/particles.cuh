@@ -75,17 +75,22 @@ __device__ __forceinline__ unsigned int make_key(float x, float y, float z, int 
 // particle_pass kernels, which already hold every record in registers inside particle_mesh (the stand-alone pass over all records is saved).
 // Lists the particles that sit within 2^-15 below an integer coordinate on any axis: only for those can the reference's tile-local cell
 // floor(fl(x + offset)) (particle_mesh_threaded.f90:139-143) differ from floor(x)+offset.
+// The value the histogram atomic returns is the particle's RANK inside its cell: it is stored (2 bytes per particle) and the scatter places the record at
+// fstart[key] + rank without touching the table again (round 1 / early round 2: the scatter drew its slot with a second atomic that counted the cell back to
+// zero — one more DRAM sector read-modify-write per particle on the sparse table; the table is now cleared by a memset that particle_mesh hides behind PP_EXT).
 // The histogram holds two 16-bit counters per 32-bit word (cell k -> word k>>1, half k&1): the table is the largest array the sort touches
 // (H^3*64 cells, ~8 per particle) and every atomic on it is a DRAM sector read-modify-write, so halving its footprint halves that traffic.
 // A fine cell with >= 65535 particles raises the 'exceeded max_llf' flag (max_llf = 100000 in cubepm.par:183 is the same kind of bound).
-struct KeyArgs { float lo, hi; int b, H; unsigned int* key; unsigned int* hist; float* cand; int cand_cap; };
+struct KeyArgs { float lo, hi; int b, H; unsigned int* key; unsigned int* hist; float* cand; int cand_cap; unsigned short* rank; };
 __device__ __forceinline__ void key_one(const KeyArgs& A, long long i, float x, float y, float z, DevCounters* __restrict__ cnt) {
   unsigned int k = KEY_DEAD;
   if (in_hoc_range(x, y, z, A.lo, A.hi)) {
     k = make_key(x, y, z, A.b, A.H);
     const unsigned sh = (k & 1u) << 4;
     const unsigned old = atomicAdd(&A.hist[k >> 1], 1u << sh);
-    if (((old >> sh) & 0xffffu) >= 0xfffeu) atomicOr(&cnt->overflow, 4);
+    const unsigned before = (old >> sh) & 0xffffu;       // particles counted into this cell before this one = its rank inside the cell
+    if (before >= 0xfffeu) atomicOr(&cnt->overflow, 4);
+    A.rank[i] = (unsigned short)before;
     const float th = 3.0517578125e-05f;   // 2^-15 >= half an ulp of any |x + offset| < 1024
     // exact integers are not candidates: x + offset is exact for them, so both binnings agree
     const float ux = ceilf(x) - x, uy = ceilf(y) - y, uz = ceilf(z) - z;
@@ -450,9 +455,16 @@ __device__ __forceinline__ unsigned margin_roles(const int g[3], const MarginGeo
 
 // ROLES: the scatter already knows every particle's fine cell (its key) and its place in the sorted array, so it also appends the particle's margin roles
 // (sorted index, tile) to the list the PP_EXT limiter works from — a separate listing kernel re-read all records (1.26 ms at 512^3).
+// Clears the cell histogram for the next step. One warp per CTA and a grid of a few CTAs per SM: the kernel is meant to run on a side stream UNDER the
+// issue-bound PP_EXT kernels (which leave the DRAM idle) without taking SM slots from them — cudaMemsetAsync's own kernel fills the SMs and cost PP_EXT
+// the 0.5 ms it was supposed to hide.
+__global__ void __launch_bounds__(32) zero_words_kernel(uint4* __restrict__ p, long long n16) {
+  for (long long i = (long long)blockIdx.x * 32 + threadIdx.x; i < n16; i += (long long)gridDim.x * 32) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 template <bool ROLES>
 __global__ void __launch_bounds__(TPB) scatter_kernel(const float* __restrict__ xv_in, const int64_t* __restrict__ pid_in,
-                                                      const unsigned int* __restrict__ key, int np, unsigned int* __restrict__ hist,
+                                                      const unsigned int* __restrict__ key, int np, const unsigned short* __restrict__ rank, unsigned int* __restrict__ hist,
                                                       const int* __restrict__ fstart, float* __restrict__ xv_out, int64_t* __restrict__ pid_out, int np_cap,
                                                       MarginGeom G, int2* __restrict__ roles, int role_cap, int* __restrict__ n_roles) {
   const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
@@ -462,10 +474,9 @@ __global__ void __launch_bounds__(TPB) scatter_kernel(const float* __restrict__ 
   if (k != KEY_DEAD) {
     float2 a, b, c;
     load_xv(xv_in, i, a, b, c);
-    // slot = cell start + (remaining count - 1): every particle decrements its cell once, so the histogram is back to all zeros
-    // after the scatter and needs no memset before the next step's key_hist_kernel
-    const unsigned sh = (k & 1u) << 4;
-    dst = fstart[k] + (int)((atomicSub(&hist[k >> 1], 1u << sh) >> sh) & 0xffffu) - 1;
+    // slot = cell start + rank inside the cell (the count the histogram atomic of key_one returned): no atomics, the cell table is read-only here
+    dst = fstart[k] + (int)rank[i];
+    if (hist) hist[k >> 1] = 0u;     // clears the cell's word for the next step's histogram: a plain store (nobody reads the table any more), not a read-modify-write
     if ((unsigned)dst >= (unsigned)np_cap) dst = -1;   // only reachable after a 16-bit cell counter overflowed (flagged by key_hist_kernel, the step fails with EMAXLLF)
     else {
       store_xv(xv_out, dst, a, b, c);

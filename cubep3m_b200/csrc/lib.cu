@@ -1360,6 +1360,15 @@ int cubep3m_b200_particle_pass(cubep3m_b200_ctx* ctx, int32_t* np_with_ghosts) {
   if (int st = do_pass(ctx, &bufmax)) return st;
   if (int st = do_sort(ctx, nullptr)) return st;
   if (np_with_ghosts) *np_with_ghosts = ctx->np_all;
+  // The stand-alone pass receives through NCCL into the same buffers a neighbour's NEXT particle_mesh packs into over peer memory. Inside a step the
+  // end-of-step all-reduce keeps a fast rank from overwriting what its neighbour has not consumed; here (the halofind / projection sequence of
+  // cubepm.f90:193-198 followed by the next step) the same guarantee needs a fence: nobody leaves particle_pass before everybody has unpacked
+  // (the reference's blocking mpi_sendrecv_replace calls give it for free, particle_pass.f90:141-144).
+  if (ctx->d.world > 1 && ctx->p2p) {
+    float mx[1] = {0.f};
+    double sm[1] = {0.0};
+    if (int st = reduce_scalars(ctx, mx, 1, sm, 1)) return st;
+  }
   return 0;
 }
 

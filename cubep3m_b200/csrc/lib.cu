@@ -627,6 +627,12 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
     LAUNCH(ctx, KC_SCAN, part::scan_apply_kernel<false>, nb, part::TPB, 0, ctx->fcur, d.NF, ctx->blocksum, ctx->fstart, d.H, d.nc_buf, d.nc_node, ctx->multi_list,
            ctx->occ_list, ctx->list_cap, ctx->cfg.ppint ? 1 : 0, 0, ctx->dcnt, nullptr, nb);
   }
+  // The histogram has had its last reader: clear it for the next sort (0.06 ms at 256^3 particles, 0.4 ms at 512^3; hiding it under the PP_EXT kernels
+  // — defer_hist_zero, an A/B knob — did not pay).
+  if (!ctx->defer_hist_zero && !ctx->hist_zero_in_scatter) {
+    CK(cudaMemsetAsync(ctx->fcur, 0, sizeof(unsigned int) * (d.NF / 2), ctx->stream));
+    ctx->hist_clean = true;
+  }
   // inside particle_mesh with PP_EXT on, the scatter also lists the margin roles for the PP_EXT limiter (do_pp_ext_margin)
   const bool roles = ctx->want_roles && ctx->cfg.pp_ext && ctx->cfg.pp_range > 0 && ctx->ppext_margin_max && ctx->margin_roles;
   ctx->roles_listed = false;
@@ -646,7 +652,7 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
   if (int st = fetch_counters(ctx)) return st;
   // the histogram stays as counted (the scatter no longer counts it down): the next sort clears it first, unless particle_mesh has meanwhile
   // cleared it behind its PP stage (hist_clean)
-  if (ctx->hcnt->overflow & (4 | 8)) return overflow_status(ctx->hcnt);
+  if (ctx->hcnt->overflow & (4 | 8)) { ctx->hist_clean = false; return overflow_status(ctx->hcnt); }   // a wrapped counter: clear everything before the next sort
   if (ctx->hist_zero_in_scatter) ctx->hist_clean = true;      // every occupied cell's word was stored back to zero by the scatter
   ctx->cur ^= 1;
   ctx->np_all = np - ctx->hcnt->np_deleted;
@@ -1147,8 +1153,8 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
     const char* e = getenv("CUBEP3M_B200_SCAN");
     ctx->scan_onepass = e && !strcmp(e, "1pass");
   }
-  {   // A/B: how the sort's cell histogram returns to zero: one low-footprint clearing kernel under the PP_EXT kernels (default) or a plain store per
-      // particle in the scatter (CUBEP3M_B200_HISTZERO=scatter; measured: the partial-sector stores cost the scatter 1.5 ms at 512^3)
+  {   // A/B: how the sort's cell histogram returns to zero: a memset after the scan (default), a low-footprint clearing kernel under the PP_EXT kernels
+      // (=under), or a plain store per particle in the scatter (=scatter; measured: the partial-sector stores cost the scatter 1.5 ms at 512^3)
     const char* e = getenv("CUBEP3M_B200_HISTZERO");
     ctx->hist_zero_in_scatter = e && !strcmp(e, "scatter");
   }
@@ -1410,7 +1416,12 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   // listing kernel. Measured at 512^3: listing kernel -1.26 ms, scatter +1.94 ms (the role arithmetic lengthens a DRAM-latency-bound kernel). Off.
   static const bool roles_in_scatter = [] { const char* e = getenv("CUBEP3M_B200_ROLES"); return e && !strcmp(e, "scatter"); }();
   ctx->want_roles = roles_in_scatter;
+  // A/B knob: CUBEP3M_B200_HISTZERO=under clears the histogram with a one-warp-per-CTA kernel under the PP_EXT kernels instead of a memset right after
+  // the scan (measured at 512^3: 60.4-60.5 vs 60.1-60.4 ms/step — the slow clearing kernel costs PP_EXT what the memset costs the sort)
+  static const bool zero_under = [] { const char* e = getenv("CUBEP3M_B200_HISTZERO"); return e && !strcmp(e, "under"); }();
+  ctx->defer_hist_zero = ctx->cfg.pp_ext && ctx->cfg.pp_range > 0 && zero_under;
   const int sort_st = do_sort(ctx, &ndel);                                                // :61 link_list as a cell sort
+  ctx->defer_hist_zero = false;
   ctx->want_roles = false;
   if (sort_st) return sort_st;
   const int np_ghost = ctx->np_all;

@@ -125,6 +125,57 @@ __global__ void __launch_bounds__(TPB) cic_density_kernel(const float* __restric
   }
 }
 
+// The same deposit as a SCATTER on the cell-sorted array (the north star's formulation): one CTA per coarse x-row (cy, cz) of the tile — a contiguous range of
+// the sorted array whose particles reach only the fine rows y in [4 cy, 4 cy + 4], z in [4 cz, 4 cz + 4] — accumulates the eight weights of every particle
+// (formed exactly as fine_cic_mass.f90:17-41 forms them, from i1 = floor(fl(x + offset))) with shared-memory atomics into a 5 x 5-row staging tile and flushes the
+// tile with coalesced global atomic adds (rows are shared with the neighbouring CTAs through the +1 spill). Cells outside [0, n) are dropped as
+// fine_cic_mass_buffer.f90 drops them. rho must be zero on entry. Summation order differs from the chain order by fp32 rounding only. The gather kernel above
+// (deterministic, no atomics) walks 8 cells' particle lists per grid point and is 7x slower at the mean density (0.67 ms per 304^3 tile).
+__global__ void __launch_bounds__(TPB) cic_scatter_kernel(const float* __restrict__ xv, const int* __restrict__ fstart, float* __restrict__ rho, int n, int b, int m,
+                                                          int H, int tx, int ty, int tz, float mass_p, double* __restrict__ sum_phys, int* __restrict__ tile_count) {
+  extern __shared__ float stile[];                       // [5 z][5 y][n + 2]
+  const int ncr = n >> 2, n2 = n + 2;
+  const int ry = blockIdx.x % ncr, rz = blockIdx.x / ncr;
+  for (int t = threadIdx.x; t < 25 * n2; t += TPB) stile[t] = 0.f;
+  const long long rk = (long long)((rz + tz * (m >> 2)) * H + (ry + ty * (m >> 2))) * H + tx * (m >> 2);
+  const int s0 = fstart[rk * 64], s1 = fstart[(rk + ncr - 1) * 64 + 64];
+  const float offx = (float)(b - tx * m), offy = (float)(b - ty * m), offz = (float)(b - tz * m);
+  __syncthreads();
+  for (int i = s0 + threadIdx.x; i < s1; i += TPB) {
+    const float2* p = reinterpret_cast<const float2*>(xv) + 3LL * i;
+    const float2 a = p[0];
+    const float xt = __fadd_rn(a.x, offx), yt = __fadd_rn(a.y, offy), zt = __fadd_rn(p[1].x, offz);
+    const int ix = (int)floorf(xt), iy = (int)floorf(yt), iz = (int)floorf(zt);             // i1 - 1
+    const float dx1 = __fmul_rn(mass_p, (float)(ix + 1) - xt), dx2 = __fmul_rn(mass_p, 1.0f - ((float)(ix + 1) - xt));
+    const float dy1 = (float)(iy + 1) - yt, dy2 = 1.0f - dy1, dz1 = (float)(iz + 1) - zt, dz2 = 1.0f - dz1;
+    const int ly = iy - 4 * ry, lz = iz - 4 * rz;       // 0..3 (4 only when fl(y + offset) rounded up to the next coarse cell: then the +1 weight is exactly 0)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int jx = ix + (q & 1), jy = ly + ((q >> 1) & 1), jz = lz + (q >> 2);
+      if (jx < n && jy < 5 && jz < 5) {
+        const float w = __fmul_rn(__fmul_rn((q & 1) ? dx2 : dx1, ((q >> 1) & 1) ? dy2 : dy1), (q >> 2) ? dz2 : dz1);
+        atomicAdd(&stile[(jz * 5 + jy) * n2 + jx], w);
+      }
+    }
+  }
+  __syncthreads();
+  double msum = 0.0;
+  for (int t = threadIdx.x; t < 25 * n; t += TPB) {
+    const int r = t / n, x = t - r * n;
+    const int y = 4 * ry + r % 5, z = 4 * rz + r / 5;
+    if (y < n && z < n) {
+      const float v = stile[r * n2 + x];
+      if (v != 0.f) {
+        atomicAdd(&rho[((long long)z * n + y) * n2 + x], v);
+        if (x >= b && x < n - b && y >= b && y < n - b && z >= b && z < n - b) msum += (double)v;
+      }
+    }
+  }
+  msum = warp_sum_d(msum);
+  if ((threadIdx.x & 31) == 0 && msum != 0.0) atomicAdd(sum_phys, msum);
+  if (threadIdx.x == 0 && tile_count && s1 > s0) atomicAdd(tile_count, s1 - s0);
+}
+
 // CIC force interpolation + kick, particle_mesh_threaded.f90:289-316 (sequential adds in the reference's corner order)
 __global__ void __launch_bounds__(TPB) cic_fine_kick_kernel(float* __restrict__ xv, const int* __restrict__ fstart, const float* __restrict__ fx,
                                                             const float* __restrict__ fy, const float* __restrict__ fz, int H, int nc_buf, int nc_tile,

@@ -687,6 +687,25 @@ int do_delete(cubep3m_b200_ctx* ctx, const float* kick = nullptr) {
   return 0;
 }
 
+// fine CIC deposit of one tile into t_rho ((n + 2) x n x n): shared-memory-staged scatter (default) or the gather kernel (CUBEP3M_B200_FINECIC=gather)
+int launch_cic_density(cubep3m_b200_ctx* ctx, float* t_rho, int tx, int ty, int tz, float mass_p, double* dsum, int* count) {
+  const Dims& d = ctx->d;
+  const int n = d.n;
+  static const bool gather = [] { const char* e = getenv("CUBEP3M_B200_FINECIC"); return e && !strcmp(e, "gather"); }();
+  const size_t smem = (size_t)25 * (n + 2) * sizeof(float);
+  if (gather || smem > 200 * 1024) {
+    LAUNCH(ctx, KC_DENSITY, fine::cic_density_kernel, NUM_SMS * 16, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, t_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p, dsum, count);
+    return 0;
+  }
+  static bool attr_dev[64] = {false};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (!attr_dev[dev & 63]) { CK(cudaFuncSetAttribute(fine::cic_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024))); attr_dev[dev & 63] = true; }
+  CK(cudaMemsetAsync(t_rho, 0, sizeof(float) * (size_t)(n + 2) * n * n, ctx->stream));
+  LAUNCH(ctx, KC_DENSITY, fine::cic_scatter_kernel, (n / 4) * (n / 4), fine::TPB, smem, ctx->xv[ctx->cur], ctx->fstart, t_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p, dsum, count);
+  return 0;
+}
+
 // fine-mesh solve of one tile: (density fused into) forward FFT -> fused z pass with the Green's functions -> inverse y, x + crop.
 // materialise = true writes rho_f to tile_rho first with the stand-alone deposit kernels (debug getter / reference ordering).
 int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, bool materialise, int* scratch_count, int set = 0) {
@@ -698,8 +717,7 @@ int fine_tile_solve(cubep3m_b200_ctx* ctx, int tile, float mass_p, bool material
   const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;   // particle_mesh_threaded.f90:86-90 (cur_tile-1, x fastest)
   const float scale = 1.0f / (((float)n * (float)n) * (float)n);       // fft_fine.f90:51
   if (!ctx->cfg.ngp) {   // fine CIC: materialised gather deposit, then the generic solve
-    LAUNCH(ctx, KC_DENSITY, fine::cic_density_kernel, NUM_SMS * 16, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, t_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
-           &ctx->dcnt->sum_rho_f, scratch_count);
+    if (int st = launch_cic_density(ctx, t_rho, tx, ty, tz, mass_p, &ctx->dcnt->sum_rho_f, scratch_count)) return st;
     return fftk::fine_solve(ctx, fine_mesh(ctx), t_rho, t_g, d.hc, ctx->kern_f, ctx->kf_stride, ctx->kf_pitch, t_force, d.b - 2, d.fdim, scale, &ctx->dcnt->f_force_max2_bits);
   }
   if (materialise) {
@@ -1643,8 +1661,7 @@ int cubep3m_b200_halofind_peaks(cubep3m_b200_ctx* ctx, float mass_p, float den_p
   for (int tile = 0; tile < d.tiles_node && !status; ++tile) {
     const int tz = tile / (T * T), ty = (tile / T) % T, tx = tile % T;
     if (!ngph) {
-      LAUNCH(ctx, KC_DENSITY, fine::cic_density_kernel, NUM_SMS * 16, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
-             dsum, scratch);
+      if ((status = launch_cic_density(ctx, ctx->tile_rho, tx, ty, tz, mass_p, dsum, scratch))) break;
     } else {
       LAUNCH(ctx, KC_DENSITY, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p, dsum, scratch);
       if (ctx->hcnt->n_cand > 0)
@@ -1688,8 +1705,7 @@ int cubep3m_b200_debug_fine_tile(cubep3m_b200_ctx* ctx, int32_t tile, float mass
   double* dsum = nullptr;
   CK(cudaMalloc(&dsum, sizeof(double)));
   if (!ctx->cfg.ngp) {
-    LAUNCH(ctx, KC_DENSITY, fine::cic_density_kernel, NUM_SMS * 16, fine::TPB, 0, ctx->xv[ctx->cur], ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p,
-           dsum, scratch);
+    if (int st = launch_cic_density(ctx, ctx->tile_rho, tx, ty, tz, mass_p, dsum, scratch)) { cudaFree(dsum); return st; }
   } else {
     LAUNCH(ctx, KC_DENSITY, fine::ngp_density_kernel, NUM_SMS * 8, fine::TPB, 0, ctx->fstart, ctx->tile_rho, n, d.b, d.m, d.H, tx, ty, tz, mass_p, dsum, scratch);
     if (ctx->hcnt->n_cand > 0)

@@ -466,7 +466,15 @@ def run_ours(args):
                     "note": "algorithmic bytes per launch / mean CUDA-event time per launch over K instrumented steps that directly follow the K timed "
                             "steps (instrumented with ONE fine tile in flight so that a launch's event time is its own; the timed steps keep two tiles "
                             "in flight; the coarse-mesh solve overlaps on its own stream in both, so a fine-mesh launch's event time can include SM "
-                            "time lent to coarse kernels)"}
+                            "time lent to coarse kernels). With PP_EXT on, the largest single kernel of the step is pp::ppext_tiled_kernel, which is "
+                            "FP32-issue-bound, not HBM-bound: its pairs/s and fraction of the measured FFMA peak are in stages.ppext (roofline_fp32 "
+                            "repeats them); this object covers the largest HBM-bound kernel class."}
+        roofline_fp32 = None
+        if "ppext" in stages and stages["ppext"].get("frac_of_fp32_peak") is not None:
+            e = stages["ppext"]
+            roofline_fp32 = {"kernel": "ppext (pp::ppext_tiled_kernel + dense-cell kernels)", "bound": "fp32", "achieved": e["achieved_TFLOPs"], "peak": e["fp32_peak_TFLOPs"],
+                             "unit": "TFLOP/s", "frac": e["frac_of_fp32_peak"], "pairs_per_s": e["pairs_per_s"], "share_of_step": e["share_of_step"],
+                             "note": "20 flop per ordered pair (SURVEY 8d) / measured FFMA peak (tools/fp32_peak.cu)"}
         cpu = None
         if world == 1 and not args.no_cpu:
             # bounded sample: for boxes beyond 256^3 particles one octant-sized node of the same workload (same tile size, flags, density and
@@ -494,7 +502,7 @@ def run_ours(args):
             "e2e": {"value": total_particles / (e2e_ms * 1e-3), "unit": "particles/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(npart) * 24, "d2h_bytes_per_step": int(npart) * 24, "steps": e2e_steps,
                     "mode": "strict drop-in: pinned host xv -> H2D, particle_mesh, D2H every step (cubepm.f90:143 semantics)", "host_numa": numa_note},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_fp32": roofline_fp32, "cpu_baseline": cpu,
             "stages": stages,
             "cic_power": power_info,
             "halofind_peaks": halo_info,

@@ -164,7 +164,7 @@ struct cubep3m_b200_ctx {
   bool want_roles = false, roles_listed = false;      // particle_mesh asks the scatter to list the margin roles; the limiter kernel then skips its own listing   // (particle index, tile) list of the PP_EXT margin roles
   int ppext_blocks = 0, ppext_fallback = 0;
   long long pairs_ppint = 0, pairs_ppext = 0;   // of the last step   // of the last step (debug getter)
-  bool hist_zero_in_scatter = false;  // CUBEP3M_B200_HISTZERO=scatter: the scatter stores zero into every occupied cell's histogram word instead of the clearing kernel under PP_EXT
+  int hist_mode = 0;                  // CUBEP3M_B200_HISTZERO: 0 = scatter by stored rank + memset after the scan (default), 1 = "scatter": + zero store per particle, 2 = "countdown": round 1's second atomic
   bool defer_hist_zero = false;       // set by particle_mesh around its sort when PP_EXT is on: the histogram is cleared under the PP_EXT kernels instead of right after the scan
   bool hist_clean = false;     // fcur (the fine-cell histogram) is all zeros
   cudaStream_t stream_main = nullptr, stream_aux[MAX_TILE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused

@@ -629,7 +629,7 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
   }
   // The histogram has had its last reader: clear it for the next sort (0.06 ms at 256^3 particles, 0.4 ms at 512^3; hiding it under the PP_EXT kernels
   // — defer_hist_zero, an A/B knob — did not pay).
-  if (!ctx->defer_hist_zero && !ctx->hist_zero_in_scatter) {
+  if (!ctx->defer_hist_zero && ctx->hist_mode == 0) {
     CK(cudaMemsetAsync(ctx->fcur, 0, sizeof(unsigned int) * (d.NF / 2), ctx->stream));
     ctx->hist_clean = true;
   }
@@ -640,12 +640,12 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
     const part::MarginGeom G{d.H, d.b, d.m, d.T, ctx->cfg.pp_range};
     if (roles) {
       CK(cudaMemsetAsync(&ctx->dcnt->n_margin_roles, 0, sizeof(int), ctx->stream));
-      LAUNCH(ctx, KC_SCATTER, part::scatter_kernel<true>, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->rank, ctx->hist_zero_in_scatter ? ctx->fcur : nullptr, ctx->fstart,
-             ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1], d.max_np, G, ctx->margin_roles, ctx->margin_cap, &ctx->dcnt->n_margin_roles);
+      LAUNCH(ctx, KC_SCATTER, part::scatter_kernel<true>, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->rank, ctx->fcur, ctx->fstart,
+             ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1], d.max_np, G, ctx->margin_roles, ctx->margin_cap, &ctx->dcnt->n_margin_roles, ctx->hist_mode);
       ctx->roles_listed = true;
     } else {
-      LAUNCH(ctx, KC_SCATTER, part::scatter_kernel<false>, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->rank, ctx->hist_zero_in_scatter ? ctx->fcur : nullptr, ctx->fstart,
-             ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1], d.max_np, G, nullptr, 0, nullptr);
+      LAUNCH(ctx, KC_SCATTER, part::scatter_kernel<false>, (np + part::TPB - 1) / part::TPB, part::TPB, 0, ctx->xv[ctx->cur], ctx->pid[ctx->cur], ctx->key, np, ctx->rank, ctx->fcur, ctx->fstart,
+             ctx->xv[ctx->cur ^ 1], ctx->pid[ctx->cur ^ 1], d.max_np, G, nullptr, 0, nullptr, ctx->hist_mode);
     }
   }
   CK(cudaGetLastError());
@@ -653,7 +653,7 @@ int do_sort(cubep3m_b200_ctx* ctx, int* np_deleted) {
   // the histogram stays as counted (the scatter no longer counts it down): the next sort clears it first, unless particle_mesh has meanwhile
   // cleared it behind its PP stage (hist_clean)
   if (ctx->hcnt->overflow & (4 | 8)) { ctx->hist_clean = false; return overflow_status(ctx->hcnt); }   // a wrapped counter: clear everything before the next sort
-  if (ctx->hist_zero_in_scatter) ctx->hist_clean = true;      // every occupied cell's word was stored back to zero by the scatter
+  if (ctx->hist_mode != 0) ctx->hist_clean = true;      // every occupied cell's word was stored / counted back to zero by the scatter
   ctx->cur ^= 1;
   ctx->np_all = np - ctx->hcnt->np_deleted;
   if (!ctx->passed) ctx->np_local = ctx->np_all;
@@ -1174,7 +1174,7 @@ int cubep3m_b200_init(const cubep3m_b200_config* cfg, const float* fine_table, c
   {   // A/B: how the sort's cell histogram returns to zero: a memset after the scan (default), a low-footprint clearing kernel under the PP_EXT kernels
       // (=under), or a plain store per particle in the scatter (=scatter; measured: the partial-sector stores cost the scatter 1.5 ms at 512^3)
     const char* e = getenv("CUBEP3M_B200_HISTZERO");
-    ctx->hist_zero_in_scatter = e && !strcmp(e, "scatter");
+    ctx->hist_mode = (e && !strcmp(e, "scatter")) ? 1 : (e && !strcmp(e, "countdown")) ? 2 : 0;
   }
   {   // A/B: "direct" = round 1's per-target / per-cell kernels, "tma" = the cell kernel with bulk-copy staging of the long source ranges
     const char* e = getenv("CUBEP3M_B200_PPEXT_DENSE");
@@ -1437,7 +1437,7 @@ int cubep3m_b200_particle_mesh(cubep3m_b200_ctx* ctx, float dt, float dt_old, fl
   // A/B knob: CUBEP3M_B200_HISTZERO=under clears the histogram with a one-warp-per-CTA kernel under the PP_EXT kernels instead of a memset right after
   // the scan (measured at 512^3: 60.4-60.5 vs 60.1-60.4 ms/step — the slow clearing kernel costs PP_EXT what the memset costs the sort)
   static const bool zero_under = [] { const char* e = getenv("CUBEP3M_B200_HISTZERO"); return e && !strcmp(e, "under"); }();
-  ctx->defer_hist_zero = ctx->cfg.pp_ext && ctx->cfg.pp_range > 0 && zero_under;
+  ctx->defer_hist_zero = ctx->cfg.pp_ext && ctx->cfg.pp_range > 0 && zero_under && ctx->hist_mode == 0;
   const int sort_st = do_sort(ctx, &ndel);                                                // :61 link_list as a cell sort
   ctx->defer_hist_zero = false;
   ctx->want_roles = false;

@@ -466,7 +466,7 @@ template <bool ROLES>
 __global__ void __launch_bounds__(TPB) scatter_kernel(const float* __restrict__ xv_in, const int64_t* __restrict__ pid_in,
                                                       const unsigned int* __restrict__ key, int np, const unsigned short* __restrict__ rank, unsigned int* __restrict__ hist,
                                                       const int* __restrict__ fstart, float* __restrict__ xv_out, int64_t* __restrict__ pid_out, int np_cap,
-                                                      MarginGeom G, int2* __restrict__ roles, int role_cap, int* __restrict__ n_roles) {
+                                                      MarginGeom G, int2* __restrict__ roles, int role_cap, int* __restrict__ n_roles, int hist_mode) {
   const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
   unsigned int k = KEY_DEAD;
   if (i < np) k = key[i];
@@ -475,8 +475,13 @@ __global__ void __launch_bounds__(TPB) scatter_kernel(const float* __restrict__ 
     float2 a, b, c;
     load_xv(xv_in, i, a, b, c);
     // slot = cell start + rank inside the cell (the count the histogram atomic of key_one returned): no atomics, the cell table is read-only here
-    dst = fstart[k] + (int)rank[i];
-    if (hist) hist[k >> 1] = 0u;     // clears the cell's word for the next step's histogram: a plain store (nobody reads the table any more), not a read-modify-write
+    if (hist_mode == 2) {             // A/B: round 1's slot draw — a second atomic that counts the cell back to zero (no rank array read, no clearing pass)
+      const unsigned sh = (k & 1u) << 4;
+      dst = fstart[k] + (int)((atomicSub(&hist[k >> 1], 1u << sh) >> sh) & 0xffffu) - 1;
+    } else {
+      dst = fstart[k] + (int)rank[i];
+      if (hist_mode == 1) hist[k >> 1] = 0u;     // A/B: clears the cell's word with a plain store (partial-sector writes: slow)
+    }
     if ((unsigned)dst >= (unsigned)np_cap) dst = -1;   // only reachable after a 16-bit cell counter overflowed (flagged by key_hist_kernel, the step fails with EMAXLLF)
     else {
       store_xv(xv_out, dst, a, b, c);

@@ -483,7 +483,8 @@ def run_ours(args):
             if npart > 64 * 1024 * 1024:
                 scfg = default_config(nf_tile=cfg.nf_tile, tiles_node_dim=cfg.tiles_node_dim // 2, ppint=cfg.ppint, pp_ext=cfg.pp_ext)
                 sxv, _ = make_ics(scfg, box, z_i)
-                snote = f"a {round(len(sxv) ** (1 / 3))}^3-particle node of the same workload (1/8 of the box: same nf_tile, flags, density and ICs)"
+                snote = (f"a {round(len(sxv) ** (1 / 3))}^3-particle node of the same workload (1/8 of the box: same nf_tile, flags, density and ICs; its "
+                         f"{scfg.tiles_node_dim ** 3} tiles leave part of the host threads idle in the tile loop - the reference arm, --impl reference, times the whole box)")
             sec, threads, ost, ran = oracle_run(scfg, sxv, z_i, 3, 0, budget_s=30.0)
             cpu = {"value": len(sxv) / sec, "unit": "particles/s", "cores": threads, "kind": "port", "ms_per_step": sec * 1e3,
                    "sample": f"{ran} full particle_mesh step(s) from the ICs on {snote}, {threads} OpenMP threads (oracle FFT: batched Stockham, not FFTW)",
